@@ -1,0 +1,292 @@
+// ts_capi.cu -- the C ABI of include/torchshifts_b200.h: argument validation, host-side border
+// logic, path selection (staged vs generic) and launch bookkeeping.  No torch types, no
+// allocation, no synchronisation; every entry point only enqueues kernels on the caller's stream.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "ts_kernels.h"
+
+namespace ts {
+
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<int> g_forced_path{0};
+static thread_local int t_last_path = TS_PATH_NONE;
+static thread_local char t_cuda_error[256] = "";
+
+void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+int check_launch() {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return TS_OK;
+    snprintf(t_cuda_error, sizeof(t_cuda_error), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    return TS_ERR_CUDA;
+}
+
+static int cuda_fail(cudaError_t e) {
+    snprintf(t_cuda_error, sizeof(t_cuda_error), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? TS_ERR_NO_DEVICE : TS_ERR_CUDA;
+}
+
+static int sm_count(int* out) {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    if (dev >= 0 && dev < 64 && cached[dev].load() > 0) { *out = cached[dev].load(); return TS_OK; }
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    if (dev >= 0 && dev < 64) cached[dev].store(n);
+    *out = n;
+    return TS_OK;
+}
+
+static int make_geo(const ts_geometry* in, int padding, Geo* g) {
+    if (!in) return TS_ERR_INVALID_ARGUMENT;
+    if (in->dim < 1 || in->dim > 3) return TS_ERR_INVALID_ARGUMENT;
+    if (padding < 0 || padding > 4) return TS_ERR_INVALID_ARGUMENT;
+    if (in->N < 0 || in->C < 0) return TS_ERR_INVALID_ARGUMENT;
+    g->dim = in->dim;
+    g->pad = padding;
+    g->N = in->N;
+    g->C = in->C;
+    long long ip = 1, op = 1;
+    for (int a = 0; a < 3; ++a) {
+        const long long S = a < in->dim ? in->size[a] : 1;
+        const long long lb = a < in->dim ? in->lb[a] : 0;
+        const long long rb = a < in->dim ? in->rb[a] : 1;
+        if (S < 0 || lb < 0 || rb > S || rb < lb) return TS_ERR_INVALID_ARGUMENT;
+        if (S >= 0x7fffffffLL) return TS_ERR_TOO_LARGE;
+        g->S[a] = (int)S;
+        g->lb[a] = (int)lb;
+        g->OS[a] = (int)(rb - lb);
+        ip *= S;
+        op *= (rb - lb);
+        if (ip >= 0x7fffffffLL) return TS_ERR_TOO_LARGE;
+    }
+    for (int a = 0; a < 5; ++a) g->xs[a] = (a < 2 + in->dim) ? in->x_stride[a] : 0;
+    g->in_plane = ip;
+    g->out_plane = op;
+    return TS_OK;
+}
+
+static bool x_is_dense(const Geo& g) {
+    long long expect = 1;
+    for (int a = g.dim - 1; a >= 0; --a) {
+        if (g.S[a] != 1 && g.xs[2 + a] != expect) return false;
+        expect *= g.S[a];
+    }
+    if (g.C != 1 && g.xs[1] != expect) return false;
+    expect *= g.C;
+    if (g.N != 1 && g.xs[0] != expect) return false;
+    return true;
+}
+
+static int elem_size(int dtype) {
+    switch (dtype) {
+    case TS_F32: return 4;
+    case TS_F64: return 8;
+    case TS_F16: case TS_BF16: return 2;
+    }
+    return 0;
+}
+
+}  // namespace ts
+
+using namespace ts;
+
+extern "C" {
+
+int ts_abi_version(void) { return TS_ABI_VERSION; }
+int ts_cuda_version(void) { return CUDART_VERSION; }
+
+const char* ts_error_string(int status) {
+    switch (status) {
+    case TS_OK: return "ok";
+    case TS_ERR_INVALID_ARGUMENT: return "invalid argument (dim must be 1..3, padding 0..4, sizes/borders consistent, pointers non-null)";
+    case TS_ERR_UNSUPPORTED: return "unsupported request (no kernel for this element type / forced kernel path not applicable)";
+    case TS_ERR_WORKSPACE: return "backward workspace missing, misaligned or smaller than ts_shift_backward_workspace_bytes()";
+    case TS_ERR_TOO_LARGE: return "a single (n,c) plane must have fewer than 2^31 elements";
+    case TS_ERR_BORDERS: return "borders produce a negative output dimension";
+    case TS_ERR_CUDA: return "CUDA error (see ts_last_cuda_error())";
+    case TS_ERR_NO_DEVICE: return "no CUDA device available: torchshifts-b200 has no CPU fallback";
+    }
+    return "unknown status";
+}
+
+const char* ts_last_cuda_error(void) { return t_cuda_error; }
+int ts_last_kernel_path(void) { return t_last_path; }
+int ts_set_kernel_path(int path) {
+    if (path < 0 || path > 2) return -1;
+    return g_forced_path.exchange(path);
+}
+uint64_t ts_launch_count(void) { return (uint64_t)g_launches.load(); }
+
+int ts_set_tuning(const char* spec) {
+    if (!spec) return TS_ERR_INVALID_ARGUMENT;
+    Tuning t = tuning();
+    const char* p = spec;
+    while (*p) {
+        char key[32];
+        int val = 0, n = 0;
+        if (sscanf(p, " %31[a-z_]=%d%n", key, &val, &n) != 2) return TS_ERR_INVALID_ARGUMENT;
+        if (!strcmp(key, "stages")) t.stages = val;
+        else if (!strcmp(key, "stage_kb")) t.stage_kb = val;
+        else if (!strcmp(key, "warps")) t.warps = val;
+        else if (!strcmp(key, "ctas_per_sm")) t.ctas_per_sm = val;
+        else if (!strcmp(key, "chunk_planes")) t.chunk_planes = val;
+        else return TS_ERR_INVALID_ARGUMENT;
+        p += n;
+        while (*p == ',' || *p == ' ') ++p;
+    }
+    if (t.stages < 1 || t.stages > 8 || t.stage_kb < 1 || t.stage_kb > 200 || t.warps < 1 || t.warps > 31 ||
+        t.ctas_per_sm < 1 || t.ctas_per_sm > 8 || t.chunk_planes < 0)
+        return TS_ERR_INVALID_ARGUMENT;
+    tuning() = t;
+    return TS_OK;
+}
+
+// ---- host logic ------------------------------------------------------------------------------
+int ts_check_borders(int dim, const int64_t* sizes, const int64_t* user, int64_t lb[3], int64_t rb[3]) {
+    if (dim < 1 || dim > 3 || !sizes || !lb || !rb) return TS_ERR_INVALID_ARGUMENT;
+    for (int a = 0; a < 3; ++a) { lb[a] = 0; rb[a] = a < dim ? sizes[a] : 1; }
+    if (!user) return TS_OK;
+    for (int a = 0; a < dim; ++a) {
+        const int size = (int)sizes[a];
+        int r = size - (int)user[2 * a + 1];
+        int l = (int)user[2 * a];
+        if (r - l < 1) r = l + 1;
+        if (l == size) { l = size - 1; r = l + 1; }
+        if (r == 0) { l = 0; r = 1; }
+        if (l < 0) l = 0;
+        if (r > size) r = size;
+        if (r - l < 0) return TS_ERR_BORDERS;
+        lb[a] = l;
+        rb[a] = r;
+    }
+    return TS_OK;
+}
+
+int ts_debug_remap(int padding, int len, int idx) { return len == 1 ? 0 : remap_literal(idx, len, padding); }
+
+int ts_debug_remap_reduced(int padding, int len, int pos, int64_t shift, int plus) {
+    const int s = reduce_shift((long long)shift, len, padding);
+    return axis_index(pos - s + plus, len, padding);
+}
+
+void ts_debug_split_f32(int backward, int active, float w, int64_t* iw, float* dw) {
+    long long i; float d;
+    if (backward) split_backward<float>(w, active != 0, i, d); else split_forward<float>(w, active != 0, i, d);
+    *iw = i; *dw = d;
+}
+void ts_debug_split_f64(int backward, int active, double w, int64_t* iw, double* dw) {
+    long long i; double d;
+    if (backward) split_backward<double>(w, active != 0, i, d); else split_forward<double>(w, active != 0, i, d);
+    *iw = i; *dw = d;
+}
+
+// ---- device entry points ---------------------------------------------------------------------
+int ts_shift_forward(const ts_geometry* gin, int dtype, int padding, int active, const void* x, const void* weights,
+                     void* y, void* stream) {
+    Geo g;
+    int rc = make_geo(gin, padding, &g);
+    if (rc != TS_OK) return rc;
+    const int es = elem_size(dtype);
+    if (!es) return TS_ERR_INVALID_ARGUMENT;
+    if (g.N * g.C == 0 || g.out_plane == 0) return TS_OK;
+    if (!x || !weights || !y) return TS_ERR_INVALID_ARGUMENT;
+    int sms = 0;
+    if ((rc = sm_count(&sms)) != TS_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int forced = g_forced_path.load();
+    StagedPlan plan;
+    plan.ok = false;
+    if (forced != TS_PATH_GENERIC) plan = plan_staged(g, active ? 1 : 0, es, dtype, x_is_dense(g), x, y, nullptr, sms);
+    if (forced == TS_PATH_STAGED && !plan.ok) return TS_ERR_UNSUPPORTED;
+    if (plan.ok) {
+        t_last_path = TS_PATH_STAGED;
+        return active ? staged_active_forward(g, plan, x, weights, y, s)
+                      : staged_gather(g, plan, dtype, x, y, 0ull, es, weights, 0, 0, s);
+    }
+    t_last_path = TS_PATH_GENERIC;
+    return active ? generic_active_forward(g, dtype, x, weights, y, s)
+                  : generic_gather(g, dtype, x, y, 0ull, es, weights, 0, 0, s);
+}
+
+size_t ts_shift_backward_workspace_bytes(const ts_geometry* gin, int dtype) {
+    Geo g;
+    if (make_geo(gin, 0, &g) != TS_OK) return 0;
+    if (g.N * g.C == 0) return 16;
+    int sms = 148;
+    sm_count(&sms);
+    const GenericBwdPlan gp = plan_generic_backward(g);
+    size_t slots = (size_t)gp.units;
+    // assume the staged path may apply (pointer alignment is unknown here)
+    const StagedPlan sp = plan_staged(g, 2, elem_size(dtype), dtype, true, nullptr, nullptr, nullptr, sms);
+    if (sp.ok && (size_t)sp.slots > slots) slots = (size_t)sp.slots;
+    return slots * (size_t)(g.C * g.dim) * sizeof(double) + 16;
+}
+
+int ts_shift_backward(const ts_geometry* gin, int dtype, int padding, int active, const void* grad, const void* x,
+                      const void* weights, void* grad_input, void* grad_weight, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    Geo g;
+    int rc = make_geo(gin, padding, &g);
+    if (rc != TS_OK) return rc;
+    const int es = elem_size(dtype);
+    if (!es) return TS_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (g.C * g.dim == 0) return TS_OK;
+    if (!grad_weight) return TS_ERR_INVALID_ARGUMENT;
+    if (g.N == 0 || g.in_plane == 0) {
+        const cudaError_t e = cudaMemsetAsync(grad_weight, 0, (size_t)(g.C * g.dim) * es, s);
+        return e == cudaSuccess ? TS_OK : cuda_fail(e);
+    }
+    if (!grad || !x || !weights || !grad_input) return TS_ERR_INVALID_ARGUMENT;
+    if (!workspace || ((uintptr_t)workspace & 15) || workspace_bytes < ts_shift_backward_workspace_bytes(gin, dtype))
+        return TS_ERR_WORKSPACE;
+    int sms = 0;
+    if ((rc = sm_count(&sms)) != TS_OK) return rc;
+    const int forced = g_forced_path.load();
+    StagedPlan plan;
+    plan.ok = false;
+    if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 2, es, dtype, x_is_dense(g), x, grad_input, grad, sms);
+    if (forced == TS_PATH_STAGED && !plan.ok) return TS_ERR_UNSUPPORTED;
+    if (plan.ok) {
+        t_last_path = TS_PATH_STAGED;
+        return staged_backward(g, plan, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, s);
+    }
+    t_last_path = TS_PATH_GENERIC;
+    return generic_backward(g, dtype, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, s);
+}
+
+int ts_qshift_forward(const ts_geometry* gin, int elem_bytes, int padding, int64_t zero_point, const void* xq,
+                      const void* qweights, int qweight_kind, int64_t weight_zero_point, void* yq, void* stream) {
+    Geo g;
+    int rc = make_geo(gin, padding, &g);
+    if (rc != TS_OK) return rc;
+    if (elem_bytes != 1 && elem_bytes != 4) return TS_ERR_UNSUPPORTED;
+    if (qweight_kind < TS_QW_U8 || qweight_kind > TS_QW_I32) return TS_ERR_INVALID_ARGUMENT;
+    if (g.N * g.C == 0 || g.out_plane == 0) return TS_OK;
+    if (!xq || !qweights || !yq) return TS_ERR_INVALID_ARGUMENT;
+    int sms = 0;
+    if ((rc = sm_count(&sms)) != TS_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned long long fill = elem_bytes == 1 ? (unsigned long long)((unsigned)zero_point & 0xffu)
+                                                    : (unsigned long long)(uint32_t)(int32_t)zero_point;
+    const int forced = g_forced_path.load();
+    StagedPlan plan;
+    plan.ok = false;
+    if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 0, elem_bytes, -1, x_is_dense(g), xq, yq, nullptr, sms);
+    if (forced == TS_PATH_STAGED && !plan.ok) return TS_ERR_UNSUPPORTED;
+    if (plan.ok) {
+        t_last_path = TS_PATH_STAGED;
+        return staged_gather(g, plan, WK_QUANT, xq, yq, fill, elem_bytes, qweights, qweight_kind, weight_zero_point, s);
+    }
+    t_last_path = TS_PATH_GENERIC;
+    return generic_gather(g, WK_QUANT, xq, yq, fill, elem_bytes, qweights, qweight_kind, weight_zero_point, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// ts_kernels.h -- internal interface between the C ABI (ts_capi.cu) and the kernel families.
+#pragma once
+#include "ts_common.cuh"
+
+namespace ts {
+
+// How the integer shifts are obtained in the sparse/quantized gather kernels.
+enum { WK_F32 = 0, WK_F64 = 1, WK_F16 = 2, WK_BF16 = 3, WK_QUANT = 4 };
+
+template <int WK> struct WType;
+template <> struct WType<WK_F32> { using type = float; };
+template <> struct WType<WK_F64> { using type = double; };
+template <> struct WType<WK_F16> { using type = __half; };
+template <> struct WType<WK_BF16> { using type = __nv_bfloat16; };
+
+template <int WK, int DIM>
+TS_D void load_int_shifts(const void* __restrict__ w, int qkind, long long wzp, long long c, const Geo& g, int* sx) {
+    if constexpr (WK == WK_QUANT) {
+        load_qshifts<DIM>(w, qkind, wzp, c, g, sx);
+    } else {
+        using ST = typename WType<WK>::type;
+        const ShiftParams<typename Elem<ST>::CT, DIM> p = load_params<ST, DIM>((const ST*)w, c, g, false, false);
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) sx[a] = p.sx[a];
+    }
+}
+
+// ---- generic family (ts_generic.cu) ----------------------------------------------------------
+struct GenericBwdPlan { int threads, tiles, n_per_chunk, units; };
+GenericBwdPlan plan_generic_backward(const Geo& g);
+
+int generic_gather(const Geo& g, int wk, const void* x, void* y, unsigned long long fill, int esize, const void* w,
+                   int qkind, long long wzp, cudaStream_t s);
+int generic_active_forward(const Geo& g, int dtype, const void* x, const void* w, void* y, cudaStream_t s);
+int generic_backward(const Geo& g, int dtype, int active, const void* grad, const void* x, const void* w, void* gi,
+                     void* gw, double* partials, cudaStream_t s);
+
+template <typename ST>
+int launch_reduce_partials(const double* partials, int slots, int outputs, void* gw, cudaStream_t stream);
+
+// ---- staged family (ts_staged.cu): bulk-async shared-memory staging ---------------------------
+struct Tuning {
+    int stages;        // ring depth
+    int stage_kb;      // target bytes per stage (KiB)
+    int warps;         // consumer warps per CTA
+    int ctas_per_sm;   // persistent CTAs per SM
+    int chunk_planes;  // planes of one channel per work unit (0 = auto)
+};
+Tuning& tuning();
+
+struct StagedPlan {
+    bool ok;           // staged path applicable
+    int vec_bytes;     // bytes per thread item (16 / 8 / 4)
+    int planes_per_step, stages, warps, grid, units, n_per_unit, slots;  // slots = partial slots (backward)
+    size_t smem_bytes;
+};
+// mode: 0 sparse/quantized forward (esize = element bytes), 1 active forward, 2 backward
+StagedPlan plan_staged(const Geo& g, int mode, int esize, int dtype, bool dense_x, const void* x, const void* y_or_gi,
+                       const void* grad, int sm_count);
+
+int staged_gather(const Geo& g, const StagedPlan& p, int wk, const void* x, void* y, unsigned long long fill, int esize,
+                  const void* w, int qkind, long long wzp, cudaStream_t s);
+int staged_active_forward(const Geo& g, const StagedPlan& p, const void* x, const void* w, void* y, cudaStream_t s);
+int staged_backward(const Geo& g, const StagedPlan& p, int active, const void* grad, const void* x, const void* w,
+                    void* gi, void* gw, double* partials, cudaStream_t s);
+
+}  // namespace ts

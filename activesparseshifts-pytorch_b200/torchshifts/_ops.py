@@ -1,0 +1,259 @@
+"""Definition of the ``torchshifts::`` operators on top of the C ABI.
+
+Operator names and schemas are the reference's (csrc/torchshifts.cpp:35-40, csrc/ops/shifts.cpp:168-181):
+
+    torchshifts::_cuda_version() -> int
+    torchshifts::shift{1,2,3}d(Tensor input, Tensor weights, Tensor borders, int padding_mode, bool active_flag) -> Tensor
+    torchshifts::_shift{1,2,3}d_forward(Tensor input, Tensor weights, Tensor borders, int[] new_size,
+                                        int padding_mode, bool active_flag) -> Tensor
+    torchshifts::_shift{1,2,3}d_backward(Tensor grad, Tensor weights, Tensor input, Tensor borders,
+                                         int padding_mode, bool active_flag) -> (Tensor, Tensor)
+
+Dispatch keys: ``shiftNd`` is CompositeImplicitAutograd (border validation, then ``_shiftNd_forward``);
+``_shiftNd_forward/_backward`` have an ``Autograd`` kernel (the autograd wiring of
+csrc/ops/autograd/shifts_autograd.cpp: saves input/weights/borders, double backward is an error),
+``CUDA`` and ``QuantizedCUDA`` kernels that call the sm_100a library, ``Meta`` kernels for tracing,
+and ``CPU`` / ``QuantizedCPU`` kernels that raise: this build has NO CPU compute path.
+"""
+import ctypes as ct
+
+import torch
+
+from ._cabi import QW_I8, QW_I32, QW_U8, make_geometry
+
+_LIB = None            # torch.library.Library handle (kept alive)
+_NATIVE = None         # NativeLibrary
+_DTYPES = {torch.float32: 0, torch.float64: 1, torch.float16: 2, torch.bfloat16: 3}
+_QKINDS = {torch.quint8: QW_U8, torch.qint8: QW_I8, torch.qint32: QW_I32}
+_QBYTES = {torch.quint8: 1, torch.qint8: 1, torch.qint32: 4}
+
+
+def _no_cpu(*args, **kwargs):
+    raise RuntimeError(
+        'torchshifts-b200 has no CPU implementation of the shift operator (no CPU fallback by design): '
+        'move the input and the weights to a CUDA device (B200 / sm_100a).')
+
+
+def _check_mode(padding_mode):
+    # the reference's switch has no default and returns an undefined tensor (cpu/shifts_cpu.cpp:267-289)
+    if padding_mode not in (0, 1, 2, 3, 4):
+        raise RuntimeError(f'torchshifts: padding_mode must be 0..4 (zeros, border, periodic, reflect, symmetric), got {padding_mode}')
+
+
+def _borders_lists(borders, dim):
+    """``borders`` is the int32[6] tensor {l0,r0,l1,r1,l2,r2} produced by check_borders."""
+    b = borders.tolist() if borders.device.type == 'cpu' else borders.cpu().tolist()
+    if len(b) < 6:
+        raise RuntimeError('torchshifts: internal borders tensor must have 6 entries')
+    return [b[0], b[2], b[4]], [b[1], b[3], b[5]]
+
+
+def _same_device_and_type(fn, input, weights, grad=None):
+    # checkAllSameGPU / checkAllSameType of cuda/shifts_cuda.cu:213-214, :282-283
+    if weights.device != input.device or (grad is not None and grad.device != input.device):
+        raise RuntimeError(f'{fn}: expected input, weights' + (', grad' if grad is not None else '') +
+                           f' to be on the same GPU, but got {input.device}, {weights.device}' +
+                           (f', {grad.device}' if grad is not None else ''))
+    if weights.dtype != input.dtype or (grad is not None and grad.dtype != input.dtype):
+        raise RuntimeError(f'{fn}: expected scalar type {input.dtype} for every tensor but found '
+                           f'weights {weights.dtype}' + (f', grad {grad.dtype}' if grad is not None else ''))
+    if input.dtype not in _DTYPES:
+        raise RuntimeError(f'{fn}: "shiftnd_cuda" not implemented for {input.dtype}')
+
+
+def _stream(device):
+    return ct.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _geometry(dim, input, lb, rb):
+    return make_geometry(dim, input.shape, input.stride(), lb, rb)
+
+
+# ------------------------------------------------------------------------------------------ CUDA
+def _forward_cuda(dim, input, weights, borders, new_size, padding_mode, active_flag):
+    fn = f'shift{dim}d_forward'
+    _check_mode(padding_mode)
+    _same_device_and_type(fn, input, weights)
+    if input.dim() != dim + 2:
+        raise RuntimeError(f'{fn}: expected a {dim + 2}-D input, got {input.dim()}-D')
+    if weights.dim() != 2 or weights.shape[0] != input.shape[1] or weights.shape[1] != dim:
+        raise RuntimeError(f'{fn}: weights must be [{input.shape[1]}, {dim}], got {list(weights.shape)}')
+    lb, rb = _borders_lists(borders, dim)
+    out = torch.empty(list(new_size), dtype=input.dtype, device=input.device)
+    w = weights.contiguous()
+    geo = _geometry(dim, input, lb, rb)
+    if list(out.shape[2:]) != [rb[a] - lb[a] for a in range(dim)]:
+        raise RuntimeError(f'{fn}: new_size {list(new_size)} does not match the borders')
+    with torch.cuda.device(input.device):
+        st = _NATIVE.lib.ts_shift_forward(ct.byref(geo), _DTYPES[input.dtype], int(padding_mode), int(bool(active_flag)),
+                                          input.data_ptr(), w.data_ptr(), out.data_ptr(), _stream(input.device))
+    _NATIVE.check(st, 'ts_shift_forward')
+    return out
+
+
+def _backward_cuda(dim, grad, weights, input, borders, padding_mode, active_flag):
+    fn = f'shift{dim}d_backward'
+    _check_mode(padding_mode)
+    _same_device_and_type(fn, input, weights, grad)
+    lb, rb = _borders_lists(borders, dim)
+    grad = grad.contiguous()
+    w = weights.contiguous()
+    out_grad = torch.empty(input.shape, dtype=input.dtype, device=input.device)
+    weights_grad = torch.empty(w.shape, dtype=w.dtype, device=w.device)
+    geo = _geometry(dim, input, lb, rb)
+    if list(grad.shape[2:]) != [rb[a] - lb[a] for a in range(dim)] or list(grad.shape[:2]) != list(input.shape[:2]):
+        raise RuntimeError(f'{fn}: grad shape {list(grad.shape)} does not match the (cropped) output of input {list(input.shape)}')
+    code = _DTYPES[input.dtype]
+    with torch.cuda.device(input.device):
+        nbytes = int(_NATIVE.lib.ts_shift_backward_workspace_bytes(ct.byref(geo), code))
+        workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=input.device)
+        st = _NATIVE.lib.ts_shift_backward(ct.byref(geo), code, int(padding_mode), int(bool(active_flag)),
+                                           grad.data_ptr(), input.data_ptr(), w.data_ptr(), out_grad.data_ptr(),
+                                           weights_grad.data_ptr(), workspace.data_ptr(), nbytes, _stream(input.device))
+    _NATIVE.check(st, 'ts_shift_backward')
+    return out_grad, weights_grad
+
+
+def _forward_qcuda(dim, input, weights, borders, new_size, padding_mode, active_flag):
+    fn = f'q_shift{dim}d_cuda'
+    _check_mode(padding_mode)
+    if not weights.is_quantized:
+        raise RuntimeError(f'{fn}: weights must be a quantized tensor (see torchshifts.quantized.modules.shifts.quantize_shift_weights)')
+    if input.qscheme() not in (torch.per_tensor_affine, torch.per_tensor_symmetric):
+        raise RuntimeError(f'{fn}: only per-tensor quantized inputs are supported')
+    if input.dtype not in _QBYTES or weights.dtype not in _QKINDS:
+        raise RuntimeError(f'{fn}: unsupported quantized dtype {input.dtype} / {weights.dtype}')
+    lb, rb = _borders_lists(borders, dim)
+    x = input if input.is_contiguous() else input.contiguous()
+    wq = weights.int_repr().to(input.device).contiguous()
+    out = torch._empty_affine_quantized(list(new_size), scale=input.q_scale(), zero_point=input.q_zero_point(),
+                                        dtype=input.dtype, device=input.device)
+    geo = _geometry(dim, x, lb, rb)
+    with torch.cuda.device(input.device):
+        st = _NATIVE.lib.ts_qshift_forward(ct.byref(geo), _QBYTES[input.dtype], int(padding_mode), int(input.q_zero_point()),
+                                           x.data_ptr(), wq.data_ptr(), _QKINDS[weights.dtype], int(weights.q_zero_point()),
+                                           out.data_ptr(), _stream(input.device))
+    _NATIVE.check(st, 'ts_qshift_forward')
+    return out
+
+
+def _backward_quantized(dim, *args):
+    # quantized/shifts_quantized.cpp:218-225
+    raise RuntimeError(f'torchshifts::_shift{dim}d_backward: backward is not supported for quantized tensors')
+
+
+# ------------------------------------------------------------------------------------------ Meta
+def _forward_meta(dim, input, weights, borders, new_size, padding_mode, active_flag):
+    return input.new_empty(list(new_size))
+
+
+def _backward_meta(dim, grad, weights, input, borders, padding_mode, active_flag):
+    return input.new_empty(input.shape), weights.new_empty(weights.shape)
+
+
+# ------------------------------------------------------------------------------------------ Autograd
+def _below_autograd():
+    return torch._C._AutoDispatchBelowAutograd()
+
+
+class _ShiftBackwardFunction(torch.autograd.Function):
+    """csrc/ops/autograd/shifts_autograd.cpp:50-72: the backward op itself is not differentiable."""
+
+    @staticmethod
+    def forward(ctx, dim, grad, weights, input, borders, padding_mode, active_flag):
+        with _below_autograd():
+            op = getattr(torch.ops.torchshifts, f'_shift{dim}d_backward')
+            return op(grad, weights, input, borders, padding_mode, active_flag)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise RuntimeError('double backwards on shiftNd not supported')
+
+
+class _ShiftFunction(torch.autograd.Function):
+    """csrc/ops/autograd/shifts_autograd.cpp:15-47 (and the 2d/3d twins)."""
+
+    @staticmethod
+    def forward(ctx, dim, input, weights, borders, new_size, padding_mode, active_flag):
+        with _below_autograd():
+            op = getattr(torch.ops.torchshifts, f'_shift{dim}d_forward')
+            output = op(input, weights, borders, new_size, padding_mode, active_flag)
+        ctx.dim, ctx.padding_mode, ctx.active_flag = dim, padding_mode, active_flag
+        ctx.save_for_backward(input, weights, borders)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, weights, borders = ctx.saved_tensors
+        op = getattr(torch.ops.torchshifts, f'_shift{ctx.dim}d_backward')
+        grad_input, grad_weight = op(grad_output, weights, input, borders, ctx.padding_mode, ctx.active_flag)
+        return None, grad_input, grad_weight, None, None, None, None
+
+
+def _forward_autograd(dim, input, weights, borders, new_size, padding_mode, active_flag):
+    return _ShiftFunction.apply(dim, input, weights, borders, list(new_size), padding_mode, active_flag)
+
+
+def _backward_autograd(dim, grad, weights, input, borders, padding_mode, active_flag):
+    out = _ShiftBackwardFunction.apply(dim, grad, weights, input, borders, padding_mode, active_flag)
+    return out[0], out[1]
+
+
+# ------------------------------------------------------------------------------------------ composite
+def check_borders(input, borders, dim):
+    """csrc/ops/shifts.cpp:93-135: -> (int32[6] CPU tensor {l0,r0,l1,r1,l2,r2}, new_size list).
+
+    Unlike the reference the border tensor stays on the host (the kernels take the six integers
+    by value), which removes the per-call host-to-device copy of shifts.cpp:134.
+    """
+    user = None
+    if borders is not None and borders.numel() != 0:
+        user = borders.to(torch.int32).cpu().reshape(-1).tolist()
+    lb, rb = _NATIVE.check_borders(dim, list(input.shape[2:2 + dim]), user)
+    std = torch.tensor([lb[0], rb[0], lb[1], rb[1], lb[2], rb[2]], dtype=torch.int32)
+    new_size = list(input.shape[:2]) + [rb[a] - lb[a] for a in range(dim)]
+    return std, new_size
+
+
+def _shift_composite(dim, input, weights, borders, padding_mode, active_flag):
+    std_borders, new_size = check_borders(input, borders, dim)
+    op = getattr(torch.ops.torchshifts, f'_shift{dim}d_forward')
+    return op(input, weights, std_borders, new_size, padding_mode, active_flag)
+
+
+def _bind(fn, dim):
+    def bound(*args):
+        return fn(dim, *args)
+    bound.__name__ = f'{fn.__name__}_{dim}d'
+    return bound
+
+
+def register(native):
+    """Define and implement the operators (idempotent)."""
+    global _LIB, _NATIVE
+    _NATIVE = native
+    if _LIB is not None:
+        return
+    lib = torch.library.Library('torchshifts', 'DEF')
+    lib.define('_cuda_version() -> int')
+    lib.impl('_cuda_version', lambda: int(native.lib.ts_cuda_version()), 'CompositeExplicitAutograd')
+    for dim in (1, 2, 3):
+        lib.define(f'shift{dim}d(Tensor input, Tensor weights, Tensor borders, int padding_mode, bool active_flag) -> Tensor')
+        lib.define(f'_shift{dim}d_forward(Tensor input, Tensor weights, Tensor borders, int[] new_size, '
+                   f'int padding_mode, bool active_flag) -> Tensor')
+        lib.define(f'_shift{dim}d_backward(Tensor grad, Tensor weights, Tensor input, Tensor borders, '
+                   f'int padding_mode, bool active_flag) -> (Tensor, Tensor)')
+        lib.impl(f'shift{dim}d', _bind(_shift_composite, dim), 'CompositeImplicitAutograd')
+        fwd, bwd = f'_shift{dim}d_forward', f'_shift{dim}d_backward'
+        lib.impl(fwd, _bind(_forward_autograd, dim), 'Autograd')
+        lib.impl(bwd, _bind(_backward_autograd, dim), 'Autograd')
+        lib.impl(fwd, _bind(_forward_cuda, dim), 'CUDA')
+        lib.impl(bwd, _bind(_backward_cuda, dim), 'CUDA')
+        lib.impl(fwd, _bind(_forward_qcuda, dim), 'QuantizedCUDA')
+        lib.impl(bwd, _bind(_backward_quantized, dim), 'QuantizedCUDA')
+        lib.impl(fwd, _bind(_forward_meta, dim), 'Meta')
+        lib.impl(bwd, _bind(_backward_meta, dim), 'Meta')
+        for key in ('CPU', 'QuantizedCPU'):
+            lib.impl(fwd, _no_cpu, key)
+            lib.impl(bwd, _no_cpu, key)
+    _LIB = lib

@@ -1,0 +1,106 @@
+"""Host-resident tensors through the GPU path: ``HostShift2dPipeline`` / ``HostShiftPipeline``.
+
+The reference's CPU operator takes host tensors and returns host tensors.  This build has no CPU
+compute path, so the equivalent service for host-resident data is a streamed offload: the batch
+is cut into chunks, and for every chunk
+
+    copy-in stream :  x[chunk], grad[chunk]  pinned host -> device       (H2D copy engine)
+    compute stream :  forward + backward kernels (the registered torchshifts ops)
+    copy-out stream:  y[chunk], grad_input[chunk]  device -> pinned host (D2H copy engine)
+
+run concurrently on three CUDA streams with a small ring of device buffers, so the two PCIe
+directions and the kernels overlap; grad_weight is accumulated on the device across chunks in a
+fixed order (deterministic) and returned as a device tensor.  bench.py's ``e2e`` number is this
+call, with every host<->device byte inside the timed region.
+"""
+import torch
+
+from .functional import shift1d_func, shift2d_func, shift3d_func  # noqa: F401  (public API re-export)
+
+_OPS = {1: ('_shift1d_forward', '_shift1d_backward'), 2: ('_shift2d_forward', '_shift2d_backward'),
+        3: ('_shift3d_forward', '_shift3d_backward')}
+
+
+class HostShiftPipeline:
+    def __init__(self, N, C, spatial, device, dtype=torch.float32, chunk=16, slots=3):
+        self.N, self.C, self.spatial = int(N), int(C), tuple(int(s) for s in spatial)
+        self.dim = len(self.spatial)
+        assert self.dim in (1, 2, 3)
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.chunk = max(1, min(int(chunk), self.N))
+        self.slots = slots
+        shape = (self.N, self.C) + self.spatial
+        pin = dict(dtype=dtype, pin_memory=True)
+        self.x_host = torch.empty(shape, **pin)
+        self.g_host = torch.empty(shape, **pin)
+        self.y_host = torch.empty(shape, **pin)
+        self.gi_host = torch.empty(shape, **pin)
+        cshape = (self.chunk, self.C) + self.spatial
+        self._xd = [torch.empty(cshape, dtype=dtype, device=self.device) for _ in range(slots)]
+        self._gd = [torch.empty(cshape, dtype=dtype, device=self.device) for _ in range(slots)]
+        self._s_in = torch.cuda.Stream(self.device)
+        self._s_comp = torch.cuda.Stream(self.device)
+        self._s_out = torch.cuda.Stream(self.device)
+        self._borders = torch.tensor([0, self.spatial[0], 0, self.spatial[1] if self.dim > 1 else 1,
+                                      0, self.spatial[2] if self.dim > 2 else 1], dtype=torch.int32)
+        esz = torch.empty((), dtype=dtype).element_size()
+        numel = self.x_host.numel()
+        self.h2d_bytes = 2 * numel * esz
+        self.d2h_bytes = 2 * numel * esz + self.C * self.dim * esz
+
+    def describe(self):
+        return (f"HostShiftPipeline: pinned host x/grad -> device in chunks of {self.chunk} images on a copy-in stream, "
+                f"torchshifts::_shift{self.dim}d_forward/_backward on a compute stream, y/grad_input -> pinned host on a "
+                f"copy-out stream ({self.slots}-slot ring); grad_weight summed on device and read back")
+
+    @torch.no_grad()
+    def forward_backward(self, weight, padding_mode=0, active_flag=False):
+        """Runs y = shift(x_host), (grad_input, grad_weight) = backward(g_host); fills ``y_host`` and
+        ``gi_host`` (complete once the current stream is synchronised) and returns grad_weight [C, dim]
+        as a device tensor ordered on the current stream."""
+        fwd = getattr(torch.ops.torchshifts, _OPS[self.dim][0])
+        bwd = getattr(torch.ops.torchshifts, _OPS[self.dim][1])
+        cur = torch.cuda.current_stream(self.device)
+        for s in (self._s_in, self._s_comp, self._s_out):
+            s.wait_stream(cur)
+        gw_total = torch.zeros(self.C, self.dim, dtype=self.dtype, device=self.device)
+        self._s_comp.wait_stream(cur)
+        free = [None] * self.slots           # event: slot's device inputs may be overwritten
+        nchunks = (self.N + self.chunk - 1) // self.chunk
+        for i in range(nchunks):
+            lo, hi = i * self.chunk, min(self.N, (i + 1) * self.chunk)
+            k = i % self.slots
+            n = hi - lo
+            with torch.cuda.stream(self._s_in):
+                if free[k] is not None:
+                    self._s_in.wait_event(free[k])
+                xd, gd = self._xd[k][:n], self._gd[k][:n]
+                xd.copy_(self.x_host[lo:hi], non_blocking=True)
+                gd.copy_(self.g_host[lo:hi], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self._s_in)
+            with torch.cuda.stream(self._s_comp):
+                self._s_comp.wait_event(ready)
+                new_size = [n, self.C] + list(self.spatial)
+                y = fwd(xd, weight, self._borders, new_size, padding_mode, active_flag)
+                gi, gw = bwd(gd, weight, xd, self._borders, padding_mode, active_flag)
+                gw_total += gw
+                done = torch.cuda.Event()
+                done.record(self._s_comp)
+                free[k] = done
+            with torch.cuda.stream(self._s_out):
+                self._s_out.wait_event(done)
+                self.y_host[lo:hi].copy_(y, non_blocking=True)
+                self.gi_host[lo:hi].copy_(gi, non_blocking=True)
+                y.record_stream(self._s_out)
+                gi.record_stream(self._s_out)
+        cur.wait_stream(self._s_comp)
+        cur.wait_stream(self._s_out)
+        cur.wait_stream(self._s_in)
+        return gw_total
+
+
+class HostShift2dPipeline(HostShiftPipeline):
+    def __init__(self, N, C, H, W, device, dtype=torch.float32, chunk=16, slots=3):
+        super().__init__(N, C, (H, W), device, dtype, chunk, slots)

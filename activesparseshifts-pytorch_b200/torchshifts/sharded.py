@@ -1,0 +1,75 @@
+"""Batch-sharded execution across the GPUs of one box (net new, the reference has no
+distributed code).
+
+Every (n, c) plane is independent in the forward pass and in grad_input; only
+``grad_weight[c, :] = sum over n and space`` couples the batch.  So: one process per GPU
+(torchrun), rank r owns ``x[shard_range(N, r, G)]``, weights are replicated, there is NO data-path
+collective in forward or grad_input, and exactly ONE all-reduce (sum) of the tiny ``C x dim``
+grad_weight per backward -- for all shift layers of a model coalesced into a single flat buffer.
+Works with any torch.distributed backend (NCCL over NVLink on the B200 box, gloo in the CPU tests).
+"""
+from typing import Iterable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [lo, hi) slice of a batch of ``n`` for ``rank`` of ``world`` (first
+    ``n % world`` ranks get one extra item; ranks beyond ``n`` get an empty slice)."""
+    assert 0 <= rank < world
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(x: torch.Tensor, rank: Optional[int] = None, world: Optional[int] = None) -> torch.Tensor:
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    lo, hi = shard_range(x.shape[0], rank, world)
+    return x[lo:hi]
+
+
+def _shift_weights(module_or_params) -> Iterable[torch.nn.Parameter]:
+    if isinstance(module_or_params, torch.nn.Module):
+        from torchshifts.modules.shifts import _Shiftnd
+        return [m.weight for m in module_or_params.modules() if isinstance(m, _Shiftnd)]
+    return list(module_or_params)
+
+
+def allreduce_grad_weights(module_or_params, group=None, average: bool = False) -> int:
+    """Sum (or average) ``weight.grad`` of every shift layer over the ranks with ONE collective.
+
+    Returns the number of elements reduced.  Parameters without a gradient contribute zeros so
+    that all ranks issue the same collective."""
+    params = [p for p in _shift_weights(module_or_params)]
+    if not params:
+        return 0
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        piece = flat[off:off + n].reshape(p.shape).to(p.dtype)
+        if p.grad is None:
+            p.grad = piece.clone()
+        else:
+            p.grad.copy_(piece)
+        off += n
+    return int(flat.numel())
+
+
+def broadcast_weights(module_or_params, src: int = 0, group=None) -> None:
+    """Make the replicated shift weights identical on every rank (one broadcast)."""
+    params = [p for p in _shift_weights(module_or_params)]
+    if not params:
+        return
+    flat = torch.cat([p.data.reshape(-1).to(torch.float32) for p in params])
+    dist.broadcast(flat, src=src, group=group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.data.copy_(flat[off:off + n].reshape(p.shape).to(p.dtype))
+        off += n

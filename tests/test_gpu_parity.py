@@ -1,0 +1,442 @@
+"""GPU parity: the CUDA path (public API -> torch.ops.torchshifts -> C ABI -> sm_100a kernels)
+against the CPU oracle on the same seeded inputs, against the golden fixtures produced by the
+reference's own extension, and -- at BASELINE.json's full sizes -- through size-independent
+properties plus an oracle check of sampled images.
+
+Tolerances (BASELINE.json north_star):
+  * forward (sparse, active, quantized) and grad_input: BIT-EXACT for fp32 / fp64 / integer;
+  * grad_weight: rtol 1e-5 against the fp64 oracle, atol 1e-5 * max|gw| (the fp32 oracle's own
+    serial sum is less accurate than that);
+  * fp16 / bf16 (no CPU oracle exists): fp32 oracle on the rounded inputs, rtol 1e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BORDERS = {1: [[1, 2]], 2: [[1, 1], [2, 1]], 3: [[1, 0], [0, 2], [1, 1]]}
+GENERIC, STAGED = 1, 2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from torchshifts.extension import native
+    return native().lib
+
+
+@pytest.fixture()
+def auto_path(lib):
+    lib.ts_set_kernel_path(0)
+    yield
+    lib.ts_set_kernel_path(0)
+
+
+def _func(dim):
+    from torchshifts import functional as F
+    return {1: F.shift1d_func, 2: F.shift2d_func, 3: F.shift3d_func}[dim]
+
+
+def _run_cuda(dev, dim, x, w, g, pad, active, borders):
+    xd = torch.from_numpy(x).to(dev).requires_grad_(True)
+    wd = torch.from_numpy(w).to(dev).requires_grad_(True)
+    b = torch.tensor(borders, dtype=torch.long) if borders is not None else None
+    y = _func(dim)(xd, wd, pad, active, b)
+    if g is None:
+        return y.detach().cpu().numpy(), None, None
+    y.backward(torch.from_numpy(g).to(dev))
+    return y.detach().cpu().numpy(), xd.grad.cpu().numpy(), wd.grad.cpu().numpy()
+
+
+def _gw_close(gw, gw64):
+    scale = np.abs(gw64).max()
+    return np.allclose(gw.astype(np.float64), gw64, rtol=1e-5, atol=1e-5 * scale + 1e-30)
+
+
+def _case_args(name):
+    parts = name.split("_")
+    if parts[0] == "cl":
+        return int(parts[1][1]), int(parts[2][1]), bool(int(parts[3][1])), None
+    return int(parts[1][1]), int(parts[4][1]), bool(int(parts[5][1])), (BORDERS[int(parts[1][1])] if int(parts[3][1]) else None)
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", [0, GENERIC])
+def test_golden_fixtures_float(dev, lib, golden, oracle_port, path):
+    """All 248 reference-generated cases (3 dims x 5 paddings x sparse/active x borders x fp32/fp64)."""
+    lib.ts_set_kernel_path(path)
+    try:
+        g = golden["shift_golden"]
+        for name in g["names"].tolist():
+            dim, pad, active, borders = _case_args(name)
+            x, w, grad = g[name + "/x"], g[name + "/w"], g[name + "/g"]
+            y, gi, gw = _run_cuda(dev, dim, x, w, grad, pad, active, borders)
+            assert np.array_equal(y, g[name + "/y"]), f"forward {name}"
+            assert np.array_equal(gi, g[name + "/gi"]), f"grad_input {name}"
+            _, gw64 = oracle_port.backward(grad.astype(np.float64), x.astype(np.float64), w.astype(np.float64), pad, active, borders)
+            assert _gw_close(gw, gw64), f"grad_weight {name}: {gw} vs {gw64}"
+            assert np.allclose(gw, g[name + "/gw"], rtol=1e-4, atol=1e-4 * np.abs(gw64).max()), f"grad_weight vs reference fp sum {name}"
+    finally:
+        lib.ts_set_kernel_path(0)
+
+
+def test_golden_fixtures_quantized(dev, lib, golden, auto_path):
+    from torchshifts.quantized.functional import shift1d_quantized, shift2d_quantized, shift3d_quantized
+    fns = {1: shift1d_quantized, 2: shift2d_quantized, 3: shift3d_quantized}
+    qd = {"quint8": torch.quint8, "qint8": torch.qint8, "quint8zp": torch.quint8, "qint32": torch.qint32}
+    g = golden["quant_golden"]
+    for path in (0, GENERIC):
+        lib.ts_set_kernel_path(path)
+        for name in g["names"].tolist():
+            parts = name.split("_")
+            dim, use_b, pad = int(parts[1][1]), int(parts[3][1]), int(parts[4][1])
+            wzp, zp = g[name + "/meta"].tolist()
+            xq = torch._make_per_tensor_quantized_tensor(torch.from_numpy(g[name + "/x"]).to(dev), float(g[name + "/xscale"][0]), int(zp))
+            assert xq.dtype == qd[parts[0]]
+            qw = torch._make_per_tensor_quantized_tensor(torch.from_numpy(g[name + "/wq"]).to(dev), float(g[name + "/wscale"][0]) or 1.0, int(wzp))
+            b = torch.tensor(BORDERS[dim], dtype=torch.long) if use_b else None
+            yq = fns[dim](xq, qw, pad, b)
+            assert yq.is_quantized and yq.dtype == xq.dtype
+            assert yq.q_scale() == xq.q_scale() and yq.q_zero_point() == xq.q_zero_point()
+            assert np.array_equal(yq.int_repr().cpu().numpy(), g[name + "/y"]), name
+
+
+def test_known_answers(dev, golden, auto_path):
+    kat = golden["kat"]
+    x = np.array([10, 11, 12, 13, 14], dtype=np.float32).reshape(1, 1, 5)
+    for si, s in enumerate(kat["shift1d_shifts"].tolist()):
+        for pad in range(5):
+            y, _, _ = _run_cuda(dev, 1, x, np.array([[s]], dtype=np.float32), None, pad, False, None)
+            assert np.array_equal(y.reshape(-1), kat["shift1d_table"][si, pad]), (s, pad)
+    x2 = np.arange(120, dtype=np.float32).reshape(2, 3, 4, 5)
+    y, _, _ = _run_cuda(dev, 2, x2, np.array([[1., 0.], [0., -1.], [0.4, 1.6]], dtype=np.float32), None, 0, False, None)
+    assert np.array_equal(y, kat["shift2d_arange_y"])
+    xt = np.arange(42, dtype=np.float32).reshape(1, 7, 6)
+    y, _, _ = _run_cuda(dev, 1, xt, kat["ties_w"].astype(np.float32), None, 2, False, None)
+    assert np.array_equal(y, kat["ties_y"])          # half-to-even, like the CPU reference
+    y, _, _ = _run_cuda(dev, 2, np.arange(4, dtype=np.float32).reshape(1, 1, 1, 4), np.array([[3., 1.]], dtype=np.float32), None, 3, False, None)
+    assert np.array_equal(y, kat["size1_reflect_y"])
+    y, _, _ = _run_cuda(dev, 2, np.arange(8, dtype=np.float32).reshape(1, 1, 2, 4), np.array([[1., 0.]], dtype=np.float32), None, 3, False, None)
+    assert np.array_equal(y, kat["len2_reflect_y"])
+
+
+SWEEP = [
+    # (shape, weight range) -- sizes picked so that the staged path applies to most (rows % 4 == 0)
+    ((3, 5, 64), 9.0), ((2, 4, 40), 70.0), ((2, 3, 12, 16), 3.0), ((3, 4, 8, 8), 12.0), ((2, 6, 28, 28), 2.0),
+    ((1, 3, 7, 9), 3.0), ((2, 2, 5, 8), 4.0), ((2, 3, 4, 6, 8), 2.5), ((1, 2, 3, 5, 4), 5.0), ((5, 7, 1, 16), 3.0),
+    ((2, 3, 16, 1), 3.0), ((1, 1, 2, 2), 1.5), ((9, 2, 4, 12), 2.0),
+]
+
+
+@pytest.mark.parametrize("path", [0, GENERIC])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_randomised_sweep_vs_oracle(dev, lib, oracle_port, path, dtype):
+    lib.ts_set_kernel_path(path)
+    staged_hits = 0
+    try:
+        rng = np.random.default_rng(123)
+        for shape, wr in SWEEP:
+            dim = len(shape) - 2
+            x = rng.standard_normal(shape).astype(dtype)
+            w = ((rng.random((shape[1], dim)) * 2 - 1) * wr).astype(dtype)
+            w.flat[0] = 0.5
+            for borders in (None, [[1, 0]] * dim if min(shape[2:]) > 1 else None, [[0, 4]] * dim if min(shape[2:]) > 4 else None):
+                for pad in range(5):
+                    for active in (False, True):
+                        y_ref = oracle_port.forward(x, w, pad, active, borders)
+                        grad = rng.standard_normal(y_ref.shape).astype(dtype)
+                        y, gi, gw = _run_cuda(dev, dim, x, w, grad, pad, active, borders)
+                        staged_hits += lib.ts_last_kernel_path() == STAGED
+                        tag = (shape, pad, active, borders, dtype.__name__)
+                        assert np.array_equal(y, y_ref), ("forward",) + tag
+                        gi_ref, _ = oracle_port.backward(grad, x, w, pad, active, borders)
+                        assert np.array_equal(gi, gi_ref), ("grad_input",) + tag
+                        _, gw64 = oracle_port.backward(grad.astype(np.float64), x.astype(np.float64), w.astype(np.float64), pad, active, borders)
+                        assert _gw_close(gw, gw64), ("grad_weight",) + tag + (gw, gw64)
+    finally:
+        lib.ts_set_kernel_path(0)
+    if path == GENERIC:
+        assert staged_hits == 0
+
+
+def test_half_precision_vs_fp32_oracle(dev, oracle_port, auto_path):
+    rng = np.random.default_rng(5)
+    for tdtype in (torch.float16, torch.bfloat16):
+        for shape in ((2, 4, 64), (2, 3, 8, 16), (1, 2, 4, 4, 8)):
+            dim = len(shape) - 2
+            x = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).to(tdtype)
+            w = torch.from_numpy(((rng.random((shape[1], dim)) * 2 - 1) * 3).astype(np.float32)).to(tdtype)
+            g = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).to(tdtype)
+            for pad in range(5):
+                for active in (False, True):
+                    xd, wd = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+                    y = _func(dim)(xd, wd, pad, active)
+                    y.backward(g.to(dev))
+                    x32, w32, g32 = x.float().numpy(), w.float().numpy(), g.float().numpy()
+                    y_ref = oracle_port.forward(x32, w32, pad, active)
+                    gi_ref, gw_ref = oracle_port.backward(g32, x32, w32, pad, active)
+                    if not active:
+                        assert np.array_equal(y.float().cpu().numpy(), y_ref)          # pure copy: exact
+                        assert np.array_equal(xd.grad.float().cpu().numpy(), gi_ref)
+                    else:
+                        assert np.allclose(y.float().cpu().numpy(), y_ref, rtol=1e-2, atol=1e-2)
+                        assert np.allclose(xd.grad.float().cpu().numpy(), gi_ref, rtol=1e-2, atol=1e-2)
+                    assert np.allclose(wd.grad.float().cpu().numpy(), gw_ref, rtol=1e-2, atol=1e-2 * np.abs(gw_ref).max())
+
+
+def test_strided_and_channels_last_inputs(dev, oracle_port, auto_path):
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((2, 6, 8, 12)).astype(np.float32)
+    w = ((rng.random((6, 2)) * 2 - 1) * 3).astype(np.float32)
+    g = rng.standard_normal(x.shape).astype(np.float32)
+    from torchshifts.functional import shift2d_func
+    for pad, active in ((0, False), (3, True), (2, True)):
+        y_ref = oracle_port.forward(x, w, pad, active)
+        gi_ref, gw_ref = oracle_port.backward(g, x, w, pad, active)
+        for make in (lambda t: t.contiguous(memory_format=torch.channels_last),
+                     lambda t: torch.cat([t, t], dim=3)[..., :12],                 # row stride 24
+                     lambda t: t.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)):
+            xd = make(torch.from_numpy(x).to(dev)).requires_grad_(True)
+            wd = torch.from_numpy(w).to(dev).requires_grad_(True)
+            y = shift2d_func(xd, wd, pad, active)
+            assert y.is_contiguous()
+            y.backward(torch.from_numpy(g).to(dev))
+            assert np.array_equal(y.detach().cpu().numpy(), y_ref)
+            assert np.array_equal(xd.grad.cpu().numpy(), gi_ref)
+            assert np.allclose(wd.grad.cpu().numpy(), gw_ref, rtol=1e-4, atol=1e-4)
+
+
+def test_edge_cases(dev, lib, oracle_port, auto_path):
+    from torchshifts.functional import shift2d_func
+    # empty batch / empty channel set
+    for shape in ((0, 3, 4, 4), (2, 0, 4, 4)):
+        x = torch.zeros(shape, device=dev, requires_grad=True)
+        w = torch.zeros(shape[1], 2, device=dev, requires_grad=True)
+        y = shift2d_func(x, w, 0, False)
+        assert list(y.shape) == list(shape)
+        y.sum().backward()
+        assert w.grad.shape == w.shape and float(w.grad.abs().sum()) == 0.0
+    # shifts far larger than the tensor, every padding
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((1, 4, 6, 8)).astype(np.float32)
+    w = np.array([[1e6, -1e6], [-123456.0, 7.0], [33.5, -0.5], [2.0 ** 40, -(2.0 ** 35)]], dtype=np.float32)
+    for pad in range(5):
+        for active in (False, True):
+            y, _, _ = _run_cuda(dev, 2, x, w, None, pad, active, None)
+            assert np.array_equal(y, oracle_port.forward(x, w, pad, active)), (pad, active)
+    # borders corner cases resolve to the reference's output shapes
+    xb = torch.zeros(1, 1, 16, 16, device=dev)
+    wb = torch.zeros(1, 2, device=dev)
+    assert list(shift2d_func(xb, wb, 0, False, torch.tensor([[16, 0], [3, 13]])).shape[2:]) == [1, 1]
+    with pytest.raises(RuntimeError, match="negative"):
+        shift2d_func(xb, wb, 0, False, torch.tensor([[20, 0], [0, 0]]))
+    # dtype mismatch and double backward are hard errors, like the reference
+    with pytest.raises(RuntimeError, match="scalar type"):
+        shift2d_func(xb, wb.double(), 0, False)
+    xg = torch.randn(1, 1, 4, 4, device=dev, requires_grad=True)
+    wg = torch.randn(1, 2, device=dev, requires_grad=True)
+    y = shift2d_func(xg, wg, 0, True)
+    (gx,) = torch.autograd.grad(y.sum(), xg, create_graph=True)
+    with pytest.raises(RuntimeError, match="double backwards"):
+        gx.sum().backward()
+
+
+def test_modules_and_quantized_convert(dev, oracle_port, auto_path):
+    """tests/shifts_test.py of the reference, with assertions instead of prints."""
+    import torchshifts
+    from torchshifts import Shift2d
+    from torchshifts.quantized.modules import Shift2d as QShift2d
+    from oracle.oracle import quantize_shift_weights_np
+    torch.manual_seed(0)
+    channels = 16
+    args = {'kernel_size': 3, 'stride': 1, 'padding': (0, 0)}
+    ia = torch.rand(8, channels, 64, 64, device=dev, requires_grad=True)
+    ib = ia.detach().clone().requires_grad_(True)
+    ta = 10 * torch.rand(8, channels, 62, 62, device=dev)
+    a = Shift2d(channels, init_shift=1, sparsity_term=0., active_flag=False, emulate_dw=dict(args), init_thumb_rule=2).to(dev)
+    b = Shift2d(channels, init_shift=1, sparsity_term=0., active_flag=True, emulate_dw=dict(args), init_thumb_rule=2).to(dev)
+    a.weight = b.weight
+    oa, la = a(ia)
+    ob, lb = b(ib)
+    assert la is None and lb is None and oa.shape == ta.shape
+    torch.nn.functional.mse_loss(oa, ta).backward()
+    ga = a.weight.grad.clone()
+    a.weight.grad = None
+    torch.nn.functional.mse_loss(ob, ta).backward()
+    assert ga is not None and b.weight.grad is not None
+    xs, ws = ia.detach().cpu().numpy(), a.weight.detach().cpu().numpy()
+    assert np.array_equal(oa.detach().cpu().numpy(), oracle_port.forward(xs, ws, 0, False, [[1, 1], [1, 1]]))
+    assert np.array_equal(ob.detach().cpu().numpy(), oracle_port.forward(xs, ws, 0, True, [[1, 1], [1, 1]]))
+    # quantized conversion, as torch.quantization.convert would do it
+    iq = torch.quantize_per_tensor(ia.detach(), 1 / 255., 0, torch.quint8)
+    aq = QShift2d.from_float(a)
+    oq = aq(iq)
+    raw, wzp = quantize_shift_weights_np(ws)
+    want = oracle_port.qforward(iq.int_repr().cpu().numpy(), raw, wzp, 0, 0, [[1, 1], [1, 1]])
+    assert np.array_equal(oq.int_repr().cpu().numpy(), want)
+    model = torch.nn.Sequential(a)
+    conv = torch.ao.quantization.convert(model, mapping=torchshifts.quant_mapping, inplace=False)
+    assert type(conv[0]) is QShift2d
+    # sparsity loss and stride-2 emulation (avg-pool reduction)
+    c = Shift2d(channels, sparsity_term=5e-4, emulate_dw={'kernel_size': 3, 'stride': 2, 'padding': 1}).to(dev)
+    oc, lc = c(ia.detach())
+    assert oc.shape[-1] == 32 and torch.allclose(lc, 5e-4 * c.weight.abs().sum())
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: properties + oracle on sampled images.
+def _sample_check(dev, oracle_port, dim, x, w, g, pad, active, y, gi, n_idx):
+    xs = x[n_idx].cpu().numpy()
+    ws = w.detach().cpu().numpy()
+    assert np.array_equal(y[n_idx].cpu().numpy(), oracle_port.forward(xs, ws, pad, active))
+    if gi is not None:
+        gi_ref, _ = oracle_port.backward(g[n_idx].cpu().numpy(), xs, ws, pad, active)
+        assert np.array_equal(gi[n_idx].cpu().numpy(), gi_ref)
+
+
+def test_full_size_cfg3_shift2d(dev, lib, oracle_port, auto_path):
+    """cfg3: N=256 C=256 56x56 fp32, sparse shift, zeros padding, fwd+bwd."""
+    from torchshifts.functional import shift2d_func
+    torch.manual_seed(0)
+    N, C, H, W = 256, 256, 56, 56
+    x = torch.randn(N, C, H, W, device=dev)
+    g = torch.randn(N, C, H, W, device=dev)
+    w = ((torch.rand(C, 2, device=dev) * 2 - 1) * 3).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    y = shift2d_func(xr, w, 0, False)
+    assert lib.ts_last_kernel_path() == STAGED, "cfg3 must run on the staged (bulk-async) path"
+    y.backward(g)
+    assert lib.ts_last_kernel_path() == STAGED
+    gi, gw = xr.grad, w.grad.clone()
+    idx = [0, 17, 255]
+    _sample_check(dev, oracle_port, 2, x, w, g, 0, False, y, gi, idx)
+    # property: zeros-padded integer shift == roll + mask, for the whole tensor
+    s = torch.round(w.detach()).long()
+    ii = torch.arange(H, device=dev).view(1, H, 1) - s[:, 0].view(C, 1, 1)
+    jj = torch.arange(W, device=dev).view(1, 1, W) - s[:, 1].view(C, 1, 1)
+    ok = (ii >= 0) & (ii < H) & (jj >= 0) & (jj < W)
+    src = (ii.clamp(0, H - 1) * W + jj.clamp(0, W - 1)).view(1, C, H * W).expand(N, C, H * W)
+    want = torch.gather(x.view(N, C, H * W), 2, src).view(N, C, H, W) * ok.view(1, C, H, W)
+    assert torch.equal(y.detach(), want)
+    # property: linearity of the sparse forward (a gather commutes with addition, bit-exactly)
+    x2 = torch.randn_like(x)
+    assert torch.equal(shift2d_func(x + x2, w.detach(), 0, False), y.detach() + shift2d_func(x2, w.detach(), 0, False))
+    del x2, want, src
+    # property: grad_weight of the full batch == sum over two half batches (the multi-GPU shard rule)
+    gws = []
+    for sl in (slice(0, 128), slice(128, 256)):
+        wh = w.detach().clone().requires_grad_(True)
+        shift2d_func(x[sl], wh, 0, False).backward(g[sl])
+        gws.append(wh.grad)
+    assert torch.allclose(gws[0] + gws[1], gw, rtol=1e-5, atol=1e-5 * float(gw.abs().max()))
+    # grad_weight vs the fp64 oracle on a sub-batch
+    wq = w.detach().clone().requires_grad_(True)
+    shift2d_func(x[:4], wq, 0, False).backward(g[:4])
+    _, gw64 = oracle_port.backward(g[:4].double().cpu().numpy(), x[:4].double().cpu().numpy(), w.detach().double().cpu().numpy(), 0, False)
+    assert _gw_close(wq.grad.cpu().numpy(), gw64)
+    # determinism: two runs give identical bits (no atomics)
+    wd = w.detach().clone().requires_grad_(True)
+    xd = x.clone().requires_grad_(True)
+    shift2d_func(xd, wd, 0, False).backward(g)
+    assert torch.equal(wd.grad, gw) and torch.equal(xd.grad, gi)
+
+
+def test_full_size_cfg2_shift1d_active_periodic(dev, lib, oracle_port, auto_path):
+    """cfg2: N=64 C=512 L=4096, periodic padding, active shift, fp32 and bf16."""
+    from torchshifts.functional import shift1d_func
+    torch.manual_seed(1)
+    N, C, L = 64, 512, 4096
+    x = torch.randn(N, C, L, device=dev)
+    g = torch.randn(N, C, L, device=dev)
+    w = ((torch.rand(C, 1, device=dev) * 2 - 1) * 3).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    y = shift1d_func(xr, w, 2, True)
+    y.backward(g)
+    _sample_check(dev, oracle_port, 1, x, w, g, 2, True, y, xr.grad, [0, 63])
+    # property: periodic active shift preserves the per-row sum up to rounding (weights sum to 1)
+    assert torch.allclose(y.detach().double().sum(-1), x.double().sum(-1), rtol=0, atol=1e-2)
+    # property: periodic sparse shift by s then by -s is the identity
+    wi = torch.round(w.detach() * 5)
+    assert torch.equal(shift1d_func(shift1d_func(x, wi, 2, False), -wi, 2, False), x)
+    wq = w.detach().clone().requires_grad_(True)
+    shift1d_func(x[:2], wq, 2, True).backward(g[:2])
+    _, gw64 = oracle_port.backward(g[:2].double().cpu().numpy(), x[:2].double().cpu().numpy(), w.detach().double().cpu().numpy(), 2, True)
+    assert _gw_close(wq.grad.cpu().numpy(), gw64)
+    # bf16 variant against the fp32 oracle on rounded inputs
+    xb, wb, gb = x[:4].bfloat16(), w.detach().bfloat16(), g[:4].bfloat16()
+    xbr, wbr = xb.clone().requires_grad_(True), wb.clone().requires_grad_(True)
+    yb = shift1d_func(xbr, wbr, 2, True)
+    yb.backward(gb)
+    y_ref = oracle_port.forward(xb.float().cpu().numpy(), wb.float().cpu().numpy(), 2, True)
+    gi_ref, gw_ref = oracle_port.backward(gb.float().cpu().numpy(), xb.float().cpu().numpy(), wb.float().cpu().numpy(), 2, True)
+    assert np.allclose(yb.float().cpu().numpy(), y_ref, rtol=1e-2, atol=1e-2)
+    assert np.allclose(xbr.grad.float().cpu().numpy(), gi_ref, rtol=1e-2, atol=1e-2)
+    assert np.allclose(wbr.grad.float().cpu().numpy(), gw_ref, rtol=1e-2, atol=1e-2 * np.abs(gw_ref).max())
+
+
+def test_full_size_cfg4_shift3d_active_all_paddings(dev, oracle_port, auto_path):
+    """cfg4: N=32 C=128 16x56x56, trilinear active shift, all five paddings."""
+    from torchshifts.functional import shift3d_func
+    torch.manual_seed(2)
+    N, C = 32, 128
+    x = torch.randn(N, C, 16, 56, 56, device=dev)
+    g = torch.randn(N, C, 16, 56, 56, device=dev)
+    w0 = (torch.rand(C, 3, device=dev) * 2 - 1) * 3
+    for pad in range(5):
+        w = w0.clone().requires_grad_(True)
+        xr = x.clone().requires_grad_(True)
+        y = shift3d_func(xr, w, pad, True)
+        y.backward(g)
+        _sample_check(dev, oracle_port, 3, x, w, g, pad, True, y, xr.grad, [pad])
+        wq = w0.clone().requires_grad_(True)
+        shift3d_func(x[:1], wq, pad, True).backward(g[:1])
+        _, gw64 = oracle_port.backward(g[:1].double().cpu().numpy(), x[:1].double().cpu().numpy(), w0.double().cpu().numpy(), pad, True)
+        assert _gw_close(wq.grad.cpu().numpy(), gw64), pad
+        del y, xr
+
+
+def test_full_size_cfg5_quantized_shift2d(dev, lib, oracle_port, auto_path):
+    """cfg5: qint8 / quint8 Shift2d forward N=256 C=256 56x56, bit-exact."""
+    from torchshifts.quantized.functional import shift2d_quantized
+    from torchshifts.quantized.modules.shifts import quantize_shift_weights
+    from oracle.oracle import quantize_shift_weights_np
+    torch.manual_seed(3)
+    x = torch.rand(256, 256, 56, 56, device=dev)
+    w = (torch.rand(256, 2, device=dev) * 2 - 1) * 3
+    raw, wzp = quantize_shift_weights_np(w.cpu().numpy())
+    for qdtype, zp in ((torch.qint8, -128), (torch.quint8, 0)):
+        xq = torch.quantize_per_tensor(x, 1 / 255., zp, qdtype)
+        qw = quantize_shift_weights(w)
+        assert np.array_equal(qw.int_repr().cpu().numpy().astype(np.int64), raw)
+        yq = shift2d_quantized(xq, qw, 0)
+        assert lib.ts_last_kernel_path() == STAGED
+        idx = [0, 100, 255]
+        want = oracle_port.qforward(xq.int_repr()[idx].cpu().numpy(), raw, wzp, zp, 0)
+        assert np.array_equal(yq.int_repr()[idx].cpu().numpy(), want)
+        # checksum property: with zeros padding every output byte is an input byte or the zero point
+        hist_in = torch.bincount(xq.int_repr().flatten().to(torch.int64) + 128, minlength=384)
+        hist_out = torch.bincount(yq.int_repr().flatten().to(torch.int64) + 128, minlength=384)
+        zp_bin = zp + 128
+        other = torch.ones_like(hist_in, dtype=torch.bool)
+        other[zp_bin] = False
+        assert bool((hist_out[other] <= hist_in[other]).all())
+
+
+def test_cfg1_small_l2_resident(dev, oracle_port, auto_path):
+    """cfg1: N=8 C=64 32x32 fp32 SSL zeros -- the reference's own CPU-runnable case, whole tensor vs oracle."""
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((8, 64, 32, 32)).astype(np.float32)
+    g = rng.standard_normal((8, 64, 32, 32)).astype(np.float32)
+    w = ((rng.random((64, 2)) * 2 - 1)).astype(np.float32)
+    y, gi, gw = _run_cuda(dev, 2, x, w, g, 0, False, None)
+    assert np.array_equal(y, oracle_port.forward(x, w, 0, False))
+    gi_ref, _ = oracle_port.backward(g, x, w, 0, False)
+    assert np.array_equal(gi, gi_ref)
+    _, gw64 = oracle_port.backward(g.astype(np.float64), x.astype(np.float64), w.astype(np.float64), 0, False)
+    assert _gw_close(gw, gw64)
