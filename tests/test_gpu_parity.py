@@ -182,10 +182,10 @@ def test_half_precision_vs_fp32_oracle(dev, oracle_port, auto_path):
                     y_ref = oracle_port.forward(x32, w32, pad, active)
                     gi_ref, gw_ref = oracle_port.backward(g32, x32, w32, pad, active)
                     if not active:
-                        assert np.array_equal(y.float().cpu().numpy(), y_ref)          # pure copy: exact
+                        assert np.array_equal(y.detach().float().cpu().numpy(), y_ref)          # pure copy: exact
                         assert np.array_equal(xd.grad.float().cpu().numpy(), gi_ref)
                     else:
-                        assert np.allclose(y.float().cpu().numpy(), y_ref, rtol=1e-2, atol=1e-2)
+                        assert np.allclose(y.detach().float().cpu().numpy(), y_ref, rtol=1e-2, atol=1e-2)
                         assert np.allclose(xd.grad.float().cpu().numpy(), gi_ref, rtol=1e-2, atol=1e-2)
                     assert np.allclose(wd.grad.float().cpu().numpy(), gw_ref, rtol=1e-2, atol=1e-2 * np.abs(gw_ref).max())
 
@@ -281,6 +281,8 @@ def test_modules_and_quantized_convert(dev, oracle_port, auto_path):
     want = oracle_port.qforward(iq.int_repr().cpu().numpy(), raw, wzp, 0, 0, [[1, 1], [1, 1]])
     assert np.array_equal(oq.int_repr().cpu().numpy(), want)
     model = torch.nn.Sequential(a)
+    model.qconfig = torch.ao.quantization.default_qconfig        # convert only swaps modules that carry a qconfig
+    torch.ao.quantization.propagate_qconfig_(model)
     conv = torch.ao.quantization.convert(model, mapping=torchshifts.quant_mapping, inplace=False)
     assert type(conv[0]) is QShift2d
     # sparsity loss and stride-2 emulation (avg-pool reduction)
@@ -294,10 +296,10 @@ def test_modules_and_quantized_convert(dev, oracle_port, auto_path):
 def _sample_check(dev, oracle_port, dim, x, w, g, pad, active, y, gi, n_idx):
     xs = x[n_idx].cpu().numpy()
     ws = w.detach().cpu().numpy()
-    assert np.array_equal(y[n_idx].cpu().numpy(), oracle_port.forward(xs, ws, pad, active))
+    assert np.array_equal(y.detach()[n_idx].cpu().numpy(), oracle_port.forward(xs, ws, pad, active))
     if gi is not None:
         gi_ref, _ = oracle_port.backward(g[n_idx].cpu().numpy(), xs, ws, pad, active)
-        assert np.array_equal(gi[n_idx].cpu().numpy(), gi_ref)
+        assert np.array_equal(gi.detach()[n_idx].cpu().numpy(), gi_ref)
 
 
 def test_full_size_cfg3_shift2d(dev, lib, oracle_port, auto_path):
@@ -375,7 +377,7 @@ def test_full_size_cfg2_shift1d_active_periodic(dev, lib, oracle_port, auto_path
     yb.backward(gb)
     y_ref = oracle_port.forward(xb.float().cpu().numpy(), wb.float().cpu().numpy(), 2, True)
     gi_ref, gw_ref = oracle_port.backward(gb.float().cpu().numpy(), xb.float().cpu().numpy(), wb.float().cpu().numpy(), 2, True)
-    assert np.allclose(yb.float().cpu().numpy(), y_ref, rtol=1e-2, atol=1e-2)
+    assert np.allclose(yb.detach().float().cpu().numpy(), y_ref, rtol=1e-2, atol=1e-2)
     assert np.allclose(xbr.grad.float().cpu().numpy(), gi_ref, rtol=1e-2, atol=1e-2)
     assert np.allclose(wbr.grad.float().cpu().numpy(), gw_ref, rtol=1e-2, atol=1e-2 * np.abs(gw_ref).max())
 
