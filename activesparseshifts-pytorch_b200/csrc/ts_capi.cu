@@ -119,7 +119,7 @@ const char* ts_error_string(int status) {
 const char* ts_last_cuda_error(void) { return t_cuda_error; }
 int ts_last_kernel_path(void) { return t_last_path; }
 int ts_set_kernel_path(int path) {
-    if (path < 0 || path > 2) return -1;
+    if (path < 0 || path > 3) return -1;
     return g_forced_path.exchange(path);
 }
 uint64_t ts_launch_count(void) { return (uint64_t)g_launches.load(); }
@@ -137,12 +137,16 @@ int ts_set_tuning(const char* spec) {
         else if (!strcmp(key, "warps")) t.warps = val;
         else if (!strcmp(key, "ctas_per_sm")) t.ctas_per_sm = val;
         else if (!strcmp(key, "chunk_planes")) t.chunk_planes = val;
+        else if (!strcmp(key, "tma_stages")) t.tma_stages = val;
+        else if (!strcmp(key, "tma_ctas_per_sm")) t.tma_ctas_per_sm = val;
+        else if (!strcmp(key, "tma_warps")) t.tma_warps = val;
         else return TS_ERR_INVALID_ARGUMENT;
         p += n;
         while (*p == ',' || *p == ' ') ++p;
     }
     if (t.stages < 1 || t.stages > 8 || t.stage_kb < 1 || t.stage_kb > 200 || t.warps < 1 || t.warps > 31 ||
-        t.ctas_per_sm < 1 || t.ctas_per_sm > 8 || t.chunk_planes < 0)
+        t.ctas_per_sm < 1 || t.ctas_per_sm > 8 || t.chunk_planes < 0 || t.tma_stages < 0 || t.tma_stages > 32 ||
+        t.tma_ctas_per_sm < 0 || t.tma_ctas_per_sm > 8 || t.tma_warps < 0 || t.tma_warps > 31)
         return TS_ERR_INVALID_ARGUMENT;
     tuning() = t;
     return TS_OK;
@@ -201,6 +205,14 @@ int ts_shift_forward(const ts_geometry* gin, int dtype, int padding, int active,
     if ((rc = sm_count(&sms)) != TS_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int forced = g_forced_path.load();
+    if (!active && (forced == TS_PATH_NONE || forced == TS_PATH_TMA)) {
+        const TmaPlan tp = plan_tma(g, 0, es, dtype, x_is_dense(g), 0ull, x, y, nullptr, sms);
+        if (tp.ok) {
+            t_last_path = TS_PATH_TMA;
+            return tma_gather(g, tp, dtype, x, y, es, weights, 0, 0, s);
+        }
+    }
+    if (forced == TS_PATH_TMA) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
     if (forced != TS_PATH_GENERIC) plan = plan_staged(g, active ? 1 : 0, es, dtype, x_is_dense(g), x, y, nullptr, sms);
@@ -277,6 +289,14 @@ int ts_qshift_forward(const ts_geometry* gin, int elem_bytes, int padding, int64
     const unsigned long long fill = elem_bytes == 1 ? (unsigned long long)((unsigned)zero_point & 0xffu)
                                                     : (unsigned long long)(uint32_t)(int32_t)zero_point;
     const int forced = g_forced_path.load();
+    if (forced == TS_PATH_NONE || forced == TS_PATH_TMA) {
+        const TmaPlan tp = plan_tma(g, 0, elem_bytes, -1, x_is_dense(g), fill, xq, yq, nullptr, sms);
+        if (tp.ok) {
+            t_last_path = TS_PATH_TMA;
+            return tma_gather(g, tp, WK_QUANT, xq, yq, elem_bytes, qweights, qweight_kind, weight_zero_point, s);
+        }
+    }
+    if (forced == TS_PATH_TMA) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
     if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 0, elem_bytes, -1, x_is_dense(g), xq, yq, nullptr, sms);

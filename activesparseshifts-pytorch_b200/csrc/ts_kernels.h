@@ -45,6 +45,9 @@ struct Tuning {
     int warps;         // consumer warps per CTA
     int ctas_per_sm;   // persistent CTAs per SM
     int chunk_planes;  // planes of one channel per work unit (0 = auto)
+    int tma_stages;    // ring depth of the TMA-tensor kernels (0 = auto)
+    int tma_ctas_per_sm;
+    int tma_warps;     // consumer warps of the TMA-tensor arithmetic kernels
 };
 Tuning& tuning();
 
@@ -63,5 +66,17 @@ int staged_gather(const Geo& g, const StagedPlan& p, int wk, const void* x, void
 int staged_active_forward(const Geo& g, const StagedPlan& p, const void* x, const void* w, void* y, cudaStream_t s);
 int staged_backward(const Geo& g, const StagedPlan& p, int active, const void* grad, const void* x, const void* w,
                     void* gi, void* gw, double* partials, cudaStream_t s);
+
+// ---- TMA-tensor family (ts_tma.cu): zeros padding done by the copy engine ----------------------
+struct TmaPlan {
+    bool ok;
+    int ta, tiles_per_plane, stages, stage_stride, n_per_unit, units, grid, warps, slots;
+    size_t smem_bytes;
+};
+// mode: 0 sparse/quantized forward, 1 active forward, 2 backward
+TmaPlan plan_tma(const Geo& g, int mode, int esize, int dtype, bool dense_x, unsigned long long fill, const void* x,
+                 const void* out, const void* grad, int sm_count);
+int tma_gather(const Geo& g, const TmaPlan& p, int wk, const void* x, void* y, int esize, const void* w, int qkind, long long wzp,
+               cudaStream_t s);
 
 }  // namespace ts

@@ -17,7 +17,6 @@
  *                               (= ops/cpu/shifts_cpu.cpp:235-255)
  *   ts_qshift_forward        <- qshiftnd<nD,pad>()                     ops/quantized/shifts_quantized.cpp:107-130
  *                               (the reference has no CUDA quantized kernel; this adds one)
- *   ts_reduce_grad_weight_*  <- (net new) the cross-GPU sum of grad_weight, SURVEY.md 8(e)
  *
  * Semantics (identical to the reference CPU path):
  *   - tensors are [N, C, S0(, S1(, S2))], last axis fastest; `x` may have arbitrary element
@@ -67,7 +66,8 @@ typedef enum ts_qweight_kind {     /* storage of the raw integer shift weights (
 typedef enum ts_kernel_path {      /* which kernel family served the last call (diagnostics)      */
     TS_PATH_NONE = 0,
     TS_PATH_GENERIC = 1,           /* stride-generic one-element-per-thread kernels               */
-    TS_PATH_STAGED = 2             /* bulk-async (cp.async.bulk + mbarrier) shared-memory staged  */
+    TS_PATH_STAGED = 2,            /* bulk-async (cp.async.bulk + mbarrier) shared-memory staged  */
+    TS_PATH_TMA = 3                /* TMA tensor copies: the copy engine applies shift + zero pad  */
 } ts_kernel_path;
 
 /* Geometry of one call.  Unused spatial axes: size 1, stride 0, lb 0, rb 1. */
@@ -86,9 +86,10 @@ int          ts_cuda_version(void);            /* CUDART_VERSION this library wa
 const char*  ts_error_string(int status);
 const char*  ts_last_cuda_error(void);         /* text of the last CUDA error seen by this thread */
 int          ts_last_kernel_path(void);        /* ts_kernel_path of this thread's last launch     */
-int          ts_set_kernel_path(int path);     /* 0 auto (default), 1 force generic, 2 force staged
-                                                  (calls fail with TS_ERR_UNSUPPORTED when the
-                                                  staged path does not apply); returns old value  */
+int          ts_set_kernel_path(int path);     /* 0 auto (default), 1 force generic, 2 force staged,
+                                                  3 force TMA (calls fail with TS_ERR_UNSUPPORTED
+                                                  when the forced family does not apply); returns
+                                                  the old value                                   */
 uint64_t     ts_launch_count(void);            /* kernels launched by this library so far         */
 int          ts_set_tuning(const char* spec);  /* "key=value,..." staged-path tuning knobs; see
                                                   DESIGN.md.  Returns TS_OK or INVALID_ARGUMENT   */

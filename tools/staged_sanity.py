@@ -23,12 +23,13 @@ dev = torch.device("cuda:0")
 fn = {1: F.shift1d_func, 2: F.shift2d_func, 3: F.shift3d_func}
 fails, ran, skipped = [], 0, 0
 quick = "--quick" in sys.argv
+FORCED = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--path=")), 2)
 
 shapes = [(3, 5, 64), (2, 4, 40), (2, 3, 12, 16), (3, 4, 8, 8), (2, 6, 28, 28), (2, 3, 4, 6, 8), (1, 2, 3, 5, 4), (5, 7, 1, 16), (9, 2, 4, 12), (37, 3, 8, 8)]
 if quick:
     shapes = shapes[:5]
 rng = np.random.default_rng(0)
-lib.ts_set_kernel_path(2)
+lib.ts_set_kernel_path(FORCED)
 for shape in shapes:
     dim = len(shape) - 2
     for wr in (2.5, 40.0):
@@ -40,24 +41,38 @@ for shape in shapes:
                     tag = (shape, wr, borders, pad, active)
                     y_ref = orc.forward(x, w, pad, active, borders)
                     g = rng.standard_normal(y_ref.shape).astype(np.float32)
+                    xd = torch.from_numpy(x).to(dev).requires_grad_(True)
+                    wd = torch.from_numpy(w).to(dev).requires_grad_(True)
+                    b = torch.tensor(borders, dtype=torch.long) if borders else None
                     try:
-                        xd = torch.from_numpy(x).to(dev).requires_grad_(True)
-                        wd = torch.from_numpy(w).to(dev).requires_grad_(True)
-                        b = torch.tensor(borders, dtype=torch.long) if borders else None
                         y = fn[dim](xd, wd, pad, active, b)
+                        torch.cuda.synchronize()
+                    except RuntimeError as e:
+                        if "UNSUPPORTED" in str(e):
+                            skipped += 1
+                        else:
+                            fails.append((tag, "fwd exception " + str(e)[:200]))
+                        y = None
+                    if y is not None:
+                        ran += 1
+                        if not np.array_equal(y.detach().cpu().numpy(), y_ref):
+                            fails.append((tag, "forward", int((y.detach().cpu().numpy() != y_ref).sum())))
+                    if y is None:      # forward family not applicable: still exercise backward through the auto path
+                        lib.ts_set_kernel_path(0)
+                        y = fn[dim](xd, wd, pad, active, b)
+                        lib.ts_set_kernel_path(FORCED)
+                    try:
                         y.backward(torch.from_numpy(g).to(dev))
                         torch.cuda.synchronize()
                     except RuntimeError as e:
                         if "UNSUPPORTED" in str(e):
                             skipped += 1
-                            continue
-                        fails.append((tag, "exception " + str(e)[:200]))
+                        else:
+                            fails.append((tag, "bwd exception " + str(e)[:200]))
                         continue
                     ran += 1
                     gi_ref, _ = orc.backward(g, x, w, pad, active, borders)
                     _, gw64 = orc.backward(g.astype(np.float64), x.astype(np.float64), w.astype(np.float64), pad, active, borders)
-                    if not np.array_equal(y.detach().cpu().numpy(), y_ref):
-                        fails.append((tag, "forward", int((y.detach().cpu().numpy() != y_ref).sum())))
                     if not np.array_equal(xd.grad.cpu().numpy(), gi_ref):
                         fails.append((tag, "grad_input", int((xd.grad.cpu().numpy() != gi_ref).sum())))
                     if not np.allclose(wd.grad.cpu().numpy(), gw64, rtol=1e-5, atol=1e-5 * np.abs(gw64).max() + 1e-30):
@@ -97,7 +112,7 @@ for shape in [(2, 3, 8, 16), (3, 2, 64), (2, 2, 4, 4, 8), (4, 3, 6, 24)]:
                 fails.append(((shape, pad, str(qdt)), "qgather", int((yq.int_repr().cpu().numpy() != want).sum())))
 lib.ts_set_kernel_path(0)
 torch.cuda.synchronize()
-print(f"staged sanity: ran {ran}, skipped (staged path not applicable) {skipped}, failures {len(fails)}")
+print(f"sanity (forced path {FORCED}): ran {ran}, skipped (staged path not applicable) {skipped}, failures {len(fails)}")
 for f in fails[:60]:
     print("  FAIL", f)
 sys.exit(1 if fails else 0)

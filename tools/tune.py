@@ -72,7 +72,14 @@ for st, kb, wp, ct in grid:
         run(spec)
     except RuntimeError as e:
         print(spec, "failed:", str(e)[:120])
-for cp in (4, 8, 16, 32, 64):
+print("--- TMA family")
+lib.ts_set_tuning(b"stages=3,stage_kb=100,warps=16,ctas_per_sm=1,chunk_planes=0")
+for st, ct in itertools.product((4, 6, 8, 12, 16), (1, 2, 3, 4)):
+    spec = f"tma_stages={st},tma_ctas_per_sm={ct}"
+    if lib.ts_set_tuning(spec.encode()) == 0:
+        run(spec)
+lib.ts_set_tuning(b"tma_stages=0,tma_ctas_per_sm=0")
+for cp in (4, 8, 16, 32, 64) if "--chunks" in sys.argv else ():
     spec = f"stages=4,stage_kb=48,warps=16,ctas_per_sm=1,chunk_planes={cp}"
     lib.ts_set_tuning(spec.encode())
     run(spec)
