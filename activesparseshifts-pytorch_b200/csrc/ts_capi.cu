@@ -140,6 +140,7 @@ int ts_set_tuning(const char* spec) {
         else if (!strcmp(key, "tma_stages")) t.tma_stages = val;
         else if (!strcmp(key, "tma_ctas_per_sm")) t.tma_ctas_per_sm = val;
         else if (!strcmp(key, "tma_warps")) t.tma_warps = val;
+        else if (!strcmp(key, "use_tma")) t.use_tma = val != 0;
         else return TS_ERR_INVALID_ARGUMENT;
         p += n;
         while (*p == ',' || *p == ' ') ++p;
@@ -205,7 +206,7 @@ int ts_shift_forward(const ts_geometry* gin, int dtype, int padding, int active,
     if ((rc = sm_count(&sms)) != TS_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int forced = g_forced_path.load();
-    if (!active && (forced == TS_PATH_NONE || forced == TS_PATH_TMA)) {
+    if (!active && ((forced == TS_PATH_NONE && tuning().use_tma) || forced == TS_PATH_TMA)) {
         const TmaPlan tp = plan_tma(g, 0, es, dtype, x_is_dense(g), 0ull, x, y, nullptr, sms);
         if (tp.ok) {
             t_last_path = TS_PATH_TMA;
@@ -289,7 +290,7 @@ int ts_qshift_forward(const ts_geometry* gin, int elem_bytes, int padding, int64
     const unsigned long long fill = elem_bytes == 1 ? (unsigned long long)((unsigned)zero_point & 0xffu)
                                                     : (unsigned long long)(uint32_t)(int32_t)zero_point;
     const int forced = g_forced_path.load();
-    if (forced == TS_PATH_NONE || forced == TS_PATH_TMA) {
+    if ((forced == TS_PATH_NONE && tuning().use_tma) || forced == TS_PATH_TMA) {
         const TmaPlan tp = plan_tma(g, 0, elem_bytes, -1, x_is_dense(g), fill, xq, yq, nullptr, sms);
         if (tp.ok) {
             t_last_path = TS_PATH_TMA;

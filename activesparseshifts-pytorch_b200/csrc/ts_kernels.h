@@ -48,6 +48,7 @@ struct Tuning {
     int tma_stages;    // ring depth of the TMA-tensor kernels (0 = auto)
     int tma_ctas_per_sm;
     int tma_warps;     // consumer warps of the TMA-tensor arithmetic kernels
+    int use_tma;       // 0: the automatic path choice never picks the TMA-tensor family
 };
 Tuning& tuning();
 

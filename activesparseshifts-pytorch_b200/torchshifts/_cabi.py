@@ -4,6 +4,7 @@ This module is the only place that talks to the native library.  It has no torch
 pointers, sizes and the stream handle are passed as plain integers.
 """
 import ctypes as ct
+import os
 from pathlib import Path
 
 LIB_NAME = 'libtorchshifts_b200.so'
@@ -72,6 +73,9 @@ class NativeLibrary:
             fn.restype, fn.argtypes = res, args
         if lib.ts_abi_version() != 1:
             raise ImportError(f'{self.path}: ABI version {lib.ts_abi_version()} != 1')
+        spec = os.environ.get('TS_TUNING')          # e.g. TS_TUNING="stages=3,use_tma=0"
+        if spec and lib.ts_set_tuning(spec.encode()) != TS_OK:
+            raise ImportError(f'TS_TUNING={spec!r} is not a valid tuning spec (see ts_set_tuning in include/torchshifts_b200.h)')
 
     def check(self, status, what):
         if status != TS_OK:

@@ -63,7 +63,7 @@ lib.ts_set_kernel_path(0)
 run("default tuning")
 grid = [(st, kb, wp, ct) for st, kb, wp, ct in itertools.product((2, 3, 4, 6), (13, 26, 40, 56, 100), (8, 12, 16), (1, 2))]
 if quick:
-    grid = [(3, 26, 16, 1), (4, 26, 16, 1), (4, 56, 16, 1), (3, 40, 8, 2), (4, 26, 8, 2), (6, 26, 16, 1)]
+    grid = [(4, 48, 16, 1), (3, 100, 16, 1), (2, 100, 16, 1), (4, 48, 31, 1), (3, 70, 31, 1), (2, 100, 31, 1), (3, 40, 8, 2), (3, 36, 16, 2), (2, 50, 16, 2), (2, 26, 8, 4), (2, 26, 7, 4)]
 for st, kb, wp, ct in grid:
     spec = f"stages={st},stage_kb={kb},warps={wp},ctas_per_sm={ct}"
     if lib.ts_set_tuning(spec.encode()) != 0:
@@ -72,6 +72,8 @@ for st, kb, wp, ct in grid:
         run(spec)
     except RuntimeError as e:
         print(spec, "failed:", str(e)[:120])
+if "--tma" not in sys.argv:
+    sys.exit(0)
 print("--- TMA family")
 lib.ts_set_tuning(b"stages=3,stage_kb=100,warps=16,ctas_per_sm=1,chunk_planes=0")
 for st, ct in itertools.product((4, 6, 8, 12, 16), (1, 2, 3, 4)):
