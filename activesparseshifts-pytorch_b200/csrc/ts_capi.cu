@@ -141,13 +141,15 @@ int ts_set_tuning(const char* spec) {
         else if (!strcmp(key, "tma_ctas_per_sm")) t.tma_ctas_per_sm = val;
         else if (!strcmp(key, "tma_warps")) t.tma_warps = val;
         else if (!strcmp(key, "use_tma")) t.use_tma = val != 0;
+        else if (!strcmp(key, "tma_stage_kb")) t.tma_stage_kb = val;
         else return TS_ERR_INVALID_ARGUMENT;
         p += n;
         while (*p == ',' || *p == ' ') ++p;
     }
     if (t.stages < 1 || t.stages > 8 || t.stage_kb < 1 || t.stage_kb > 200 || t.warps < 1 || t.warps > 31 ||
         t.ctas_per_sm < 1 || t.ctas_per_sm > 8 || t.chunk_planes < 0 || t.tma_stages < 0 || t.tma_stages > 32 ||
-        t.tma_ctas_per_sm < 0 || t.tma_ctas_per_sm > 8 || t.tma_warps < 0 || t.tma_warps > 31)
+        t.tma_ctas_per_sm < 0 || t.tma_ctas_per_sm > 8 || t.tma_warps < 0 || t.tma_warps > 31 || t.tma_stage_kb < 0 ||
+        t.tma_stage_kb > 220)
         return TS_ERR_INVALID_ARGUMENT;
     tuning() = t;
     return TS_OK;
@@ -206,11 +208,11 @@ int ts_shift_forward(const ts_geometry* gin, int dtype, int padding, int active,
     if ((rc = sm_count(&sms)) != TS_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int forced = g_forced_path.load();
-    if (!active && ((forced == TS_PATH_NONE && tuning().use_tma) || forced == TS_PATH_TMA)) {
-        const TmaPlan tp = plan_tma(g, 0, es, dtype, x_is_dense(g), 0ull, x, y, nullptr, sms);
+    if ((forced == TS_PATH_NONE && tuning().use_tma) || forced == TS_PATH_TMA) {
+        const TmaPlan tp = plan_tma(g, active ? 1 : 0, active, es, dtype, x_is_dense(g), 0ull, x, y, nullptr, sms);
         if (tp.ok) {
             t_last_path = TS_PATH_TMA;
-            return tma_gather(g, tp, dtype, x, y, es, weights, 0, 0, s);
+            return active ? tma_active_forward(g, tp, x, weights, y, s) : tma_gather(g, tp, dtype, x, y, es, weights, 0, 0, s);
         }
     }
     if (forced == TS_PATH_TMA) return TS_ERR_UNSUPPORTED;
@@ -239,6 +241,12 @@ size_t ts_shift_backward_workspace_bytes(const ts_geometry* gin, int dtype) {
     // assume the staged path may apply (pointer alignment is unknown here)
     const StagedPlan sp = plan_staged(g, 2, elem_size(dtype), dtype, true, nullptr, nullptr, nullptr, sms);
     if (sp.ok && (size_t)sp.slots > slots) slots = (size_t)sp.slots;
+    Geo gz = g;
+    gz.pad = TS_PAD_ZEROS;
+    for (int active = 0; active < 2; ++active) {
+        const TmaPlan tp = plan_tma(gz, 2, active, elem_size(dtype), dtype, true, 0ull, nullptr, nullptr, nullptr, sms);
+        if (tp.ok && (size_t)tp.slots > slots) slots = (size_t)tp.slots;
+    }
     return slots * (size_t)(g.C * g.dim) * sizeof(double) + 16;
 }
 
@@ -263,6 +271,14 @@ int ts_shift_backward(const ts_geometry* gin, int dtype, int padding, int active
     int sms = 0;
     if ((rc = sm_count(&sms)) != TS_OK) return rc;
     const int forced = g_forced_path.load();
+    if ((forced == TS_PATH_NONE && tuning().use_tma) || forced == TS_PATH_TMA) {
+        const TmaPlan tp = plan_tma(g, 2, active, es, dtype, x_is_dense(g), 0ull, x, grad_input, grad, sms);
+        if (tp.ok) {
+            t_last_path = TS_PATH_TMA;
+            return tma_backward(g, tp, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, s);
+        }
+    }
+    if (forced == TS_PATH_TMA) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
     if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 2, es, dtype, x_is_dense(g), x, grad_input, grad, sms);
@@ -291,7 +307,7 @@ int ts_qshift_forward(const ts_geometry* gin, int elem_bytes, int padding, int64
                                                     : (unsigned long long)(uint32_t)(int32_t)zero_point;
     const int forced = g_forced_path.load();
     if ((forced == TS_PATH_NONE && tuning().use_tma) || forced == TS_PATH_TMA) {
-        const TmaPlan tp = plan_tma(g, 0, elem_bytes, -1, x_is_dense(g), fill, xq, yq, nullptr, sms);
+        const TmaPlan tp = plan_tma(g, 0, 0, elem_bytes, -1, x_is_dense(g), fill, xq, yq, nullptr, sms);
         if (tp.ok) {
             t_last_path = TS_PATH_TMA;
             return tma_gather(g, tp, WK_QUANT, xq, yq, elem_bytes, qweights, qweight_kind, weight_zero_point, s);

@@ -49,6 +49,7 @@ struct Tuning {
     int tma_ctas_per_sm;
     int tma_warps;     // consumer warps of the TMA-tensor arithmetic kernels
     int use_tma;       // 0: the automatic path choice never picks the TMA-tensor family
+    int tma_stage_kb;  // target bytes per stage of the TMA-tensor kernels (0 = auto)
 };
 Tuning& tuning();
 
@@ -71,13 +72,20 @@ int staged_backward(const Geo& g, const StagedPlan& p, int active, const void* g
 // ---- TMA-tensor family (ts_tma.cu): zeros padding done by the copy engine ----------------------
 struct TmaPlan {
     bool ok;
-    int ta, tiles_per_plane, stages, stage_stride, n_per_unit, units, grid, warps, slots;
+    int ta, tb, tg;            // tile extents: slabs, rows, 16-byte column groups
+    int xa, xb;                // x box slabs / rows (tile + the +1 neighbours of the arithmetic kernels)
+    int tiles_per_plane, np;   // np = images per stage
+    int off_gv, off_g2, tx_bytes;
+    int stages, stage_stride, n_per_unit, units, grid, warps, slots;
     size_t smem_bytes;
 };
-// mode: 0 sparse/quantized forward, 1 active forward, 2 backward
-TmaPlan plan_tma(const Geo& g, int mode, int esize, int dtype, bool dense_x, unsigned long long fill, const void* x,
+// mode: 0 sparse/quantized forward, 1 active forward, 2 backward (active = interpolating backward)
+TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool dense_x, unsigned long long fill, const void* x,
                  const void* out, const void* grad, int sm_count);
 int tma_gather(const Geo& g, const TmaPlan& p, int wk, const void* x, void* y, int esize, const void* w, int qkind, long long wzp,
                cudaStream_t s);
+int tma_active_forward(const Geo& g, const TmaPlan& p, const void* x, const void* w, void* y, cudaStream_t s);
+int tma_backward(const Geo& g, const TmaPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
+                 double* partials, cudaStream_t s);
 
 }  // namespace ts

@@ -24,7 +24,7 @@
 namespace ts {
 
 Tuning& tuning() {
-    static Tuning t = {4, 48, 16, 1, 0, 0, 0, 0, 1};
+    static Tuning t = {4, 48, 16, 1, 0, 0, 0, 0, 1, 0};
     return t;
 }
 

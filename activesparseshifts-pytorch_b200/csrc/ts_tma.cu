@@ -1,19 +1,29 @@
-// ts_tma.cu -- zero-padding fast path built on TMA *tensor* copies (cp.async.bulk.tensor, SASS
-// UTMALDG).  Idea: a tiled TMA load whose box starts at (possibly negative) coordinates
-// (col - s_col, row - s_row, slab - s_slab, plane) delivers the plane already SHIFTED, with every
-// out-of-bounds element filled with zero by the copy engine.  That is exactly the reference's
-// zeros-padded integer gather (ops/kernels/shifts_kernels.h:10-54 with BIPadding::Zeros), done
-// by hardware:
+// ts_tma.cu -- the zero-padding fast path, built on TMA *tensor* copies (cp.async.bulk.tensor.5d,
+// SASS UTMALDG).
 //
-//   * sparse forward (and grad_input of the sparse backward without borders): TMA load of the
-//     shifted tile -> 1-D bulk store of the tile to the dense output.  ONE thread per CTA drives a
-//     ring of stages; no SM instruction touches the data.
-//   * backward / active forward: tiles arrive pre-shifted and 16-byte aligned, with one extra
-//     column group / row / slab for the +1 neighbours, so consumers use aligned LDS.128 only: no
-//     masks, no funnel shifts, no index remapping.
+// Idea.  A tiled TMA load whose box starts at the (possibly negative) coordinates
+//     (col0 - s_col rounded down to 16 bytes, row0 - s_row, slab0 - s_slab, c, n0)
+// delivers a tile of the plane(s) already SHIFTED along every axis, with every element that lies
+// outside the tensor filled with zero by the copy engine.  That is the reference's zero-padded
+// gather (ops/kernels/shifts_kernels.h:10-54 with BIPadding::Zeros) done by hardware, so the
+// consumers have no index remapping, no validity masks and no edge cases at all: every item reads
+// aligned 16-byte groups from shared memory and only resolves the residual sub-16-byte column
+// misalignment (0..3 fp32 elements; the copy engine requires the innermost coordinate to be a
+// multiple of 16 bytes -- measured: an unaligned inner coordinate raises "illegal instruction").
+// The box carries one extra 16-byte group per row (and one extra row / slab for the arithmetic
+// kernels) for the residual window and the +1 interpolation neighbours.
 //
-// Applicability (plan_tma): zeros padding, dense NCHW x, row bytes multiple of 16, every box
-// extent <= 256, pad value 0 (so not qint8 with a non-zero zero point).  Everything else runs on
+//   mode 0  sparse / quantized forward (pad value 0): y item = funnel-shifted pair of groups
+//   mode 1  active forward:  x box (TA+1, TB+1, TG+1 groups) -> exact unfused lerp nest
+//   mode 2  backward (no border crop): x box as mode 1, grad box unshifted (gv), and grad box
+//           shifted by +s (sparse: grad_input is a gather) or by -s with +1 neighbours (active)
+//
+// CTA = `nw` consumer warps + 1 producer warp (one elected lane issues the TMA loads), persistent,
+// one CTA per SM, ring of `stages` stages with full/empty mbarriers; grad_weight partials are
+// per-(unit, warp) in fp64, fixed shuffle tree, second pass in ts_generic.cu -> deterministic.
+//
+// Applicability (plan_tma): zeros padding, dense NCHW x, row bytes a multiple of 16, pad value 0,
+// fp32 for the arithmetic modes, no border crop for the backward.  Everything else runs on
 // ts_staged.cu / ts_generic.cu.
 #include <cuda.h>
 
@@ -24,6 +34,20 @@ namespace ts {
 namespace {
 
 constexpr int SMEM_LIMIT = 232448;
+constexpr int MAXT_TMA_GATHER = 1024, MAXT_TMA_ARITH = 832;
+
+// ---- exact division by a launch-invariant (n < 2^31) ------------------------------------------
+struct FastDiv { unsigned m, l, d; };
+FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.d = d ? d : 1;
+    unsigned l = 0;
+    while ((1ull << l) < f.d) ++l;
+    f.l = l;
+    f.m = (unsigned)(((((unsigned long long)1 << l) - f.d) << 32) / f.d + 1);
+    return f;
+}
+TS_D unsigned fdiv(unsigned n, const FastDiv& f) { return (__umulhi(n, f.m) + n) >> f.l; }
 
 // ---- driver entry point (no libcuda link dependency) ------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -40,17 +64,19 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// rank-4 map over a dense [planes][A][B][L] tensor of `es`-byte elements with box {bl, bb, ba, 1}
-bool make_map(CUtensorMap* map, const void* base, int es, long long planes, int A, int B, int L, int bl, int bb, int ba) {
+// rank-5 map over a dense [N][C][A][B][L] tensor of `es`-byte elements, box {bl, bb, ba, 1, bn}
+bool make_map(CUtensorMap* map, const void* base, int es, long long N, long long C, int A, int B, int L, int bl, int bb, int ba,
+              int bn) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
     const CUtensorMapDataType dt = es == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : es == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
                                  : es == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
-    cuuint64_t dims[4] = {(cuuint64_t)L, (cuuint64_t)B, (cuuint64_t)A, (cuuint64_t)planes};
-    cuuint64_t strides[3] = {(cuuint64_t)L * es, (cuuint64_t)L * B * es, (cuuint64_t)L * B * A * es};
-    cuuint32_t box[4] = {(cuuint32_t)bl, (cuuint32_t)bb, (cuuint32_t)ba, 1u};
-    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    return enc(map, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t dims[5] = {(cuuint64_t)L, (cuuint64_t)B, (cuuint64_t)A, (cuuint64_t)C, (cuuint64_t)N};
+    const cuuint64_t row = (cuuint64_t)L * es;
+    cuuint64_t strides[4] = {row, row * B, row * B * A, row * B * A * (cuuint64_t)C};
+    cuuint32_t box[5] = {(cuuint32_t)bl, (cuuint32_t)bb, (cuuint32_t)ba, 1u, (cuuint32_t)bn};
+    cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    return enc(map, dt, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -80,132 +106,506 @@ TS_D void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// tiled 4-D TMA load global -> shared; coordinates innermost first; OOB elements arrive as zero
-TS_D void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+// tiled 5-D TMA load global -> shared; coordinates innermost first; OOB elements arrive as zero.
+// c0 must be a multiple of 16 bytes worth of elements.
+TS_D void tma_load_5d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
             smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
         : "memory");
 }
-// 1-D bulk store shared -> global (dense destination), tracked by bulk async-groups
-TS_D void bulk_s2g(void* dst, const void* src, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-}
-TS_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> TS_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N> TS_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- arguments -------------------------------------------------------------------------------
 struct alignas(64) TArgs {
-    CUtensorMap map_x;       // source of the shifted tiles
-    CUtensorMap map_g;       // grad (backward)
+    CUtensorMap map_x;       // x,    box {(TG+1)*vec, xb, xa, 1, np}
+    CUtensorMap map_gs;      // grad, box {(TG+1)*vec, TB, TA, 1, np}     (backward)
+    CUtensorMap map_gb;      // grad, box {(TG+1)*vec, xb, xa, 1, np}     (active backward)
     Geo g;
     unsigned char* out;
     const void* w;
     double* partials;
     long long wzp;
-    int qkind, wk, es;
-    int A, B, L, OA, OB, OL, lbA, lbB, lbL;
-    int ta;                  // output slabs per tile (== OA unless 3-D volumes are tiled)
-    int tiles_per_plane;
-    int stages, stage_stride, np;
-    int n_per_unit, units, nw;
-    int tile_bytes;          // bytes of one shifted output tile (box bytes)
+    int qkind, wk, es, vec;  // vec = elements per 16-byte group
+    int mode, active;
+    int OA, OB, OGR;         // output slabs, rows, 16-byte groups per row
+    int lbA, lbB, lbL;
+    int TA, TB, TG;          // tile extents (slabs, rows, groups)
+    int xa, xb;              // x box slabs / rows (TA or TA+1, TB or TB+1)
+    int tiles_b, tiles_g, tiles;
+    int np;                  // images per stage (1 unless a whole plane is one tile)
+    int x_img_chunks;        // 16-byte groups of one image's x box
+    int g_img_chunks;        // 16-byte groups of one image's small grad box
+    int off_gv, off_g2;      // byte offsets of the grad boxes inside a stage
+    int tx_bytes;            // bytes landing per stage
+    int stage_stride, stages, nw, n_per_unit, units;
+    FastDiv d_img, d_TG, d_TB, d_tg, d_tb;
 };
 
 TS_D int level_axis(int level, int dim) { return level - (3 - dim); }
+TS_D int floor_to(int v, int q) { return v - pmod(v, q); }
 
-TS_D long long raw_int_shift(const TArgs& a, long long idx) {
-    long long iw;
-    switch (a.wk) {
-    case WK_F32: { float d; split_forward<float>(((const float*)a.w)[idx], false, iw, d); return iw; }
-    case WK_F64: { double d; split_forward<double>(((const double*)a.w)[idx], false, iw, d); return iw; }
-    case WK_F16: { float d; split_forward<float>(__half2float(((const __half*)a.w)[idx]), false, iw, d); return iw; }
-    case WK_BF16: { float d; split_forward<float>(__bfloat162float(((const __nv_bfloat16*)a.w)[idx]), false, iw, d); return iw; }
-    default:
-        if (a.qkind == TS_QW_U8) return (long long)((const uint8_t*)a.w)[idx] - a.wzp;
-        if (a.qkind == TS_QW_I8) return (long long)((const int8_t*)a.w)[idx] - a.wzp;
-        return (long long)((const int32_t*)a.w)[idx] - a.wzp;
+struct UnitShift {
+    int sh[3];     // integer shift per level (0 slab, 1 row, 2 column); absent levels 0
+    float d[3];    // fractional part per TENSOR AXIS (reference order), 0 for the sparse forward
+};
+
+TS_D UnitShift unit_shift(const TArgs& a, long long c) {
+    UnitShift u;
+    const int dim = a.g.dim;
+    u.d[0] = u.d[1] = u.d[2] = 0.f;
+#pragma unroll
+    for (int lev = 0; lev < 3; ++lev) {
+        const int ax = level_axis(lev, dim);
+        long long iw = 0;
+        if (ax >= 0) {
+            const long long idx = c * dim + ax;
+            if (a.mode == 0) {
+                switch (a.wk) {
+                case WK_F32: { float d; split_forward<float>(((const float*)a.w)[idx], false, iw, d); break; }
+                case WK_F64: { double d; split_forward<double>(((const double*)a.w)[idx], false, iw, d); break; }
+                case WK_F16: { float d; split_forward<float>(__half2float(((const __half*)a.w)[idx]), false, iw, d); break; }
+                case WK_BF16: { float d; split_forward<float>(__bfloat162float(((const __nv_bfloat16*)a.w)[idx]), false, iw, d); break; }
+                default:
+                    if (a.qkind == TS_QW_U8) iw = (long long)((const uint8_t*)a.w)[idx] - a.wzp;
+                    else if (a.qkind == TS_QW_I8) iw = (long long)((const int8_t*)a.w)[idx] - a.wzp;
+                    else iw = (long long)((const int32_t*)a.w)[idx] - a.wzp;
+                }
+            } else {
+                float d;
+                if (a.mode == 1) split_forward<float>(((const float*)a.w)[idx], true, iw, d);
+                else split_backward<float>(((const float*)a.w)[idx], a.active != 0, iw, d);
+                u.d[ax] = d;
+            }
+            u.sh[lev] = reduce_shift(iw, a.g.S[ax], TS_PAD_ZEROS);
+        } else {
+            u.sh[lev] = 0;
+        }
+    }
+    return u;
+}
+
+struct Tile { int a0, b0, g0; };
+TS_D Tile tile_of(const TArgs& a, int t) {
+    Tile tl;
+    const int tg = (int)fdiv((unsigned)t, a.d_tg);          // t / tiles_g
+    tl.g0 = (t - tg * a.tiles_g) * a.TG;
+    const int ta = (int)fdiv((unsigned)tg, a.d_tb);         // (t / tiles_g) / tiles_b
+    tl.b0 = (tg - ta * a.tiles_b) * a.TB;
+    tl.a0 = ta * a.TA;
+    return tl;
+}
+
+// ---- producer ---------------------------------------------------------------------------------
+TS_D void producer(const TArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty) {
+    int s = 0, k = 0;
+    const long long C = a.g.C, N = a.g.N;
+    const int dim = a.g.dim;
+    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
+        const long long c = u % C, chunk = u / C;
+        const long long n0 = chunk * a.n_per_unit;
+        const long long n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
+        const UnitShift us = unit_shift(a, c);
+        for (long long nb = n0; nb < n1; nb += a.np) {
+            for (int t = 0; t < a.tiles; ++t) {
+                if (k > 0) mbar_wait(&empty[s], (unsigned)((k - 1) & 1));
+                const Tile tl = tile_of(a, t);
+                unsigned char* st = smem + (size_t)s * a.stage_stride;
+                mbar_expect_tx(&full[s], (unsigned)a.tx_bytes);
+                const int l0 = tl.g0 * a.vec;
+                // x box: source coordinates of the tile's first output element, column rounded down to a group
+                const int xc = floor_to(l0 + a.lbL - us.sh[2], a.vec);
+                const int xr = dim >= 2 ? tl.b0 + a.lbB - us.sh[1] : 0;
+                const int xs = dim == 3 ? tl.a0 + a.lbA - us.sh[0] : 0;
+                tma_load_5d(st, &a.map_x, xc, xr, xs, (int)c, (int)nb, &full[s]);
+                if (a.mode == 2) {
+                    tma_load_5d(st + a.off_gv, &a.map_gs, l0, dim >= 2 ? tl.b0 : 0, dim == 3 ? tl.a0 : 0, (int)c, (int)nb, &full[s]);
+                    if (a.active) {      // grad at (o - s) with +1 neighbours: same geometry as the x box
+                        tma_load_5d(st + a.off_g2, &a.map_gb, xc, xr, xs, (int)c, (int)nb, &full[s]);
+                    } else {             // grad_input of the sparse shift gathers grad at (o + s)
+                        tma_load_5d(st + a.off_g2, &a.map_gs, floor_to(l0 + us.sh[2], a.vec), dim >= 2 ? tl.b0 + us.sh[1] : 0,
+                                    dim == 3 ? tl.a0 + us.sh[0] : 0, (int)c, (int)nb, &full[s]);
+                    }
+                }
+                if (++s == a.stages) { s = 0; ++k; }
+            }
+        }
     }
 }
 
-// ================================================================================================
-// Sparse forward, zeros padding: the copy engines do everything.  One thread per CTA.
-//   step q: TMA-load tile(q) into stage q % S;  after it lands, bulk-store it to y.
-// The loads run D = S-2 steps ahead of the stores; a stage is reloaded only after the store that
-// read it has finished reading shared memory (cp.async.bulk.wait_group.read 1).
-__global__ void __launch_bounds__(32, 1) k_tma_shiftcopy(const __grid_constant__ TArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
-    if (threadIdx.x != 0) return;
-    for (int s = 0; s < a.stages; ++s) mbar_init(&full[s], 1);
-    fence_barrier_init();
-
-    const int S = a.stages, D = S - 2;
+// ---- consumer skeleton -----------------------------------------------------------------------
+template <class Body>
+TS_D void consumer_loop(const TArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int lane, Body& body) {
+    int s = 0, k = 0;
     const long long C = a.g.C, N = a.g.N;
-    const int dim = a.g.dim;
-    // two cursors over the same step sequence: `ld` (loads) runs D steps ahead of `st` (stores)
-    struct Cursor { int u; long long n, n1, c; int tile; int sh[3]; bool valid; };
-    auto open_unit = [&](Cursor& k) {
-        if (k.u >= a.units) { k.valid = false; return; }
-        k.c = k.u % C;
-        const long long chunk = k.u / C;
-        k.n = chunk * a.n_per_unit;
-        k.n1 = k.n + a.n_per_unit < N ? k.n + a.n_per_unit : N;
-        k.tile = 0;
-        for (int lev = 0; lev < 3; ++lev) {
-            const int ax = level_axis(lev, dim);
-            k.sh[lev] = ax >= 0 ? reduce_shift(raw_int_shift(a, k.c * dim + ax), a.g.S[ax], TS_PAD_ZEROS) : 0;
+    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
+        const long long c = u % C, chunk = u / C;
+        const long long n0 = chunk * a.n_per_unit;
+        const long long n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
+        body.begin_unit(c);
+        for (long long nb = n0; nb < n1; nb += a.np) {
+            const int npl = (int)(n1 - nb < a.np ? n1 - nb : a.np);
+            for (int t = 0; t < a.tiles; ++t) {
+                mbar_wait(&full[s], (unsigned)(k & 1));
+                body.step(smem + (size_t)s * a.stage_stride, npl, nb, c, tile_of(a, t));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == a.stages) { s = 0; ++k; }
+            }
         }
-        k.valid = true;
-    };
-    auto advance = [&](Cursor& k) {
-        if (++k.tile < a.tiles_per_plane) return;
-        k.tile = 0;
-        if (++k.n < k.n1) return;
-        k.u += gridDim.x;
-        open_unit(k);
-    };
-    Cursor ld, st;
-    ld.u = st.u = blockIdx.x;
-    open_unit(ld);
-    open_unit(st);
-    int q_ld = 0, q_st = 0;
-    const long long tile_out_elems = (long long)a.ta * a.OB * a.OL;
-    while (st.valid) {
-        // issue loads until D steps ahead
-        while (ld.valid && q_ld < q_st + D + 1) {
-            const int s = q_ld % S;
-            if (q_ld >= S) bulk_wait_read<1>();          // the store that last read stage s is done reading
-            mbar_expect_tx(&full[s], (unsigned)a.tile_bytes);
-            const int a0 = ld.tile * a.ta;
-            tma_load_4d(smem + (size_t)s * a.stage_stride, &a.map_x, a.lbL - ld.sh[2], a.lbB - ld.sh[1], a0 + a.lbA - ld.sh[0],
-                        (int)(ld.n * C + ld.c), &full[s]);
-            ++q_ld;
-            advance(ld);
-        }
-        // store the oldest landed tile
-        {
-            const int s = q_st % S;
-            mbar_wait(&full[s], (unsigned)((q_st / S) & 1));
-            const int a0 = st.tile * a.ta;
-            const int slabs = a.OA - a0 < a.ta ? a.OA - a0 : a.ta;
-            unsigned char* dst = a.out + ((st.n * C + st.c) * a.g.out_plane + (long long)a0 * a.OB * a.OL) * a.es;
-            bulk_s2g(dst, smem + (size_t)s * a.stage_stride, (unsigned)((long long)slabs * a.OB * a.OL * a.es));
-            bulk_commit();
-            ++q_st;
-            advance(st);
-            (void)tile_out_elems;
+        body.end_unit(c, chunk);
+    }
+}
+
+// item -> (image, slab, row, group) inside a tile
+struct ItemPos { int pl, a, b, cg; };
+TS_D ItemPos decode_item(const TArgs& a, int item, bool has_slabs) {
+    ItemPos p;
+    p.pl = (int)fdiv((unsigned)item, a.d_img);
+    const int rem = item - p.pl * (int)a.d_img.d;
+    const int row = (int)fdiv((unsigned)rem, a.d_TG);
+    p.cg = rem - row * a.TG;
+    p.a = 0;
+    p.b = row;
+    if (has_slabs) { p.a = (int)fdiv((unsigned)row, a.d_TB); p.b = row - p.a * a.TB; }
+    return p;
+}
+
+// ================================================================================================
+// mode 0: sparse / quantized forward.  WS = word misalignment of the source window (0..3), the
+// sub-word byte shift (elements narrower than 4 bytes) is a run-time funnel-shift amount.
+struct GatherBody {
+    const TArgs& a;
+    const int tid, nt;
+    int ws, bs8;
+
+    TS_D GatherBody(const TArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), ws(0), bs8(0) {}
+    TS_D void begin_unit(long long c) {
+        const UnitShift us = unit_shift(a, c);
+        const int mb = pmod((a.lbL - us.sh[2]) * a.es, 16);    // tiles start at multiples of 16 bytes
+        ws = mb >> 2;
+        bs8 = (mb & 3) * 8;
+    }
+    TS_D void end_unit(long long, long long) {}
+
+    template <int WS>
+    TS_D void run(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) const {
+        const int total = npl * (int)a.d_img.d;
+        const bool slabs = a.TA > 1 || a.OA > 1;
+        const bool partial = tl.a0 + a.TA > a.OA || tl.b0 + a.TB > a.OB || tl.g0 + a.TG > a.OGR;
+        const uint4* box = (const uint4*)st;
+        const long long out_plane_bytes = a.g.out_plane * a.es;
+        for (int item = tid; item < total; item += nt) {
+            const ItemPos p = decode_item(a, item, slabs);
+            if (partial && (tl.a0 + p.a >= a.OA || tl.b0 + p.b >= a.OB || tl.g0 + p.cg >= a.OGR)) continue;
+            const int ch = p.pl * a.x_img_chunks + (p.a * a.xb + p.b) * (a.TG + 1) + p.cg;
+            const uint4 A = box[ch], B = box[ch + 1];
+            const unsigned W[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+            unsigned o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = __funnelshift_r(W[k + WS], W[(k + WS + 1) & 7], bs8);
+            unsigned char* dst = a.out + ((nb + p.pl) * a.g.C + c) * out_plane_bytes +
+                                 ((long long)((tl.a0 + p.a) * a.OB + tl.b0 + p.b) * a.OGR + tl.g0 + p.cg) * 16;
+            __stcs((uint4*)dst, make_uint4(o[0], o[1], o[2], o[3]));
         }
     }
-    bulk_wait_all<0>();
+    TS_D void step(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) const {
+        switch (ws) {
+        case 0: run<0>(st, npl, nb, c, tl); break;
+        case 1: run<1>(st, npl, nb, c, tl); break;
+        case 2: run<2>(st, npl, nb, c, tl); break;
+        default: run<3>(st, npl, nb, c, tl); break;
+        }
+    }
+};
+
+// ================================================================================================
+// fp32 arithmetic bodies.  A window of NV consecutive elements starting M elements into the
+// aligned group `ch` of a staged box.
+template <int M, int NV>
+TS_D void load_win(const float4* __restrict__ box, int ch, float* out) {
+    const float4 A = box[ch];
+    float W[8] = {A.x, A.y, A.z, A.w, 0.f, 0.f, 0.f, 0.f};
+    if (M + NV > 4) {
+        const float4 B = box[ch + 1];
+        W[4] = B.x; W[5] = B.y; W[6] = B.z; W[7] = B.w;
+    }
+#pragma unroll
+    for (int t = 0; t < NV; ++t) out[t] = W[t + M];
+}
+
+// group index of (slab a + da, row b + db) inside a box with `rows` rows per slab
+template <int DIM>
+TS_D int box_row_chunk(int a, int b, int rv, int rows, int tg1) {
+    if (DIM == 1) return 0;
+    if (DIM == 2) return (b + (rv & 1)) * tg1;
+    return ((a + (rv & 1)) * rows + b + ((rv >> 1) & 1)) * tg1;
+}
+
+template <int DIM>
+TS_D void neighbours_from_rows(const float (*X)[5], int t, float* v) {
+    constexpr int NR = 1 << (DIM - 1);
+#pragma unroll
+    for (int q = 0; q < (1 << DIM); ++q) v[q] = X[q & (NR - 1)][t + (q >> (DIM - 1))];
+}
+
+// The reference's per-element weight-gradient factors (ts_common.cuh weight_partials) written with
+// ordinary, contractable arithmetic: grad_weight is tolerance-checked (rtol 1e-5 vs an fp64 CPU
+// evaluation of the reference formulas), only forward / grad_input have to be bit-exact.
+template <int DIM>
+TS_D void weight_partials_fast(const float* v, const float* d, float* g) {
+    if (DIM == 1) { g[0] = v[1] - v[0]; return; }
+    if (DIM == 2) {
+        const float p = v[2] - v[0], q = (v[3] - v[1]) - p;   // both factors are p + frac * q
+        g[0] = fmaf(d[1], q, p);
+        g[1] = fmaf(d[0], q, p);
+        return;
+    }
+    const float p0 = v[2] - v[0], q0 = (v[3] - v[1]) - p0, p1 = v[6] - v[4], q1 = (v[7] - v[5]) - p1;
+    const float x0 = fmaf(d[1], q0, p0), x1 = fmaf(d[1], q1, p1);
+    const float y0 = fmaf(d[0], q0, p0), y1 = fmaf(d[0], q1, p1);
+    g[0] = fmaf(d[2], x1 - x0, x0);
+    g[1] = fmaf(d[2], y1 - y0, y0);
+    const float i0 = fmaf(d[0], v[1] - v[0], v[0]), i1 = fmaf(d[0], v[3] - v[2], v[2]);
+    const float i2 = fmaf(d[0], v[5] - v[4], v[4]), i3 = fmaf(d[0], v[7] - v[6], v[6]);
+    g[2] = fmaf(d[1], i3 - i2, i2) - fmaf(d[1], i1 - i0, i0);
+}
+
+template <int DIM>
+struct ActiveFwdBody {
+    const TArgs& a;
+    const int tid, nt;
+    UnitShift us;
+    int m;
+
+    TS_D ActiveFwdBody(const TArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), m(0) {}
+    TS_D void begin_unit(long long c) {
+        us = unit_shift(a, c);
+        m = pmod(a.lbL - us.sh[2], 4);
+    }
+    TS_D void end_unit(long long, long long) {}
+
+    template <int M>
+    TS_D void run(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) const {
+        constexpr int NR = 1 << (DIM - 1);
+        const int total = npl * (int)a.d_img.d;
+        const bool partial = tl.a0 + a.TA > a.OA || tl.b0 + a.TB > a.OB || tl.g0 + a.TG > a.OGR;
+        const float4* box = (const float4*)st;
+        const int tg1 = a.TG + 1;
+        for (int item = tid; item < total; item += nt) {
+            const ItemPos p = decode_item(a, item, DIM == 3);
+            if (partial && (tl.a0 + p.a >= a.OA || tl.b0 + p.b >= a.OB || tl.g0 + p.cg >= a.OGR)) continue;
+            const int base = p.pl * a.x_img_chunks + p.cg;
+            float X[NR][5];
+#pragma unroll
+            for (int rv = 0; rv < NR; ++rv) load_win<M, 5>(box, base + box_row_chunk<DIM>(p.a, p.b, rv, a.xb, tg1), X[rv]);
+            float o[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float v[8];
+                neighbours_from_rows<DIM>(X, t, v);
+                o[t] = interpolate<float, DIM>(v, us.d);
+            }
+            float* dst = (float*)a.out + ((nb + p.pl) * a.g.C + c) * a.g.out_plane +
+                         ((long long)((tl.a0 + p.a) * a.OB + tl.b0 + p.b) * a.OGR + tl.g0 + p.cg) * 4;
+            __stcs((float4*)dst, make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+    TS_D void step(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) const {
+        switch (m) {
+        case 0: run<0>(st, npl, nb, c, tl); break;
+        case 1: run<1>(st, npl, nb, c, tl); break;
+        case 2: run<2>(st, npl, nb, c, tl); break;
+        default: run<3>(st, npl, nb, c, tl); break;
+        }
+    }
+};
+
+template <int DIM, bool ACTIVE>
+struct BackwardBody {
+    const TArgs& a;
+    const int tid, nt, wid, lane;
+    UnitShift us;
+    int m;
+    double acc[DIM];
+
+    TS_D BackwardBody(const TArgs& a_, int tid_, int nt_, int wid_, int lane_) : a(a_), tid(tid_), nt(nt_), wid(wid_), lane(lane_), m(0) {}
+    TS_D void begin_unit(long long c) {
+        us = unit_shift(a, c);
+        m = pmod(-us.sh[2], 4);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) acc[d] = 0.0;
+    }
+    // one partial per (unit, consumer warp): fixed shuffle tree, no atomics
+    TS_D void end_unit(long long c, long long chunk) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            double v = acc[d];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) a.partials[((long long)chunk * a.nw + wid) * (a.g.C * DIM) + c * DIM + d] = v;
+        }
+    }
+
+    template <int M>
+    TS_D void run(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) {
+        constexpr int NR = 1 << (DIM - 1);
+        constexpr int MG = ACTIVE ? M : ((4 - M) & 3);      // misalignment of the grad window used for grad_input
+        const int total = npl * (int)a.d_img.d;
+        const bool partial = tl.a0 + a.TA > a.OA || tl.b0 + a.TB > a.OB || tl.g0 + a.TG > a.OGR;
+        const float4* xbox = (const float4*)st;
+        const float4* gv_box = (const float4*)(st + a.off_gv);
+        const float4* g2_box = (const float4*)(st + a.off_g2);
+        const int tg1 = a.TG + 1;
+        float ts[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) ts[d] = 0.f;
+        for (int item = tid; item < total; item += nt) {
+            const ItemPos p = decode_item(a, item, DIM == 3);
+            if (partial && (tl.a0 + p.a >= a.OA || tl.b0 + p.b >= a.OB || tl.g0 + p.cg >= a.OGR)) continue;
+            const int gch = p.pl * a.g_img_chunks + (p.a * a.TB + p.b) * tg1 + p.cg;
+            const int xbase = p.pl * a.x_img_chunks + p.cg;
+            float gv[4];
+            load_win<0, 4>(gv_box, gch, gv);
+            // ---- grad_weight terms ----
+            float X[NR][5];
+#pragma unroll
+            for (int rv = 0; rv < NR; ++rv) load_win<M, 5>(xbox, xbase + box_row_chunk<DIM>(p.a, p.b, rv, a.xb, tg1), X[rv]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float v[8], wg[3];
+                neighbours_from_rows<DIM>(X, t, v);
+                weight_partials_fast<DIM>(v, us.d, wg);
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) ts[d] = fmaf(gv[t], wg[d], ts[d]);
+            }
+            // ---- grad_input ----
+            float o[4];
+            if (ACTIVE) {
+                float G[NR][5];
+#pragma unroll
+                for (int rv = 0; rv < NR; ++rv) load_win<MG, 5>(g2_box, xbase + box_row_chunk<DIM>(p.a, p.b, rv, a.xb, tg1), G[rv]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float v[8];
+                    neighbours_from_rows<DIM>(G, t, v);
+                    o[t] = interpolate<float, DIM>(v, us.d);
+                }
+            } else {
+                load_win<MG, 4>(g2_box, gch, o);
+            }
+            float* dst = (float*)a.out + ((nb + p.pl) * a.g.C + c) * a.g.in_plane +
+                         ((long long)((tl.a0 + p.a) * a.OB + tl.b0 + p.b) * a.OGR + tl.g0 + p.cg) * 4;
+            __stcs((float4*)dst, make_float4(o[0], o[1], o[2], o[3]));
+        }
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) acc[d] += (double)ts[d];   // fp32 inside a tile, fp64 across tiles
+    }
+    TS_D void step(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) {
+        switch (m) {
+        case 0: run<0>(st, npl, nb, c, tl); break;
+        case 1: run<1>(st, npl, nb, c, tl); break;
+        case 2: run<2>(st, npl, nb, c, tl); break;
+        default: run<3>(st, npl, nb, c, tl); break;
+        }
+    }
+};
+
+// ---- kernels -----------------------------------------------------------------------------------
+TS_D void setup_barriers(const TArgs& a, unsigned char* smem, uint64_t*& full, uint64_t*& empty) {
+    full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
+    empty = full + a.stages;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)a.nw); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(MAXT_TMA_GATHER, 1) k_tma_gather(const __grid_constant__ TArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *full, *empty;
+    setup_barriers(a, smem, full, empty);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
+    GatherBody body(a, threadIdx.x, a.nw * 32);
+    consumer_loop(a, smem, full, empty, lane, body);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(MAXT_TMA_ARITH, 1) k_tma_active_forward(const __grid_constant__ TArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *full, *empty;
+    setup_barriers(a, smem, full, empty);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
+    ActiveFwdBody<DIM> body(a, threadIdx.x, a.nw * 32);
+    consumer_loop(a, smem, full, empty, lane, body);
+}
+
+template <int DIM, bool ACTIVE>
+__global__ void __launch_bounds__(MAXT_TMA_ARITH, 1) k_tma_backward(const __grid_constant__ TArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *full, *empty;
+    setup_barriers(a, smem, full, empty);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
+    BackwardBody<DIM, ACTIVE> body(a, threadIdx.x, a.nw * 32, wid, lane);
+    consumer_loop(a, smem, full, empty, lane, body);
+}
+
+template <class K>
+int launch(K kernel, const TArgs& a, const TmaPlan& p, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+    if (e != cudaSuccess) return check_launch();
+    kernel<<<p.grid, (p.warps + 1) * 32, p.smem_bytes, s>>>(a);
+    note_launch();
+    return check_launch();
+}
+
+long long round_up(long long v, long long q) { return (v + q - 1) / q * q; }
+
+// fills everything of TArgs that does not depend on pointers
+bool make_args(const Geo& g, const TmaPlan& p, int mode, int active, int es, TArgs* out) {
+    TArgs& a = *out;
+    memset(&a, 0, sizeof(a));
+    const int d = g.dim;
+    a.g = g;
+    a.es = es;
+    a.vec = 16 / es;
+    a.mode = mode;
+    a.active = active;
+    a.OA = d == 3 ? g.OS[0] : 1;      a.lbA = d == 3 ? g.lb[0] : 0;
+    a.OB = d >= 2 ? g.OS[d - 2] : 1;  a.lbB = d >= 2 ? g.lb[d - 2] : 0;
+    a.OGR = g.OS[d - 1] / a.vec;      a.lbL = g.lb[d - 1];
+    a.TA = p.ta; a.TB = p.tb; a.TG = p.tg;
+    a.xa = p.xa; a.xb = p.xb;
+    a.tiles_b = (a.OB + a.TB - 1) / a.TB;
+    a.tiles_g = (a.OGR + a.TG - 1) / a.TG;
+    a.tiles = p.tiles_per_plane;
+    a.np = p.np;
+    a.x_img_chunks = a.xa * a.xb * (a.TG + 1);
+    a.g_img_chunks = a.TA * a.TB * (a.TG + 1);
+    a.off_gv = p.off_gv;
+    a.off_g2 = p.off_g2;
+    a.tx_bytes = p.tx_bytes;
+    a.stage_stride = p.stage_stride;
+    a.stages = p.stages;
+    a.nw = p.warps;
+    a.n_per_unit = p.n_per_unit;
+    a.units = p.units;
+    a.d_img = make_fastdiv((unsigned)(a.TA * a.TB * a.TG));
+    a.d_TG = make_fastdiv((unsigned)a.TG);
+    a.d_TB = make_fastdiv((unsigned)a.TB);
+    a.d_tg = make_fastdiv((unsigned)a.tiles_g);
+    a.d_tb = make_fastdiv((unsigned)a.tiles_b);
+    return true;
 }
 
 }  // namespace
 
 // ---- planning -----------------------------------------------------------------------------------
-TmaPlan plan_tma(const Geo& g, int mode, int esize, int dtype, bool dense_x, unsigned long long fill, const void* x,
+TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool dense_x, unsigned long long fill, const void* x,
                  const void* out, const void* grad, int sm_count) {
     TmaPlan p;
     memset(&p, 0, sizeof(p));
@@ -213,81 +613,177 @@ TmaPlan plan_tma(const Geo& g, int mode, int esize, int dtype, bool dense_x, uns
     if (!encode_tiled()) return p;
     if (g.pad != TS_PAD_ZEROS || !dense_x || fill != 0ull) return p;
     if (g.N * g.C == 0 || g.in_plane == 0 || g.out_plane == 0) return p;
-    if (mode != 0) return p;                     // (backward / active forward tiles: added below as they land)
+    if (mode != 0 && dtype != TS_F32) return p;          // arithmetic kernels: fp32
+    if (mode != 0) esize = 4;
+    if (esize != 1 && esize != 2 && esize != 4 && esize != 8) return p;
     const int d = g.dim;
+    if (mode == 2)                                       // the backward tiles assume output space == input space
+        for (int ax = 0; ax < d; ++ax)
+            if (g.lb[ax] != 0 || g.OS[ax] != g.S[ax]) return p;
+    if (mode != 0)                                       // a size-1 axis ignores its shift AND its +1 neighbour is the element
+        for (int ax = 0; ax < d; ++ax)                   // itself (shifts_kernels.h:40-50), not the zero the copy engine would fill
+            if (g.S[ax] == 1) return p;
+    const int vec = 16 / esize;
     const int L = g.S[d - 1], OL = g.OS[d - 1];
-    const int B = d >= 2 ? g.S[d - 2] : 1, OB = d >= 2 ? g.OS[d - 2] : 1;
-    const int A = d == 3 ? g.S[0] : 1, OA = d == 3 ? g.OS[0] : 1;
-    if (((long long)L * esize) % 16 || ((long long)OL * esize) % 16) return p;      // global strides / box rows: 16-byte multiples
-    if (OL > 256 || OB > 256) return p;
-    if (((uintptr_t)x & 15) || ((uintptr_t)out & 15)) return p;
-    if (g.N * g.C >= (1ll << 31)) return p;
-    // slabs per tile: whole volume if it fits a stage of <= 48 KB, else as many slabs as fit
-    const long long slab_bytes = (long long)OB * OL * esize;
-    long long ta = OA;
-    const long long target = 48 * 1024;
-    if (ta * slab_bytes > target) ta = target / slab_bytes;
-    if (ta < 1) ta = 1;
-    if (ta > 256) ta = 256;
-    if (ta * slab_bytes > 100 * 1024) return p;
+    const int OB = d >= 2 ? g.OS[d - 2] : 1, OA = d == 3 ? g.OS[0] : 1;
+    if (((long long)L * esize) % 16 || ((long long)OL * esize) % 16) return p;   // global strides / output rows: 16-byte multiples
+    if (((uintptr_t)x & 15) || ((uintptr_t)out & 15) || ((uintptr_t)grad & 15)) return p;
+    if (g.N >= (1ll << 31) || g.C >= (1ll << 31)) return p;
+    if (g.in_plane * esize >= (1ll << 40) / (g.C > 0 ? g.C : 1)) return p;       // tensor-map strides < 2^40
+
     const Tuning& t = tuning();
-    const long long stride = ((ta * slab_bytes + 127) / 128) * 128;
-    int ctas = t.tma_ctas_per_sm > 0 ? t.tma_ctas_per_sm : 2;
-    long long stages = t.tma_stages > 0 ? t.tma_stages : 8;
-    const long long budget = SMEM_LIMIT / ctas - 1024;
-    if (stages * stride + 8 * stages > budget) stages = budget / (stride + 8);
-    if (stages < 3) { ctas = 1; stages = (SMEM_LIMIT - 1024) / (stride + 8); }
-    if (stages < 3) return p;
-    if (stages > 16) stages = 16;
+    const int OGR = OL / vec;
+    const int max_groups = 256 / vec - 1;               // box inner extent (TG+1)*vec <= 256 elements
+    const int tiles_g = (OGR + max_groups - 1) / max_groups;
+    const int TG = (OGR + tiles_g - 1) / tiles_g;
+    const int ex = mode != 0 ? 1 : 0;                   // +1 neighbour row / slab in the arithmetic boxes
+    const int exb = d >= 2 ? ex : 0, exa = d == 3 ? ex : 0;
+    long long TB = OB < 256 - exb ? OB : 256 - exb;
+    long long TA = OA < 256 - exa ? OA : 256 - exa;
+    auto image_bytes = [&](long long ta, long long tb, int* off_gv, int* off_g2) {
+        const long long xbytes = round_up((ta + exa) * (tb + exb) * (TG + 1) * 16, 128);
+        const long long gsbytes = round_up(ta * tb * (TG + 1) * 16, 128);
+        if (off_gv) *off_gv = (int)xbytes;
+        if (off_g2) *off_g2 = (int)(xbytes + gsbytes);
+        if (mode != 2) return xbytes;
+        return xbytes + gsbytes + (active ? xbytes : gsbytes);
+    };
+    const long long budget = SMEM_LIMIT - 1024;
+    const int want_stages = t.tma_stages > 0 ? t.tma_stages : (mode == 2 ? 5 : 6);
+    const long long target = t.tma_stage_kb > 0 ? (long long)t.tma_stage_kb * 1024 : budget / want_stages - 64;
+    while (image_bytes(TA, TB, nullptr, nullptr) > target) {
+        if (TA > 1) TA = (TA + 1) / 2;
+        else if (TB > 1) TB = (TB + 1) / 2;
+        else return p;
+    }
+    const int tiles_a = (int)((OA + TA - 1) / TA), tiles_b = (int)((OB + TB - 1) / TB);
+    const long long tiles = (long long)tiles_a * tiles_b * tiles_g;
+    if (tiles > 0x7fffffffLL) return p;
+    long long np = 1;
+    if (tiles == 1) {
+        // several images per stage only through a rank-5 box; the sub-box offsets then scale with np
+        np = target / image_bytes(TA, TB, nullptr, nullptr);
+        if (np < 1) np = 1;
+        if (np > 256) np = 256;
+        if (np > g.N) np = g.N;
+    }
+    int off_gv = 0, off_g2 = 0;
+    // with np images the three regions are [np x-boxes][np gv-boxes][np g2-boxes]
+    const long long xbytes1 = (TA + exa) * (TB + exb) * (TG + 1) * 16, gsbytes1 = TA * TB * (TG + 1) * 16;
+    const long long xreg = round_up(np * xbytes1, 128), gsreg = round_up(np * gsbytes1, 128);
+    off_gv = (int)xreg;
+    off_g2 = (int)(xreg + gsreg);
+    long long stage_bytes = xreg, tx = np * xbytes1;
+    if (mode == 2) {
+        stage_bytes += gsreg + (active ? xreg : gsreg);
+        tx += np * gsbytes1 + np * (active ? xbytes1 : gsbytes1);
+    }
+    const long long stride = round_up(stage_bytes, 1024);
+    long long stages = budget / (stride + 16);
+    if (stages > want_stages) stages = want_stages;
+    if (stages < 2) return p;
+    if (tx >= (1 << 20)) return p;                       // mbarrier tx-count range
+
     const long long planes = g.N * g.C;
-    const long long grid_max = (long long)sm_count * ctas;
+    const long long grid_max = (long long)sm_count;
     long long npu = t.chunk_planes > 0 ? t.chunk_planes : planes / (grid_max * 32);
-    if (npu < 1) npu = 1;
+    npu = (npu / np) * np;
+    if (npu < np) npu = np;
     if (npu > g.N) npu = g.N;
     const long long chunks = (g.N + npu - 1) / npu;
     const long long units = chunks * g.C;
     if (units > 0x7fffffffLL) return p;
+
+    // consumer warps: fill the last pass over a stage's items as well as possible
+    const long long items = np * TA * TB * TG;
+    const int max_warps = mode == 0 ? MAXT_TMA_GATHER / 32 - 1 : MAXT_TMA_ARITH / 32 - 1;
+    int warps = t.tma_warps > 0 ? (t.tma_warps < max_warps ? t.tma_warps : max_warps) : 0;
+    if (!warps) {
+        auto eff = [&](int w) {
+            const long long nt = 32ll * w, passes = (items + nt - 1) / nt;
+            return (double)items / (double)(passes * nt);
+        };
+        int best_all = 8, best_hi = 16 <= max_warps ? 16 : max_warps;
+        for (int w = 8; w <= max_warps; ++w) {
+            if (eff(w) >= eff(best_all) - 1e-9) best_all = w;
+            if (w >= 16 && eff(w) >= eff(best_hi) - 1e-9) best_hi = w;
+        }
+        warps = eff(best_hi) >= eff(best_all) - 0.05 ? best_hi : best_all;
+    }
+    if (chunks * warps > 0x7fffffffLL) return p;
+
     p.ok = true;
-    p.ta = (int)ta;
-    p.tiles_per_plane = (int)((OA + ta - 1) / ta);
+    p.ta = (int)TA; p.tb = (int)TB; p.tg = TG;
+    p.xa = (int)(TA + exa); p.xb = (int)(TB + exb);
+    p.tiles_per_plane = (int)tiles;
+    p.np = (int)np;
+    p.off_gv = off_gv; p.off_g2 = off_g2;
+    p.tx_bytes = (int)tx;
     p.stages = (int)stages;
     p.stage_stride = (int)stride;
     p.n_per_unit = (int)npu;
     p.units = (int)units;
     p.grid = (int)(units < grid_max ? units : grid_max);
-    p.smem_bytes = (size_t)(stages * stride + 8 * stages + 64);
-    (void)A; (void)B; (void)grad; (void)dtype;
+    p.warps = warps;
+    p.slots = (int)(chunks * warps);
+    p.smem_bytes = (size_t)(stages * stride + 16 * stages + 64);
     return p;
 }
 
 int tma_gather(const Geo& g, const TmaPlan& p, int wk, const void* x, void* y, int esize, const void* w, int qkind, long long wzp,
                cudaStream_t s) {
     TArgs a;
-    memset(&a, 0, sizeof(a));
+    make_args(g, p, 0, 0, esize, &a);
     const int d = g.dim;
-    a.g = g;
-    a.es = esize;
-    a.A = d == 3 ? g.S[0] : 1;        a.OA = d == 3 ? g.OS[0] : 1;      a.lbA = d == 3 ? g.lb[0] : 0;
-    a.B = d >= 2 ? g.S[d - 2] : 1;    a.OB = d >= 2 ? g.OS[d - 2] : 1;  a.lbB = d >= 2 ? g.lb[d - 2] : 0;
-    a.L = g.S[d - 1];                 a.OL = g.OS[d - 1];               a.lbL = g.lb[d - 1];
-    a.ta = p.ta;
-    a.tiles_per_plane = p.tiles_per_plane;
-    a.stages = p.stages;
-    a.stage_stride = p.stage_stride;
-    a.n_per_unit = p.n_per_unit;
-    a.units = p.units;
-    a.tile_bytes = p.ta * a.OB * a.OL * esize;
     a.out = (unsigned char*)y;
     a.w = w;
     a.wk = wk;
     a.qkind = qkind;
     a.wzp = wzp;
-    if (!make_map(&a.map_x, x, esize, g.N * g.C, a.A, a.B, a.L, a.OL, a.OB, p.ta)) return TS_ERR_UNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(k_tma_shiftcopy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
-    if (e != cudaSuccess) return check_launch();
-    k_tma_shiftcopy<<<p.grid, 32, p.smem_bytes, s>>>(a);
-    note_launch();
-    return check_launch();
+    if (!make_map(&a.map_x, x, esize, g.N, g.C, d == 3 ? g.S[0] : 1, d >= 2 ? g.S[d - 2] : 1, g.S[d - 1], (a.TG + 1) * a.vec, a.xb,
+                  a.xa, a.np))
+        return TS_ERR_UNSUPPORTED;
+    return launch(k_tma_gather, a, p, s);
+}
+
+int tma_active_forward(const Geo& g, const TmaPlan& p, const void* x, const void* w, void* y, cudaStream_t s) {
+    TArgs a;
+    make_args(g, p, 1, 1, 4, &a);
+    const int d = g.dim;
+    a.out = (unsigned char*)y;
+    a.w = w;
+    if (!make_map(&a.map_x, x, 4, g.N, g.C, d == 3 ? g.S[0] : 1, d >= 2 ? g.S[d - 2] : 1, g.S[d - 1], (a.TG + 1) * 4, a.xb, a.xa, a.np))
+        return TS_ERR_UNSUPPORTED;
+    switch (d) {
+    case 1: return launch(k_tma_active_forward<1>, a, p, s);
+    case 2: return launch(k_tma_active_forward<2>, a, p, s);
+    default: return launch(k_tma_active_forward<3>, a, p, s);
+    }
+}
+
+int tma_backward(const Geo& g, const TmaPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
+                 double* partials, cudaStream_t s) {
+    TArgs a;
+    make_args(g, p, 2, active ? 1 : 0, 4, &a);
+    const int d = g.dim;
+    a.out = (unsigned char*)gi;
+    a.w = w;
+    a.partials = partials;
+    const int A = d == 3 ? g.S[0] : 1, B = d >= 2 ? g.S[d - 2] : 1, L = g.S[d - 1];
+    if (!make_map(&a.map_x, x, 4, g.N, g.C, A, B, L, (a.TG + 1) * 4, a.xb, a.xa, a.np)) return TS_ERR_UNSUPPORTED;
+    if (!make_map(&a.map_gs, grad, 4, g.N, g.C, A, B, L, (a.TG + 1) * 4, a.TB, a.TA, a.np)) return TS_ERR_UNSUPPORTED;
+    if (active && !make_map(&a.map_gb, grad, 4, g.N, g.C, A, B, L, (a.TG + 1) * 4, a.xb, a.xa, a.np)) return TS_ERR_UNSUPPORTED;
+    int rc;
+    switch (d * 2 + (active ? 1 : 0)) {
+    case 2: rc = launch(k_tma_backward<1, false>, a, p, s); break;
+    case 3: rc = launch(k_tma_backward<1, true>, a, p, s); break;
+    case 4: rc = launch(k_tma_backward<2, false>, a, p, s); break;
+    case 5: rc = launch(k_tma_backward<2, true>, a, p, s); break;
+    case 6: rc = launch(k_tma_backward<3, false>, a, p, s); break;
+    default: rc = launch(k_tma_backward<3, true>, a, p, s); break;
+    }
+    if (rc != TS_OK) return rc;
+    return launch_reduce_partials<float>(partials, p.slots, (int)(g.C * g.dim), gw, s);
 }
 
 }  // namespace ts

@@ -12,7 +12,7 @@ LIB_NAME = 'libtorchshifts_b200.so'
 TS_OK = 0
 STATUS_NAMES = {0: 'TS_OK', 1: 'TS_ERR_INVALID_ARGUMENT', 2: 'TS_ERR_UNSUPPORTED', 3: 'TS_ERR_WORKSPACE',
                 4: 'TS_ERR_TOO_LARGE', 5: 'TS_ERR_BORDERS', 6: 'TS_ERR_CUDA', 7: 'TS_ERR_NO_DEVICE'}
-PATH_NONE, PATH_GENERIC, PATH_STAGED = 0, 1, 2
+PATH_NONE, PATH_GENERIC, PATH_STAGED, PATH_TMA = 0, 1, 2, 3
 QW_U8, QW_I8, QW_I32 = 0, 1, 2
 
 # every symbol include/torchshifts_b200.h declares (tests check the library exports all of them)

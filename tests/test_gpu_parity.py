@@ -34,8 +34,21 @@ def lib():
 @pytest.fixture()
 def auto_path(lib):
     lib.ts_set_kernel_path(0)
+    lib.ts_set_tuning(b"use_tma=1")
     yield
     lib.ts_set_kernel_path(0)
+    lib.ts_set_tuning(b"use_tma=1")
+
+
+# kernel-family selection modes exercised by the sweeps: the automatic choice (TMA-tensor family for
+# zeros padding, bulk-staged otherwise, generic for odd shapes), the automatic choice without the
+# TMA-tensor family (so the bulk-staged kernels also see zeros padding), and the generic family only.
+MODES = ["auto", "no_tma", "generic"]
+
+
+def _set_mode(lib, mode):
+    lib.ts_set_kernel_path(GENERIC if mode == "generic" else 0)
+    lib.ts_set_tuning(b"use_tma=0" if mode == "no_tma" else b"use_tma=1")
 
 
 def _func(dim):
@@ -67,10 +80,10 @@ def _case_args(name):
 
 
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("path", [0, GENERIC])
-def test_golden_fixtures_float(dev, lib, golden, oracle_port, path):
+@pytest.mark.parametrize("mode", MODES)
+def test_golden_fixtures_float(dev, lib, golden, oracle_port, mode):
     """All 248 reference-generated cases (3 dims x 5 paddings x sparse/active x borders x fp32/fp64)."""
-    lib.ts_set_kernel_path(path)
+    _set_mode(lib, mode)
     try:
         g = golden["shift_golden"]
         for name in g["names"].tolist():
@@ -83,7 +96,7 @@ def test_golden_fixtures_float(dev, lib, golden, oracle_port, path):
             assert _gw_close(gw, gw64), f"grad_weight {name}: {gw} vs {gw64}"
             assert np.allclose(gw, g[name + "/gw"], rtol=1e-4, atol=1e-4 * np.abs(gw64).max()), f"grad_weight vs reference fp sum {name}"
     finally:
-        lib.ts_set_kernel_path(0)
+        _set_mode(lib, "auto")
 
 
 def test_golden_fixtures_quantized(dev, lib, golden, auto_path):
@@ -91,8 +104,8 @@ def test_golden_fixtures_quantized(dev, lib, golden, auto_path):
     fns = {1: shift1d_quantized, 2: shift2d_quantized, 3: shift3d_quantized}
     qd = {"quint8": torch.quint8, "qint8": torch.qint8, "quint8zp": torch.quint8, "qint32": torch.qint32}
     g = golden["quant_golden"]
-    for path in (0, GENERIC):
-        lib.ts_set_kernel_path(path)
+    for mode in MODES:
+        _set_mode(lib, mode)
         for name in g["names"].tolist():
             parts = name.split("_")
             dim, use_b, pad = int(parts[1][1]), int(parts[3][1]), int(parts[4][1])
@@ -134,11 +147,11 @@ SWEEP = [
 ]
 
 
-@pytest.mark.parametrize("path", [0, GENERIC])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_randomised_sweep_vs_oracle(dev, lib, oracle_port, path, dtype):
-    lib.ts_set_kernel_path(path)
-    staged_hits = 0
+def test_randomised_sweep_vs_oracle(dev, lib, oracle_port, mode, dtype):
+    _set_mode(lib, mode)
+    staged_hits = tma_hits = 0
     try:
         rng = np.random.default_rng(123)
         for shape, wr in SWEEP:
@@ -153,6 +166,7 @@ def test_randomised_sweep_vs_oracle(dev, lib, oracle_port, path, dtype):
                         grad = rng.standard_normal(y_ref.shape).astype(dtype)
                         y, gi, gw = _run_cuda(dev, dim, x, w, grad, pad, active, borders)
                         staged_hits += lib.ts_last_kernel_path() in (STAGED, TMA)
+                        tma_hits += lib.ts_last_kernel_path() == TMA
                         tag = (shape, pad, active, borders, dtype.__name__)
                         assert np.array_equal(y, y_ref), ("forward",) + tag
                         gi_ref, _ = oracle_port.backward(grad, x, w, pad, active, borders)
@@ -160,9 +174,13 @@ def test_randomised_sweep_vs_oracle(dev, lib, oracle_port, path, dtype):
                         _, gw64 = oracle_port.backward(grad.astype(np.float64), x.astype(np.float64), w.astype(np.float64), pad, active, borders)
                         assert _gw_close(gw, gw64), ("grad_weight",) + tag + (gw, gw64)
     finally:
-        lib.ts_set_kernel_path(0)
-    if path == GENERIC:
+        _set_mode(lib, "auto")
+    if mode == "generic":
         assert staged_hits == 0
+    if mode == "no_tma":
+        assert tma_hits == 0
+    if mode == "auto" and dtype is np.float32:
+        assert tma_hits > 0 and staged_hits > tma_hits
 
 
 def test_half_precision_vs_fp32_oracle(dev, oracle_port, auto_path):

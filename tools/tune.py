@@ -60,10 +60,13 @@ print(f"workload {cfg} {shape} pad={pad} active={active}")
 lib.ts_set_kernel_path(1)
 run("generic")
 lib.ts_set_kernel_path(0)
+lib.ts_set_tuning(b"use_tma=0")
 run("default tuning")
 grid = [(st, kb, wp, ct) for st, kb, wp, ct in itertools.product((2, 3, 4, 6), (13, 26, 40, 56, 100), (8, 12, 16), (1, 2))]
 if quick:
     grid = [(4, 48, 16, 1), (3, 100, 16, 1), (2, 100, 16, 1), (4, 48, 31, 1), (3, 70, 31, 1), (2, 100, 31, 1), (3, 40, 8, 2), (3, 36, 16, 2), (2, 50, 16, 2), (2, 26, 8, 4), (2, 26, 7, 4)]
+if "--tma" in sys.argv:
+    grid = []
 for st, kb, wp, ct in grid:
     spec = f"stages={st},stage_kb={kb},warps={wp},ctas_per_sm={ct}"
     if lib.ts_set_tuning(spec.encode()) != 0:
@@ -75,13 +78,13 @@ for st, kb, wp, ct in grid:
 if "--tma" not in sys.argv:
     sys.exit(0)
 print("--- TMA family")
-lib.ts_set_tuning(b"stages=3,stage_kb=100,warps=16,ctas_per_sm=1,chunk_planes=0")
-for st, ct in itertools.product((4, 6, 8, 12, 16), (1, 2, 3, 4)):
-    spec = f"tma_stages={st},tma_ctas_per_sm={ct}"
+lib.ts_set_tuning(b"use_tma=1")
+run("tma default")
+for st, kb, wp in itertools.product((3, 4, 5, 6), (0, 14, 28, 42, 84), (7, 9, 11, 13, 16, 19, 25, 31)):
+    spec = f"tma_stages={st},tma_stage_kb={kb},tma_warps={wp}"
     if lib.ts_set_tuning(spec.encode()) == 0:
-        run(spec)
-lib.ts_set_tuning(b"tma_stages=0,tma_ctas_per_sm=0")
-for cp in (4, 8, 16, 32, 64) if "--chunks" in sys.argv else ():
-    spec = f"stages=4,stage_kb=48,warps=16,ctas_per_sm=1,chunk_planes={cp}"
-    lib.ts_set_tuning(spec.encode())
-    run(spec)
+        try:
+            run(spec)
+        except RuntimeError as e:
+            print(spec, "failed:", str(e)[:120])
+lib.ts_set_tuning(b"tma_stages=0,tma_stage_kb=0,tma_warps=0")
