@@ -72,7 +72,7 @@ int staged_backward(const Geo& g, const StagedPlan& p, int active, const void* g
 // ---- TMA-tensor family (ts_tma.cu): zeros padding done by the copy engine ----------------------
 struct TmaPlan {
     bool ok;
-    int ta, tb, tg;            // tile extents: slabs, rows, 16-byte column groups
+    int ta, tb, tg, gp;        // tile extents: slabs, rows, 16-byte column groups; gp = padded groups per row (index space)
     int xa, xb;                // x box slabs / rows (tile + the +1 neighbours of the arithmetic kernels)
     int tiles_per_plane, np;   // np = images per stage
     int off_gv, off_g2, tx_bytes;

@@ -34,7 +34,7 @@ namespace ts {
 namespace {
 
 constexpr int SMEM_LIMIT = 232448;
-constexpr int MAXT_TMA_GATHER = 1024, MAXT_TMA_ARITH = 832;
+constexpr int MAXT_TMA_GATHER = 1024, MAXT_TMA_ARITH = 544;
 
 // ---- exact division by a launch-invariant (n < 2^31) ------------------------------------------
 struct FastDiv { unsigned m, l, d; };
@@ -139,7 +139,9 @@ struct alignas(64) TArgs {
     int off_gv, off_g2;      // byte offsets of the grad boxes inside a stage
     int tx_bytes;            // bytes landing per stage
     int stage_stride, stages, nw, n_per_unit, units;
-    FastDiv d_img, d_TG, d_TB, d_tg, d_tb;
+    int GP, img_items;       // padded groups per row of the item index space; items per image = TA*TB*GP
+    int img_stride16;        // output distance between consecutive images of one channel, in 16-byte units
+    FastDiv d_img, d_GP, d_TB, d_tg, d_tb;
 };
 
 TS_D int level_axis(int level, int dim) { return level - (3 - dim); }
@@ -234,87 +236,123 @@ TS_D void producer(const TArgs& a, unsigned char* smem, uint64_t* full, uint64_t
 }
 
 // ---- consumer skeleton -----------------------------------------------------------------------
+// Everything a body needs about the current stage; all values are CTA-uniform.
+struct Stage {
+    const unsigned char* st;   // stage base in shared memory
+    unsigned char* dst;        // output address of (first image of the stage, channel c, tile origin)
+    int total;                 // items of this stage in the padded index space: images * img_items
+    int an, bn, gn;            // valid extents of this tile (slabs, rows, groups)
+};
+
 template <class Body>
 TS_D void consumer_loop(const TArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int lane, Body& body) {
-    int s = 0, k = 0;
-    const long long C = a.g.C, N = a.g.N;
+    int s = 0;
+    unsigned phase = 0;
+    const int C = (int)a.g.C, N = (int)a.g.N, np = a.np, tiles = a.tiles, stages = a.stages;
+    const long long plane_bytes = (a.mode == 2 ? a.g.in_plane : a.g.out_plane) * a.es;
     for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
-        const long long c = u % C, chunk = u / C;
-        const long long n0 = chunk * a.n_per_unit;
-        const long long n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
+        const int chunk = u / C, c = u - chunk * C;
+        const int n0 = chunk * a.n_per_unit;
+        const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         body.begin_unit(c);
-        for (long long nb = n0; nb < n1; nb += a.np) {
-            const int npl = (int)(n1 - nb < a.np ? n1 - nb : a.np);
-            for (int t = 0; t < a.tiles; ++t) {
-                mbar_wait(&full[s], (unsigned)(k & 1));
-                body.step(smem + (size_t)s * a.stage_stride, npl, nb, c, tile_of(a, t));
+        for (int nb = n0; nb < n1; nb += np) {
+            Stage sg;
+            sg.total = (n1 - nb < np ? n1 - nb : np) * a.img_items;
+            unsigned char* img = a.out + ((long long)nb * C + c) * plane_bytes;
+            for (int t = 0; t < tiles; ++t) {
+                sg.an = a.TA; sg.bn = a.TB; sg.gn = a.TG;
+                sg.dst = img;
+                if (tiles > 1) {
+                    const Tile tl = tile_of(a, t);
+                    sg.an = a.OA - tl.a0 < a.TA ? a.OA - tl.a0 : a.TA;
+                    sg.bn = a.OB - tl.b0 < a.TB ? a.OB - tl.b0 : a.TB;
+                    sg.gn = a.OGR - tl.g0 < a.TG ? a.OGR - tl.g0 : a.TG;
+                    sg.dst = img + ((long long)(tl.a0 * a.OB + tl.b0) * a.OGR + tl.g0) * 16;
+                }
+                sg.st = smem + (size_t)s * a.stage_stride;
+                mbar_wait(&full[s], phase);
+                body.step(sg);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
-                if (++s == a.stages) { s = 0; ++k; }
+                if (++s == stages) { s = 0; phase ^= 1u; }
             }
         }
         body.end_unit(c, chunk);
     }
 }
 
-// item -> (image, slab, row, group) inside a tile
-struct ItemPos { int pl, a, b, cg; };
-TS_D ItemPos decode_item(const TArgs& a, int item, bool has_slabs) {
-    ItemPos p;
-    p.pl = (int)fdiv((unsigned)item, a.d_img);
-    const int rem = item - p.pl * (int)a.d_img.d;
-    const int row = (int)fdiv((unsigned)rem, a.d_TG);
-    p.cg = rem - row * a.TG;
+// item (padded index space: [image][slab][row][GP groups]) -> position inside the tile.  The
+// padded row length GP is a multiple of 8 when that wastes <= 15 % of the lanes: a quarter-warp
+// then never straddles two box rows, which keeps the 128-bit shared-memory loads conflict-free.
+struct Item { int pl, a, b, cg; };
+template <bool SLABS>
+TS_D bool decode_item(const TArgs& a, const Stage& sg, int item, Item& p) {
+    p.pl = 0;
+    int rem = item;
+    if (a.np > 1) { p.pl = (int)fdiv((unsigned)item, a.d_img); rem = item - p.pl * a.img_items; }
+    const int row = (int)fdiv((unsigned)rem, a.d_GP);
+    p.cg = rem - row * a.GP;
     p.a = 0;
     p.b = row;
-    if (has_slabs) { p.a = (int)fdiv((unsigned)row, a.d_TB); p.b = row - p.a * a.TB; }
-    return p;
+    if (SLABS) { p.a = (int)fdiv((unsigned)row, a.d_TB); p.b = row - p.a * a.TB; }
+    return p.cg < sg.gn && p.b < sg.bn && p.a < sg.an;
+}
+// 16-byte offset of the item's output inside the stage's destination
+TS_D unsigned char* item_dst(const TArgs& a, const Stage& sg, const Item& p) {
+    const int off16 = p.pl * a.img_stride16 + (p.a * a.OB + p.b) * a.OGR + p.cg;
+    return sg.dst + (size_t)(unsigned)off16 * 16;
 }
 
 // ================================================================================================
-// mode 0: sparse / quantized forward.  WS = word misalignment of the source window (0..3), the
-// sub-word byte shift (elements narrower than 4 bytes) is a run-time funnel-shift amount.
+// mode 0: sparse / quantized forward.  WS = word misalignment of the source window (0..3); SUB =
+// elements narrower than 4 bytes, whose residual byte shift is a run-time funnel-shift amount.
+template <bool SLABS>
 struct GatherBody {
     const TArgs& a;
     const int tid, nt;
     int ws, bs8;
 
     TS_D GatherBody(const TArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), ws(0), bs8(0) {}
-    TS_D void begin_unit(long long c) {
+    TS_D void begin_unit(int c) {
         const UnitShift us = unit_shift(a, c);
         const int mb = pmod((a.lbL - us.sh[2]) * a.es, 16);    // tiles start at multiples of 16 bytes
         ws = mb >> 2;
         bs8 = (mb & 3) * 8;
     }
-    TS_D void end_unit(long long, long long) {}
+    TS_D void end_unit(int, int) {}
 
-    template <int WS>
-    TS_D void run(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) const {
-        const int total = npl * (int)a.d_img.d;
-        const bool slabs = a.TA > 1 || a.OA > 1;
-        const bool partial = tl.a0 + a.TA > a.OA || tl.b0 + a.TB > a.OB || tl.g0 + a.TG > a.OGR;
-        const uint4* box = (const uint4*)st;
-        const long long out_plane_bytes = a.g.out_plane * a.es;
-        for (int item = tid; item < total; item += nt) {
-            const ItemPos p = decode_item(a, item, slabs);
-            if (partial && (tl.a0 + p.a >= a.OA || tl.b0 + p.b >= a.OB || tl.g0 + p.cg >= a.OGR)) continue;
-            const int ch = p.pl * a.x_img_chunks + (p.a * a.xb + p.b) * (a.TG + 1) + p.cg;
-            const uint4 A = box[ch], B = box[ch + 1];
-            const unsigned W[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+    template <int WS, bool SUB>
+    TS_D void run(const Stage& sg) const {
+        const uint4* box = (const uint4*)sg.st;
+        const int pitch = a.TG + 1, ximg = a.x_img_chunks, xb = a.xb;
+        for (int item = tid; item < sg.total; item += nt) {
+            Item p;
+            if (!decode_item<SLABS>(a, sg, item, p)) continue;
+            const int ch = p.pl * ximg + (p.a * xb + p.b) * pitch + p.cg;
+            const uint4 A = box[ch];
+            unsigned W[8] = {A.x, A.y, A.z, A.w, 0u, 0u, 0u, 0u};
+            if (WS > 0 || SUB) { const uint4 B = box[ch + 1]; W[4] = B.x; W[5] = B.y; W[6] = B.z; W[7] = B.w; }
             unsigned o[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = __funnelshift_r(W[k + WS], W[(k + WS + 1) & 7], bs8);
-            unsigned char* dst = a.out + ((nb + p.pl) * a.g.C + c) * out_plane_bytes +
-                                 ((long long)((tl.a0 + p.a) * a.OB + tl.b0 + p.b) * a.OGR + tl.g0 + p.cg) * 16;
-            __stcs((uint4*)dst, make_uint4(o[0], o[1], o[2], o[3]));
+            for (int k = 0; k < 4; ++k) o[k] = SUB ? __funnelshift_r(W[k + WS], W[(k + WS + 1) & 7], bs8) : W[k + WS];
+            __stcs((uint4*)item_dst(a, sg, p), make_uint4(o[0], o[1], o[2], o[3]));
         }
     }
-    TS_D void step(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) const {
-        switch (ws) {
-        case 0: run<0>(st, npl, nb, c, tl); break;
-        case 1: run<1>(st, npl, nb, c, tl); break;
-        case 2: run<2>(st, npl, nb, c, tl); break;
-        default: run<3>(st, npl, nb, c, tl); break;
+    TS_D void step(const Stage& sg) const {
+        if (bs8 == 0) {
+            switch (ws) {
+            case 0: run<0, false>(sg); break;
+            case 1: run<1, false>(sg); break;
+            case 2: run<2, false>(sg); break;
+            default: run<3, false>(sg); break;
+            }
+        } else {
+            switch (ws) {
+            case 0: run<0, true>(sg); break;
+            case 1: run<1, true>(sg); break;
+            case 2: run<2, true>(sg); break;
+            default: run<3, true>(sg); break;
+            }
         }
     }
 };
@@ -334,12 +372,12 @@ TS_D void load_win(const float4* __restrict__ box, int ch, float* out) {
     for (int t = 0; t < NV; ++t) out[t] = W[t + M];
 }
 
-// group index of (slab a + da, row b + db) inside a box with `rows` rows per slab
+// group offset of the +1 neighbour rows inside a box with `rows` rows per slab, `pitch` groups per row
 template <int DIM>
-TS_D int box_row_chunk(int a, int b, int rv, int rows, int tg1) {
+TS_D int neighbour_row_offset(int rv, int rows, int pitch) {
     if (DIM == 1) return 0;
-    if (DIM == 2) return (b + (rv & 1)) * tg1;
-    return ((a + (rv & 1)) * rows + b + ((rv >> 1) & 1)) * tg1;
+    if (DIM == 2) return (rv & 1) * pitch;
+    return ((rv & 1) * rows + ((rv >> 1) & 1)) * pitch;
 }
 
 template <int DIM>
@@ -379,44 +417,41 @@ struct ActiveFwdBody {
     int m;
 
     TS_D ActiveFwdBody(const TArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), m(0) {}
-    TS_D void begin_unit(long long c) {
+    TS_D void begin_unit(int c) {
         us = unit_shift(a, c);
         m = pmod(a.lbL - us.sh[2], 4);
     }
-    TS_D void end_unit(long long, long long) {}
+    TS_D void end_unit(int, int) {}
 
     template <int M>
-    TS_D void run(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) const {
+    TS_D void run(const Stage& sg) const {
         constexpr int NR = 1 << (DIM - 1);
-        const int total = npl * (int)a.d_img.d;
-        const bool partial = tl.a0 + a.TA > a.OA || tl.b0 + a.TB > a.OB || tl.g0 + a.TG > a.OGR;
-        const float4* box = (const float4*)st;
-        const int tg1 = a.TG + 1;
-        for (int item = tid; item < total; item += nt) {
-            const ItemPos p = decode_item(a, item, DIM == 3);
-            if (partial && (tl.a0 + p.a >= a.OA || tl.b0 + p.b >= a.OB || tl.g0 + p.cg >= a.OGR)) continue;
-            const int base = p.pl * a.x_img_chunks + p.cg;
+        const float4* box = (const float4*)sg.st;
+        const int pitch = a.TG + 1, ximg = a.x_img_chunks, xb = a.xb;
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        for (int item = tid; item < sg.total; item += nt) {
+            Item p;
+            if (!decode_item<DIM == 3>(a, sg, item, p)) continue;
+            const int base = p.pl * ximg + (p.a * xb + p.b) * pitch + p.cg;
             float X[NR][5];
 #pragma unroll
-            for (int rv = 0; rv < NR; ++rv) load_win<M, 5>(box, base + box_row_chunk<DIM>(p.a, p.b, rv, a.xb, tg1), X[rv]);
+            for (int rv = 0; rv < NR; ++rv) load_win<M, 5>(box, base + neighbour_row_offset<DIM>(rv, xb, pitch), X[rv]);
             float o[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 float v[8];
                 neighbours_from_rows<DIM>(X, t, v);
-                o[t] = interpolate<float, DIM>(v, us.d);
+                o[t] = interpolate<float, DIM>(v, d);
             }
-            float* dst = (float*)a.out + ((nb + p.pl) * a.g.C + c) * a.g.out_plane +
-                         ((long long)((tl.a0 + p.a) * a.OB + tl.b0 + p.b) * a.OGR + tl.g0 + p.cg) * 4;
-            __stcs((float4*)dst, make_float4(o[0], o[1], o[2], o[3]));
+            __stcs((float4*)item_dst(a, sg, p), make_float4(o[0], o[1], o[2], o[3]));
         }
     }
-    TS_D void step(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) const {
+    TS_D void step(const Stage& sg) const {
         switch (m) {
-        case 0: run<0>(st, npl, nb, c, tl); break;
-        case 1: run<1>(st, npl, nb, c, tl); break;
-        case 2: run<2>(st, npl, nb, c, tl); break;
-        default: run<3>(st, npl, nb, c, tl); break;
+        case 0: run<0>(sg); break;
+        case 1: run<1>(sg); break;
+        case 2: run<2>(sg); break;
+        default: run<3>(sg); break;
         }
     }
 };
@@ -430,83 +465,80 @@ struct BackwardBody {
     double acc[DIM];
 
     TS_D BackwardBody(const TArgs& a_, int tid_, int nt_, int wid_, int lane_) : a(a_), tid(tid_), nt(nt_), wid(wid_), lane(lane_), m(0) {}
-    TS_D void begin_unit(long long c) {
+    TS_D void begin_unit(int c) {
         us = unit_shift(a, c);
         m = pmod(-us.sh[2], 4);
 #pragma unroll
         for (int d = 0; d < DIM; ++d) acc[d] = 0.0;
     }
     // one partial per (unit, consumer warp): fixed shuffle tree, no atomics
-    TS_D void end_unit(long long c, long long chunk) {
+    TS_D void end_unit(int c, int chunk) {
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
             double v = acc[d];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-            if (lane == 0) a.partials[((long long)chunk * a.nw + wid) * (a.g.C * DIM) + c * DIM + d] = v;
+            if (lane == 0) a.partials[((long long)chunk * a.nw + wid) * (a.g.C * DIM) + (long long)c * DIM + d] = v;
         }
     }
 
     template <int M>
-    TS_D void run(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) {
+    TS_D void run(const Stage& sg) {
         constexpr int NR = 1 << (DIM - 1);
         constexpr int MG = ACTIVE ? M : ((4 - M) & 3);      // misalignment of the grad window used for grad_input
-        const int total = npl * (int)a.d_img.d;
-        const bool partial = tl.a0 + a.TA > a.OA || tl.b0 + a.TB > a.OB || tl.g0 + a.TG > a.OGR;
-        const float4* xbox = (const float4*)st;
-        const float4* gv_box = (const float4*)(st + a.off_gv);
-        const float4* g2_box = (const float4*)(st + a.off_g2);
-        const int tg1 = a.TG + 1;
+        const float4* xbox = (const float4*)sg.st;
+        const float4* gv_box = (const float4*)(sg.st + a.off_gv);
+        const float4* g2_box = (const float4*)(sg.st + a.off_g2);
+        const int pitch = a.TG + 1, ximg = a.x_img_chunks, gimg = a.g_img_chunks, xb = a.xb, tb = a.TB;
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
         float ts[DIM];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) ts[d] = 0.f;
-        for (int item = tid; item < total; item += nt) {
-            const ItemPos p = decode_item(a, item, DIM == 3);
-            if (partial && (tl.a0 + p.a >= a.OA || tl.b0 + p.b >= a.OB || tl.g0 + p.cg >= a.OGR)) continue;
-            const int gch = p.pl * a.g_img_chunks + (p.a * a.TB + p.b) * tg1 + p.cg;
-            const int xbase = p.pl * a.x_img_chunks + p.cg;
+        for (int k = 0; k < DIM; ++k) ts[k] = 0.f;
+        for (int item = tid; item < sg.total; item += nt) {
+            Item p;
+            if (!decode_item<DIM == 3>(a, sg, item, p)) continue;
+            const int gch = p.pl * gimg + (p.a * tb + p.b) * pitch + p.cg;
+            const int xch = p.pl * ximg + (p.a * xb + p.b) * pitch + p.cg;
             float gv[4];
             load_win<0, 4>(gv_box, gch, gv);
             // ---- grad_weight terms ----
             float X[NR][5];
 #pragma unroll
-            for (int rv = 0; rv < NR; ++rv) load_win<M, 5>(xbox, xbase + box_row_chunk<DIM>(p.a, p.b, rv, a.xb, tg1), X[rv]);
+            for (int rv = 0; rv < NR; ++rv) load_win<M, 5>(xbox, xch + neighbour_row_offset<DIM>(rv, xb, pitch), X[rv]);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 float v[8], wg[3];
                 neighbours_from_rows<DIM>(X, t, v);
-                weight_partials_fast<DIM>(v, us.d, wg);
+                weight_partials_fast<DIM>(v, d, wg);
 #pragma unroll
-                for (int d = 0; d < DIM; ++d) ts[d] = fmaf(gv[t], wg[d], ts[d]);
+                for (int k = 0; k < DIM; ++k) ts[k] = fmaf(gv[t], wg[k], ts[k]);
             }
             // ---- grad_input ----
             float o[4];
             if (ACTIVE) {
                 float G[NR][5];
 #pragma unroll
-                for (int rv = 0; rv < NR; ++rv) load_win<MG, 5>(g2_box, xbase + box_row_chunk<DIM>(p.a, p.b, rv, a.xb, tg1), G[rv]);
+                for (int rv = 0; rv < NR; ++rv) load_win<MG, 5>(g2_box, xch + neighbour_row_offset<DIM>(rv, xb, pitch), G[rv]);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     float v[8];
                     neighbours_from_rows<DIM>(G, t, v);
-                    o[t] = interpolate<float, DIM>(v, us.d);
+                    o[t] = interpolate<float, DIM>(v, d);
                 }
             } else {
                 load_win<MG, 4>(g2_box, gch, o);
             }
-            float* dst = (float*)a.out + ((nb + p.pl) * a.g.C + c) * a.g.in_plane +
-                         ((long long)((tl.a0 + p.a) * a.OB + tl.b0 + p.b) * a.OGR + tl.g0 + p.cg) * 4;
-            __stcs((float4*)dst, make_float4(o[0], o[1], o[2], o[3]));
+            __stcs((float4*)item_dst(a, sg, p), make_float4(o[0], o[1], o[2], o[3]));
         }
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) acc[d] += (double)ts[d];   // fp32 inside a tile, fp64 across tiles
+        for (int k = 0; k < DIM; ++k) acc[k] += (double)ts[k];   // fp32 inside a stage, fp64 across stages
     }
-    TS_D void step(const unsigned char* st, int npl, long long nb, long long c, const Tile& tl) {
+    TS_D void step(const Stage& sg) {
         switch (m) {
-        case 0: run<0>(st, npl, nb, c, tl); break;
-        case 1: run<1>(st, npl, nb, c, tl); break;
-        case 2: run<2>(st, npl, nb, c, tl); break;
-        default: run<3>(st, npl, nb, c, tl); break;
+        case 0: run<0>(sg); break;
+        case 1: run<1>(sg); break;
+        case 2: run<2>(sg); break;
+        default: run<3>(sg); break;
         }
     }
 };
@@ -522,13 +554,14 @@ TS_D void setup_barriers(const TArgs& a, unsigned char* smem, uint64_t*& full, u
     __syncthreads();
 }
 
+template <bool SLABS>
 __global__ void __launch_bounds__(MAXT_TMA_GATHER, 1) k_tma_gather(const __grid_constant__ TArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
     setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
-    GatherBody body(a, threadIdx.x, a.nw * 32);
+    GatherBody<SLABS> body(a, threadIdx.x, a.nw * 32);
     consumer_loop(a, smem, full, empty, lane, body);
 }
 
@@ -594,8 +627,11 @@ bool make_args(const Geo& g, const TmaPlan& p, int mode, int active, int es, TAr
     a.nw = p.warps;
     a.n_per_unit = p.n_per_unit;
     a.units = p.units;
-    a.d_img = make_fastdiv((unsigned)(a.TA * a.TB * a.TG));
-    a.d_TG = make_fastdiv((unsigned)a.TG);
+    a.GP = p.gp;
+    a.img_items = a.TA * a.TB * a.GP;
+    a.img_stride16 = (int)(g.C * (mode == 2 ? g.in_plane : g.out_plane) * es / 16);
+    a.d_img = make_fastdiv((unsigned)a.img_items);
+    a.d_GP = make_fastdiv((unsigned)a.GP);
     a.d_TB = make_fastdiv((unsigned)a.TB);
     a.d_tg = make_fastdiv((unsigned)a.tiles_g);
     a.d_tb = make_fastdiv((unsigned)a.tiles_b);
@@ -649,8 +685,11 @@ TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool 
         return xbytes + gsbytes + (active ? xbytes : gsbytes);
     };
     const long long budget = SMEM_LIMIT - 1024;
+    // defaults from the cfg3 sweep on B200 (tools/tune.py --tma): forward 6 x 28 KB, backward 5 x 42 KB
     const int want_stages = t.tma_stages > 0 ? t.tma_stages : (mode == 2 ? 5 : 6);
-    const long long target = t.tma_stage_kb > 0 ? (long long)t.tma_stage_kb * 1024 : budget / want_stages - 64;
+    const long long auto_target = mode == 2 ? 42 * 1024 : 28 * 1024;
+    const long long target = t.tma_stage_kb > 0 ? (long long)t.tma_stage_kb * 1024
+                                                : (auto_target < budget / want_stages - 64 ? auto_target : budget / want_stages - 64);
     while (image_bytes(TA, TB, nullptr, nullptr) > target) {
         if (TA > 1) TA = (TA + 1) / 2;
         else if (TB > 1) TB = (TB + 1) / 2;
@@ -694,8 +733,14 @@ TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool 
     const long long units = chunks * g.C;
     if (units > 0x7fffffffLL) return p;
 
+    // padded row length of the item index space: a multiple of 8 groups keeps every quarter-warp inside
+    // one box row (conflict-free 128-bit shared loads) -- used when it idles <= 15 % of the lanes
+    int GP = TG;
+    if (TG % 8 != 0 && (double)TG / (double)((TG + 7) / 8 * 8) >= 0.85) GP = (TG + 7) / 8 * 8;
+    const long long plane16 = g.C * (mode == 2 ? g.in_plane : g.out_plane) * esize / 16;
+    if (np * plane16 >= 0x7fffffffLL || np * TA * TB * (long long)GP >= 0x7fffffffLL) return p;
     // consumer warps: fill the last pass over a stage's items as well as possible
-    const long long items = np * TA * TB * TG;
+    const long long items = np * TA * TB * GP;
     const int max_warps = mode == 0 ? MAXT_TMA_GATHER / 32 - 1 : MAXT_TMA_ARITH / 32 - 1;
     int warps = t.tma_warps > 0 ? (t.tma_warps < max_warps ? t.tma_warps : max_warps) : 0;
     if (!warps) {
@@ -703,17 +748,21 @@ TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool 
             const long long nt = 32ll * w, passes = (items + nt - 1) / nt;
             return (double)items / (double)(passes * nt);
         };
-        int best_all = 8, best_hi = 16 <= max_warps ? 16 : max_warps;
-        for (int w = 8; w <= max_warps; ++w) {
+        // best fill of the last pass over a stage's items, preferring 8..16 warps: on cfg3 more
+        // consumer warps never helped (the kernels are HBM-bound) and 25+ were measurably slower
+        const int lo = 8, hi = 16;
+        int best = lo;
+        for (int w = lo; w <= hi && w <= max_warps; ++w)
+            if (eff(w) >= eff(best) - 1e-9) best = w;
+        int best_all = 8;
+        for (int w = 8; w <= max_warps; ++w)
             if (eff(w) >= eff(best_all) - 1e-9) best_all = w;
-            if (w >= 16 && eff(w) >= eff(best_hi) - 1e-9) best_hi = w;
-        }
-        warps = eff(best_hi) >= eff(best_all) - 0.05 ? best_hi : best_all;
+        warps = eff(best) >= eff(best_all) - 0.08 ? best : best_all;
     }
     if (chunks * warps > 0x7fffffffLL) return p;
 
     p.ok = true;
-    p.ta = (int)TA; p.tb = (int)TB; p.tg = TG;
+    p.ta = (int)TA; p.tb = (int)TB; p.tg = TG; p.gp = GP;
     p.xa = (int)(TA + exa); p.xb = (int)(TB + exb);
     p.tiles_per_plane = (int)tiles;
     p.np = (int)np;
@@ -743,7 +792,7 @@ int tma_gather(const Geo& g, const TmaPlan& p, int wk, const void* x, void* y, i
     if (!make_map(&a.map_x, x, esize, g.N, g.C, d == 3 ? g.S[0] : 1, d >= 2 ? g.S[d - 2] : 1, g.S[d - 1], (a.TG + 1) * a.vec, a.xb,
                   a.xa, a.np))
         return TS_ERR_UNSUPPORTED;
-    return launch(k_tma_gather, a, p, s);
+    return a.TA > 1 ? launch(k_tma_gather<true>, a, p, s) : launch(k_tma_gather<false>, a, p, s);
 }
 
 int tma_active_forward(const Geo& g, const TmaPlan& p, const void* x, const void* w, void* y, cudaStream_t s) {

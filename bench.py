@@ -306,7 +306,8 @@ def run_ours(args):
         "config": {"workload": f"cfg3 Shift2d SSL zeros fwd+bwd, global N={N * world} C={C} {H}x{W} fp32, batch-sharded over {world} GPU(s)",
                    "per_gpu_batch": N, "padding": "zeros", "active": False, "weights": "U(-1,1)",
                    "l2": "inputs (822 MB per tensor at N=256) are larger than the 126 MB L2; no flush needed",
-                   "kernel_path": {1: "generic", 2: "staged (cp.async.bulk + mbarrier)"}.get(path, str(path)),
+                   "kernel_path": {1: "generic", 2: "staged (cp.async.bulk + mbarrier)",
+                                   3: "TMA tensor boxes (cp.async.bulk.tensor.5d, shift + zero pad by the copy engine)"}.get(path, str(path)),
                    "collective": "torch.distributed all_reduce (NCCL) of grad_weight [C,2]" if world > 1 else "none"},
         "elements_per_s": elems_job / (ms * 1e-3),
         "frac_of_hbm_peak": value / world / peak,
