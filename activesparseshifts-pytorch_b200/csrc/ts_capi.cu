@@ -218,11 +218,11 @@ int ts_shift_forward(const ts_geometry* gin, int dtype, int padding, int active,
     if (forced == TS_PATH_TMA) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
-    if (forced != TS_PATH_GENERIC) plan = plan_staged(g, active ? 1 : 0, es, dtype, x_is_dense(g), x, y, nullptr, sms);
+    if (forced != TS_PATH_GENERIC) plan = plan_staged(g, active ? 1 : 0, active, es, dtype, x_is_dense(g), x, y, nullptr, sms);
     if (forced == TS_PATH_STAGED && !plan.ok) return TS_ERR_UNSUPPORTED;
     if (plan.ok) {
         t_last_path = TS_PATH_STAGED;
-        return active ? staged_active_forward(g, plan, x, weights, y, s)
+        return active ? staged_active_forward(g, plan, dtype, x, weights, y, s)
                       : staged_gather(g, plan, dtype, x, y, 0ull, es, weights, 0, 0, s);
     }
     t_last_path = TS_PATH_GENERIC;
@@ -239,8 +239,10 @@ size_t ts_shift_backward_workspace_bytes(const ts_geometry* gin, int dtype) {
     const GenericBwdPlan gp = plan_generic_backward(g);
     size_t slots = (size_t)gp.units;
     // assume the staged path may apply (pointer alignment is unknown here)
-    const StagedPlan sp = plan_staged(g, 2, elem_size(dtype), dtype, true, nullptr, nullptr, nullptr, sms);
-    if (sp.ok && (size_t)sp.slots > slots) slots = (size_t)sp.slots;
+    for (int active = 0; active < 2; ++active) {
+        const StagedPlan sp = plan_staged(g, 2, active, elem_size(dtype), dtype, true, nullptr, nullptr, nullptr, sms);
+        if (sp.ok && (size_t)sp.slots > slots) slots = (size_t)sp.slots;
+    }
     Geo gz = g;
     gz.pad = TS_PAD_ZEROS;
     for (int active = 0; active < 2; ++active) {
@@ -281,11 +283,11 @@ int ts_shift_backward(const ts_geometry* gin, int dtype, int padding, int active
     if (forced == TS_PATH_TMA) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
-    if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 2, es, dtype, x_is_dense(g), x, grad_input, grad, sms);
+    if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 2, active, es, dtype, x_is_dense(g), x, grad_input, grad, sms);
     if (forced == TS_PATH_STAGED && !plan.ok) return TS_ERR_UNSUPPORTED;
     if (plan.ok) {
         t_last_path = TS_PATH_STAGED;
-        return staged_backward(g, plan, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, s);
+        return staged_backward(g, plan, dtype, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, s);
     }
     t_last_path = TS_PATH_GENERIC;
     return generic_backward(g, dtype, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, s);
@@ -316,7 +318,7 @@ int ts_qshift_forward(const ts_geometry* gin, int elem_bytes, int padding, int64
     if (forced == TS_PATH_TMA) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
-    if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 0, elem_bytes, -1, x_is_dense(g), xq, yq, nullptr, sms);
+    if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 0, 0, elem_bytes, -1, x_is_dense(g), xq, yq, nullptr, sms);
     if (forced == TS_PATH_STAGED && !plan.ok) return TS_ERR_UNSUPPORTED;
     if (plan.ok) {
         t_last_path = TS_PATH_STAGED;

@@ -56,17 +56,21 @@ Tuning& tuning();
 struct StagedPlan {
     bool ok;           // staged path applicable
     int vec_bytes;     // bytes per thread item (16 / 8 / 4)
-    int planes_per_step, stages, warps, grid, units, n_per_unit, slots;  // slots = partial slots (backward)
+    int planes_per_step, stages, stage_stride, warps, grid, units, n_per_unit, slots;  // slots = partial slots (backward)
+    int ta, tiles;     // slabs per tile (3-D volumes are tiled over their first axis), tiles per image
+    int xs, gvs, gis;  // slab slots per image: x, grad at the output position, grad for grad_input (0: shares gvs)
+    int gp;            // padded items per row of the item index space
+    int off_gv, off_gi;
     size_t smem_bytes;
 };
 // mode: 0 sparse/quantized forward (esize = element bytes), 1 active forward, 2 backward
-StagedPlan plan_staged(const Geo& g, int mode, int esize, int dtype, bool dense_x, const void* x, const void* y_or_gi,
+StagedPlan plan_staged(const Geo& g, int mode, int active, int esize, int dtype, bool dense_x, const void* x, const void* y_or_gi,
                        const void* grad, int sm_count);
 
 int staged_gather(const Geo& g, const StagedPlan& p, int wk, const void* x, void* y, unsigned long long fill, int esize,
                   const void* w, int qkind, long long wzp, cudaStream_t s);
-int staged_active_forward(const Geo& g, const StagedPlan& p, const void* x, const void* w, void* y, cudaStream_t s);
-int staged_backward(const Geo& g, const StagedPlan& p, int active, const void* grad, const void* x, const void* w,
+int staged_active_forward(const Geo& g, const StagedPlan& p, int dtype, const void* x, const void* w, void* y, cudaStream_t s);
+int staged_backward(const Geo& g, const StagedPlan& p, int dtype, int active, const void* grad, const void* x, const void* w,
                     void* gi, void* gw, double* partials, cudaStream_t s);
 
 // ---- TMA-tensor family (ts_tma.cu): zeros padding done by the copy engine ----------------------

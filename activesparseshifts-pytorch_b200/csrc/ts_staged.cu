@@ -1,24 +1,31 @@
-// ts_staged.cu -- the bandwidth path: persistent, warp-specialised kernels that stage whole
-// (n,c) planes in shared memory with 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) signalled
-// through mbarriers, resolve the per-channel shift while READING shared memory, and write global
-// memory with 128-bit streaming stores.
+// ts_staged.cu -- the general bandwidth path (every padding mode, border crops, 1-/2-/4-/8-byte
+// elements, fp32 / fp16 / bf16 arithmetic, 3-D volumes): persistent, warp-specialised kernels that
+// stage whole slabs of the (n,c) planes in shared memory with 1-D bulk async copies
+// (cp.async.bulk -> SASS UBLKCP) signalled through mbarriers, resolve the per-channel shift while
+// READING shared memory and write global memory with 128-bit streaming stores.
 //
-//   CTA = `nw` consumer warps + 1 producer warp (one elected lane), one CTA per SM, persistent.
-//   Work unit = (channel c, chunk of the batch); units are dealt round-robin to CTAs.  Inside a
-//   unit the shift parameters are registers and (backward) the grad_weight terms accumulate in
-//   per-thread registers; every consumer warp writes ONE partial per unit -> deterministic.
-//   Step = up to `np` planes of the unit = one ring stage.  full[s]: producer's expect_tx +
-//   the copies' complete_tx.  empty[s]: one arrive per consumer warp.  No __syncthreads in the loop.
+//   CTA  = `nw` consumer warps + 1 producer warp (one elected lane), one CTA per SM, persistent.
+//   Unit = (channel c, chunk of the batch), dealt round-robin to CTAs; the shift parameters are
+//          registers for the whole unit and (backward) the grad_weight terms accumulate in
+//          per-thread registers; every consumer warp writes ONE fp64 partial per unit -> no atomics.
+//   Step = one ring stage = `np` images x one slab tile.  A slab (all rows x columns of one index of
+//          the first of three axes; the whole plane for 1-D / 2-D) is contiguous in NCHW, so it is
+//          ONE bulk copy.  The PRODUCER resolves the shift along the slab axis: slot k of a stage
+//          holds source slab P(a0 - s + k), so consumers never remap that axis and 3-D volumes are
+//          tiled over it (16x56x56 fp32 does not fit a stage).
+//   Item = 16 bytes of output.  Each stage is processed in two passes:
+//          (1) INTERIOR items -- every source window lies inside its row and every source row
+//              inside its slab, so there is no index remapping, no validity mask, no padding rule:
+//              aligned LDS.128 pairs + a compile-time word select (the column shift misaligns the
+//              source by a unit-uniform amount).  This is the padding-independent fast path.
+//          (2) EDGE items (rows / columns whose windows touch a border, ~10 % on 56x56 planes),
+//              enumerated COMPACTLY so warps stay full, run the element-wise path with the
+//              reference's remapping rules (ops/kernels/shifts_kernels.h:10-54).
 //
-// Planes are contiguous in NCHW, so a plane (or a plane of grad) is ONE bulk copy, 16-byte
-// aligned and a multiple of 16 bytes (checked by plan_staged; otherwise the generic path runs).
-// A shift along the fastest axis breaks 16-byte alignment of the source: the consumer loads the
-// two aligned 16-byte groups that cover its item from shared memory (conflict-free LDS.128) and
-// funnel-shifts by the (unit-uniform) misalignment.  Row shifts are just a different row index.
-//
-// Semantics: identical to ts_generic.cu / the reference (ops/kernels/shifts_kernels.h:156-327,
-// :532-571); the arithmetic helpers are the same functions (ts_common.cuh), so active forward and
-// grad_input are bit-identical to the generic path and to the CPU reference.
+// Semantics: ops/kernels/shifts_kernels.h:156-327, :532-571; the arithmetic helpers are the shared
+// ones of ts_common.cuh (unfused lerp nest), so forward and grad_input are bit-identical to the
+// generic family and to the CPU reference; grad_weight terms are summed in fp32 per stage, fp64
+// across stages.
 #include "ts_kernels.h"
 
 namespace ts {
@@ -31,9 +38,10 @@ Tuning& tuning() {
 namespace {
 
 constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
-constexpr int GUARD = 16;            // readable slack before/after the planes of a stage
+constexpr int GUARD = 32;            // readable slack around the slabs of a stage (second group of a window pair)
+constexpr int MAXT_GATHER = 1024, MAXT_ARITH = 544;
 
-// ---- exact division by a launch-invariant (Granlund-Montgomery, n < 2^31) -------------------
+// ---- exact division by a launch-invariant (n < 2^31) ------------------------------------------
 struct FastDiv { unsigned m, l, d; };
 FastDiv make_fastdiv(unsigned d) {
     FastDiv f;
@@ -89,395 +97,874 @@ struct SArgs {
     double* partials;
     long long wzp;
     unsigned long long fill;
-    int qkind, wk, es;
-    int xpb, gpb;                  // bytes of one staged x plane / grad plane (0 unless backward)
-    int np, stages, stage_stride, nw;
-    int n_per_unit, units;
-    int A, B, L, OA, OB, OL, lbA, lbB, lbL;   // slab / row / column structure (absent levels: 1, 0)
-    int gpr, ipp;                  // items per row, items per plane
-    FastDiv d_ipp, d_gpr, d_rows;
+    int qkind, wk, es, mode, active;
+    int A, B, L, OA, OB, OL, lbA, lbB, lbL;   // sizes per level (0 slab, 1 row, 2 column); absent levels 1 / 0
+    int IA, IB;                               // iteration space: output space (forward) / input space (backward)
+    int VB, V;                                // bytes / elements per item
+    int gpr, GP;                              // items per iteration-space row; padded row length of the index space
+    int TA, tiles;                            // slabs per tile, tiles per image
+    int xs, gvs, gis;                         // slab slots per image: x, grad at the output position, grad for grad_input (0: shares gvs)
+    int slab_x, slab_g;                       // bytes of one slab of x / of grad
+    int np, stages, stage_stride, nw, n_per_unit, units;
+    int off_gv, off_gi;                       // byte offsets of the grad regions inside a stage (after GUARD)
+    int img_items;                            // TA * IB * GP
+    long long img_stride;                     // output bytes between consecutive images of one channel
+    FastDiv d_img, d_GP, d_IB;
 };
 
-// level (0 slab, 1 row, 2 col) -> tensor axis, or -1 when the level is absent for this dim
 TS_D int level_axis(int level, int dim) { return level - (3 - dim); }
 
+// Per-unit shift parameters by LEVEL (0 slab, 1 row, 2 column).
+struct UnitShift {
+    int sx[3];     // integer shift reduced against the input sizes
+    int sg[3];     // integer shift reduced against the output sizes (fetches from grad)
+    float d[3];    // fractional parts per TENSOR AXIS (reference order)
+};
+
+TS_D UnitShift unit_shift(const SArgs& a, long long c) {
+    UnitShift u;
+    const int dim = a.g.dim;
+    u.d[0] = u.d[1] = u.d[2] = 0.f;
+#pragma unroll
+    for (int lev = 0; lev < 3; ++lev) {
+        const int ax = level_axis(lev, dim);
+        u.sx[lev] = u.sg[lev] = 0;
+        if (ax < 0) continue;
+        const long long idx = c * dim + ax;
+        long long iw = 0;
+        if (a.mode == 0) {
+            switch (a.wk) {
+            case WK_F32: { float d; split_forward<float>(((const float*)a.w)[idx], false, iw, d); break; }
+            case WK_F64: { double d; split_forward<double>(((const double*)a.w)[idx], false, iw, d); break; }
+            case WK_F16: { float d; split_forward<float>(__half2float(((const __half*)a.w)[idx]), false, iw, d); break; }
+            case WK_BF16: { float d; split_forward<float>(__bfloat162float(((const __nv_bfloat16*)a.w)[idx]), false, iw, d); break; }
+            default:
+                if (a.qkind == TS_QW_U8) iw = (long long)((const uint8_t*)a.w)[idx] - a.wzp;
+                else if (a.qkind == TS_QW_I8) iw = (long long)((const int8_t*)a.w)[idx] - a.wzp;
+                else iw = (long long)((const int32_t*)a.w)[idx] - a.wzp;
+            }
+        } else {
+            float wv;
+            if (a.wk == WK_F16) wv = __half2float(((const __half*)a.w)[idx]);
+            else if (a.wk == WK_BF16) wv = __bfloat162float(((const __nv_bfloat16*)a.w)[idx]);
+            else wv = ((const float*)a.w)[idx];
+            float d;
+            if (a.mode == 1) split_forward<float>(wv, true, iw, d);
+            else split_backward<float>(wv, a.active != 0, iw, d);
+            u.d[ax] = d;
+        }
+        u.sx[lev] = reduce_shift(iw, a.g.S[ax], a.g.pad);
+        u.sg[lev] = reduce_shift(iw, a.g.OS[ax], a.g.pad);
+    }
+    return u;
+}
+
 // ---- producer ---------------------------------------------------------------------------------
+// slab held by slot k of the three regions for tile origin a0 (negative: nothing to copy -> zeros padding)
+TS_D int x_slot_slab(const SArgs& a, const UnitShift& us, int a0, int k) {
+    if (a.g.dim < 3) return 0;
+    const int j = (a.mode == 2 ? a0 : a0 + a.lbA) - us.sx[0] + k;
+    return axis_index(j, a.A, a.g.pad);
+}
+TS_D int gv_slot_slab(const SArgs& a, int a0, int k) {
+    if (a.g.dim < 3) return 0;
+    const int oa = a0 - a.lbA + k;
+    return (oa >= 0 && oa < a.OA) ? oa : -1;
+}
+TS_D int gi_slot_slab(const SArgs& a, const UnitShift& us, int a0, int k) {
+    if (a.g.dim < 3) return 0;
+    const int oa = a0 - a.lbA + k;              // output slab of the iteration slab (k may include the +1 neighbour)
+    if (a.active) return axis_index(oa - us.sg[0], a.OA, a.g.pad);
+    return axis_index(oa + us.sg[0], a.OA, a.g.pad);
+}
+
 TS_D void producer(const SArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty) {
     int s = 0, k = 0;
-    const long long C = a.g.C, N = a.g.N;
+    const int C = (int)a.g.C, N = (int)a.g.N;
     for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
-        const long long c = u % C, chunk = u / C;
-        const long long n0 = chunk * a.n_per_unit;
-        const long long n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
-        for (long long nb = n0; nb < n1; nb += a.np) {
-            if (k > 0) mbar_wait(&empty[s], (unsigned)((k - 1) & 1));
-            const int npl = (int)(n1 - nb < a.np ? n1 - nb : a.np);
-            unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
-            mbar_expect_tx(&full[s], (unsigned)(npl * (a.xpb + a.gpb)));
-            for (int pl = 0; pl < npl; ++pl) {
-                const long long plane = (nb + pl) * C + c;
-                bulk_g2s(st + (size_t)pl * a.xpb, a.x + plane * a.xpb, (unsigned)a.xpb, &full[s]);
-                if (a.gpb)
-                    bulk_g2s(st + (size_t)a.np * a.xpb + (size_t)pl * a.gpb, a.grad + plane * a.gpb, (unsigned)a.gpb, &full[s]);
+        const int chunk = u / C, c = u - chunk * C;
+        const int n0 = chunk * a.n_per_unit;
+        const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
+        const UnitShift us = unit_shift(a, c);
+        for (int nb = n0; nb < n1; nb += a.np) {
+            const int npl = n1 - nb < a.np ? n1 - nb : a.np;
+            for (int t = 0; t < a.tiles; ++t) {
+                if (k > 0) mbar_wait(&empty[s], (unsigned)((k - 1) & 1));
+                const int a0 = t * a.TA;
+                unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
+                // bytes first (slots outside the tensor under zeros padding are not copied)
+                int vx = 0, vgv = 0, vgi = 0;
+                for (int q = 0; q < a.xs; ++q) vx += x_slot_slab(a, us, a0, q) >= 0;
+                if (a.mode == 2) {
+                    for (int q = 0; q < a.gvs; ++q) vgv += gv_slot_slab(a, a0, q) >= 0;
+                    for (int q = 0; q < a.gis; ++q) vgi += gi_slot_slab(a, us, a0, q) >= 0;
+                }
+                const unsigned tx = (unsigned)npl * ((unsigned)vx * a.slab_x + (unsigned)(vgv + vgi) * a.slab_g);
+                mbar_expect_tx(&full[s], tx);
+                for (int pl = 0; pl < npl; ++pl) {
+                    const long long plane = (long long)(nb + pl) * C + c;
+                    for (int q = 0; q < a.xs; ++q) {
+                        const int slab = x_slot_slab(a, us, a0, q);
+                        if (slab >= 0)
+                            bulk_g2s(st + (size_t)(pl * a.xs + q) * a.slab_x, a.x + (plane * a.A + slab) * a.slab_x, (unsigned)a.slab_x, &full[s]);
+                    }
+                    if (a.mode == 2) {
+                        for (int q = 0; q < a.gvs; ++q) {
+                            const int slab = gv_slot_slab(a, a0, q);
+                            if (slab >= 0)
+                                bulk_g2s(st + a.off_gv + (size_t)(pl * a.gvs + q) * a.slab_g, a.grad + (plane * a.OA + slab) * a.slab_g,
+                                         (unsigned)a.slab_g, &full[s]);
+                        }
+                        for (int q = 0; q < a.gis; ++q) {
+                            const int slab = gi_slot_slab(a, us, a0, q);
+                            if (slab >= 0)
+                                bulk_g2s(st + a.off_gi + (size_t)(pl * a.gis + q) * a.slab_g, a.grad + (plane * a.OA + slab) * a.slab_g,
+                                         (unsigned)a.slab_g, &full[s]);
+                        }
+                    }
+                }
+                if (++s == a.stages) { s = 0; ++k; }
             }
-            if (++s == a.stages) { s = 0; ++k; }
         }
     }
 }
 
 // ---- consumer skeleton -----------------------------------------------------------------------
+struct Stage {
+    const unsigned char* st;   // stage base (after GUARD)
+    unsigned char* dst;        // output address of (first image of the stage, channel c, slab a0)
+    int npl, a0, an;           // images in the stage, tile origin, valid slabs of the tile
+};
+
 template <class Body>
 TS_D void consumer_loop(const SArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int lane, Body& body) {
-    int s = 0, k = 0;
-    const long long C = a.g.C, N = a.g.N;
+    int s = 0;
+    unsigned phase = 0;
+    const int C = (int)a.g.C, N = (int)a.g.N;
+    const long long plane_bytes = a.img_stride / C;
+    const long long out_slab = (long long)a.IB * a.gpr * a.VB;
     for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
-        const long long c = u % C, chunk = u / C;
-        const long long n0 = chunk * a.n_per_unit;
-        const long long n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
+        const int chunk = u / C, c = u - chunk * C;
+        const int n0 = chunk * a.n_per_unit;
+        const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         body.begin_unit(c);
-        for (long long nb = n0; nb < n1; nb += a.np) {
-            mbar_wait(&full[s], (unsigned)(k & 1));
-            const int npl = (int)(n1 - nb < a.np ? n1 - nb : a.np);
-            body.step(smem + (size_t)s * a.stage_stride + GUARD, npl, nb, c);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-            if (++s == a.stages) { s = 0; ++k; }
+        for (int nb = n0; nb < n1; nb += a.np) {
+            Stage sg;
+            sg.npl = n1 - nb < a.np ? n1 - nb : a.np;
+            unsigned char* img = a.out + ((long long)nb * C + c) * plane_bytes;
+            for (int t = 0; t < a.tiles; ++t) {
+                sg.a0 = t * a.TA;
+                sg.an = a.IA - sg.a0 < a.TA ? a.IA - sg.a0 : a.TA;
+                sg.dst = img + sg.a0 * out_slab;
+                sg.st = smem + (size_t)s * a.stage_stride + GUARD;
+                mbar_wait(&full[s], phase);
+                body.step(sg);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == a.stages) { s = 0; phase ^= 1u; }
+            }
         }
         body.end_unit(c, chunk);
     }
 }
 
-// ---- word-vector helpers ----------------------------------------------------------------------
-template <int G> TS_D void lds_words(const unsigned char* p, unsigned* w);
-template <> TS_D void lds_words<4>(const unsigned char* p, unsigned* w) { const uint4 v = *(const uint4*)p; w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
-template <> TS_D void lds_words<2>(const unsigned char* p, unsigned* w) { const uint2 v = *(const uint2*)p; w[0] = v.x; w[1] = v.y; }
-template <> TS_D void lds_words<1>(const unsigned char* p, unsigned* w) { w[0] = *(const unsigned*)p; }
-template <int G> TS_D void stg_words(unsigned char* p, const unsigned* w);
-template <> TS_D void stg_words<4>(unsigned char* p, const unsigned* w) { __stcs((uint4*)p, make_uint4(w[0], w[1], w[2], w[3])); }
-template <> TS_D void stg_words<2>(unsigned char* p, const unsigned* w) { __stcs((uint2*)p, make_uint2(w[0], w[1])); }
-template <> TS_D void stg_words<1>(unsigned char* p, const unsigned* w) { __stcs((unsigned*)p, w[0]); }
+// item of the padded index space -> (image, tile-local slab, row, group)
+struct Item { int pl, a, b, cg; };
+template <bool SLABS>
+TS_D void decode_item(const SArgs& a, int item, Item& p) {
+    p.pl = 0;
+    int rem = item;
+    if (a.np > 1) { p.pl = (int)fdiv((unsigned)item, a.d_img); rem = item - p.pl * a.img_items; }
+    const int row = (int)fdiv((unsigned)rem, a.d_GP);
+    p.cg = rem - row * a.GP;
+    p.a = 0;
+    p.b = row;
+    if (SLABS) { p.a = (int)fdiv((unsigned)row, a.d_IB); p.b = row - p.a * a.IB; }
+}
+TS_D unsigned char* item_dst(const SArgs& a, const Stage& sg, const Item& p) {
+    return sg.dst + p.pl * a.img_stride + (long long)((p.a * a.IB + p.b) * a.gpr + p.cg) * a.VB;
+}
 
-// ================================================================================================
-// Sparse / quantized forward: a pure byte mover.  G = 32-bit words per item (4: 128-bit stores),
-// ES = element bytes.  dim / padding / weight kind are run-time (they only touch per-unit setup,
-// the row remap and the rare edge path).
-template <int G, int ES>
-struct GatherBody {
-    static constexpr int VB = 4 * G, VEC = VB / ES;
-    const SArgs& a;
-    const int tid, nt;
-    int sh[3];        // reduced shifts per level
-    int mb;           // byte misalignment of the source inside its 4G-byte group (unit-uniform)
-    unsigned fillw[G];
+// Interior box of a unit (rows, groups): items inside need no remap / mask.
+struct Interior { int b_lo, b_hi, c_lo, c_hi; };
+TS_D int ceil_div(int n, int d) { return n >= 0 ? (n + d - 1) / d : -((-n) / d); }
+TS_D int floor_div(int n, int d) { return n >= 0 ? n / d : -((-n + d - 1) / d); }
+TS_D void clamp_range(int& lo, int& hi, int n) {
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > n ? n : hi;
+    if (hi < lo) hi = lo;
+}
 
-    TS_D GatherBody(const SArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_) {
-#pragma unroll
-        for (int k = 0; k < G; ++k) {
-            if (ES == 1) fillw[k] = 0x01010101u * (unsigned)(a.fill & 0xffu);
-            else if (ES == 2) fillw[k] = 0x00010001u * (unsigned)(a.fill & 0xffffu);
-            else if (ES == 4) fillw[k] = (unsigned)a.fill;
-            else fillw[k] = (k & 1) ? (unsigned)(a.fill >> 32) : (unsigned)a.fill;
-        }
+// compact enumeration of the items OUTSIDE the interior box of a tile:
+//   E1: every slab, every row, edge groups            E2: every slab, edge rows, interior groups
+//   E3: edge slabs, interior rows, interior groups
+struct EdgeSets {
+    int a_lo, a_hi, b_lo, b_hi, c_lo, c_hi;   // interior box in tile coordinates
+    int A, B, G;                              // tile extents (valid slabs, rows, groups)
+    int n1, n2, n3;                           // set sizes per image
+    TS_D void init() {
+        const int ce = c_lo + (G - c_hi), ci = c_hi - c_lo;
+        const int be = b_lo + (B - b_hi), bi = b_hi - b_lo;
+        const int ae = a_lo + (A - a_hi);
+        n1 = A * B * ce;
+        n2 = A * be * ci;
+        n3 = ae * bi * ci;
     }
-
-    TS_D long long raw_shift(long long idx) const {
-        long long iw;
-        switch (a.wk) {
-        case WK_F32: { float d; split_forward<float>(((const float*)a.w)[idx], false, iw, d); return iw; }
-        case WK_F64: { double d; split_forward<double>(((const double*)a.w)[idx], false, iw, d); return iw; }
-        case WK_F16: { float d; split_forward<float>(__half2float(((const __half*)a.w)[idx]), false, iw, d); return iw; }
-        case WK_BF16: { float d; split_forward<float>(__bfloat162float(((const __nv_bfloat16*)a.w)[idx]), false, iw, d); return iw; }
-        default:
-            if (a.qkind == TS_QW_U8) return (long long)((const uint8_t*)a.w)[idx] - a.wzp;
-            if (a.qkind == TS_QW_I8) return (long long)((const int8_t*)a.w)[idx] - a.wzp;
-            return (long long)((const int32_t*)a.w)[idx] - a.wzp;
-        }
-    }
-
-    TS_D void begin_unit(long long c) {
-        const int dim = a.g.dim;
-#pragma unroll
-        for (int lev = 0; lev < 3; ++lev) {
-            const int ax = level_axis(lev, dim);
-            sh[lev] = ax >= 0 ? reduce_shift(raw_shift(c * dim + ax), a.g.S[ax], a.g.pad) : 0;
-        }
-        mb = pmod((a.lbL - sh[2]) * ES, VB);
-    }
-    TS_D void end_unit(long long, long long) {}
-
-    TS_D void step(const unsigned char* st, int npl, long long nb, long long c) {
-        const int pad = a.g.pad;
-        const int total = npl * a.ipp;
-        const int ws = mb >> 2, bs8 = (mb & 3) * 8;
-        for (int item = tid; item < total; item += nt) {
-            const int pl = (int)fdiv((unsigned)item, a.d_ipp);
-            const int rem = item - pl * a.ipp;
-            const int orow = (int)fdiv((unsigned)rem, a.d_gpr);
-            const int cg = rem - orow * a.gpr;
-            int oa = 0, ob = orow;
-            if (a.OA > 1 || a.A > 1) { oa = (int)fdiv((unsigned)orow, a.d_rows); ob = orow - oa * a.OB; }
-            const int ra = axis_index(oa + a.lbA - sh[0], a.A, pad);
-            const int rb = axis_index(ob + a.lbB - sh[1], a.B, pad);
-            const int cs = cg * VEC + a.lbL - sh[2];
-            unsigned char* dst = a.out + (((nb + pl) * a.g.C + c) * a.g.out_plane + (long long)orow * a.OL) * ES + (long long)cg * VB;
-            unsigned o[G];
-            const bool interior = cs >= 0 && cs + VEC <= a.L;
-            if (ra < 0 || rb < 0 || cs + VEC <= 0 || cs >= a.L) {
-                // nothing of this item lies inside the source (only possible with zeros padding,
-                // or a column window fully outside which non-zero paddings resolve element-wise)
-                if (pad == TS_PAD_ZEROS || ra < 0 || rb < 0) {
-#pragma unroll
-                    for (int k = 0; k < G; ++k) o[k] = fillw[k];
-                    stg_words<G>(dst, o);
-                    continue;
-                }
-            }
-            const unsigned char* pb = st + (size_t)pl * a.xpb;
-            const long long rowoff = ((long long)ra * a.B + rb) * a.L;
-            if (interior || pad == TS_PAD_ZEROS) {
-                const long long bo = (rowoff + cs) * ES;
-                const unsigned char* ag = pb + (bo - mb);          // aligned to VB by construction
-                unsigned W[2 * G];
-                lds_words<G>(ag, W);
-                lds_words<G>(ag + VB, W + G);
-#pragma unroll
-                for (int k = 0; k < G; ++k) {
-                    unsigned lo = W[k], hi = W[k + 1];
-#pragma unroll
-                    for (int j = 1; j < G; ++j)
-                        if (ws == j) { lo = W[k + j]; hi = (k + j + 1 < 2 * G) ? W[k + j + 1] : 0u; }
-                    o[k] = __funnelshift_r(lo, hi, bs8);
-                }
-                if (!interior) {   // zeros padding, partially outside: blend the pad value in
-                    const int lo_b = (cs < 0 ? -cs : 0) * ES;
-                    const int hi_b = (a.L - cs < VEC ? a.L - cs : VEC) * ES;
-#pragma unroll
-                    for (int k = 0; k < G; ++k) {
-                        int l = lo_b - 4 * k, h = hi_b - 4 * k;
-                        l = l < 0 ? 0 : (l > 4 ? 4 : l);
-                        h = h < 0 ? 0 : (h > 4 ? 4 : h);
-                        const unsigned m = h > l ? ((0xffffffffu >> (8 * (4 - h))) & (0xffffffffu << (8 * l))) : 0u;
-                        o[k] = (o[k] & m) | (fillw[k] & ~m);
-                    }
-                }
-            } else {               // wrap / reflect / clamp at a row edge: element by element
-#pragma unroll
-                for (int k = 0; k < G; ++k) o[k] = 0u;
-#pragma unroll
-                for (int t = 0; t < VEC; ++t) {
-                    const int col = axis_index(cs + t, a.L, pad);
-                    const unsigned char* ep = pb + (rowoff + col) * ES;
-                    if (ES == 1) o[t / 4] |= (unsigned)(*ep) << (8 * (t % 4));
-                    else if (ES == 2) o[t / 2] |= (unsigned)(*(const unsigned short*)ep) << (16 * (t % 2));
-                    else if (ES == 4) o[t] = *(const unsigned*)ep;
-                    else { const uint2 v = *(const uint2*)ep; o[(2 * t) % G] = v.x; o[(2 * t + 1) % G] = v.y; }
-                }
-            }
-            stg_words<G>(dst, o);
+    TS_D int per_image() const { return n1 + n2 + n3; }
+    static TS_D int pick(int k, int lo, int hi) { return k < lo ? k : hi + (k - lo); }
+    TS_D void decode(int e, Item& p) const {
+        const int ce = c_lo + (G - c_hi), ci = c_hi - c_lo;
+        if (e < n1) {
+            const int k = e % ce, r = e / ce;
+            p.cg = pick(k, c_lo, c_hi);
+            p.b = r % B;
+            p.a = r / B;
+        } else if (e < n1 + n2) {
+            e -= n1;
+            const int be = b_lo + (B - b_hi);
+            const int j = e % ci, r = e / ci;
+            p.cg = c_lo + j;
+            p.b = pick(r % be, b_lo, b_hi);
+            p.a = r / be;
+        } else {
+            e -= n1 + n2;
+            const int bi = b_hi - b_lo;
+            const int j = e % ci, r = e / ci;
+            p.cg = c_lo + j;
+            p.b = b_lo + r % bi;
+            p.a = pick(r / bi, a_lo, a_hi);
         }
     }
 };
 
-// ================================================================================================
-// fp32 arithmetic kernels (active forward, backward).  Items are 4 consecutive elements of a row.
-//
-// load_seg: NV consecutive source columns cs..cs+NV-1 of row `r` of a staged plane with the
-// padding rule applied.  Fast path: the two aligned float4 that cover the window + a
-// (warp-uniform) select; zeros padding blends zeros in at the row ends; the other paddings fall
-// back to element-wise remapped loads only for windows that cross a row end.
-template <int NV>
-TS_D void load_seg(const float* __restrict__ plane, int r, int L, int cs, int pad, float* out) {
-    const bool interior = cs >= 0 && cs + NV <= L;
-    if (r < 0 || (pad == TS_PAD_ZEROS && (cs + NV <= 0 || cs >= L))) {
-#pragma unroll
-        for (int t = 0; t < NV; ++t) out[t] = 0.f;
-        return;
-    }
-    if (interior || pad == TS_PAD_ZEROS) {
-        const int f = r * L + cs;
-        const int a0 = f & ~3;
-        const float4 A = *(const float4*)(plane + a0);
-        const float4 B = *(const float4*)(plane + a0 + 4);
-        const float W[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
-        const int m = f & 3;
-#pragma unroll
-        for (int t = 0; t < NV; ++t) {
-            float v = W[t];
-#pragma unroll
-            for (int j = 1; j < 4; ++j)
-                if (m == j) v = W[t + j];
-            out[t] = v;
-        }
-        if (!interior) {
-#pragma unroll
-            for (int t = 0; t < NV; ++t)
-                if (cs + t < 0 || cs + t >= L) out[t] = 0.f;
-        }
-        return;
+// ---- window loads -----------------------------------------------------------------------------
+// NW 32-bit words starting WS words into the aligned 16-byte group at byte offset `off` of `base`
+// (off is a multiple of 16).  Loads the second group only when the window needs it.
+template <int WS, int NW>
+TS_D void load_words(const unsigned char* base, int off, unsigned* w) {
+    const uint4 A = *(const uint4*)(base + off);
+    unsigned W[8] = {A.x, A.y, A.z, A.w, 0u, 0u, 0u, 0u};
+    if (WS + NW > 4) {
+        const uint4 B = *(const uint4*)(base + off + 16);
+        W[4] = B.x; W[5] = B.y; W[6] = B.z; W[7] = B.w;
     }
 #pragma unroll
-    for (int t = 0; t < NV; ++t) out[t] = plane[r * L + axis_index(cs + t, L, pad)];
+    for (int t = 0; t < NW; ++t) w[t] = W[(t + WS) & 7];
+}
+template <int NW>
+TS_D void load_words_rt(const unsigned char* base, int off, int ws, unsigned* w) {
+    switch (ws) {
+    case 0: load_words<0, NW>(base, off, w); break;
+    case 1: load_words<1, NW>(base, off, w); break;
+    case 2: load_words<2, NW>(base, off, w); break;
+    default: load_words<3, NW>(base, off, w); break;
+    }
 }
 
-// Row index inside a staged plane for (slab a, row b) shifted by the reduced shifts, with the +1
-// neighbour selected by `rv` (bit0 = +1 on tensor axis 0, bit1 = +1 on tensor axis 1).
-template <int DIM>
-TS_D int source_row(int a, int b, const int* s, int rv, int A, int B, int pad) {
-    if (DIM == 1) return 0;
-    if (DIM == 2) return axis_index(b - s[0] + (rv & 1), B, pad);
-    const int ra = axis_index(a - s[0] + (rv & 1), A, pad);
-    const int rb = axis_index(b - s[1] + ((rv >> 1) & 1), B, pad);
-    return (ra < 0 || rb < 0) ? -1 : ra * B + rb;
+// Element-type traits of the arithmetic kernels: V elements per 16-byte item; a window of NV
+// elements spans words(NV) 32-bit words (one more than NV/2 for 16-bit types: half-word shift).
+template <typename ST> struct Pack;
+template <> struct Pack<float> {
+    static constexpr int V = 4;
+    static __host__ __device__ constexpr int words(int nv) { return nv; }
+    template <int NV> static TS_D void unpack(const unsigned* w, int, float* out) {
+#pragma unroll
+        for (int t = 0; t < NV; ++t) out[t] = __uint_as_float(w[t]);
+    }
+    static TS_D uint4 pack(const float* o) {
+        return make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
+    }
+};
+template <> struct Pack<__nv_bfloat16> {
+    static constexpr int V = 8;
+    static __host__ __device__ constexpr int words(int nv) { return nv / 2 + 1; }
+    template <int NV> static TS_D void unpack(const unsigned* w, int hs, float* out) {
+#pragma unroll
+        for (int k = 0; k < (NV + 1) / 2; ++k) {
+            const unsigned v = __funnelshift_r(w[k], w[k + 1], hs);
+            out[2 * k] = __uint_as_float(v << 16);
+            if (2 * k + 1 < NV) out[2 * k + 1] = __uint_as_float(v & 0xffff0000u);
+        }
+    }
+    static TS_D uint4 pack(const float* o) {
+        unsigned r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 v = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+            r[k] = *(const unsigned*)&v;
+        }
+        return make_uint4(r[0], r[1], r[2], r[3]);
+    }
+};
+template <> struct Pack<__half> {
+    static constexpr int V = 8;
+    static __host__ __device__ constexpr int words(int nv) { return nv / 2 + 1; }
+    template <int NV> static TS_D void unpack(const unsigned* w, int hs, float* out) {
+#pragma unroll
+        for (int k = 0; k < (NV + 1) / 2; ++k) {
+            const unsigned v = __funnelshift_r(w[k], w[k + 1], hs);
+            const float2 f = __half22float2(*(const __half2*)&v);
+            out[2 * k] = f.x;
+            if (2 * k + 1 < NV) out[2 * k + 1] = f.y;
+        }
+    }
+    static TS_D uint4 pack(const float* o) {
+        unsigned r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __half2 v = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+            r[k] = *(const unsigned*)&v;
+        }
+        return make_uint4(r[0], r[1], r[2], r[3]);
+    }
+};
+
+// window of NV elements starting at element index `e0` (>= 0, window inside the region) of a staged region
+template <typename ST, int WS, int NV>
+TS_D void load_window(const unsigned char* region, int e0, float* out) {
+    constexpr int NW = Pack<ST>::words(NV);
+    const int byte = e0 * (int)sizeof(ST);
+    unsigned w[NW + 1];
+    load_words<WS, NW>(region, byte & ~15, w);
+    w[NW] = 0u;
+    Pack<ST>::template unpack<NV>(w, (byte & 2) * 8, out);
+}
+template <typename ST, int NV>
+TS_D void load_window_rt(const unsigned char* region, int e0, float* out) {
+    constexpr int NW = Pack<ST>::words(NV);
+    const int byte = e0 * (int)sizeof(ST);
+    unsigned w[NW + 1];
+    load_words_rt<NW>(region, byte & ~15, (byte >> 2) & 3, w);
+    w[NW] = 0u;
+    Pack<ST>::template unpack<NV>(w, (byte & 2) * 8, out);
 }
 
-// Gather the 2^DIM neighbours of the 4 elements of an item from 2^(DIM-1) row segments of 5.
-template <int DIM>
-TS_D void neighbours_from_rows(const float (*X)[5], int t, float* v) {
+// element-wise window with the padding rule (edge items): row < 0 -> zeros
+template <typename ST, int NV>
+TS_D void load_window_edge(const unsigned char* region, int row, int L, int c0, int pad, float* out) {
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+        const int col = axis_index(c0 + t, L, pad);
+        out[t] = (row >= 0 && col >= 0) ? Elem<ST>::ld(((const ST*)region)[row * L + col]) : 0.f;
+    }
+}
+
+template <int DIM, int NVW>
+TS_D void neighbours_from_rows(const float (*X)[NVW], int t, float* v) {
     constexpr int NR = 1 << (DIM - 1);
 #pragma unroll
     for (int q = 0; q < (1 << DIM); ++q) v[q] = X[q & (NR - 1)][t + (q >> (DIM - 1))];
 }
 
+// grad_weight factors with ordinary (contractable) arithmetic: tolerance-checked only
 template <int DIM>
-struct ActiveFwdBody {
+TS_D void weight_partials_fast(const float* v, const float* d, float* g) {
+    if (DIM == 1) { g[0] = v[1] - v[0]; return; }
+    if (DIM == 2) {
+        const float p = v[2] - v[0], q = (v[3] - v[1]) - p;
+        g[0] = fmaf(d[1], q, p);
+        g[1] = fmaf(d[0], q, p);
+        return;
+    }
+    const float p0 = v[2] - v[0], q0 = (v[3] - v[1]) - p0, p1 = v[6] - v[4], q1 = (v[7] - v[5]) - p1;
+    const float x0 = fmaf(d[1], q0, p0), x1 = fmaf(d[1], q1, p1);
+    const float y0 = fmaf(d[0], q0, p0), y1 = fmaf(d[0], q1, p1);
+    g[0] = fmaf(d[2], x1 - x0, x0);
+    g[1] = fmaf(d[2], y1 - y0, y0);
+    const float i0 = fmaf(d[0], v[1] - v[0], v[0]), i1 = fmaf(d[0], v[3] - v[2], v[2]);
+    const float i2 = fmaf(d[0], v[5] - v[4], v[4]), i3 = fmaf(d[0], v[7] - v[6], v[6]);
+    g[2] = fmaf(d[1], i3 - i2, i2) - fmaf(d[1], i1 - i0, i0);
+}
+
+// flat row (slot * rows + row) of neighbour variant rv for an edge item, or -1 (zeros).  DIM 3:
+// bit0 of rv = +1 slab slot (the producer resolved that axis), bit1 = +1 row; DIM 2: bit0 = +1 row.
+template <int DIM>
+TS_D int edge_row(int slot, bool slot1_ok, bool slot0_ok, int rowv, int rv, int rows, int pad) {
+    if (DIM == 1) return 0;
+    if (DIM == 2) return axis_index(rowv + (rv & 1), rows, pad);
+    const bool ok = (rv & 1) ? slot1_ok : slot0_ok;
+    const int r = axis_index(rowv + ((rv >> 1) & 1), rows, pad);
+    return (ok && r >= 0) ? (slot + (rv & 1)) * rows + r : -1;
+}
+// same for an interior item: plain arithmetic
+template <int DIM>
+TS_D int interior_row(int row0, int rv, int rows) {
+    if (DIM == 1) return row0;
+    if (DIM == 2) return row0 + (rv & 1);
+    return row0 + (rv & 1) * rows + ((rv >> 1) & 1);
+}
+
+// ================================================================================================
+// mode 0: sparse / quantized forward -- a byte mover.  G = 32-bit words per item (4/2/1), ES =
+// element bytes.
+template <int G, int ES>
+struct GatherBody {
+    static constexpr int VB = 4 * G, V = VB / ES;
     const SArgs& a;
     const int tid, nt;
-    ShiftParams<float, DIM> sp;
+    UnitShift us;
+    Interior in;
+    int mb;
 
-    TS_D ActiveFwdBody(const SArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_) {}
-    TS_D void begin_unit(long long c) { sp = load_params<float, DIM>((const float*)a.w, c, a.g, true, false); }
-    TS_D void end_unit(long long, long long) {}
+    TS_D GatherBody(const SArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), mb(0) {}
+    TS_D void begin_unit(int c) {
+        us = unit_shift(a, c);
+        mb = pmod((a.lbL - us.sx[2]) * ES, VB);
+        // rows: 0 <= ob + lbB - s1 < B ; groups: 0 <= V*cg + lbL - s2, V*cg + lbL - s2 + V <= L
+        in.b_lo = us.sx[1] - a.lbB;
+        in.b_hi = a.B - a.lbB + us.sx[1];
+        clamp_range(in.b_lo, in.b_hi, a.OB);
+        in.c_lo = ceil_div(us.sx[2] - a.lbL, V);
+        in.c_hi = floor_div(a.L - V - a.lbL + us.sx[2], V) + 1;
+        clamp_range(in.c_lo, in.c_hi, a.gpr);
+    }
+    TS_D void end_unit(int, int) {}
 
-    TS_D void step(const unsigned char* st, int npl, long long nb, long long c) {
-        constexpr int NR = 1 << (DIM - 1);
-        const int pad = a.g.pad;
-        const int total = npl * a.ipp;
-        for (int item = tid; item < total; item += nt) {
-            const int pl = (int)fdiv((unsigned)item, a.d_ipp);
-            const int rem = item - pl * a.ipp;
-            const int orow = (int)fdiv((unsigned)rem, a.d_gpr);
-            const int cg = rem - orow * a.gpr;
-            int oa = 0, ob = orow;
-            if (DIM == 3) { oa = (int)fdiv((unsigned)orow, a.d_rows); ob = orow - oa * a.OB; }
-            const float* plane = (const float*)(st + (size_t)pl * a.xpb);
-            const int cs = cg * 4 + a.lbL - sp.sx[DIM - 1];
-            float X[NR][5];
-#pragma unroll
-            for (int rv = 0; rv < NR; ++rv)
-                load_seg<5>(plane, source_row<DIM>(oa + a.lbA, ob + a.lbB, sp.sx, rv, a.A, a.B, pad), a.L, cs, pad, X[rv]);
-            float o[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                float v[8];
-                neighbours_from_rows<DIM>(X, t, v);
-                o[t] = interpolate<float, DIM>(v, sp.d);
-            }
-            float* dst = (float*)a.out + ((nb + pl) * a.g.C + c) * a.g.out_plane + (long long)orow * a.OL + cg * 4;
-            __stcs((float4*)dst, make_float4(o[0], o[1], o[2], o[3]));
+    // slots whose slab lies outside the tensor (zeros padding) make the tile slab an edge slab
+    TS_D void slab_range(const Stage& sg, int& a_lo, int& a_hi) const {
+        a_lo = 0;
+        a_hi = sg.an;
+        if (a.g.dim == 3 && a.g.pad == TS_PAD_ZEROS && a.A > 1) {
+            a_lo = us.sx[0] - a.lbA - sg.a0;                 // a0 + a + lbA - s0 >= 0
+            a_hi = a.A - a.lbA + us.sx[0] - sg.a0;           // ... < A
+            clamp_range(a_lo, a_hi, sg.an);
         }
+    }
+
+    template <int WS, bool SUB>
+    TS_D void interior(const Stage& sg, int a_lo, int a_hi) const {
+        const int total = sg.npl * a.img_items;
+        const int bs8 = (mb & 3) * 8;
+        const int rowb = a.L * ES;
+        const int img_bytes = a.xs * a.slab_x;
+        const int col0 = (a.lbL - us.sx[2]) * ES - mb;        // aligned byte offset of group 0's window inside its row
+        const int rsh = a.lbB - us.sx[1];
+        for (int item = tid; item < total; item += nt) {
+            Item p;
+            decode_item<true>(a, item, p);
+            if (p.cg < in.c_lo || p.cg >= in.c_hi || p.b < in.b_lo || p.b >= in.b_hi || p.a < a_lo || p.a >= a_hi) continue;
+            const unsigned char* src = sg.st + p.pl * img_bytes + (p.a * a.B + p.b + rsh) * rowb + col0 + p.cg * VB;
+            unsigned W[2 * G + 1];
+            if constexpr (G == 4) {
+                const uint4 A = *(const uint4*)src;
+                W[0] = A.x; W[1] = A.y; W[2] = A.z; W[3] = A.w;
+                if (WS > 0 || SUB) { const uint4 Bv = *(const uint4*)(src + 16); W[4] = Bv.x; W[5] = Bv.y; W[6] = Bv.z; W[7] = Bv.w; }
+            } else if constexpr (G == 2) {
+                const uint2 A = *(const uint2*)src;
+                W[0] = A.x; W[1] = A.y;
+                if (WS > 0 || SUB) { const uint2 Bv = *(const uint2*)(src + 8); W[2] = Bv.x; W[3] = Bv.y; }
+            } else {
+                W[0] = *(const unsigned*)src;
+                if (WS > 0 || SUB) W[1] = *(const unsigned*)(src + 4);
+            }
+            W[2 * G] = 0u;
+            unsigned o[G];
+#pragma unroll
+            for (int k = 0; k < G; ++k) o[k] = SUB ? __funnelshift_r(W[k + WS], W[k + WS + 1], bs8) : W[k + WS];
+            unsigned char* dst = item_dst(a, sg, p);
+            if constexpr (G == 4) __stcs((uint4*)dst, make_uint4(o[0], o[1], o[2], o[3]));
+            else if constexpr (G == 2) __stcs((uint2*)dst, make_uint2(o[0], o[1]));
+            else __stcs((unsigned*)dst, o[0]);
+        }
+    }
+
+    TS_D void edges(const Stage& sg, int a_lo, int a_hi) const {
+        EdgeSets es;
+        es.a_lo = a_lo; es.a_hi = a_hi; es.b_lo = in.b_lo; es.b_hi = in.b_hi; es.c_lo = in.c_lo; es.c_hi = in.c_hi;
+        es.A = sg.an; es.B = a.OB; es.G = a.gpr;
+        es.init();
+        const int per = es.per_image(), total = sg.npl * per;
+        const int pad = a.g.pad;
+        for (int e = tid; e < total; e += nt) {
+            Item p;
+            p.pl = e / per;
+            es.decode(e - p.pl * per, p);
+            const bool slab_ok = x_slot_slab(a, us, sg.a0, p.a) >= 0;     // the producer already applied the slab shift
+            const int rb = a.g.dim >= 2 ? axis_index(p.b + a.lbB - us.sx[1], a.B, pad) : 0;
+            const int cs = p.cg * V + a.lbL - us.sx[2];
+            const unsigned char* slab = sg.st + (size_t)(p.pl * a.xs + p.a) * a.slab_x;
+            unsigned o[G];
+#pragma unroll
+            for (int k = 0; k < G; ++k) o[k] = 0u;
+#pragma unroll
+            for (int t = 0; t < V; ++t) {
+                const int col = axis_index(cs + t, a.L, pad);
+                const bool ok = slab_ok && rb >= 0 && col >= 0;
+                const unsigned char* ep = slab + ((long long)(ok ? rb : 0) * a.L + (ok ? col : 0)) * ES;
+                if (ES == 1) o[(t / 4) % G] |= (ok ? (unsigned)(*ep) : (unsigned)(a.fill & 0xffu)) << (8 * (t % 4));
+                else if (ES == 2) o[(t / 2) % G] |= (ok ? (unsigned)(*(const unsigned short*)ep) : (unsigned)(a.fill & 0xffffu)) << (16 * (t % 2));
+                else if (ES == 4) o[t % G] = ok ? *(const unsigned*)ep : (unsigned)a.fill;
+                else {
+                    uint2 v = make_uint2((unsigned)a.fill, (unsigned)(a.fill >> 32));
+                    if (ok) v = *(const uint2*)ep;
+                    o[(2 * t) % G] = v.x; o[(2 * t + 1) % G] = v.y;
+                }
+            }
+            unsigned char* dst = item_dst(a, sg, p);
+            if constexpr (G == 4) __stcs((uint4*)dst, make_uint4(o[0], o[1], o[2], o[3]));
+            else if constexpr (G == 2) __stcs((uint2*)dst, make_uint2(o[0], o[1]));
+            else __stcs((unsigned*)dst, o[0]);
+        }
+    }
+
+    TS_D void step(const Stage& sg) const {
+        int a_lo, a_hi;
+        slab_range(sg, a_lo, a_hi);
+        const int ws = mb >> 2;
+        if ((mb & 3) == 0) {
+            switch (ws) {
+            case 0: interior<0, false>(sg, a_lo, a_hi); break;
+            case 1: interior<1 % G, false>(sg, a_lo, a_hi); break;
+            case 2: interior<2 % G, false>(sg, a_lo, a_hi); break;
+            default: interior<3 % G, false>(sg, a_lo, a_hi); break;
+            }
+        } else {
+            switch (ws) {
+            case 0: interior<0, true>(sg, a_lo, a_hi); break;
+            case 1: interior<1 % G, true>(sg, a_lo, a_hi); break;
+            case 2: interior<2 % G, true>(sg, a_lo, a_hi); break;
+            default: interior<3 % G, true>(sg, a_lo, a_hi); break;
+            }
+        }
+        edges(sg, a_lo, a_hi);
     }
 };
 
-template <int DIM, bool ACTIVE>
-struct BackwardBody {
+// ================================================================================================
+// mode 1: active (interpolating) forward.
+template <typename ST, int DIM>
+struct ActiveFwdBody {
+    static constexpr int V = Pack<ST>::V, ES = (int)sizeof(ST), NVW = V + 1, NR = 1 << (DIM - 1);
     const SArgs& a;
-    const int tid, nt, wid, lane;
-    ShiftParams<float, DIM> sp;
-    double acc[DIM];
+    const int tid, nt;
+    UnitShift us;
+    Interior in;
+    bool any_interior;
 
-    TS_D BackwardBody(const SArgs& a_, int tid_, int nt_, int wid_, int lane_) : a(a_), tid(tid_), nt(nt_), wid(wid_), lane(lane_) {}
-    TS_D void begin_unit(long long c) {
-        sp = load_params<float, DIM>((const float*)a.w, c, a.g, ACTIVE, true);
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) acc[d] = 0.0;
+    TS_D ActiveFwdBody(const SArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), any_interior(false) {}
+    TS_D void begin_unit(int c) {
+        us = unit_shift(a, c);
+        // rows: 0 <= ob + lbB - s1, ob + lbB - s1 + 1 <= B-1 ; groups: 0 <= cs, cs + V + 1 <= L
+        in.b_lo = us.sx[1] - a.lbB;
+        in.b_hi = a.B - 1 - a.lbB + us.sx[1];
+        if (DIM == 1) { in.b_lo = 0; in.b_hi = 1; }
+        clamp_range(in.b_lo, in.b_hi, a.OB);
+        in.c_lo = ceil_div(us.sx[2] - a.lbL, V);
+        in.c_hi = floor_div(a.L - V - 1 - a.lbL + us.sx[2], V) + 1;
+        clamp_range(in.c_lo, in.c_hi, a.gpr);
+        // a size-1 axis ignores its shift and its +1 neighbour is the element itself: edge path only
+        any_interior = a.L > 1 && (DIM < 2 || a.B > 1) && (DIM < 3 || a.A > 1);
+        if (!any_interior) in.b_hi = in.b_lo = in.c_hi = in.c_lo = 0;
     }
-    // one partial per (unit, consumer warp): fixed shuffle tree, no atomics
-    TS_D void end_unit(long long c, long long chunk) {
+    TS_D void end_unit(int, int) {}
+
+    TS_D void slab_range(const Stage& sg, int& a_lo, int& a_hi) const {
+        a_lo = 0;
+        a_hi = sg.an;
+        if (DIM == 3 && a.g.pad == TS_PAD_ZEROS) {
+            a_lo = us.sx[0] - a.lbA - sg.a0;
+            a_hi = a.A - 1 - a.lbA + us.sx[0] - sg.a0;        // the +1 slot must exist as well
+            clamp_range(a_lo, a_hi, sg.an);
+        }
+        if (!any_interior) a_lo = a_hi = 0;
+    }
+
+    template <int WS>
+    TS_D void interior(const Stage& sg, int a_lo, int a_hi) const {
+        const int total = sg.npl * a.img_items;
+        const int img_bytes = a.xs * a.slab_x;
+        const int col0 = a.lbL - us.sx[2];
+        const int rsh = DIM >= 2 ? a.lbB - us.sx[1] : 0;
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        for (int item = tid; item < total; item += nt) {
+            Item p;
+            decode_item<DIM == 3>(a, item, p);
+            if (p.cg < in.c_lo || p.cg >= in.c_hi || p.b < in.b_lo || p.b >= in.b_hi || p.a < a_lo || p.a >= a_hi) continue;
+            const unsigned char* img = sg.st + p.pl * img_bytes;
+            const int row0 = p.a * a.B + p.b + rsh;
+            float X[NR][NVW];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) {
-            double v = acc[d];
+            for (int rv = 0; rv < NR; ++rv) load_window<ST, WS, NVW>(img, interior_row<DIM>(row0, rv, a.B) * a.L + col0 + p.cg * V, X[rv]);
+            float o[V];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-            if (lane == 0) a.partials[((long long)chunk * a.nw + wid) * (a.g.C * DIM) + c * DIM + d] = v;
+            for (int t = 0; t < V; ++t) {
+                float v[8];
+                neighbours_from_rows<DIM, NVW>(X, t, v);
+                o[t] = interpolate<float, DIM>(v, d);
+            }
+            __stcs((uint4*)item_dst(a, sg, p), Pack<ST>::pack(o));
         }
     }
 
-    TS_D void step(const unsigned char* st, int npl, long long nb, long long c) {
-        constexpr int NR = 1 << (DIM - 1);
+    TS_D void edges(const Stage& sg, int a_lo, int a_hi) const {
+        EdgeSets es;
+        es.a_lo = a_lo; es.a_hi = a_hi; es.b_lo = in.b_lo; es.b_hi = in.b_hi; es.c_lo = in.c_lo; es.c_hi = in.c_hi;
+        es.A = sg.an; es.B = a.OB; es.G = a.gpr;
+        es.init();
+        const int per = es.per_image(), total = sg.npl * per;
         const int pad = a.g.pad;
-        const int total = npl * a.ipp;
-        for (int item = tid; item < total; item += nt) {
-            const int pl = (int)fdiv((unsigned)item, a.d_ipp);
-            const int rem = item - pl * a.ipp;
-            const int row = (int)fdiv((unsigned)rem, a.d_gpr);      // input-space row (slab*B + b)
-            const int cg = rem - row * a.gpr;
-            int ia = 0, ib = row;
-            if (DIM == 3) { ia = (int)fdiv((unsigned)row, a.d_rows); ib = row - ia * a.B; }
-            const int oa = ia - a.lbA, ob = ib - a.lbB, oj0 = cg * 4 - a.lbL;
-            float* dst = (float*)a.out + ((nb + pl) * a.g.C + c) * a.g.in_plane + (long long)row * a.L + cg * 4;
-            const bool row_ok = oa >= 0 && oa < a.OA && ob >= 0 && ob < a.OB;
-            if (!row_ok || oj0 + 4 <= 0 || oj0 >= a.OL) {
-                __stcs((float4*)dst, make_float4(0.f, 0.f, 0.f, 0.f));
-                continue;
-            }
-            const float* xpl = (const float*)(st + (size_t)pl * a.xpb);
-            const float* gpl = (const float*)(st + (size_t)a.np * a.xpb + (size_t)pl * a.gpb);
-            const int grow = oa * a.OB + ob;
-            float gv[4];
-            load_seg<4>(gpl, grow, a.OL, oj0, TS_PAD_ZEROS, gv);     // zero outside the output window
-            // ---- grad_weight terms ----
-            float X[NR][5];
-            const int cs = cg * 4 - sp.sx[DIM - 1];
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        for (int e = tid; e < total; e += nt) {
+            Item p;
+            p.pl = e / per;
+            es.decode(e - p.pl * per, p);
+            const unsigned char* img = sg.st + (size_t)p.pl * a.xs * a.slab_x;
+            const int cs = p.cg * V + a.lbL - us.sx[2];
+            const bool ok0 = DIM < 3 || x_slot_slab(a, us, sg.a0, p.a) >= 0;
+            const bool ok1 = DIM < 3 || x_slot_slab(a, us, sg.a0, p.a + 1) >= 0;
+            float X[NR][NVW];
 #pragma unroll
             for (int rv = 0; rv < NR; ++rv)
-                load_seg<5>(xpl, source_row<DIM>(ia, ib, sp.sx, rv, a.A, a.B, pad), a.L, cs, pad, X[rv]);
-            float ts[DIM];
+                load_window_edge<ST, NVW>(img, edge_row<DIM>(p.a, ok1, ok0, p.b + a.lbB - us.sx[1], rv, a.B, pad), a.L, cs, pad, X[rv]);
+            float o[V];
 #pragma unroll
-            for (int d = 0; d < DIM; ++d) ts[d] = 0.f;
-            bool okc[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                okc[t] = oj0 + t >= 0 && oj0 + t < a.OL;
-                float v[8], wg[3];
-                neighbours_from_rows<DIM>(X, t, v);
-                weight_partials<float, DIM>(v, sp.d, wg);
-#pragma unroll
-                for (int d = 0; d < DIM; ++d) ts[d] += okc[t] ? Arith<float>::mul(gv[t], wg[d]) : 0.f;
+            for (int t = 0; t < V; ++t) {
+                float v[8];
+                neighbours_from_rows<DIM, NVW>(X, t, v);
+                o[t] = interpolate<float, DIM>(v, d);
             }
+            __stcs((uint4*)item_dst(a, sg, p), Pack<ST>::pack(o));
+        }
+    }
+
+    TS_D void step(const Stage& sg) const {
+        int a_lo, a_hi;
+        slab_range(sg, a_lo, a_hi);
+        const int ws = (pmod((a.lbL - us.sx[2]) * ES, 16)) >> 2;
+        switch (ws) {
+        case 0: interior<0>(sg, a_lo, a_hi); break;
+        case 1: interior<1>(sg, a_lo, a_hi); break;
+        case 2: interior<2>(sg, a_lo, a_hi); break;
+        default: interior<3>(sg, a_lo, a_hi); break;
+        }
+        edges(sg, a_lo, a_hi);
+    }
+};
+
+// ================================================================================================
+// mode 2: backward (grad_input + grad_weight partials); iterates the INPUT space.
+template <typename ST, int DIM, bool ACTIVE>
+struct BackwardBody {
+    static constexpr int V = Pack<ST>::V, ES = (int)sizeof(ST), NVW = V + 1, NR = 1 << (DIM - 1);
+    const SArgs& a;
+    const int tid, nt, wid, lane;
+    UnitShift us;
+    Interior in;
+    bool any_interior;
+    double acc[DIM];
+
+    TS_D BackwardBody(const SArgs& a_, int tid_, int nt_, int wid_, int lane_)
+        : a(a_), tid(tid_), nt(nt_), wid(wid_), lane(lane_), any_interior(false) {}
+
+    TS_D void begin_unit(int c) {
+        us = unit_shift(a, c);
 #pragma unroll
-            for (int d = 0; d < DIM; ++d) acc[d] += (double)ts[d];
+        for (int k = 0; k < DIM; ++k) acc[k] = 0.0;
+        // rows (input row ib, output row ob = ib - lbB):
+        //   inside the crop          lbB <= ib < lbB + OB
+        //   x window                 0 <= ib - sx1,  ib - sx1 + 1 <= B - 1
+        //   grad window  sparse      0 <= ob + sg1 < OB          active   0 <= ob - sg1, ob - sg1 + 1 <= OB - 1
+        int lo = a.lbB, hi = a.lbB + a.OB;
+        if (DIM >= 2) {
+            lo = max(lo, us.sx[1]);
+            hi = min(hi, a.B - 1 + us.sx[1]);
+            if (ACTIVE) { lo = max(lo, a.lbB + us.sg[1]); hi = min(hi, a.lbB + a.OB - 1 + us.sg[1]); }
+            else { lo = max(lo, a.lbB - us.sg[1]); hi = min(hi, a.lbB + a.OB - us.sg[1]); }
+        }
+        in.b_lo = lo; in.b_hi = hi;
+        clamp_range(in.b_lo, in.b_hi, a.B);
+        // groups (input columns V*cg .. V*cg+V-1, output column oj0 = V*cg - lbL):
+        //   inside the crop          lbL <= V*cg, V*cg + V <= lbL + OL
+        //   x window                 0 <= V*cg - sx2,  V*cg - sx2 + V + 1 <= L
+        //   grad window  sparse      0 <= oj0 + sg2, oj0 + sg2 + V <= OL     active  0 <= oj0 - sg2, oj0 - sg2 + V + 1 <= OL
+        int clo = ceil_div(a.lbL, V), chi = floor_div(a.lbL + a.OL - V, V) + 1;
+        clo = max(clo, ceil_div(us.sx[2], V));
+        chi = min(chi, floor_div(a.L - V - 1 + us.sx[2], V) + 1);
+        if (ACTIVE) { clo = max(clo, ceil_div(a.lbL + us.sg[2], V)); chi = min(chi, floor_div(a.lbL + a.OL - V - 1 + us.sg[2], V) + 1); }
+        else { clo = max(clo, ceil_div(a.lbL - us.sg[2], V)); chi = min(chi, floor_div(a.lbL + a.OL - V - us.sg[2], V) + 1); }
+        in.c_lo = clo; in.c_hi = chi;
+        clamp_range(in.c_lo, in.c_hi, a.gpr);
+        // the fast path needs the unshifted grad window 16-byte aligned and no size-1 axis
+        any_interior = (a.lbL * ES) % 16 == 0 && a.L > 1 && (DIM < 2 || a.B > 1) && (DIM < 3 || a.A > 1);
+        if (!any_interior) in.b_hi = in.b_lo = in.c_hi = in.c_lo = 0;
+    }
+    // one partial per (unit, consumer warp): fixed shuffle tree, no atomics
+    TS_D void end_unit(int c, int chunk) {
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) a.partials[((long long)chunk * a.nw + wid) * (a.g.C * DIM) + (long long)c * DIM + k] = v;
+        }
+    }
+
+    // tile-local slabs whose x slots (a, a+1), gv slot and grad_input slots are all real slabs
+    TS_D void slab_range(const Stage& sg, int& a_lo, int& a_hi) const {
+        a_lo = 0;
+        a_hi = sg.an;
+        if (DIM == 3) {
+            int lo = a.lbA - sg.a0, hi = a.lbA + a.OA - sg.a0;          // inside the crop
+            if (a.g.pad == TS_PAD_ZEROS) {
+                lo = max(lo, us.sx[0] - sg.a0);
+                hi = min(hi, a.A - 1 + us.sx[0] - sg.a0);
+                if (ACTIVE) { lo = max(lo, a.lbA + us.sg[0] - sg.a0); hi = min(hi, a.lbA + a.OA - 1 + us.sg[0] - sg.a0); }
+                else { lo = max(lo, a.lbA - us.sg[0] - sg.a0); hi = min(hi, a.lbA + a.OA - us.sg[0] - sg.a0); }
+            }
+            a_lo = lo; a_hi = hi;
+            clamp_range(a_lo, a_hi, sg.an);
+        }
+        if (!any_interior) a_lo = a_hi = 0;
+    }
+
+    template <int WS>
+    TS_D void interior(const Stage& sg, int a_lo, int a_hi, float* ts) const {
+        const int total = sg.npl * a.img_items;
+        const int ximg = a.xs * a.slab_x, gvimg = a.gvs * a.slab_g, giimg = (a.gis ? a.gis : a.gvs) * a.slab_g;
+        const unsigned char* gibase = sg.st + (a.gis ? a.off_gi : a.off_gv);
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        const int gsh = ACTIVE ? -us.sg[2] : us.sg[2];
+        const int grow_sh = DIM >= 2 ? (ACTIVE ? -us.sg[1] : us.sg[1]) : 0;
+        const int xrsh = DIM >= 2 ? -us.sx[1] : 0;
+        for (int item = tid; item < total; item += nt) {
+            Item p;
+            decode_item<DIM == 3>(a, item, p);
+            if (p.cg < in.c_lo || p.cg >= in.c_hi || p.b < in.b_lo || p.b >= in.b_hi || p.a < a_lo || p.a >= a_hi) continue;
+            const unsigned char* x_p = sg.st + p.pl * ximg;
+            const unsigned char* gv_p = sg.st + a.off_gv + p.pl * gvimg;
+            const unsigned char* gi_p = gibase + p.pl * giimg;
+            const int ob = p.b - a.lbB, oj0 = p.cg * V - a.lbL;
+            float gv[V];
+            load_window<ST, 0, V>(gv_p, (p.a * a.OB + ob) * a.OL + oj0, gv);
+            // ---- grad_weight terms ----
+            const int xrow0 = p.a * a.B + p.b + xrsh;
+            float X[NR][NVW];
+#pragma unroll
+            for (int rv = 0; rv < NR; ++rv) load_window<ST, WS, NVW>(x_p, interior_row<DIM>(xrow0, rv, a.B) * a.L + p.cg * V - us.sx[2], X[rv]);
+#pragma unroll
+            for (int t = 0; t < V; ++t) {
+                float v[8], wg[3];
+                neighbours_from_rows<DIM, NVW>(X, t, v);
+                weight_partials_fast<DIM>(v, d, wg);
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) ts[k] = fmaf(gv[t], wg[k], ts[k]);
+            }
             // ---- grad_input ----
-            float o[4];
+            float o[V];
+            const int grow0 = p.a * a.OB + ob + grow_sh;
             if (ACTIVE) {
-                float Gs[NR][5];
-                const int gcs = oj0 - sp.sg[DIM - 1];
+                float Gw[NR][NVW];
 #pragma unroll
-                for (int rv = 0; rv < NR; ++rv)
-                    load_seg<5>(gpl, source_row<DIM>(oa, ob, sp.sg, rv, a.OA, a.OB, pad), a.OL, gcs, pad, Gs[rv]);
+                for (int rv = 0; rv < NR; ++rv) load_window_rt<ST, NVW>(gi_p, interior_row<DIM>(grow0, rv, a.OB) * a.OL + oj0 + gsh, Gw[rv]);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
+                for (int t = 0; t < V; ++t) {
                     float v[8];
-                    neighbours_from_rows<DIM>(Gs, t, v);
-                    o[t] = okc[t] ? interpolate<float, DIM>(v, sp.d) : 0.f;
+                    neighbours_from_rows<DIM, NVW>(Gw, t, v);
+                    o[t] = interpolate<float, DIM>(v, d);
                 }
             } else {
-                int ns[3] = {0, 0, 0};
-#pragma unroll
-                for (int d = 0; d < DIM; ++d) ns[d] = -sp.sg[d];       // gather at o + shift
-                float Gs[4];
-                load_seg<4>(gpl, source_row<DIM>(oa, ob, ns, 0, a.OA, a.OB, pad), a.OL, oj0 + sp.sg[DIM - 1], pad, Gs);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) o[t] = okc[t] ? Gs[t] : 0.f;
+                load_window_rt<ST, V>(gi_p, grow0 * a.OL + oj0 + gsh, o);
             }
-            __stcs((float4*)dst, make_float4(o[0], o[1], o[2], o[3]));
+            __stcs((uint4*)item_dst(a, sg, p), Pack<ST>::pack(o));
         }
+    }
+
+    TS_D void edges(const Stage& sg, int a_lo, int a_hi, float* ts) const {
+        EdgeSets es;
+        es.a_lo = a_lo; es.a_hi = a_hi; es.b_lo = in.b_lo; es.b_hi = in.b_hi; es.c_lo = in.c_lo; es.c_hi = in.c_hi;
+        es.A = sg.an; es.B = a.B; es.G = a.gpr;
+        es.init();
+        const int per = es.per_image(), total = sg.npl * per;
+        const int pad = a.g.pad;
+        const int ximg = a.xs * a.slab_x, gvimg = a.gvs * a.slab_g, giimg = (a.gis ? a.gis : a.gvs) * a.slab_g;
+        const unsigned char* gibase = sg.st + (a.gis ? a.off_gi : a.off_gv);
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        for (int e = tid; e < total; e += nt) {
+            Item p;
+            p.pl = e / per;
+            es.decode(e - p.pl * per, p);
+            const unsigned char* x_p = sg.st + (size_t)p.pl * ximg;
+            const unsigned char* gv_p = sg.st + a.off_gv + (size_t)p.pl * gvimg;
+            const unsigned char* gi_p = gibase + (size_t)p.pl * giimg;
+            const int oa = sg.a0 + p.a - a.lbA, ob = p.b - a.lbB, oj0 = p.cg * V - a.lbL;
+            const bool row_ok = ob >= 0 && ob < a.OB && (DIM < 3 || (oa >= 0 && oa < a.OA));
+            float o[V];
+            if (!row_ok || oj0 + V <= 0 || oj0 >= a.OL) {
+#pragma unroll
+                for (int t = 0; t < V; ++t) o[t] = 0.f;
+                __stcs((uint4*)item_dst(a, sg, p), Pack<ST>::pack(o));
+                continue;
+            }
+            bool okc[V];
+#pragma unroll
+            for (int t = 0; t < V; ++t) okc[t] = oj0 + t >= 0 && oj0 + t < a.OL;
+            // gv: unshifted grad, zero outside the crop (slot p.a of the gv region holds output slab oa)
+            float gv[V];
+            load_window_edge<ST, V>(gv_p, (DIM == 3 ? p.a * a.OB : 0) + ob, a.OL, oj0, TS_PAD_ZEROS, gv);
+            // ---- grad_weight terms ----
+            const bool xok0 = DIM < 3 || x_slot_slab(a, us, sg.a0, p.a) >= 0;
+            const bool xok1 = DIM < 3 || x_slot_slab(a, us, sg.a0, p.a + 1) >= 0;
+            float X[NR][NVW];
+#pragma unroll
+            for (int rv = 0; rv < NR; ++rv)
+                load_window_edge<ST, NVW>(x_p, edge_row<DIM>(p.a, xok1, xok0, p.b - us.sx[1], rv, a.B, pad), a.L, p.cg * V - us.sx[2], pad, X[rv]);
+#pragma unroll
+            for (int t = 0; t < V; ++t) {
+                float v[8], wg[3];
+                neighbours_from_rows<DIM, NVW>(X, t, v);
+                weight_partials_fast<DIM>(v, d, wg);
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) ts[k] += okc[t] ? gv[t] * wg[k] : 0.f;
+            }
+            // ---- grad_input ----
+            const bool gok0 = DIM < 3 || gi_slot_slab(a, us, sg.a0, p.a) >= 0;
+            if (ACTIVE) {
+                const bool gok1 = DIM < 3 || gi_slot_slab(a, us, sg.a0, p.a + 1) >= 0;
+                float Gw[NR][NVW];
+#pragma unroll
+                for (int rv = 0; rv < NR; ++rv)
+                    load_window_edge<ST, NVW>(gi_p, edge_row<DIM>(p.a, gok1, gok0, ob - us.sg[1], rv, a.OB, pad), a.OL, oj0 - us.sg[2], pad, Gw[rv]);
+#pragma unroll
+                for (int t = 0; t < V; ++t) {
+                    float v[8];
+                    neighbours_from_rows<DIM, NVW>(Gw, t, v);
+                    o[t] = okc[t] ? interpolate<float, DIM>(v, d) : 0.f;
+                }
+            } else {
+                int row = 0;
+                if (DIM >= 2) {
+                    const int r = axis_index(ob + us.sg[1], a.OB, pad);
+                    row = (gok0 && r >= 0) ? (DIM == 3 ? p.a * a.OB : 0) + r : -1;
+                }
+                float Gs[V];
+                load_window_edge<ST, V>(gi_p, row, a.OL, oj0 + us.sg[2], pad, Gs);
+#pragma unroll
+                for (int t = 0; t < V; ++t) o[t] = okc[t] ? Gs[t] : 0.f;
+            }
+            __stcs((uint4*)item_dst(a, sg, p), Pack<ST>::pack(o));
+        }
+    }
+
+    TS_D void step(const Stage& sg) {
+        int a_lo, a_hi;
+        slab_range(sg, a_lo, a_hi);
+        float ts[DIM];
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) ts[k] = 0.f;
+        const int ws = (pmod(-us.sx[2] * ES, 16)) >> 2;
+        switch (ws) {
+        case 0: interior<0>(sg, a_lo, a_hi, ts); break;
+        case 1: interior<1>(sg, a_lo, a_hi, ts); break;
+        case 2: interior<2>(sg, a_lo, a_hi, ts); break;
+        default: interior<3>(sg, a_lo, a_hi, ts); break;
+        }
+        edges(sg, a_lo, a_hi, ts);
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) acc[k] += (double)ts[k];   // fp32 inside a stage, fp64 across stages
     }
 };
 
 // ---- kernels -----------------------------------------------------------------------------------
-constexpr int MAXT_GATHER = 1024, MAXT_ARITH = 544;
-
-template <int MAXT>
 TS_D void setup_barriers(const SArgs& a, unsigned char* smem, uint64_t*& full, uint64_t*& empty) {
     full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
     empty = full + a.stages;
@@ -492,32 +979,32 @@ template <int G, int ES>
 __global__ void __launch_bounds__(MAXT_GATHER, 1) k_staged_gather(const __grid_constant__ SArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    setup_barriers<MAXT_GATHER>(a, smem, full, empty);
+    setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
     GatherBody<G, ES> body(a, threadIdx.x, a.nw * 32);
     consumer_loop(a, smem, full, empty, lane, body);
 }
 
-template <int DIM>
+template <typename ST, int DIM>
 __global__ void __launch_bounds__(MAXT_ARITH, 1) k_staged_active_forward(const __grid_constant__ SArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    setup_barriers<MAXT_ARITH>(a, smem, full, empty);
+    setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
-    ActiveFwdBody<DIM> body(a, threadIdx.x, a.nw * 32);
+    ActiveFwdBody<ST, DIM> body(a, threadIdx.x, a.nw * 32);
     consumer_loop(a, smem, full, empty, lane, body);
 }
 
-template <int DIM, bool ACTIVE>
+template <typename ST, int DIM, bool ACTIVE>
 __global__ void __launch_bounds__(MAXT_ARITH, 1) k_staged_backward(const __grid_constant__ SArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    setup_barriers<MAXT_ARITH>(a, smem, full, empty);
+    setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
-    BackwardBody<DIM, ACTIVE> body(a, threadIdx.x, a.nw * 32, wid, lane);
+    BackwardBody<ST, DIM, ACTIVE> body(a, threadIdx.x, a.nw * 32, wid, lane);
     consumer_loop(a, smem, full, empty, lane, body);
 }
 
@@ -530,50 +1017,63 @@ int launch(K kernel, const SArgs& a, const StagedPlan& p, cudaStream_t s) {
     return check_launch();
 }
 
-SArgs make_args(const Geo& g, const StagedPlan& p, int mode, int es) {
+long long round_up(long long v, long long q) { return (v + q - 1) / q * q; }
+
+SArgs make_args(const Geo& g, const StagedPlan& p, int mode, int active, int es) {
     SArgs a;
     memset(&a, 0, sizeof(a));
     a.g = g;
     a.es = es;
-    a.xpb = (int)(g.in_plane * es);
-    a.gpb = mode == 2 ? (int)(g.out_plane * es) : 0;
-    a.np = p.planes_per_step;
-    a.stages = p.stages;
-    a.nw = p.warps;
-    a.stage_stride = (int)((p.smem_bytes - 2 * 8 * p.stages) / p.stages);
-    a.n_per_unit = p.n_per_unit;
-    a.units = p.units;
+    a.mode = mode;
+    a.active = active;
     const int d = g.dim;
     a.A = d == 3 ? g.S[0] : 1;        a.OA = d == 3 ? g.OS[0] : 1;      a.lbA = d == 3 ? g.lb[0] : 0;
     a.B = d >= 2 ? g.S[d - 2] : 1;    a.OB = d >= 2 ? g.OS[d - 2] : 1;  a.lbB = d >= 2 ? g.lb[d - 2] : 0;
     a.L = g.S[d - 1];                 a.OL = g.OS[d - 1];               a.lbL = g.lb[d - 1];
-    const int vec = p.vec_bytes / es;
-    if (mode == 2) {                  // items tile the INPUT plane
-        a.gpr = a.L / vec;
-        a.ipp = a.A * a.B * a.gpr;
-        a.d_rows = make_fastdiv((unsigned)a.B);
-    } else {                          // items tile the OUTPUT plane
-        a.gpr = a.OL / vec;
-        a.ipp = a.OA * a.OB * a.gpr;
-        a.d_rows = make_fastdiv((unsigned)a.OB);
-    }
-    a.d_ipp = make_fastdiv((unsigned)a.ipp);
-    a.d_gpr = make_fastdiv((unsigned)a.gpr);
+    a.IA = mode == 2 ? a.A : a.OA;
+    a.IB = mode == 2 ? a.B : a.OB;
+    a.VB = p.vec_bytes;
+    a.V = p.vec_bytes / es;
+    a.gpr = (mode == 2 ? a.L : a.OL) / a.V;
+    a.GP = p.gp;
+    a.TA = p.ta;
+    a.tiles = p.tiles;
+    a.xs = p.xs; a.gvs = p.gvs; a.gis = p.gis;
+    a.slab_x = (int)((long long)a.B * a.L * es);
+    a.slab_g = (int)((long long)a.OB * a.OL * es);
+    a.np = p.planes_per_step;
+    a.stages = p.stages;
+    a.stage_stride = p.stage_stride;
+    a.nw = p.warps;
+    a.n_per_unit = p.n_per_unit;
+    a.units = p.units;
+    a.off_gv = p.off_gv;
+    a.off_gi = p.off_gi;
+    a.img_items = a.TA * a.IB * a.GP;
+    a.img_stride = g.C * (mode == 2 ? g.in_plane : g.out_plane) * es;
+    a.d_img = make_fastdiv((unsigned)a.img_items);
+    a.d_GP = make_fastdiv((unsigned)a.GP);
+    a.d_IB = make_fastdiv((unsigned)a.IB);
     return a;
 }
 
 }  // namespace
 
 // ---- planning -----------------------------------------------------------------------------------
-StagedPlan plan_staged(const Geo& g, int mode, int esize, int dtype, bool dense_x, const void* x, const void* y_or_gi,
+StagedPlan plan_staged(const Geo& g, int mode, int active, int esize, int dtype, bool dense_x, const void* x, const void* y_or_gi,
                        const void* grad, int sm_count) {
     StagedPlan p;
     memset(&p, 0, sizeof(p));
     p.ok = false;
     if (!dense_x || g.N * g.C == 0 || g.in_plane == 0 || g.out_plane == 0) return p;
-    if (mode != 0 && dtype != TS_F32) return p;                    // arithmetic kernels: fp32 only (so far)
-    if (mode != 0) esize = 4;
+    if (mode != 0) {
+        if (dtype != TS_F32 && dtype != TS_F16 && dtype != TS_BF16) return p;     // fp64 arithmetic: generic family
+        esize = dtype == TS_F32 ? 4 : 2;
+    }
+    if (g.N >= (1ll << 31) || g.C >= (1ll << 31)) return p;
     const int d = g.dim;
+    const int A = d == 3 ? g.S[0] : 1, OA = d == 3 ? g.OS[0] : 1;
+    const long long B = d >= 2 ? g.S[d - 2] : 1, OB = d >= 2 ? g.OS[d - 2] : 1;
     const long long Lb = (long long)g.S[d - 1] * esize, OLb = (long long)g.OS[d - 1] * esize;
     int vb = 0;
     if (mode == 0) {
@@ -581,60 +1081,100 @@ StagedPlan plan_staged(const Geo& g, int mode, int esize, int dtype, bool dense_
             if (cand >= esize && Lb % cand == 0 && OLb % cand == 0) { vb = cand; break; }
     } else if (Lb % 16 == 0 && OLb % 16 == 0) vb = 16;
     if (!vb) return p;
-    const long long xpb = g.in_plane * esize, gpb = mode == 2 ? g.out_plane * esize : 0;
-    if (xpb % 16 || gpb % 16) return p;
+    const long long slab_x = B * Lb, slab_g = OB * OLb;
+    if (slab_x % 16 || (mode == 2 && slab_g % 16)) return p;                      // bulk copies: 16-byte granules
+    if (slab_x >= (1 << 20) || slab_g >= (1 << 20)) return p;
     if (((uintptr_t)x & 15) || ((uintptr_t)grad & 15) || ((uintptr_t)y_or_gi & (uintptr_t)(vb - 1))) return p;
-    if ((g.out_plane * esize) % vb) return p;
 
     const Tuning& t = tuning();
-    int stages = t.stages, ctas = t.ctas_per_sm, warps = t.warps;
-    const int max_warps = mode == 0 ? 31 : 16;
-    if (warps > max_warps) warps = max_warps;
-    const long long per_plane = xpb + gpb;
-    const long long budget_cta = SMEM_LIMIT / ctas - 1024;
-    if (per_plane + 2 * GUARD > budget_cta / 2) {                  // cannot even double-buffer one plane
-        if (ctas > 1) { ctas = 1; }
-        if (per_plane + 2 * GUARD > (long long)(SMEM_LIMIT - 1024) / 2) return p;
+    const int IA = mode == 2 ? A : OA;
+    const long long IB = mode == 2 ? B : OB;
+    const int ex = mode != 0 ? 1 : 0;                       // +1 neighbour slab for the arithmetic kernels
+    const long long budget = SMEM_LIMIT - 1024;
+    // bytes of one image's slots for a tile of `ta` slabs
+    auto slots = [&](long long ta, int* xs, int* gvs, int* gis) {
+        const int x_ = (int)(d == 3 ? ta + ex : 1);
+        int gv_ = 0, gi_ = 0;
+        if (mode == 2) {
+            gv_ = (int)(d == 3 ? ta : 1);
+            gi_ = d == 3 ? (int)(active ? ta + 1 : ta) : 0;  // 1-D / 2-D: grad_input reads the same grad plane
+        }
+        if (xs) { *xs = x_; *gvs = gv_; *gis = gi_; }
+        return x_ * slab_x + (gv_ + gi_) * slab_g;
+    };
+    int stages = t.stages;
+    long long TA = IA;
+    const long long stage_target = (long long)t.stage_kb * 1024;
+    // shrink the slab tile until it meets the stage target (or is a single slab) and double-buffers
+    for (;;) {
+        const long long need = round_up(slots(TA, nullptr, nullptr, nullptr) + 2 * GUARD, 128);
+        if (need * 2 + 64 <= budget && (need <= stage_target * 2 || TA == 1)) break;
+        if (TA > 1) TA = (TA + 1) / 2;
+        else return p;                                        // not even one slab (+ neighbours) double-buffers: generic family
     }
-    const long long budget = SMEM_LIMIT / ctas - 1024;
-    long long np = ((long long)t.stage_kb * 1024) / per_plane;
-    if (np < 1) np = 1;
-    if (np > g.N) np = g.N;
-    auto stride_of = [&](long long n) { return ((n * per_plane + 2 * GUARD + 127) / 128) * 128; };
-    for (;;) {                                                     // shrink until the ring fits
-        if (stages * stride_of(np) + 16 * stages <= budget) break;
+    const int tiles = (int)((IA + TA - 1) / TA);
+    int xs, gvs, gis;
+    const long long per_image = slots(TA, &xs, &gvs, &gis);
+    long long np = 1;
+    if (tiles == 1) {
+        np = stage_target / per_image;
+        if (np < 1) np = 1;
+        if (np > g.N) np = g.N;
+    }
+    auto stride_of = [&](long long n) { return round_up(n * per_image + 2 * GUARD, 128); };
+    for (;;) {
+        if (stages * stride_of(np) + 16 * stages + 64 <= budget) break;
         if (np > 1) --np;
         else if (stages > 2) --stages;
         else return p;
     }
+    if (np * per_image >= (1 << 20)) return p;                // mbarrier tx-count range
+
+    // padded row length of the item index space (see ts_tma.cu)
+    const int gpr = (int)((mode == 2 ? Lb : OLb) / vb);
+    int GP = gpr;
+    if (gpr % 8 != 0 && (double)gpr / (double)((gpr + 7) / 8 * 8) >= 0.85) GP = (gpr + 7) / 8 * 8;
+    const long long img_items = TA * IB * GP;
+    if (np * img_items >= 0x7fffffffLL) return p;
+    if ((long long)xs * slab_x * np >= 0x7fffffffLL) return p;
 
     const long long planes = g.N * g.C;
-    const long long grid_max = (long long)sm_count * ctas;
+    const long long grid_max = (long long)sm_count;
     long long npu = t.chunk_planes > 0 ? t.chunk_planes : planes / (grid_max * 32);
     npu = (npu / np) * np;
     if (npu < np) npu = np;
     if (npu > g.N) npu = g.N;
     const long long chunks = (g.N + npu - 1) / npu;
     const long long units = chunks * g.C;
+    int warps = t.warps;
+    const int max_warps = (mode == 0 ? MAXT_GATHER : MAXT_ARITH) / 32 - 1;
+    if (warps > max_warps) warps = max_warps;
     if (units > 0x7fffffffLL || chunks * warps > 0x7fffffffLL) return p;
 
     p.ok = true;
     p.vec_bytes = vb;
     p.planes_per_step = (int)np;
     p.stages = stages;
+    p.stage_stride = (int)stride_of(np);
     p.warps = warps;
     p.n_per_unit = (int)npu;
     p.units = (int)units;
     p.grid = (int)(units < grid_max ? units : grid_max);
     p.slots = (int)(chunks * warps);
-    p.smem_bytes = (size_t)(stages * stride_of(np) + 16 * stages);
+    p.ta = (int)TA;
+    p.tiles = tiles;
+    p.xs = xs; p.gvs = gvs; p.gis = gis;
+    p.gp = GP;
+    p.off_gv = (int)(np * xs * slab_x);
+    p.off_gi = (int)(np * xs * slab_x + np * gvs * slab_g);
+    p.smem_bytes = (size_t)(stages * stride_of(np) + 16 * stages + 64);
     return p;
 }
 
 // ---- launchers ----------------------------------------------------------------------------------
 int staged_gather(const Geo& g, const StagedPlan& p, int wk, const void* x, void* y, unsigned long long fill, int esize,
                   const void* w, int qkind, long long wzp, cudaStream_t s) {
-    SArgs a = make_args(g, p, 0, esize);
+    SArgs a = make_args(g, p, 0, 0, esize);
     a.x = (const unsigned char*)x;
     a.out = (unsigned char*)y;
     a.w = w;
@@ -652,37 +1192,62 @@ int staged_gather(const Geo& g, const StagedPlan& p, int wk, const void* x, void
     return TS_ERR_UNSUPPORTED;
 }
 
-int staged_active_forward(const Geo& g, const StagedPlan& p, const void* x, const void* w, void* y, cudaStream_t s) {
-    SArgs a = make_args(g, p, 1, 4);
-    a.x = (const unsigned char*)x;
-    a.out = (unsigned char*)y;
-    a.w = w;
+template <typename ST>
+static int active_forward_t(const Geo& g, const SArgs& a, const StagedPlan& p, cudaStream_t s) {
     switch (g.dim) {
-    case 1: return launch(k_staged_active_forward<1>, a, p, s);
-    case 2: return launch(k_staged_active_forward<2>, a, p, s);
-    default: return launch(k_staged_active_forward<3>, a, p, s);
+    case 1: return launch(k_staged_active_forward<ST, 1>, a, p, s);
+    case 2: return launch(k_staged_active_forward<ST, 2>, a, p, s);
+    default: return launch(k_staged_active_forward<ST, 3>, a, p, s);
     }
 }
 
-int staged_backward(const Geo& g, const StagedPlan& p, int active, const void* grad, const void* x, const void* w,
+int staged_active_forward(const Geo& g, const StagedPlan& p, int dtype, const void* x, const void* w, void* y, cudaStream_t s) {
+    SArgs a = make_args(g, p, 1, 1, dtype == TS_F32 ? 4 : 2);
+    a.x = (const unsigned char*)x;
+    a.out = (unsigned char*)y;
+    a.w = w;
+    a.wk = dtype == TS_F32 ? WK_F32 : dtype == TS_F16 ? WK_F16 : WK_BF16;
+    switch (dtype) {
+    case TS_F32: return active_forward_t<float>(g, a, p, s);
+    case TS_F16: return active_forward_t<__half>(g, a, p, s);
+    default: return active_forward_t<__nv_bfloat16>(g, a, p, s);
+    }
+}
+
+template <typename ST>
+static int backward_t(const Geo& g, const SArgs& a, const StagedPlan& p, int active, cudaStream_t s) {
+    switch (g.dim * 2 + (active ? 1 : 0)) {
+    case 2: return launch(k_staged_backward<ST, 1, false>, a, p, s);
+    case 3: return launch(k_staged_backward<ST, 1, true>, a, p, s);
+    case 4: return launch(k_staged_backward<ST, 2, false>, a, p, s);
+    case 5: return launch(k_staged_backward<ST, 2, true>, a, p, s);
+    case 6: return launch(k_staged_backward<ST, 3, false>, a, p, s);
+    default: return launch(k_staged_backward<ST, 3, true>, a, p, s);
+    }
+}
+
+int staged_backward(const Geo& g, const StagedPlan& p, int dtype, int active, const void* grad, const void* x, const void* w,
                     void* gi, void* gw, double* partials, cudaStream_t s) {
-    SArgs a = make_args(g, p, 2, 4);
+    SArgs a = make_args(g, p, 2, active ? 1 : 0, dtype == TS_F32 ? 4 : 2);
     a.x = (const unsigned char*)x;
     a.grad = (const unsigned char*)grad;
     a.out = (unsigned char*)gi;
     a.w = w;
+    a.wk = dtype == TS_F32 ? WK_F32 : dtype == TS_F16 ? WK_F16 : WK_BF16;
     a.partials = partials;
     int rc;
-    switch (g.dim * 2 + (active ? 1 : 0)) {
-    case 2: rc = launch(k_staged_backward<1, false>, a, p, s); break;
-    case 3: rc = launch(k_staged_backward<1, true>, a, p, s); break;
-    case 4: rc = launch(k_staged_backward<2, false>, a, p, s); break;
-    case 5: rc = launch(k_staged_backward<2, true>, a, p, s); break;
-    case 6: rc = launch(k_staged_backward<3, false>, a, p, s); break;
-    default: rc = launch(k_staged_backward<3, true>, a, p, s); break;
+    switch (dtype) {
+    case TS_F32: rc = backward_t<float>(g, a, p, active, s); break;
+    case TS_F16: rc = backward_t<__half>(g, a, p, active, s); break;
+    default: rc = backward_t<__nv_bfloat16>(g, a, p, active, s); break;
     }
     if (rc != TS_OK) return rc;
-    return launch_reduce_partials<float>(partials, p.slots, (int)(g.C * g.dim), gw, s);
+    const int outputs = (int)(g.C * g.dim);
+    switch (dtype) {
+    case TS_F32: return launch_reduce_partials<float>(partials, p.slots, outputs, gw, s);
+    case TS_F16: return launch_reduce_partials<__half>(partials, p.slots, outputs, gw, s);
+    default: return launch_reduce_partials<__nv_bfloat16>(partials, p.slots, outputs, gw, s);
+    }
 }
 
 }  // namespace ts

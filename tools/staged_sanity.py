@@ -23,9 +23,13 @@ dev = torch.device("cuda:0")
 fn = {1: F.shift1d_func, 2: F.shift2d_func, 3: F.shift3d_func}
 fails, ran, skipped = [], 0, 0
 quick = "--quick" in sys.argv
+TUNING = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--tuning=")), None)
+if TUNING:
+    assert lib.ts_set_tuning(TUNING.encode()) == 0, TUNING
 FORCED = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--path=")), 2)
 
-shapes = [(3, 5, 64), (2, 4, 40), (2, 3, 12, 16), (3, 4, 8, 8), (2, 6, 28, 28), (2, 3, 4, 6, 8), (1, 2, 3, 5, 4), (5, 7, 1, 16), (9, 2, 4, 12), (37, 3, 8, 8)]
+shapes = [(3, 5, 64), (2, 4, 40), (2, 3, 12, 16), (3, 4, 8, 8), (2, 6, 28, 28), (2, 3, 4, 6, 8), (1, 2, 3, 5, 4), (5, 7, 1, 16), (9, 2, 4, 12), (37, 3, 8, 8),
+          (2, 3, 7, 6, 16), (1, 2, 1, 6, 8), (2, 2, 5, 1, 8), (3, 2, 1040)]
 if quick:
     shapes = shapes[:5]
 rng = np.random.default_rng(0)
