@@ -39,7 +39,7 @@ namespace {
 
 constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
 constexpr int GUARD = 32;            // readable slack around the slabs of a stage (second group of a window pair)
-constexpr int MAXT_GATHER = 1024, MAXT_ARITH = 544;
+constexpr int MAXT_GATHER = 1024, MAXT_ARITH = 512;   // 512 threads -> 128 registers per thread
 
 // ---- exact division by a launch-invariant (n < 2^31) ------------------------------------------
 struct FastDiv { unsigned m, l, d; };
@@ -270,7 +270,6 @@ TS_D void consumer_loop(const SArgs& a, unsigned char* smem, uint64_t* full, uin
 
 // item of the padded index space -> (image, tile-local slab, row, group)
 struct Item { int pl, a, b, cg; };
-template <bool SLABS>
 TS_D void decode_item(const SArgs& a, int item, Item& p) {
     p.pl = 0;
     int rem = item;
@@ -279,11 +278,15 @@ TS_D void decode_item(const SArgs& a, int item, Item& p) {
     p.cg = rem - row * a.GP;
     p.a = 0;
     p.b = row;
-    if (SLABS) { p.a = (int)fdiv((unsigned)row, a.d_IB); p.b = row - p.a * a.IB; }
+    if (a.TA > 1) { p.a = (int)fdiv((unsigned)row, a.d_IB); p.b = row - p.a * a.IB; }
 }
+// np * img_stride < 2^31 (plan_staged), so the offset inside a stage's destination fits 32 bits
 TS_D unsigned char* item_dst(const SArgs& a, const Stage& sg, const Item& p) {
-    return sg.dst + p.pl * a.img_stride + (long long)((p.a * a.IB + p.b) * a.gpr + p.cg) * a.VB;
+    const unsigned off = (unsigned)p.pl * (unsigned)a.img_stride + (unsigned)(((p.a * a.IB + p.b) * a.gpr + p.cg) * a.VB);
+    return sg.dst + off;
 }
+// (unsigned)(v - lo) < (unsigned)(hi - lo)  <=>  lo <= v < hi
+TS_D bool in_range(int v, int lo, int hi) { return (unsigned)(v - lo) < (unsigned)(hi - lo); }
 
 // Interior box of a unit (rows, groups): items inside need no remap / mask.
 struct Interior { int b_lo, b_hi, c_lo, c_hi; };
@@ -295,14 +298,37 @@ TS_D void clamp_range(int& lo, int& hi, int n) {
     if (hi < lo) hi = lo;
 }
 
+// exact n / d for a divisor that is uniform over a unit: one real division per unit, then umulhi
+// (exact for n * d < 2^32; here n < 2^20 items, d < 2^11)
+struct UDiv { unsigned m; int d; };
+TS_D UDiv make_udiv(int d) {
+    UDiv u;
+    u.d = d > 0 ? d : 1;
+    u.m = u.d == 1 ? 0u : (unsigned)(0xFFFFFFFFu / (unsigned)u.d) + 1u;
+    return u;
+}
+TS_D int udiv(int n, const UDiv& u) { return u.d == 1 ? n : (int)__umulhi((unsigned)n, u.m); }
+
 // compact enumeration of the items OUTSIDE the interior box of a tile:
 //   E1: every slab, every row, edge groups            E2: every slab, edge rows, interior groups
 //   E3: edge slabs, interior rows, interior groups
 struct EdgeSets {
-    int a_lo, a_hi, b_lo, b_hi, c_lo, c_hi;   // interior box in tile coordinates
-    int A, B, G;                              // tile extents (valid slabs, rows, groups)
-    int n1, n2, n3;                           // set sizes per image
-    TS_D void init() {
+    int b_lo, b_hi, c_lo, c_hi;               // interior box (rows, groups): per unit
+    int B, G;                                 // rows, groups of the iteration space
+    UDiv d_ce, d_ci, d_be, d_bi, d_B;
+    int a_lo, a_hi, A;                        // interior slabs / valid slabs of the tile: per stage
+    int n1, n2, n3;                           // set sizes per image (per stage)
+    TS_D void init_unit(const Interior& in, int rows, int groups) {
+        b_lo = in.b_lo; b_hi = in.b_hi; c_lo = in.c_lo; c_hi = in.c_hi;
+        B = rows; G = groups;
+        d_ce = make_udiv(c_lo + (G - c_hi));
+        d_ci = make_udiv(c_hi - c_lo);
+        d_be = make_udiv(b_lo + (B - b_hi));
+        d_bi = make_udiv(b_hi - b_lo);
+        d_B = make_udiv(B);
+    }
+    TS_D void init_stage(int alo, int ahi, int an) {
+        a_lo = alo; a_hi = ahi; A = an;
         const int ce = c_lo + (G - c_hi), ci = c_hi - c_lo;
         const int be = b_lo + (B - b_hi), bi = b_hi - b_lo;
         const int ae = a_lo + (A - a_hi);
@@ -313,27 +339,42 @@ struct EdgeSets {
     TS_D int per_image() const { return n1 + n2 + n3; }
     static TS_D int pick(int k, int lo, int hi) { return k < lo ? k : hi + (k - lo); }
     TS_D void decode(int e, Item& p) const {
-        const int ce = c_lo + (G - c_hi), ci = c_hi - c_lo;
         if (e < n1) {
-            const int k = e % ce, r = e / ce;
+            const int r = udiv(e, d_ce), k = e - r * d_ce.d;
             p.cg = pick(k, c_lo, c_hi);
-            p.b = r % B;
-            p.a = r / B;
+            p.a = udiv(r, d_B);
+            p.b = r - p.a * B;
         } else if (e < n1 + n2) {
             e -= n1;
-            const int be = b_lo + (B - b_hi);
-            const int j = e % ci, r = e / ci;
+            const int r = udiv(e, d_ci), j = e - r * d_ci.d;
             p.cg = c_lo + j;
-            p.b = pick(r % be, b_lo, b_hi);
-            p.a = r / be;
+            p.a = udiv(r, d_be);
+            p.b = pick(r - p.a * d_be.d, b_lo, b_hi);
         } else {
             e -= n1 + n2;
-            const int bi = b_hi - b_lo;
-            const int j = e % ci, r = e / ci;
+            const int r = udiv(e, d_ci), j = e - r * d_ci.d;
             p.cg = c_lo + j;
-            p.b = b_lo + r % bi;
-            p.a = pick(r / bi, a_lo, a_hi);
+            const int ka = udiv(r, d_bi);
+            p.b = b_lo + (r - ka * d_bi.d);
+            p.a = pick(ka, a_lo, a_hi);
         }
+    }
+};
+
+// Edge items are few (~10 %), compact (so a warp that has any is full of them) and several times
+// more expensive than interior items: hand them to a DIFFERENT group of warps every stage, so that
+// over the ring depth every consumer warp does the same amount of work.
+struct EdgeRotor {
+    int seq;
+    TS_D EdgeRotor() : seq(0) {}
+    // first edge index of this thread for a stage with `total` edge items
+    TS_D int first(int tid, int nt, int total) {
+        const int span = ((total + 31) >> 5) << 5;
+        const int rot = (int)(((long long)seq * span) % nt);
+        ++seq;
+        int vt = tid - rot;
+        if (vt < 0) vt += nt;
+        return vt;
     }
 };
 
@@ -439,15 +480,34 @@ TS_D void load_window_rt(const unsigned char* region, int e0, float* out) {
     Pack<ST>::template unpack<NV>(w, (byte & 2) * 8, out);
 }
 
-// element-wise window with the padding rule (edge items): row < 0 -> zeros
+// Column part of an edge item's window, shared by all its rows: either fully inside the row (vector
+// loads with a run-time misalignment) or remapped element by element (hoisted out of the row loop).
 template <typename ST, int NV>
-TS_D void load_window_edge(const unsigned char* region, int row, int L, int c0, int pad, float* out) {
+struct EdgeCols {
+    bool inside;
+    int c0;
+    int cols[NV];
+    TS_D void init(int c0_, int L, int pad) {
+        c0 = c0_;
+        inside = c0 >= 0 && c0 + NV <= L;
+        if (!inside) {
 #pragma unroll
-    for (int t = 0; t < NV; ++t) {
-        const int col = axis_index(c0 + t, L, pad);
-        out[t] = (row >= 0 && col >= 0) ? Elem<ST>::ld(((const ST*)region)[row * L + col]) : 0.f;
+            for (int t = 0; t < NV; ++t) cols[t] = axis_index(c0 + t, L, pad);
+        }
     }
-}
+    // row: flat row index inside `region` or -1 (zeros)
+    TS_D void load(const unsigned char* region, int row, int L, float* out) const {
+        if (row < 0) {
+#pragma unroll
+            for (int t = 0; t < NV; ++t) out[t] = 0.f;
+        } else if (inside) {
+            load_window_rt<ST, NV>(region, row * L + c0, out);
+        } else {
+#pragma unroll
+            for (int t = 0; t < NV; ++t) out[t] = cols[t] >= 0 ? Elem<ST>::ld(((const ST*)region)[row * L + cols[t]]) : 0.f;
+        }
+    }
+};
 
 template <int DIM, int NVW>
 TS_D void neighbours_from_rows(const float (*X)[NVW], int t, float* v) {
@@ -504,9 +564,13 @@ struct GatherBody {
     const int tid, nt;
     UnitShift us;
     Interior in;
+    EdgeSets es;
+    EdgeRotor rotor;
     int mb;
+    int R, nchunk;        // rows per strip / strips per column of the interior box (per unit)
+    UDiv d_nchunk;
 
-    TS_D GatherBody(const SArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), mb(0) {}
+    TS_D GatherBody(const SArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), mb(0), R(1), nchunk(1) {}
     TS_D void begin_unit(int c) {
         us = unit_shift(a, c);
         mb = pmod((a.lbL - us.sx[2]) * ES, VB);
@@ -517,6 +581,14 @@ struct GatherBody {
         in.c_lo = ceil_div(us.sx[2] - a.lbL, V);
         in.c_hi = floor_div(a.L - V - a.lbL + us.sx[2], V) + 1;
         clamp_range(in.c_lo, in.c_hi, a.gpr);
+        es.init_unit(in, a.OB, a.gpr);
+        // strips: about three per thread and stage, each at most all interior rows
+        const int ci = in.c_hi - in.c_lo, bi = in.b_hi - in.b_lo;
+        const unsigned items = (unsigned)a.np * (unsigned)a.TA * (unsigned)(bi > 0 ? bi : 0) * (unsigned)(ci > 0 ? ci : 0);   // < 2^31 (plan_staged)
+        R = (int)((items + 3u * (unsigned)nt - 1u) / (3u * (unsigned)nt));
+        R = R < 1 ? 1 : (R > bi ? (bi > 0 ? bi : 1) : R);
+        nchunk = bi > 0 ? (bi + R - 1) / R : 1;
+        d_nchunk = make_udiv(nchunk);
     }
     TS_D void end_unit(int, int) {}
 
@@ -531,73 +603,120 @@ struct GatherBody {
         }
     }
 
+    // Interior pass, strip-mined: a thread owns (image, slab, group, chunk of `R` consecutive rows) and
+    // walks down the rows with two pointer increments per item -- no per-item index decoding.
     template <int WS, bool SUB>
     TS_D void interior(const Stage& sg, int a_lo, int a_hi) const {
-        const int total = sg.npl * a.img_items;
+        const int ci = in.c_hi - in.c_lo, bi = in.b_hi - in.b_lo, ai = a_hi - a_lo;
+        if (ci <= 0 || bi <= 0 || ai <= 0) return;
         const int bs8 = (mb & 3) * 8;
-        const int rowb = a.L * ES;
+        const int rowb = a.L * ES, orowb = a.gpr * VB;
         const int img_bytes = a.xs * a.slab_x;
         const int col0 = (a.lbL - us.sx[2]) * ES - mb;        // aligned byte offset of group 0's window inside its row
         const int rsh = a.lbB - us.sx[1];
-        for (int item = tid; item < total; item += nt) {
+        const int strips = sg.npl * ai * nchunk * ci;
+        for (int sidx = tid; sidx < strips; sidx += nt) {
+            const int r = udiv(sidx, es.d_ci), j = sidx - r * ci;
+            const int r2 = udiv(r, d_nchunk), k = r - r2 * nchunk;
+            int pl = r2, ia = 0;
+            if (ai > 1) { pl = r2 / ai; ia = r2 - pl * ai; }
             Item p;
-            decode_item<true>(a, item, p);
-            if (p.cg < in.c_lo || p.cg >= in.c_hi || p.b < in.b_lo || p.b >= in.b_hi || p.a < a_lo || p.a >= a_hi) continue;
+            p.pl = pl; p.a = a_lo + ia; p.b = in.b_lo + k * R; p.cg = in.c_lo + j;
+            const int bend = p.b + R < in.b_hi ? p.b + R : in.b_hi;
             const unsigned char* src = sg.st + p.pl * img_bytes + (p.a * a.B + p.b + rsh) * rowb + col0 + p.cg * VB;
-            unsigned W[2 * G + 1];
-            if constexpr (G == 4) {
-                const uint4 A = *(const uint4*)src;
-                W[0] = A.x; W[1] = A.y; W[2] = A.z; W[3] = A.w;
-                if (WS > 0 || SUB) { const uint4 Bv = *(const uint4*)(src + 16); W[4] = Bv.x; W[5] = Bv.y; W[6] = Bv.z; W[7] = Bv.w; }
-            } else if constexpr (G == 2) {
-                const uint2 A = *(const uint2*)src;
-                W[0] = A.x; W[1] = A.y;
-                if (WS > 0 || SUB) { const uint2 Bv = *(const uint2*)(src + 8); W[2] = Bv.x; W[3] = Bv.y; }
-            } else {
-                W[0] = *(const unsigned*)src;
-                if (WS > 0 || SUB) W[1] = *(const unsigned*)(src + 4);
-            }
-            W[2 * G] = 0u;
-            unsigned o[G];
-#pragma unroll
-            for (int k = 0; k < G; ++k) o[k] = SUB ? __funnelshift_r(W[k + WS], W[k + WS + 1], bs8) : W[k + WS];
             unsigned char* dst = item_dst(a, sg, p);
-            if constexpr (G == 4) __stcs((uint4*)dst, make_uint4(o[0], o[1], o[2], o[3]));
-            else if constexpr (G == 2) __stcs((uint2*)dst, make_uint2(o[0], o[1]));
-            else __stcs((unsigned*)dst, o[0]);
+            for (int b = p.b; b < bend; ++b, src += rowb, dst += orowb) {
+                unsigned W[2 * G + 1];
+                if constexpr (G == 4) {
+                    const uint4 A = *(const uint4*)src;
+                    W[0] = A.x; W[1] = A.y; W[2] = A.z; W[3] = A.w;
+                    if (WS > 0 || SUB) { const uint4 Bv = *(const uint4*)(src + 16); W[4] = Bv.x; W[5] = Bv.y; W[6] = Bv.z; W[7] = Bv.w; }
+                } else if constexpr (G == 2) {
+                    const uint2 A = *(const uint2*)src;
+                    W[0] = A.x; W[1] = A.y;
+                    if (WS > 0 || SUB) { const uint2 Bv = *(const uint2*)(src + 8); W[2] = Bv.x; W[3] = Bv.y; }
+                } else {
+                    W[0] = *(const unsigned*)src;
+                    if (WS > 0 || SUB) W[1] = *(const unsigned*)(src + 4);
+                }
+                W[2 * G] = 0u;
+                unsigned o[G];
+#pragma unroll
+                for (int q = 0; q < G; ++q) o[q] = SUB ? __funnelshift_r(W[q + WS], W[q + WS + 1], bs8) : W[q + WS];
+                if constexpr (G == 4) __stcs((uint4*)dst, make_uint4(o[0], o[1], o[2], o[3]));
+                else if constexpr (G == 2) __stcs((uint2*)dst, make_uint2(o[0], o[1]));
+                else __stcs((unsigned*)dst, o[0]);
+            }
         }
     }
 
-    TS_D void edges(const Stage& sg, int a_lo, int a_hi) const {
-        EdgeSets es;
-        es.a_lo = a_lo; es.a_hi = a_hi; es.b_lo = in.b_lo; es.b_hi = in.b_hi; es.c_lo = in.c_lo; es.c_hi = in.c_hi;
-        es.A = sg.an; es.B = a.OB; es.G = a.gpr;
-        es.init();
-        const int per = es.per_image(), total = sg.npl * per;
+    // Edge items: rows remapped per item; a window that lies inside its row (edge ROWS) or any
+    // window under zeros padding takes the same aligned-pair load as the interior (zeros: the pad
+    // value is blended in with byte masks); only windows that wrap / reflect / clamp at a row end
+    // are gathered element by element.
+    template <int WS, bool SUB>
+    TS_D void edges(const Stage& sg, int a_lo, int a_hi, int first, int total, int per) const {
         const int pad = a.g.pad;
-        for (int e = tid; e < total; e += nt) {
+        const int bs8 = (mb & 3) * 8;
+        unsigned fillw[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            if (ES == 1) fillw[k] = 0x01010101u * (unsigned)(a.fill & 0xffu);
+            else if (ES == 2) fillw[k] = 0x00010001u * (unsigned)(a.fill & 0xffffu);
+            else if (ES == 4) fillw[k] = (unsigned)a.fill;
+            else fillw[k] = (k & 1) ? (unsigned)(a.fill >> 32) : (unsigned)a.fill;
+        }
+        for (int e = first; e < total; e += nt) {
             Item p;
-            p.pl = e / per;
+            p.pl = a.np > 1 ? e / per : 0;
             es.decode(e - p.pl * per, p);
             const bool slab_ok = x_slot_slab(a, us, sg.a0, p.a) >= 0;     // the producer already applied the slab shift
             const int rb = a.g.dim >= 2 ? axis_index(p.b + a.lbB - us.sx[1], a.B, pad) : 0;
             const int cs = p.cg * V + a.lbL - us.sx[2];
             const unsigned char* slab = sg.st + (size_t)(p.pl * a.xs + p.a) * a.slab_x;
+            const bool inside = cs >= 0 && cs + V <= a.L;
             unsigned o[G];
+            if (!slab_ok || rb < 0 || (pad == TS_PAD_ZEROS && (cs + V <= 0 || cs >= a.L))) {
 #pragma unroll
-            for (int k = 0; k < G; ++k) o[k] = 0u;
+                for (int k = 0; k < G; ++k) o[k] = fillw[k];
+            } else if (inside || pad == TS_PAD_ZEROS) {
+                const unsigned char* src = slab + ((long long)rb * a.L + cs) * ES - mb;       // aligned to VB by construction
+                unsigned W[2 * G + 1];
+                if constexpr (G == 4) {
+                    const uint4 A = *(const uint4*)src, Bv = *(const uint4*)(src + 16);
+                    W[0] = A.x; W[1] = A.y; W[2] = A.z; W[3] = A.w; W[4] = Bv.x; W[5] = Bv.y; W[6] = Bv.z; W[7] = Bv.w;
+                } else if constexpr (G == 2) {
+                    const uint2 A = *(const uint2*)src, Bv = *(const uint2*)(src + 8);
+                    W[0] = A.x; W[1] = A.y; W[2] = Bv.x; W[3] = Bv.y;
+                } else {
+                    W[0] = *(const unsigned*)src; W[1] = *(const unsigned*)(src + 4);
+                }
+                W[2 * G] = 0u;
 #pragma unroll
-            for (int t = 0; t < V; ++t) {
-                const int col = axis_index(cs + t, a.L, pad);
-                const bool ok = slab_ok && rb >= 0 && col >= 0;
-                const unsigned char* ep = slab + ((long long)(ok ? rb : 0) * a.L + (ok ? col : 0)) * ES;
-                if (ES == 1) o[(t / 4) % G] |= (ok ? (unsigned)(*ep) : (unsigned)(a.fill & 0xffu)) << (8 * (t % 4));
-                else if (ES == 2) o[(t / 2) % G] |= (ok ? (unsigned)(*(const unsigned short*)ep) : (unsigned)(a.fill & 0xffffu)) << (16 * (t % 2));
-                else if (ES == 4) o[t % G] = ok ? *(const unsigned*)ep : (unsigned)a.fill;
-                else {
-                    uint2 v = make_uint2((unsigned)a.fill, (unsigned)(a.fill >> 32));
-                    if (ok) v = *(const uint2*)ep;
-                    o[(2 * t) % G] = v.x; o[(2 * t + 1) % G] = v.y;
+                for (int q = 0; q < G; ++q) o[q] = SUB ? __funnelshift_r(W[q + WS], W[q + WS + 1], bs8) : W[q + WS];
+                if (!inside) {          // zeros padding, partially outside: blend the pad value in
+                    const int lo_b = (cs < 0 ? -cs : 0) * ES;
+                    const int hi_b = (a.L - cs < V ? a.L - cs : V) * ES;
+#pragma unroll
+                    for (int k = 0; k < G; ++k) {
+                        int l = lo_b - 4 * k, h = hi_b - 4 * k;
+                        l = l < 0 ? 0 : (l > 4 ? 4 : l);
+                        h = h < 0 ? 0 : (h > 4 ? 4 : h);
+                        const unsigned m = h > l ? ((0xffffffffu >> (8 * (4 - h))) & (0xffffffffu << (8 * l))) : 0u;
+                        o[k] = (o[k] & m) | (fillw[k] & ~m);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < G; ++k) o[k] = 0u;
+#pragma unroll
+                for (int t = 0; t < V; ++t) {
+                    const int col = axis_index(cs + t, a.L, pad);
+                    const unsigned char* ep = slab + ((long long)rb * a.L + col) * ES;
+                    if (ES == 1) o[(t / 4) % G] |= (unsigned)(*ep) << (8 * (t % 4));
+                    else if (ES == 2) o[(t / 2) % G] |= (unsigned)(*(const unsigned short*)ep) << (16 * (t % 2));
+                    else if (ES == 4) o[t % G] = *(const unsigned*)ep;
+                    else { const uint2 v = *(const uint2*)ep; o[(2 * t) % G] = v.x; o[(2 * t + 1) % G] = v.y; }
                 }
             }
             unsigned char* dst = item_dst(a, sg, p);
@@ -607,26 +726,34 @@ struct GatherBody {
         }
     }
 
-    TS_D void step(const Stage& sg) const {
+    template <int WS, bool SUB>
+    TS_D void both(const Stage& sg, int a_lo, int a_hi, int first, int total, int per) const {
+        interior<WS, SUB>(sg, a_lo, a_hi);
+        edges<WS, SUB>(sg, a_lo, a_hi, first, total, per);
+    }
+
+    TS_D void step(const Stage& sg) {
         int a_lo, a_hi;
         slab_range(sg, a_lo, a_hi);
+        es.init_stage(a_lo, a_hi, sg.an);
+        const int per = es.per_image(), total = sg.npl * per;
+        const int first = rotor.first(tid, nt, total);
         const int ws = mb >> 2;
         if ((mb & 3) == 0) {
             switch (ws) {
-            case 0: interior<0, false>(sg, a_lo, a_hi); break;
-            case 1: interior<1 % G, false>(sg, a_lo, a_hi); break;
-            case 2: interior<2 % G, false>(sg, a_lo, a_hi); break;
-            default: interior<3 % G, false>(sg, a_lo, a_hi); break;
+            case 0: both<0, false>(sg, a_lo, a_hi, first, total, per); break;
+            case 1: both<1 % G, false>(sg, a_lo, a_hi, first, total, per); break;
+            case 2: both<2 % G, false>(sg, a_lo, a_hi, first, total, per); break;
+            default: both<3 % G, false>(sg, a_lo, a_hi, first, total, per); break;
             }
         } else {
             switch (ws) {
-            case 0: interior<0, true>(sg, a_lo, a_hi); break;
-            case 1: interior<1 % G, true>(sg, a_lo, a_hi); break;
-            case 2: interior<2 % G, true>(sg, a_lo, a_hi); break;
-            default: interior<3 % G, true>(sg, a_lo, a_hi); break;
+            case 0: both<0, true>(sg, a_lo, a_hi, first, total, per); break;
+            case 1: both<1 % G, true>(sg, a_lo, a_hi, first, total, per); break;
+            case 2: both<2 % G, true>(sg, a_lo, a_hi, first, total, per); break;
+            default: both<3 % G, true>(sg, a_lo, a_hi, first, total, per); break;
             }
         }
-        edges(sg, a_lo, a_hi);
     }
 };
 
@@ -639,6 +766,8 @@ struct ActiveFwdBody {
     const int tid, nt;
     UnitShift us;
     Interior in;
+    EdgeSets es;
+    EdgeRotor rotor;
     bool any_interior;
 
     TS_D ActiveFwdBody(const SArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), any_interior(false) {}
@@ -655,6 +784,7 @@ struct ActiveFwdBody {
         // a size-1 axis ignores its shift and its +1 neighbour is the element itself: edge path only
         any_interior = a.L > 1 && (DIM < 2 || a.B > 1) && (DIM < 3 || a.A > 1);
         if (!any_interior) in.b_hi = in.b_lo = in.c_hi = in.c_lo = 0;
+        es.init_unit(in, a.OB, a.gpr);
     }
     TS_D void end_unit(int, int) {}
 
@@ -678,8 +808,8 @@ struct ActiveFwdBody {
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
         for (int item = tid; item < total; item += nt) {
             Item p;
-            decode_item<DIM == 3>(a, item, p);
-            if (p.cg < in.c_lo || p.cg >= in.c_hi || p.b < in.b_lo || p.b >= in.b_hi || p.a < a_lo || p.a >= a_hi) continue;
+            decode_item(a, item, p);
+            if (!(in_range(p.cg, in.c_lo, in.c_hi) && in_range(p.b, in.b_lo, in.b_hi) && in_range(p.a, a_lo, a_hi))) continue;
             const unsigned char* img = sg.st + p.pl * img_bytes;
             const int row0 = p.a * a.B + p.b + rsh;
             float X[NR][NVW];
@@ -696,26 +826,23 @@ struct ActiveFwdBody {
         }
     }
 
-    TS_D void edges(const Stage& sg, int a_lo, int a_hi) const {
-        EdgeSets es;
-        es.a_lo = a_lo; es.a_hi = a_hi; es.b_lo = in.b_lo; es.b_hi = in.b_hi; es.c_lo = in.c_lo; es.c_hi = in.c_hi;
-        es.A = sg.an; es.B = a.OB; es.G = a.gpr;
-        es.init();
+    TS_D void edges(const Stage& sg, int a_lo, int a_hi) {
+        es.init_stage(a_lo, a_hi, sg.an);
         const int per = es.per_image(), total = sg.npl * per;
         const int pad = a.g.pad;
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
-        for (int e = tid; e < total; e += nt) {
+        for (int e = rotor.first(tid, nt, total); e < total; e += nt) {
             Item p;
-            p.pl = e / per;
+            p.pl = a.np > 1 ? e / per : 0;
             es.decode(e - p.pl * per, p);
             const unsigned char* img = sg.st + (size_t)p.pl * a.xs * a.slab_x;
-            const int cs = p.cg * V + a.lbL - us.sx[2];
             const bool ok0 = DIM < 3 || x_slot_slab(a, us, sg.a0, p.a) >= 0;
             const bool ok1 = DIM < 3 || x_slot_slab(a, us, sg.a0, p.a + 1) >= 0;
+            EdgeCols<ST, NVW> xc;
+            xc.init(p.cg * V + a.lbL - us.sx[2], a.L, pad);
             float X[NR][NVW];
 #pragma unroll
-            for (int rv = 0; rv < NR; ++rv)
-                load_window_edge<ST, NVW>(img, edge_row<DIM>(p.a, ok1, ok0, p.b + a.lbB - us.sx[1], rv, a.B, pad), a.L, cs, pad, X[rv]);
+            for (int rv = 0; rv < NR; ++rv) xc.load(img, edge_row<DIM>(p.a, ok1, ok0, p.b + a.lbB - us.sx[1], rv, a.B, pad), a.L, X[rv]);
             float o[V];
 #pragma unroll
             for (int t = 0; t < V; ++t) {
@@ -727,7 +854,7 @@ struct ActiveFwdBody {
         }
     }
 
-    TS_D void step(const Stage& sg) const {
+    TS_D void step(const Stage& sg) {
         int a_lo, a_hi;
         slab_range(sg, a_lo, a_hi);
         const int ws = (pmod((a.lbL - us.sx[2]) * ES, 16)) >> 2;
@@ -750,6 +877,8 @@ struct BackwardBody {
     const int tid, nt, wid, lane;
     UnitShift us;
     Interior in;
+    EdgeSets es;
+    EdgeRotor rotor;
     bool any_interior;
     double acc[DIM];
 
@@ -787,6 +916,7 @@ struct BackwardBody {
         // the fast path needs the unshifted grad window 16-byte aligned and no size-1 axis
         any_interior = (a.lbL * ES) % 16 == 0 && a.L > 1 && (DIM < 2 || a.B > 1) && (DIM < 3 || a.A > 1);
         if (!any_interior) in.b_hi = in.b_lo = in.c_hi = in.c_lo = 0;
+        es.init_unit(in, a.B, a.gpr);
     }
     // one partial per (unit, consumer warp): fixed shuffle tree, no atomics
     TS_D void end_unit(int c, int chunk) {
@@ -828,8 +958,8 @@ struct BackwardBody {
         const int xrsh = DIM >= 2 ? -us.sx[1] : 0;
         for (int item = tid; item < total; item += nt) {
             Item p;
-            decode_item<DIM == 3>(a, item, p);
-            if (p.cg < in.c_lo || p.cg >= in.c_hi || p.b < in.b_lo || p.b >= in.b_hi || p.a < a_lo || p.a >= a_hi) continue;
+            decode_item(a, item, p);
+            if (!(in_range(p.cg, in.c_lo, in.c_hi) && in_range(p.b, in.b_lo, in.b_hi) && in_range(p.a, a_lo, a_hi))) continue;
             const unsigned char* x_p = sg.st + p.pl * ximg;
             const unsigned char* gv_p = sg.st + a.off_gv + p.pl * gvimg;
             const unsigned char* gi_p = gibase + p.pl * giimg;
@@ -869,19 +999,16 @@ struct BackwardBody {
         }
     }
 
-    TS_D void edges(const Stage& sg, int a_lo, int a_hi, float* ts) const {
-        EdgeSets es;
-        es.a_lo = a_lo; es.a_hi = a_hi; es.b_lo = in.b_lo; es.b_hi = in.b_hi; es.c_lo = in.c_lo; es.c_hi = in.c_hi;
-        es.A = sg.an; es.B = a.B; es.G = a.gpr;
-        es.init();
+    TS_D void edges(const Stage& sg, int a_lo, int a_hi, float* ts) {
+        es.init_stage(a_lo, a_hi, sg.an);
         const int per = es.per_image(), total = sg.npl * per;
         const int pad = a.g.pad;
         const int ximg = a.xs * a.slab_x, gvimg = a.gvs * a.slab_g, giimg = (a.gis ? a.gis : a.gvs) * a.slab_g;
         const unsigned char* gibase = sg.st + (a.gis ? a.off_gi : a.off_gv);
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
-        for (int e = tid; e < total; e += nt) {
+        for (int e = rotor.first(tid, nt, total); e < total; e += nt) {
             Item p;
-            p.pl = e / per;
+            p.pl = a.np > 1 ? e / per : 0;
             es.decode(e - p.pl * per, p);
             const unsigned char* x_p = sg.st + (size_t)p.pl * ximg;
             const unsigned char* gv_p = sg.st + a.off_gv + (size_t)p.pl * gvimg;
@@ -900,14 +1027,21 @@ struct BackwardBody {
             for (int t = 0; t < V; ++t) okc[t] = oj0 + t >= 0 && oj0 + t < a.OL;
             // gv: unshifted grad, zero outside the crop (slot p.a of the gv region holds output slab oa)
             float gv[V];
-            load_window_edge<ST, V>(gv_p, (DIM == 3 ? p.a * a.OB : 0) + ob, a.OL, oj0, TS_PAD_ZEROS, gv);
+            {
+                EdgeCols<ST, V> gc;
+                gc.init(oj0, a.OL, TS_PAD_ZEROS);
+                gc.load(gv_p, (DIM == 3 ? p.a * a.OB : 0) + ob, a.OL, gv);
+            }
             // ---- grad_weight terms ----
             const bool xok0 = DIM < 3 || x_slot_slab(a, us, sg.a0, p.a) >= 0;
             const bool xok1 = DIM < 3 || x_slot_slab(a, us, sg.a0, p.a + 1) >= 0;
             float X[NR][NVW];
+            {
+                EdgeCols<ST, NVW> xc;
+                xc.init(p.cg * V - us.sx[2], a.L, pad);
 #pragma unroll
-            for (int rv = 0; rv < NR; ++rv)
-                load_window_edge<ST, NVW>(x_p, edge_row<DIM>(p.a, xok1, xok0, p.b - us.sx[1], rv, a.B, pad), a.L, p.cg * V - us.sx[2], pad, X[rv]);
+                for (int rv = 0; rv < NR; ++rv) xc.load(x_p, edge_row<DIM>(p.a, xok1, xok0, p.b - us.sx[1], rv, a.B, pad), a.L, X[rv]);
+            }
 #pragma unroll
             for (int t = 0; t < V; ++t) {
                 float v[8], wg[3];
@@ -921,9 +1055,10 @@ struct BackwardBody {
             if (ACTIVE) {
                 const bool gok1 = DIM < 3 || gi_slot_slab(a, us, sg.a0, p.a + 1) >= 0;
                 float Gw[NR][NVW];
+                EdgeCols<ST, NVW> gc;
+                gc.init(oj0 - us.sg[2], a.OL, pad);
 #pragma unroll
-                for (int rv = 0; rv < NR; ++rv)
-                    load_window_edge<ST, NVW>(gi_p, edge_row<DIM>(p.a, gok1, gok0, ob - us.sg[1], rv, a.OB, pad), a.OL, oj0 - us.sg[2], pad, Gw[rv]);
+                for (int rv = 0; rv < NR; ++rv) gc.load(gi_p, edge_row<DIM>(p.a, gok1, gok0, ob - us.sg[1], rv, a.OB, pad), a.OL, Gw[rv]);
 #pragma unroll
                 for (int t = 0; t < V; ++t) {
                     float v[8];
@@ -937,7 +1072,9 @@ struct BackwardBody {
                     row = (gok0 && r >= 0) ? (DIM == 3 ? p.a * a.OB : 0) + r : -1;
                 }
                 float Gs[V];
-                load_window_edge<ST, V>(gi_p, row, a.OL, oj0 + us.sg[2], pad, Gs);
+                EdgeCols<ST, V> gc;
+                gc.init(oj0 + us.sg[2], a.OL, pad);
+                gc.load(gi_p, row, a.OL, Gs);
 #pragma unroll
                 for (int t = 0; t < V; ++t) o[t] = okc[t] ? Gs[t] : 0.f;
             }
@@ -1120,6 +1257,8 @@ StagedPlan plan_staged(const Geo& g, int mode, int active, int esize, int dtype,
         np = stage_target / per_image;
         if (np < 1) np = 1;
         if (np > g.N) np = g.N;
+        const long long img_stride = g.C * (mode == 2 ? g.in_plane : g.out_plane) * esize;
+        while (np > 1 && np * img_stride >= 0x7fffffffLL) --np;      // 32-bit offsets inside a stage's destination
     }
     auto stride_of = [&](long long n) { return round_up(n * per_image + 2 * GUARD, 128); };
     for (;;) {
@@ -1140,7 +1279,13 @@ StagedPlan plan_staged(const Geo& g, int mode, int active, int esize, int dtype,
 
     const long long planes = g.N * g.C;
     const long long grid_max = (long long)sm_count;
+    // images per unit: the per-unit setup (shift split, interior box, magic divisors) is amortised over
+    // >= 4 stages while every CTA still gets >= 8 units
     long long npu = t.chunk_planes > 0 ? t.chunk_planes : planes / (grid_max * 32);
+    if (t.chunk_planes <= 0) {
+        if (npu < 4 * np) npu = 4 * np;
+        while (npu > np && ((g.N + npu - 1) / npu) * g.C < 8 * grid_max) npu -= np;
+    }
     npu = (npu / np) * np;
     if (npu < np) npu = np;
     if (npu > g.N) npu = g.N;

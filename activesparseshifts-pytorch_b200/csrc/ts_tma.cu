@@ -34,7 +34,7 @@ namespace ts {
 namespace {
 
 constexpr int SMEM_LIMIT = 232448;
-constexpr int MAXT_TMA_GATHER = 1024, MAXT_TMA_ARITH = 544;
+constexpr int MAXT_TMA_GATHER = 1024, MAXT_TMA_ARITH = 512;
 
 // ---- exact division by a launch-invariant (n < 2^31) ------------------------------------------
 struct FastDiv { unsigned m, l, d; };
@@ -750,7 +750,7 @@ TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool 
         };
         // best fill of the last pass over a stage's items, preferring 8..16 warps: on cfg3 more
         // consumer warps never helped (the kernels are HBM-bound) and 25+ were measurably slower
-        const int lo = 8, hi = 16;
+        const int lo = 8, hi = 15;
         int best = lo;
         for (int w = lo; w <= hi && w <= max_warps; ++w)
             if (eff(w) >= eff(best) - 1e-9) best = w;
