@@ -16,6 +16,7 @@ static thread_local int t_last_path = TS_PATH_NONE;
 static thread_local char t_cuda_error[256] = "";
 
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+void note_error(const char* text) { snprintf(t_cuda_error, sizeof(t_cuda_error), "%s", text); }
 
 int check_launch() {
     const cudaError_t e = cudaGetLastError();

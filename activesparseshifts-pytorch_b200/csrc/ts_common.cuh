@@ -264,6 +264,7 @@ struct LaunchCtx {
     int sm_count;
 };
 void note_launch(int n = 1);
+void note_error(const char* text);  // text returned by ts_last_cuda_error() for non-CUDA-runtime failures
 int check_launch();               // cudaGetLastError -> ts_status
 
 }  // namespace ts

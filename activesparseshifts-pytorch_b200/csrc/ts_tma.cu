@@ -27,6 +27,8 @@
 // ts_staged.cu / ts_generic.cu.
 #include <cuda.h>
 
+#include <cstdio>
+
 #include "ts_kernels.h"
 
 namespace ts {
@@ -69,6 +71,11 @@ bool make_map(CUtensorMap* map, const void* base, int es, long long N, long long
               int bn) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
+    // cuTensorMapEncodeTiled is a DRIVER call: it needs the primary context current on the calling
+    // thread.  A thread that has only used cached allocations so far (PyTorch's autograd worker on
+    // its first backward) has none yet (CUDA_ERROR_INVALID_CONTEXT); cudaFree(0) binds it.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) { (void)cudaFree(nullptr); ctx_bound = true; }
     const CUtensorMapDataType dt = es == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : es == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
                                  : es == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
     cuuint64_t dims[5] = {(cuuint64_t)L, (cuuint64_t)B, (cuuint64_t)A, (cuuint64_t)C, (cuuint64_t)N};
@@ -76,8 +83,15 @@ bool make_map(CUtensorMap* map, const void* base, int es, long long N, long long
     cuuint64_t strides[4] = {row, row * B, row * B * A, row * B * A * (cuuint64_t)C};
     cuuint32_t box[5] = {(cuuint32_t)bl, (cuuint32_t)bb, (cuuint32_t)ba, 1u, (cuuint32_t)bn};
     cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
-    return enc(map, dt, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    const CUresult r = enc(map, dt, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[240];
+        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled -> %d: es %d dims {%d,%d,%d,%lld,%lld} box {%d,%d,%d,1,%d} base %p", (int)r, es, L, B,
+                 A, C, N, bl, bb, ba, bn, base);
+        note_error(msg);
+    }
+    return r == CUDA_SUCCESS;
 }
 
 // ---- PTX wrappers -----------------------------------------------------------------------------

@@ -80,7 +80,7 @@ class NativeLibrary:
     def check(self, status, what):
         if status != TS_OK:
             msg = self.lib.ts_error_string(status).decode()
-            extra = self.lib.ts_last_cuda_error().decode() if status in (6, 7) else ''
+            extra = self.lib.ts_last_cuda_error().decode() if status in (2, 6, 7) else ''
             raise RuntimeError(f'torchshifts-b200: {what} failed with {STATUS_NAMES.get(status, status)}: {msg}'
                                + (f' [{extra}]' if extra else ''))
 

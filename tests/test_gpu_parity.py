@@ -460,3 +460,15 @@ def test_cfg1_small_l2_resident(dev, oracle_port, auto_path):
     assert np.array_equal(gi, gi_ref)
     _, gw64 = oracle_port.backward(g.astype(np.float64), x.astype(np.float64), w.astype(np.float64), 0, False)
     assert _gw_close(gw, gw64)
+
+
+def test_smoke_in_a_fresh_process():
+    """__graft_entry__.smoke() in a new interpreter: the first backward of a process runs on the autograd
+    worker thread before that thread has a CUDA context (the TMA path's tensor-map encode is a driver call)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "[smoke] ok" in out.stdout
