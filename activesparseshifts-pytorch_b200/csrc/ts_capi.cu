@@ -147,7 +147,7 @@ int ts_set_tuning(const char* spec) {
         p += n;
         while (*p == ',' || *p == ' ') ++p;
     }
-    if (t.stages < 1 || t.stages > 8 || t.stage_kb < 1 || t.stage_kb > 200 || t.warps < 1 || t.warps > 31 ||
+    if (t.stages < 0 || t.stages > 8 || t.stage_kb < 0 || t.stage_kb > 220 || t.warps < 1 || t.warps > 31 ||
         t.ctas_per_sm < 1 || t.ctas_per_sm > 8 || t.chunk_planes < 0 || t.tma_stages < 0 || t.tma_stages > 32 ||
         t.tma_ctas_per_sm < 0 || t.tma_ctas_per_sm > 8 || t.tma_warps < 0 || t.tma_warps > 31 || t.tma_stage_kb < 0 ||
         t.tma_stage_kb > 220)

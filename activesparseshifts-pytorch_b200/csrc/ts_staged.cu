@@ -31,7 +31,7 @@
 namespace ts {
 
 Tuning& tuning() {
-    static Tuning t = {4, 48, 16, 1, 0, 0, 0, 0, 1, 0};
+    static Tuning t = {0, 0, 15, 1, 0, 0, 0, 0, 1, 0};   // 0 = automatic (per-mode defaults in the planners)
     return t;
 }
 
@@ -1239,9 +1239,11 @@ StagedPlan plan_staged(const Geo& g, int mode, int active, int esize, int dtype,
         if (xs) { *xs = x_; *gvs = gv_; *gis = gi_; }
         return x_ * slab_x + (gv_ + gi_) * slab_g;
     };
-    int stages = t.stages;
+    // defaults from the B200 sweeps (tools/tune.py cfg2 / cfg3r / cfg4r): few, large stages -- the
+    // per-stage hand-off is what limits these kernels, not the bytes in flight
+    int stages = t.stages > 0 ? t.stages : (mode == 2 ? 2 : 3);
     long long TA = IA;
-    const long long stage_target = (long long)t.stage_kb * 1024;
+    const long long stage_target = (long long)(t.stage_kb > 0 ? t.stage_kb : (mode == 2 ? 108 : 72)) * 1024;
     // shrink the slab tile until it meets the stage target (or is a single slab) and double-buffers
     for (;;) {
         const long long need = round_up(slots(TA, nullptr, nullptr, nullptr) + 2 * GUARD, 128);

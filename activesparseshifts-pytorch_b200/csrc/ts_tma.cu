@@ -700,8 +700,9 @@ TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool 
     };
     const long long budget = SMEM_LIMIT - 1024;
     // defaults from the cfg3 sweep on B200 (tools/tune.py --tma): forward 6 x 28 KB, backward 5 x 42 KB
-    const int want_stages = t.tma_stages > 0 ? t.tma_stages : (mode == 2 ? 5 : 6);
-    const long long auto_target = mode == 2 ? 42 * 1024 : 28 * 1024;
+    // 3-D volumes: few large stages (deep slab tiles re-read fewer +1 neighbour slabs)
+    const int want_stages = t.tma_stages > 0 ? t.tma_stages : d == 3 ? (mode == 2 ? 2 : 3) : (mode == 2 ? 5 : 6);
+    const long long auto_target = d == 3 ? (mode == 2 ? 108 * 1024 : 72 * 1024) : (mode == 2 ? 42 * 1024 : 28 * 1024);
     const long long target = t.tma_stage_kb > 0 ? (long long)t.tma_stage_kb * 1024
                                                 : (auto_target < budget / want_stages - 64 ? auto_target : budget / want_stages - 64);
     while (image_bytes(TA, TB, nullptr, nullptr) > target) {

@@ -25,6 +25,10 @@ elif cfg == "cfg2":
     shape, dim, pad, active = (64, 512, 4096), 1, 2, True
 elif cfg == "cfg4":
     shape, dim, pad, active = (32, 128, 16, 56, 56), 3, 0, True
+elif cfg == "cfg4r":
+    shape, dim, pad, active = (32, 128, 16, 56, 56), 3, 3, True
+elif cfg == "cfg3r":
+    shape, dim, pad, active = (256, 256, 56, 56), 2, 3, False
 else:
     shape, dim, pad, active = (8, 64, 32, 32), 2, 0, False
 x = torch.randn(shape, device=dev)
@@ -66,7 +70,7 @@ lib.ts_set_tuning(b"use_tma=0")
 run("default tuning")
 grid = [(st, kb, wp, ct) for st, kb, wp, ct in itertools.product((2, 3, 4, 6), (13, 26, 40, 56, 100), (8, 12, 16), (1, 2))]
 if quick:
-    grid = [(4, 48, 16, 1), (3, 100, 16, 1), (2, 100, 16, 1), (4, 48, 31, 1), (3, 70, 31, 1), (2, 100, 31, 1), (3, 40, 8, 2), (3, 36, 16, 2), (2, 50, 16, 2), (2, 26, 8, 4), (2, 26, 7, 4)]
+    grid = [(4, 48, 15, 1), (3, 64, 15, 1), (3, 72, 15, 1), (2, 100, 15, 1), (6, 32, 15, 1), (4, 48, 8, 1), (4, 48, 11, 1), (3, 72, 8, 1), (3, 72, 11, 1), (2, 110, 11, 1), (2, 110, 15, 1)]
 if "--tma" in sys.argv:
     grid = []
 for st, kb, wp, ct in grid:
