@@ -378,6 +378,16 @@ struct EdgeRotor {
     }
 };
 
+// rows per strip (about three strips per thread and stage) and strips per column of the interior box
+TS_D void strip_plan(const Interior& in, int images_x_slabs, int nt, int& R, int& nchunk, UDiv& d_nchunk) {
+    const int ci = in.c_hi - in.c_lo, bi = in.b_hi - in.b_lo;
+    const unsigned items = (unsigned)images_x_slabs * (unsigned)(bi > 0 ? bi : 0) * (unsigned)(ci > 0 ? ci : 0);   // < 2^31 (plan_staged)
+    R = (int)((items + 3u * (unsigned)nt - 1u) / (3u * (unsigned)nt));
+    R = R < 1 ? 1 : (R > bi ? (bi > 0 ? bi : 1) : R);
+    nchunk = bi > 0 ? (bi + R - 1) / R : 1;
+    d_nchunk = make_udiv(nchunk);
+}
+
 // ---- window loads -----------------------------------------------------------------------------
 // NW 32-bit words starting WS words into the aligned 16-byte group at byte offset `off` of `base`
 // (off is a multiple of 16).  Loads the second group only when the window needs it.
@@ -582,13 +592,7 @@ struct GatherBody {
         in.c_hi = floor_div(a.L - V - a.lbL + us.sx[2], V) + 1;
         clamp_range(in.c_lo, in.c_hi, a.gpr);
         es.init_unit(in, a.OB, a.gpr);
-        // strips: about three per thread and stage, each at most all interior rows
-        const int ci = in.c_hi - in.c_lo, bi = in.b_hi - in.b_lo;
-        const unsigned items = (unsigned)a.np * (unsigned)a.TA * (unsigned)(bi > 0 ? bi : 0) * (unsigned)(ci > 0 ? ci : 0);   // < 2^31 (plan_staged)
-        R = (int)((items + 3u * (unsigned)nt - 1u) / (3u * (unsigned)nt));
-        R = R < 1 ? 1 : (R > bi ? (bi > 0 ? bi : 1) : R);
-        nchunk = bi > 0 ? (bi + R - 1) / R : 1;
-        d_nchunk = make_udiv(nchunk);
+        strip_plan(in, a.np * a.TA, nt, R, nchunk, d_nchunk);
     }
     TS_D void end_unit(int, int) {}
 
@@ -880,6 +884,8 @@ struct BackwardBody {
     EdgeSets es;
     EdgeRotor rotor;
     bool any_interior;
+    int R, nchunk;        // rows per strip / strips per column of the interior box (per unit)
+    UDiv d_nchunk;
     double acc[DIM];
 
     TS_D BackwardBody(const SArgs& a_, int tid_, int nt_, int wid_, int lane_)
@@ -917,6 +923,7 @@ struct BackwardBody {
         any_interior = (a.lbL * ES) % 16 == 0 && a.L > 1 && (DIM < 2 || a.B > 1) && (DIM < 3 || a.A > 1);
         if (!any_interior) in.b_hi = in.b_lo = in.c_hi = in.c_lo = 0;
         es.init_unit(in, a.B, a.gpr);
+        strip_plan(in, a.np * a.TA, nt, R, nchunk, d_nchunk);
     }
     // one partial per (unit, consumer warp): fixed shuffle tree, no atomics
     TS_D void end_unit(int c, int chunk) {
@@ -947,8 +954,127 @@ struct BackwardBody {
         if (!any_interior) a_lo = a_hi = 0;
     }
 
+    // Strip-mined interior (fp32): a thread owns (image, slab, group, chunk of R consecutive rows).
+    // Walking down the rows, the "+1 row" windows of one item are the "+0 row" windows of the next:
+    // they stay in registers, so an item loads half of its x / grad windows and no index is decoded.
+    // WSG: word misalignment of the grad_input window, or -1 when it is only known at run time.
+    template <int WS, int WSG>
+    TS_D void interior_strip(const Stage& sg, int a_lo, int a_hi, float* ts) const {
+        constexpr int S = DIM == 3 ? 2 : 1;                 // slab variants of a window: slot a (and a + 1)
+        const int ci = in.c_hi - in.c_lo, bi = in.b_hi - in.b_lo, ai = a_hi - a_lo;
+        if (ci <= 0 || bi <= 0 || ai <= 0) return;
+        const int ximg = a.xs * a.slab_x, gvimg = a.gvs * a.slab_g, giimg = (a.gis ? a.gis : a.gvs) * a.slab_g;
+        const unsigned char* gibase = sg.st + (a.gis ? a.off_gi : a.off_gv);
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        const int gsh = ACTIVE ? -us.sg[2] : us.sg[2];
+        const int grow_sh = DIM >= 2 ? (ACTIVE ? -us.sg[1] : us.sg[1]) : 0;
+        const int xrsh = DIM >= 2 ? -us.sx[1] : 0;
+        const int L = a.L, OL = a.OL, xslab = a.B * a.L, gslab = a.OB * a.OL, orowb = a.gpr * 16;
+        const int strips = sg.npl * ai * nchunk * ci;
+        auto load_g = [&](const unsigned char* base, int e0, float* out) {
+            if constexpr (WSG >= 0) load_window<ST, WSG, NVW>(base, e0, out); else load_window_rt<ST, NVW>(base, e0, out);
+        };
+        for (int sidx = tid; sidx < strips; sidx += nt) {
+            const int r = udiv(sidx, es.d_ci), j = sidx - r * ci;
+            const int r2 = udiv(r, d_nchunk), k = r - r2 * nchunk;
+            int pl = r2, ia = 0;
+            if (ai > 1) { pl = r2 / ai; ia = r2 - pl * ai; }
+            Item p;
+            p.pl = pl; p.a = a_lo + ia; p.b = in.b_lo + k * R; p.cg = in.c_lo + j;
+            const int bend = p.b + R < in.b_hi ? p.b + R : in.b_hi;
+            const unsigned char* x_p = sg.st + p.pl * ximg;
+            const unsigned char* gv_p = sg.st + a.off_gv + p.pl * gvimg;
+            const unsigned char* gi_p = gibase + p.pl * giimg;
+            int xe = (p.a * a.B + p.b + xrsh) * L + p.cg * V - us.sx[2];
+            int gve = (p.a * a.OB + p.b - a.lbB) * OL + p.cg * V - a.lbL;
+            int gie = gve + grow_sh * OL + gsh;
+            unsigned char* dst = item_dst(a, sg, p);
+            float Xlo[S][NVW], Glo[S][NVW];
+            if (DIM >= 2) {
+#pragma unroll
+                for (int q = 0; q < S; ++q) load_window<ST, WS, NVW>(x_p, xe + q * xslab, Xlo[q]);
+                if (ACTIVE) {
+#pragma unroll
+                    for (int q = 0; q < S; ++q) load_g(gi_p, gie + q * gslab, Glo[q]);
+                }
+            }
+            for (int b = p.b; b < bend; ++b) {
+                float gv[V];
+                load_window<ST, 0, V>(gv_p, gve, gv);
+                // ---- grad_weight terms ----
+                float X[NR][NVW];
+                if (DIM == 1) {
+                    load_window<ST, WS, NVW>(x_p, xe, X[0]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < S; ++q) {
+                        load_window<ST, WS, NVW>(x_p, xe + L + q * xslab, X[S + q]);
+#pragma unroll
+                        for (int t = 0; t < NVW; ++t) X[q][t] = Xlo[q][t];
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < V; ++t) {
+                    float v[8], wg[3];
+                    neighbours_from_rows<DIM, NVW>(X, t, v);
+                    weight_partials_fast<DIM>(v, d, wg);
+#pragma unroll
+                    for (int q = 0; q < DIM; ++q) ts[q] = fmaf(gv[t], wg[q], ts[q]);
+                }
+                // ---- grad_input ----
+                float o[V];
+                if (ACTIVE) {
+                    float Gw[NR][NVW];
+                    if (DIM == 1) {
+                        load_g(gi_p, gie, Gw[0]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < S; ++q) {
+                            load_g(gi_p, gie + OL + q * gslab, Gw[S + q]);
+#pragma unroll
+                            for (int t = 0; t < NVW; ++t) Gw[q][t] = Glo[q][t];
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < V; ++t) {
+                        float v[8];
+                        neighbours_from_rows<DIM, NVW>(Gw, t, v);
+                        o[t] = interpolate<float, DIM>(v, d);
+                    }
+                    if (DIM >= 2) {
+#pragma unroll
+                        for (int q = 0; q < S; ++q)
+#pragma unroll
+                            for (int t = 0; t < NVW; ++t) Glo[q][t] = Gw[S + q][t];
+                    }
+                } else {
+                    if constexpr (WSG >= 0) load_window<ST, WSG, V>(gi_p, gie, o); else load_window_rt<ST, V>(gi_p, gie, o);
+                }
+                __stcs((uint4*)dst, Pack<ST>::pack(o));
+                if (DIM >= 2) {
+#pragma unroll
+                    for (int q = 0; q < S; ++q)
+#pragma unroll
+                        for (int t = 0; t < NVW; ++t) Xlo[q][t] = X[S + q][t];
+                }
+                xe += L; gve += OL; gie += OL; dst += orowb;
+            }
+        }
+    }
+
     template <int WS>
     TS_D void interior(const Stage& sg, int a_lo, int a_hi, float* ts) const {
+        if constexpr (sizeof(ST) == 4) {
+            // the grad_input window's misalignment follows from the x window's when both shifts agree
+            if (a.lbL == 0 && us.sg[2] == us.sx[2]) interior_strip<WS, ACTIVE ? WS : ((4 - WS) & 3)>(sg, a_lo, a_hi, ts);
+            else interior_strip<WS, -1>(sg, a_lo, a_hi, ts);
+        } else {
+            interior_flat<WS>(sg, a_lo, a_hi, ts);
+        }
+    }
+
+    template <int WS>
+    TS_D void interior_flat(const Stage& sg, int a_lo, int a_hi, float* ts) const {
         const int total = sg.npl * a.img_items;
         const int ximg = a.xs * a.slab_x, gvimg = a.gvs * a.slab_g, giimg = (a.gis ? a.gis : a.gvs) * a.slab_g;
         const unsigned char* gibase = sg.st + (a.gis ? a.off_gi : a.off_gv);
