@@ -365,13 +365,13 @@ struct EdgeSets {
 // more expensive than interior items: hand them to a DIFFERENT group of warps every stage, so that
 // over the ring depth every consumer warp does the same amount of work.
 struct EdgeRotor {
-    int seq;
-    TS_D EdgeRotor() : seq(0) {}
+    int rot;
+    TS_D EdgeRotor() : rot(0) {}
     // first edge index of this thread for a stage with `total` edge items
     TS_D int first(int tid, int nt, int total) {
         const int span = ((total + 31) >> 5) << 5;
-        const int rot = (int)(((long long)seq * span) % nt);
-        ++seq;
+        rot += span;                       // running offset modulo nt (span <= a few thousand)
+        while (rot >= nt) rot -= nt;
         int vt = tid - rot;
         if (vt < 0) vt += nt;
         return vt;
@@ -383,7 +383,8 @@ TS_D void strip_plan(const Interior& in, int images_x_slabs, int nt, int& R, int
     const int ci = in.c_hi - in.c_lo, bi = in.b_hi - in.b_lo;
     const unsigned items = (unsigned)images_x_slabs * (unsigned)(bi > 0 ? bi : 0) * (unsigned)(ci > 0 ? ci : 0);   // < 2^31 (plan_staged)
     R = (int)((items + 3u * (unsigned)nt - 1u) / (3u * (unsigned)nt));
-    R = R < 1 ? 1 : (R > bi ? (bi > 0 ? bi : 1) : R);
+    if (R < 2) R = 2;                  // a strip of one row reuses nothing
+    R = R > bi ? (bi > 0 ? bi : 1) : R;
     nchunk = bi > 0 ? (bi + R - 1) / R : 1;
     d_nchunk = make_udiv(nchunk);
 }
@@ -619,11 +620,12 @@ struct GatherBody {
         const int col0 = (a.lbL - us.sx[2]) * ES - mb;        // aligned byte offset of group 0's window inside its row
         const int rsh = a.lbB - us.sx[1];
         const int strips = sg.npl * ai * nchunk * ci;
+        const UDiv d_ai = make_udiv(ai);
         for (int sidx = tid; sidx < strips; sidx += nt) {
             const int r = udiv(sidx, es.d_ci), j = sidx - r * ci;
             const int r2 = udiv(r, d_nchunk), k = r - r2 * nchunk;
             int pl = r2, ia = 0;
-            if (ai > 1) { pl = r2 / ai; ia = r2 - pl * ai; }
+            if (ai > 1) { pl = udiv(r2, d_ai); ia = r2 - pl * ai; }
             Item p;
             p.pl = pl; p.a = a_lo + ia; p.b = in.b_lo + k * R; p.cg = in.c_lo + j;
             const int bend = p.b + R < in.b_hi ? p.b + R : in.b_hi;
@@ -971,6 +973,7 @@ struct BackwardBody {
         const int xrsh = DIM >= 2 ? -us.sx[1] : 0;
         const int L = a.L, OL = a.OL, xslab = a.B * a.L, gslab = a.OB * a.OL, orowb = a.gpr * 16;
         const int strips = sg.npl * ai * nchunk * ci;
+        const UDiv d_ai = make_udiv(ai);
         auto load_g = [&](const unsigned char* base, int e0, float* out) {
             if constexpr (WSG >= 0) load_window<ST, WSG, NVW>(base, e0, out); else load_window_rt<ST, NVW>(base, e0, out);
         };
@@ -978,7 +981,7 @@ struct BackwardBody {
             const int r = udiv(sidx, es.d_ci), j = sidx - r * ci;
             const int r2 = udiv(r, d_nchunk), k = r - r2 * nchunk;
             int pl = r2, ia = 0;
-            if (ai > 1) { pl = r2 / ai; ia = r2 - pl * ai; }
+            if (ai > 1) { pl = udiv(r2, d_ai); ia = r2 - pl * ai; }
             Item p;
             p.pl = pl; p.a = a_lo + ia; p.b = in.b_lo + k * R; p.cg = in.c_lo + j;
             const int bend = p.b + R < in.b_hi ? p.b + R : in.b_hi;
