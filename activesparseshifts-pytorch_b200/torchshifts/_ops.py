@@ -10,9 +10,9 @@ Operator names and schemas are the reference's (csrc/torchshifts.cpp:35-40, csrc
                                          int padding_mode, bool active_flag) -> (Tensor, Tensor)
 
 Dispatch keys: ``shiftNd`` is CompositeImplicitAutograd (border validation, then ``_shiftNd_forward``);
-``_shiftNd_forward/_backward`` have an ``Autograd`` kernel (the autograd wiring of
-csrc/ops/autograd/shifts_autograd.cpp: saves input/weights/borders, double backward is an error),
-``CUDA`` and ``QuantizedCUDA`` kernels that call the sm_100a library, ``Meta`` kernels for tracing,
+``_shiftNd_forward/_backward`` carry the autograd wiring of csrc/ops/autograd/shifts_autograd.cpp
+(``torch.library.register_autograd``: saves input/weights/borders, double backward is an error),
+``CUDA`` and ``QuantizedCUDA`` kernels that call the sm_100a library, fake kernels for tracing,
 and ``CPU`` / ``QuantizedCPU`` kernels that raise: this build has NO CPU compute path.
 """
 import ctypes as ct
@@ -152,51 +152,31 @@ def _backward_meta(dim, grad, weights, input, borders, padding_mode, active_flag
 
 
 # ------------------------------------------------------------------------------------------ Autograd
-def _below_autograd():
-    return torch._C._AutoDispatchBelowAutograd()
+# csrc/ops/autograd/shifts_autograd.cpp:15-47 (and the 2d/3d twins): forward saves input, weights and
+# borders; backward calls _shiftNd_backward and returns grads for input and weights only; the backward
+# op itself is not differentiable (:50-72).  Registered with torch.library.register_autograd (not an
+# Autograd-key kernel wrapping an autograd.Function) so that AOTAutograd / torch.compile can trace it.
+def _setup_forward_context(ctx, inputs, output):
+    input, weights, borders, new_size, padding_mode, active_flag = inputs
+    ctx.save_for_backward(input, weights, borders)
+    ctx.padding_mode, ctx.active_flag = padding_mode, active_flag
 
 
-class _ShiftBackwardFunction(torch.autograd.Function):
-    """csrc/ops/autograd/shifts_autograd.cpp:50-72: the backward op itself is not differentiable."""
-
-    @staticmethod
-    def forward(ctx, dim, grad, weights, input, borders, padding_mode, active_flag):
-        with _below_autograd():
-            op = getattr(torch.ops.torchshifts, f'_shift{dim}d_backward')
-            return op(grad, weights, input, borders, padding_mode, active_flag)
-
-    @staticmethod
-    def backward(ctx, *grads):
-        raise RuntimeError('double backwards on shiftNd not supported')
-
-
-class _ShiftFunction(torch.autograd.Function):
-    """csrc/ops/autograd/shifts_autograd.cpp:15-47 (and the 2d/3d twins)."""
-
-    @staticmethod
-    def forward(ctx, dim, input, weights, borders, new_size, padding_mode, active_flag):
-        with _below_autograd():
-            op = getattr(torch.ops.torchshifts, f'_shift{dim}d_forward')
-            output = op(input, weights, borders, new_size, padding_mode, active_flag)
-        ctx.dim, ctx.padding_mode, ctx.active_flag = dim, padding_mode, active_flag
-        ctx.save_for_backward(input, weights, borders)
-        return output
-
-    @staticmethod
+def _make_forward_backward(dim):
     def backward(ctx, grad_output):
         input, weights, borders = ctx.saved_tensors
-        op = getattr(torch.ops.torchshifts, f'_shift{ctx.dim}d_backward')
+        op = getattr(torch.ops.torchshifts, f'_shift{dim}d_backward')
         grad_input, grad_weight = op(grad_output, weights, input, borders, ctx.padding_mode, ctx.active_flag)
-        return None, grad_input, grad_weight, None, None, None, None
+        return grad_input, grad_weight, None, None, None, None
+    return backward
 
 
-def _forward_autograd(dim, input, weights, borders, new_size, padding_mode, active_flag):
-    return _ShiftFunction.apply(dim, input, weights, borders, list(new_size), padding_mode, active_flag)
+def _setup_backward_context(ctx, inputs, output):
+    pass
 
 
-def _backward_autograd(dim, grad, weights, input, borders, padding_mode, active_flag):
-    out = _ShiftBackwardFunction.apply(dim, grad, weights, input, borders, padding_mode, active_flag)
-    return out[0], out[1]
+def _double_backward(ctx, *grads):
+    raise RuntimeError('double backwards on shiftNd not supported')
 
 
 # ------------------------------------------------------------------------------------------ composite
@@ -245,14 +225,16 @@ def register(native):
                    f'int padding_mode, bool active_flag) -> (Tensor, Tensor)')
         lib.impl(f'shift{dim}d', _bind(_shift_composite, dim), 'CompositeImplicitAutograd')
         fwd, bwd = f'_shift{dim}d_forward', f'_shift{dim}d_backward'
-        lib.impl(fwd, _bind(_forward_autograd, dim), 'Autograd')
-        lib.impl(bwd, _bind(_backward_autograd, dim), 'Autograd')
         lib.impl(fwd, _bind(_forward_cuda, dim), 'CUDA')
         lib.impl(bwd, _bind(_backward_cuda, dim), 'CUDA')
         lib.impl(fwd, _bind(_forward_qcuda, dim), 'QuantizedCUDA')
         lib.impl(bwd, _bind(_backward_quantized, dim), 'QuantizedCUDA')
-        lib.impl(fwd, _bind(_forward_meta, dim), 'Meta')
-        lib.impl(bwd, _bind(_backward_meta, dim), 'Meta')
+        # fake (meta) implementations: `borders` is a host tensor next to device tensors, so the output
+        # device is stated here instead of being inferred from the arguments
+        torch.library.register_fake(f'torchshifts::{fwd}', _bind(_forward_meta, dim), lib=lib)
+        torch.library.register_fake(f'torchshifts::{bwd}', _bind(_backward_meta, dim), lib=lib)
+        torch.library.register_autograd(f'torchshifts::{fwd}', _make_forward_backward(dim), setup_context=_setup_forward_context, lib=lib)
+        torch.library.register_autograd(f'torchshifts::{bwd}', _double_backward, setup_context=_setup_backward_context, lib=lib)
         for key in ('CPU', 'QuantizedCPU'):
             lib.impl(fwd, _no_cpu, key)
             lib.impl(bwd, _no_cpu, key)

@@ -506,8 +506,8 @@ def test_more_than_2_31_elements(dev, lib, oracle_port, auto_path):
 
 
 def test_torch_compile_and_state_dict(dev, auto_path):
-    """The ops are registered with Meta kernels: a module with a shift layer traces under torch.compile
-    (falling back to eager for the custom op is fine) and its state_dict has the single `weight` parameter."""
+    """The ops carry fake kernels and a registered autograd formula: a module with a shift layer traces under
+    torch.compile as ONE graph, and its state_dict has the single `weight` parameter."""
     import torchshifts
     torch.manual_seed(0)
     m = torch.nn.Sequential(torch.nn.Conv2d(8, 8, 1), ).to(dev)
@@ -523,10 +523,9 @@ def test_torch_compile_and_state_dict(dev, auto_path):
     want.sum().backward()
     gx, gw = x.grad.clone(), sh.weight.grad.clone()
     x.grad = None; sh.weight.grad = None
-    try:
-        got = torch.compile(f, dynamic=False)(x)
-        got.sum().backward()
-    except Exception as e:   # torch.compile needs a host compiler / triton for the surrounding graph
-        pytest.skip(f"torch.compile unavailable in this environment: {type(e).__name__}: {str(e)[:200]}")
+    # backend "aot_eager": dynamo + AOTAutograd trace the ops through their fake kernels and the registered
+    # autograd formula; no Inductor code generation (this image has no working host compiler for it)
+    got = torch.compile(f, dynamic=False, backend="aot_eager", fullgraph=True)(x)
+    got.sum().backward()
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
     assert torch.allclose(x.grad, gx, rtol=1e-5, atol=1e-6) and torch.allclose(sh.weight.grad, gw, rtol=1e-4, atol=1e-5)
