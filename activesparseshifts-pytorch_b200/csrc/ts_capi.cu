@@ -12,6 +12,7 @@ namespace ts {
 
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_forced_path{0};
+static std::atomic<unsigned> g_tuning_epoch{0};     // bumped by ts_set_tuning: invalidates memoised plans
 static thread_local int t_last_path = TS_PATH_NONE;
 static thread_local char t_cuda_error[256] = "";
 
@@ -153,6 +154,7 @@ int ts_set_tuning(const char* spec) {
         t.tma_stage_kb > 220)
         return TS_ERR_INVALID_ARGUMENT;
     tuning() = t;
+    g_tuning_epoch.fetch_add(1);
     return TS_OK;
 }
 
@@ -232,25 +234,37 @@ int ts_shift_forward(const ts_geometry* gin, int dtype, int padding, int active,
 }
 
 size_t ts_shift_backward_workspace_bytes(const ts_geometry* gin, int dtype) {
+    if (!gin) return 0;
+    // memo of the last query of this thread: ts_shift_backward validates its workspace on every call
+    static thread_local ts_geometry last_geo;
+    static thread_local int last_dtype = -1;
+    static thread_local unsigned last_epoch = 0;
+    static thread_local size_t last_bytes = 0;
+    const unsigned epoch = g_tuning_epoch.load();
+    if (last_dtype == dtype && last_epoch == epoch && !memcmp(&last_geo, gin, sizeof(ts_geometry))) return last_bytes;
     Geo g;
     if (make_geo(gin, 0, &g) != TS_OK) return 0;
-    if (g.N * g.C == 0) return 16;
-    int sms = 148;
-    sm_count(&sms);
-    const GenericBwdPlan gp = plan_generic_backward(g);
-    size_t slots = (size_t)gp.units;
-    // assume the staged path may apply (pointer alignment is unknown here)
-    for (int active = 0; active < 2; ++active) {
-        const StagedPlan sp = plan_staged(g, 2, active, elem_size(dtype), dtype, true, nullptr, nullptr, nullptr, sms);
-        if (sp.ok && (size_t)sp.slots > slots) slots = (size_t)sp.slots;
+    size_t bytes = 16;
+    if (g.N * g.C != 0) {
+        int sms = 148;
+        sm_count(&sms);
+        const GenericBwdPlan gp = plan_generic_backward(g);
+        size_t slots = (size_t)gp.units;
+        // assume the staged / TMA paths may apply (pointer alignment is unknown here)
+        for (int active = 0; active < 2; ++active) {
+            const StagedPlan sp = plan_staged(g, 2, active, elem_size(dtype), dtype, true, nullptr, nullptr, nullptr, sms);
+            if (sp.ok && (size_t)sp.slots > slots) slots = (size_t)sp.slots;
+        }
+        Geo gz = g;
+        gz.pad = TS_PAD_ZEROS;
+        for (int active = 0; active < 2; ++active) {
+            const TmaPlan tp = plan_tma(gz, 2, active, elem_size(dtype), dtype, true, 0ull, nullptr, nullptr, nullptr, sms);
+            if (tp.ok && (size_t)tp.slots > slots) slots = (size_t)tp.slots;
+        }
+        bytes = slots * (size_t)(g.C * g.dim) * sizeof(double) + 16;
     }
-    Geo gz = g;
-    gz.pad = TS_PAD_ZEROS;
-    for (int active = 0; active < 2; ++active) {
-        const TmaPlan tp = plan_tma(gz, 2, active, elem_size(dtype), dtype, true, 0ull, nullptr, nullptr, nullptr, sms);
-        if (tp.ok && (size_t)tp.slots > slots) slots = (size_t)tp.slots;
-    }
-    return slots * (size_t)(g.C * g.dim) * sizeof(double) + 16;
+    last_geo = *gin; last_dtype = dtype; last_epoch = epoch; last_bytes = bytes;
+    return bytes;
 }
 
 int ts_shift_backward(const ts_geometry* gin, int dtype, int padding, int active, const void* grad, const void* x,

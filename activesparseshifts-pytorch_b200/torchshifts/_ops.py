@@ -65,8 +65,30 @@ def _stream(device):
     return ct.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+_GEO_CACHE = {}        # (dim, shape, strides, lb, rb) -> ts_geometry; shift layers see the same few shapes every step
+
+
 def _geometry(dim, input, lb, rb):
-    return make_geometry(dim, input.shape, input.stride(), lb, rb)
+    key = (dim, tuple(input.shape), tuple(input.stride()), tuple(lb), tuple(rb))
+    geo = _GEO_CACHE.get(key)
+    if geo is None:
+        if len(_GEO_CACHE) > 256:
+            _GEO_CACHE.clear()
+        geo = _GEO_CACHE[key] = make_geometry(dim, input.shape, input.stride(), lb, rb)
+    return geo
+
+
+_WS_CACHE = {}         # (id(geometry), dtype code) -> backward workspace bytes
+
+
+def _workspace_bytes(geo, code):
+    key = (id(geo), code)
+    n = _WS_CACHE.get(key)
+    if n is None:
+        if len(_WS_CACHE) > 256:
+            _WS_CACHE.clear()
+        n = _WS_CACHE[key] = int(_NATIVE.lib.ts_shift_backward_workspace_bytes(ct.byref(geo), code))
+    return n
 
 
 # ------------------------------------------------------------------------------------------ CUDA
@@ -105,11 +127,16 @@ def _backward_cuda(dim, grad, weights, input, borders, padding_mode, active_flag
         raise RuntimeError(f'{fn}: grad shape {list(grad.shape)} does not match the (cropped) output of input {list(input.shape)}')
     code = _DTYPES[input.dtype]
     with torch.cuda.device(input.device):
-        nbytes = int(_NATIVE.lib.ts_shift_backward_workspace_bytes(ct.byref(geo), code))
+        nbytes = _workspace_bytes(geo, code)
         workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=input.device)
-        st = _NATIVE.lib.ts_shift_backward(ct.byref(geo), code, int(padding_mode), int(bool(active_flag)),
-                                           grad.data_ptr(), input.data_ptr(), w.data_ptr(), out_grad.data_ptr(),
-                                           weights_grad.data_ptr(), workspace.data_ptr(), nbytes, _stream(input.device))
+        args = (ct.byref(geo), code, int(padding_mode), int(bool(active_flag)), grad.data_ptr(), input.data_ptr(), w.data_ptr(),
+                out_grad.data_ptr(), weights_grad.data_ptr())
+        st = _NATIVE.lib.ts_shift_backward(*args, workspace.data_ptr(), nbytes, _stream(input.device))
+        if st == 3:       # TS_ERR_WORKSPACE: the tuning knobs changed since the size was cached
+            _WS_CACHE.clear()
+            nbytes = _workspace_bytes(geo, code)
+            workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=input.device)
+            st = _NATIVE.lib.ts_shift_backward(*args, workspace.data_ptr(), nbytes, _stream(input.device))
     _NATIVE.check(st, 'ts_shift_backward')
     return out_grad, weights_grad
 
