@@ -258,6 +258,31 @@ TS_D void load_qshifts(const void* __restrict__ qw, int kind, long long wzp, lon
 }
 
 // ------------------------------------------------------------------------------------------
+// Shared-memory vector loads as opaque instructions.  Written as plain C++ (`*(const uint4*)p`) the
+// compiler narrows a 128-bit load to the words a misaligned window actually uses (LDS.32 + LDS.64 ...),
+// and those narrower loads are 16-byte strided across a warp: 4-way bank conflicts (measured with ncu:
+// half of all shared-memory wavefronts of the first TMA kernels).  LDS.128 of consecutive lanes is
+// conflict-free, so the loads are pinned with inline PTX.  Addresses are 32-bit shared-window addresses.
+#ifdef __CUDACC__
+TS_D unsigned shared_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+TS_D uint4 lds128(unsigned addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+TS_D uint2 lds64(unsigned addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+TS_D unsigned lds32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------
 // Launch bookkeeping shared by the translation units.
 struct LaunchCtx {
     cudaStream_t stream;

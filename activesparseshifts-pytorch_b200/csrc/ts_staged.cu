@@ -318,6 +318,7 @@ struct EdgeSets {
     UDiv d_ce, d_ci, d_be, d_bi, d_B;
     int a_lo, a_hi, A;                        // interior slabs / valid slabs of the tile: per stage
     int n1, n2, n3;                           // set sizes per image (per stage)
+    UDiv d_per;                               // divisor "edge items per image", recomputed only when it changes
     TS_D void init_unit(const Interior& in, int rows, int groups) {
         b_lo = in.b_lo; b_hi = in.b_hi; c_lo = in.c_lo; c_hi = in.c_hi;
         B = rows; G = groups;
@@ -326,6 +327,7 @@ struct EdgeSets {
         d_be = make_udiv(b_lo + (B - b_hi));
         d_bi = make_udiv(b_hi - b_lo);
         d_B = make_udiv(B);
+        d_per.d = -1;
     }
     TS_D void init_stage(int alo, int ahi, int an) {
         a_lo = alo; a_hi = ahi; A = an;
@@ -335,8 +337,10 @@ struct EdgeSets {
         n1 = A * B * ce;
         n2 = A * be * ci;
         n3 = ae * bi * ci;
+        if (n1 + n2 + n3 != d_per.d) d_per = make_udiv(n1 + n2 + n3);
     }
     TS_D int per_image() const { return n1 + n2 + n3; }
+    TS_D int image_of(int e) const { return udiv(e, d_per); }
     static TS_D int pick(int k, int lo, int hi) { return k < lo ? k : hi + (k - lo); }
     TS_D void decode(int e, Item& p) const {
         if (e < n1) {
@@ -393,18 +397,18 @@ TS_D void strip_plan(const Interior& in, int images_x_slabs, int nt, int& R, int
 // NW 32-bit words starting WS words into the aligned 16-byte group at byte offset `off` of `base`
 // (off is a multiple of 16).  Loads the second group only when the window needs it.
 template <int WS, int NW>
-TS_D void load_words(const unsigned char* base, int off, unsigned* w) {
-    const uint4 A = *(const uint4*)(base + off);
+TS_D void load_words(unsigned base, int off, unsigned* w) {
+    const uint4 A = lds128(base + off);
     unsigned W[8] = {A.x, A.y, A.z, A.w, 0u, 0u, 0u, 0u};
     if (WS + NW > 4) {
-        const uint4 B = *(const uint4*)(base + off + 16);
+        const uint4 B = lds128(base + off + 16);
         W[4] = B.x; W[5] = B.y; W[6] = B.z; W[7] = B.w;
     }
 #pragma unroll
     for (int t = 0; t < NW; ++t) w[t] = W[(t + WS) & 7];
 }
 template <int NW>
-TS_D void load_words_rt(const unsigned char* base, int off, int ws, unsigned* w) {
+TS_D void load_words_rt(unsigned base, int off, int ws, unsigned* w) {
     switch (ws) {
     case 0: load_words<0, NW>(base, off, w); break;
     case 1: load_words<1, NW>(base, off, w); break;
@@ -472,8 +476,9 @@ template <> struct Pack<__half> {
 };
 
 // window of NV elements starting at element index `e0` (>= 0, window inside the region) of a staged region
+// (`region` = 32-bit shared-window address)
 template <typename ST, int WS, int NV>
-TS_D void load_window(const unsigned char* region, int e0, float* out) {
+TS_D void load_window(unsigned region, int e0, float* out) {
     constexpr int NW = Pack<ST>::words(NV);
     const int byte = e0 * (int)sizeof(ST);
     unsigned w[NW + 1];
@@ -482,7 +487,7 @@ TS_D void load_window(const unsigned char* region, int e0, float* out) {
     Pack<ST>::template unpack<NV>(w, (byte & 2) * 8, out);
 }
 template <typename ST, int NV>
-TS_D void load_window_rt(const unsigned char* region, int e0, float* out) {
+TS_D void load_window_rt(unsigned region, int e0, float* out) {
     constexpr int NW = Pack<ST>::words(NV);
     const int byte = e0 * (int)sizeof(ST);
     unsigned w[NW + 1];
@@ -512,7 +517,7 @@ struct EdgeCols {
 #pragma unroll
             for (int t = 0; t < NV; ++t) out[t] = 0.f;
         } else if (inside) {
-            load_window_rt<ST, NV>(region, row * L + c0, out);
+            load_window_rt<ST, NV>(shared_addr(region), row * L + c0, out);
         } else {
 #pragma unroll
             for (int t = 0; t < NV; ++t) out[t] = cols[t] >= 0 ? Elem<ST>::ld(((const ST*)region)[row * L + cols[t]]) : 0.f;
@@ -621,6 +626,7 @@ struct GatherBody {
         const int rsh = a.lbB - us.sx[1];
         const int strips = sg.npl * ai * nchunk * ci;
         const UDiv d_ai = make_udiv(ai);
+        const unsigned sst = shared_addr(sg.st);
         for (int sidx = tid; sidx < strips; sidx += nt) {
             const int r = udiv(sidx, es.d_ci), j = sidx - r * ci;
             const int r2 = udiv(r, d_nchunk), k = r - r2 * nchunk;
@@ -629,21 +635,21 @@ struct GatherBody {
             Item p;
             p.pl = pl; p.a = a_lo + ia; p.b = in.b_lo + k * R; p.cg = in.c_lo + j;
             const int bend = p.b + R < in.b_hi ? p.b + R : in.b_hi;
-            const unsigned char* src = sg.st + p.pl * img_bytes + (p.a * a.B + p.b + rsh) * rowb + col0 + p.cg * VB;
+            unsigned src = sst + p.pl * img_bytes + (p.a * a.B + p.b + rsh) * rowb + col0 + p.cg * VB;
             unsigned char* dst = item_dst(a, sg, p);
             for (int b = p.b; b < bend; ++b, src += rowb, dst += orowb) {
                 unsigned W[2 * G + 1];
                 if constexpr (G == 4) {
-                    const uint4 A = *(const uint4*)src;
+                    const uint4 A = lds128(src);
                     W[0] = A.x; W[1] = A.y; W[2] = A.z; W[3] = A.w;
-                    if (WS > 0 || SUB) { const uint4 Bv = *(const uint4*)(src + 16); W[4] = Bv.x; W[5] = Bv.y; W[6] = Bv.z; W[7] = Bv.w; }
+                    if (WS > 0 || SUB) { const uint4 Bv = lds128(src + 16); W[4] = Bv.x; W[5] = Bv.y; W[6] = Bv.z; W[7] = Bv.w; }
                 } else if constexpr (G == 2) {
-                    const uint2 A = *(const uint2*)src;
+                    const uint2 A = lds64(src);
                     W[0] = A.x; W[1] = A.y;
-                    if (WS > 0 || SUB) { const uint2 Bv = *(const uint2*)(src + 8); W[2] = Bv.x; W[3] = Bv.y; }
+                    if (WS > 0 || SUB) { const uint2 Bv = lds64(src + 8); W[2] = Bv.x; W[3] = Bv.y; }
                 } else {
-                    W[0] = *(const unsigned*)src;
-                    if (WS > 0 || SUB) W[1] = *(const unsigned*)(src + 4);
+                    W[0] = lds32(src);
+                    if (WS > 0 || SUB) W[1] = lds32(src + 4);
                 }
                 W[2 * G] = 0u;
                 unsigned o[G];
@@ -674,7 +680,7 @@ struct GatherBody {
         }
         for (int e = first; e < total; e += nt) {
             Item p;
-            p.pl = a.np > 1 ? e / per : 0;
+            p.pl = a.np > 1 ? es.image_of(e) : 0;
             es.decode(e - p.pl * per, p);
             const bool slab_ok = x_slot_slab(a, us, sg.a0, p.a) >= 0;     // the producer already applied the slab shift
             const int rb = a.g.dim >= 2 ? axis_index(p.b + a.lbB - us.sx[1], a.B, pad) : 0;
@@ -811,12 +817,13 @@ struct ActiveFwdBody {
         const int img_bytes = a.xs * a.slab_x;
         const int col0 = a.lbL - us.sx[2];
         const int rsh = DIM >= 2 ? a.lbB - us.sx[1] : 0;
+        const unsigned sst = shared_addr(sg.st);
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
         for (int item = tid; item < total; item += nt) {
             Item p;
             decode_item(a, item, p);
             if (!(in_range(p.cg, in.c_lo, in.c_hi) && in_range(p.b, in.b_lo, in.b_hi) && in_range(p.a, a_lo, a_hi))) continue;
-            const unsigned char* img = sg.st + p.pl * img_bytes;
+            const unsigned img = sst + p.pl * img_bytes;
             const int row0 = p.a * a.B + p.b + rsh;
             float X[NR][NVW];
 #pragma unroll
@@ -839,7 +846,7 @@ struct ActiveFwdBody {
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
         for (int e = rotor.first(tid, nt, total); e < total; e += nt) {
             Item p;
-            p.pl = a.np > 1 ? e / per : 0;
+            p.pl = a.np > 1 ? es.image_of(e) : 0;
             es.decode(e - p.pl * per, p);
             const unsigned char* img = sg.st + (size_t)p.pl * a.xs * a.slab_x;
             const bool ok0 = DIM < 3 || x_slot_slab(a, us, sg.a0, p.a) >= 0;
@@ -966,7 +973,7 @@ struct BackwardBody {
         const int ci = in.c_hi - in.c_lo, bi = in.b_hi - in.b_lo, ai = a_hi - a_lo;
         if (ci <= 0 || bi <= 0 || ai <= 0) return;
         const int ximg = a.xs * a.slab_x, gvimg = a.gvs * a.slab_g, giimg = (a.gis ? a.gis : a.gvs) * a.slab_g;
-        const unsigned char* gibase = sg.st + (a.gis ? a.off_gi : a.off_gv);
+        const unsigned sst = shared_addr(sg.st), gibase = sst + (a.gis ? a.off_gi : a.off_gv);
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
         const int gsh = ACTIVE ? -us.sg[2] : us.sg[2];
         const int grow_sh = DIM >= 2 ? (ACTIVE ? -us.sg[1] : us.sg[1]) : 0;
@@ -974,7 +981,7 @@ struct BackwardBody {
         const int L = a.L, OL = a.OL, xslab = a.B * a.L, gslab = a.OB * a.OL, orowb = a.gpr * 16;
         const int strips = sg.npl * ai * nchunk * ci;
         const UDiv d_ai = make_udiv(ai);
-        auto load_g = [&](const unsigned char* base, int e0, float* out) {
+        auto load_g = [&](unsigned base, int e0, float* out) {
             if constexpr (WSG >= 0) load_window<ST, WSG, NVW>(base, e0, out); else load_window_rt<ST, NVW>(base, e0, out);
         };
         for (int sidx = tid; sidx < strips; sidx += nt) {
@@ -985,9 +992,9 @@ struct BackwardBody {
             Item p;
             p.pl = pl; p.a = a_lo + ia; p.b = in.b_lo + k * R; p.cg = in.c_lo + j;
             const int bend = p.b + R < in.b_hi ? p.b + R : in.b_hi;
-            const unsigned char* x_p = sg.st + p.pl * ximg;
-            const unsigned char* gv_p = sg.st + a.off_gv + p.pl * gvimg;
-            const unsigned char* gi_p = gibase + p.pl * giimg;
+            const unsigned x_p = sst + p.pl * ximg;
+            const unsigned gv_p = sst + a.off_gv + p.pl * gvimg;
+            const unsigned gi_p = gibase + p.pl * giimg;
             int xe = (p.a * a.B + p.b + xrsh) * L + p.cg * V - us.sx[2];
             int gve = (p.a * a.OB + p.b - a.lbB) * OL + p.cg * V - a.lbL;
             int gie = gve + grow_sh * OL + gsh;
@@ -1080,7 +1087,7 @@ struct BackwardBody {
     TS_D void interior_flat(const Stage& sg, int a_lo, int a_hi, float* ts) const {
         const int total = sg.npl * a.img_items;
         const int ximg = a.xs * a.slab_x, gvimg = a.gvs * a.slab_g, giimg = (a.gis ? a.gis : a.gvs) * a.slab_g;
-        const unsigned char* gibase = sg.st + (a.gis ? a.off_gi : a.off_gv);
+        const unsigned sst = shared_addr(sg.st), gibase = sst + (a.gis ? a.off_gi : a.off_gv);
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
         const int gsh = ACTIVE ? -us.sg[2] : us.sg[2];
         const int grow_sh = DIM >= 2 ? (ACTIVE ? -us.sg[1] : us.sg[1]) : 0;
@@ -1089,9 +1096,9 @@ struct BackwardBody {
             Item p;
             decode_item(a, item, p);
             if (!(in_range(p.cg, in.c_lo, in.c_hi) && in_range(p.b, in.b_lo, in.b_hi) && in_range(p.a, a_lo, a_hi))) continue;
-            const unsigned char* x_p = sg.st + p.pl * ximg;
-            const unsigned char* gv_p = sg.st + a.off_gv + p.pl * gvimg;
-            const unsigned char* gi_p = gibase + p.pl * giimg;
+            const unsigned x_p = sst + p.pl * ximg;
+            const unsigned gv_p = sst + a.off_gv + p.pl * gvimg;
+            const unsigned gi_p = gibase + p.pl * giimg;
             const int ob = p.b - a.lbB, oj0 = p.cg * V - a.lbL;
             float gv[V];
             load_window<ST, 0, V>(gv_p, (p.a * a.OB + ob) * a.OL + oj0, gv);
@@ -1137,7 +1144,7 @@ struct BackwardBody {
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
         for (int e = rotor.first(tid, nt, total); e < total; e += nt) {
             Item p;
-            p.pl = a.np > 1 ? e / per : 0;
+            p.pl = a.np > 1 ? es.image_of(e) : 0;
             es.decode(e - p.pl * per, p);
             const unsigned char* x_p = sg.st + (size_t)p.pl * ximg;
             const unsigned char* gv_p = sg.st + a.off_gv + (size_t)p.pl * gvimg;

@@ -337,15 +337,15 @@ struct GatherBody {
 
     template <int WS, bool SUB>
     TS_D void run(const Stage& sg) const {
-        const uint4* box = (const uint4*)sg.st;
+        const unsigned box = shared_addr(sg.st);
         const int pitch = a.TG + 1, ximg = a.x_img_chunks, xb = a.xb;
         for (int item = tid; item < sg.total; item += nt) {
             Item p;
             if (!decode_item<SLABS>(a, sg, item, p)) continue;
             const int ch = p.pl * ximg + (p.a * xb + p.b) * pitch + p.cg;
-            const uint4 A = box[ch];
+            const uint4 A = lds128(box + ch * 16);
             unsigned W[8] = {A.x, A.y, A.z, A.w, 0u, 0u, 0u, 0u};
-            if (WS > 0 || SUB) { const uint4 B = box[ch + 1]; W[4] = B.x; W[5] = B.y; W[6] = B.z; W[7] = B.w; }
+            if (WS > 0 || SUB) { const uint4 B = lds128(box + ch * 16 + 16); W[4] = B.x; W[5] = B.y; W[6] = B.z; W[7] = B.w; }
             unsigned o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = SUB ? __funnelshift_r(W[k + WS], W[(k + WS + 1) & 7], bs8) : W[k + WS];
@@ -375,12 +375,12 @@ struct GatherBody {
 // fp32 arithmetic bodies.  A window of NV consecutive elements starting M elements into the
 // aligned group `ch` of a staged box.
 template <int M, int NV>
-TS_D void load_win(const float4* __restrict__ box, int ch, float* out) {
-    const float4 A = box[ch];
-    float W[8] = {A.x, A.y, A.z, A.w, 0.f, 0.f, 0.f, 0.f};
+TS_D void load_win(unsigned box, int ch, float* out) {
+    const uint4 A = lds128(box + ch * 16);
+    float W[8] = {__uint_as_float(A.x), __uint_as_float(A.y), __uint_as_float(A.z), __uint_as_float(A.w), 0.f, 0.f, 0.f, 0.f};
     if (M + NV > 4) {
-        const float4 B = box[ch + 1];
-        W[4] = B.x; W[5] = B.y; W[6] = B.z; W[7] = B.w;
+        const uint4 B = lds128(box + ch * 16 + 16);
+        W[4] = __uint_as_float(B.x); W[5] = __uint_as_float(B.y); W[6] = __uint_as_float(B.z); W[7] = __uint_as_float(B.w);
     }
 #pragma unroll
     for (int t = 0; t < NV; ++t) out[t] = W[t + M];
@@ -440,7 +440,7 @@ struct ActiveFwdBody {
     template <int M>
     TS_D void run(const Stage& sg) const {
         constexpr int NR = 1 << (DIM - 1);
-        const float4* box = (const float4*)sg.st;
+        const unsigned box = shared_addr(sg.st);
         const int pitch = a.TG + 1, ximg = a.x_img_chunks, xb = a.xb;
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
         for (int item = tid; item < sg.total; item += nt) {
@@ -500,9 +500,9 @@ struct BackwardBody {
     TS_D void run(const Stage& sg) {
         constexpr int NR = 1 << (DIM - 1);
         constexpr int MG = ACTIVE ? M : ((4 - M) & 3);      // misalignment of the grad window used for grad_input
-        const float4* xbox = (const float4*)sg.st;
-        const float4* gv_box = (const float4*)(sg.st + a.off_gv);
-        const float4* g2_box = (const float4*)(sg.st + a.off_g2);
+        const unsigned xbox = shared_addr(sg.st);
+        const unsigned gv_box = xbox + a.off_gv;
+        const unsigned g2_box = xbox + a.off_g2;
         const int pitch = a.TG + 1, ximg = a.x_img_chunks, gimg = a.g_img_chunks, xb = a.xb, tb = a.TB;
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
         float ts[DIM];
