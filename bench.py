@@ -48,7 +48,11 @@ def parse_args():
                     help="weak (default): every rank owns a full BASELINE shard, N=256 images (global batch 256*G, batch-sharded); "
                          "strong: the global batch N=256 is split over the ranks")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks during the timed region")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample clocks during the timed region")
+    ap.add_argument("--clocks", default="auto", choices=["auto", "thread", "inline", "off"],
+                    help="how the SM clock / throttle reasons are sampled during the timed region: a 4 ms NVML polling "
+                         "thread (default), or three NVML reads from the launching thread while the GPU works through the "
+                         "queued steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-n", type=int, default=16)
     return ap.parse_args()
@@ -67,15 +71,14 @@ def peaks():
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region, in-process through NVML
-    (nvidia_ml_py).  A polling `nvidia-smi -lms 50` subprocess is NOT used: on a multi-GPU box its
-    queries serialise against kernel launches of every rank (measured: 0.70 -> 8.3 ms per step at
-    2 GPUs); an NVML query of one device costs microseconds."""
+    (nvidia_ml_py; no nvidia-smi subprocess to spawn and parse).  Only rank 0 samples; its start-up
+    happens BEFORE the barrier that opens the timed region, so it cannot skew the ranks."""
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index=0, period_s=0.004):
         self.rows, self.index, self.period, self.h, self.stop_flag, self.err = [], index, period_s, None, False, None
 
-    def start(self):
+    def start(self, poll=True):
         try:
             import pynvml
             import torch
@@ -87,10 +90,27 @@ class ClockSampler:
             except Exception:
                 self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.thread = threading.Thread(target=self._poll, daemon=True)
-            self.thread.start()
+            self.thread = None
+            if poll:
+                self.thread = threading.Thread(target=self._poll, daemon=True)
+                self.thread.start()
         except Exception as e:
             self.h, self.err = None, f"NVML unavailable: {e}"
+
+    def sample_once(self):
+        """one NVML read from the calling thread (used between enqueued steps)"""
+        if self.h is None:
+            return
+        nv = self.nv
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.rows.append((time.perf_counter(), sm, mask))
+        except Exception as e:
+            self.err = str(e)
 
     def _poll(self):
         nv = self.nv
@@ -111,12 +131,15 @@ class ClockSampler:
         self.stop_flag = True
         if self.h is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "not sampled"]}
-        self.thread.join(timeout=1.0)
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
         rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
         sm = [r[1] for r in rows]
         reasons = sorted({name for r in rows for bit, name in self.REASONS if r[2] & bit})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
-                "samples": len(sm), "how": "NVML (nvidia_ml_py) polled every 4 ms inside the timed region"}
+                "samples": len(sm), "how": "NVML (nvidia_ml_py), " + ("polled every 4 ms by a thread" if self.thread is not None else
+                                                                       "read from the launching thread between enqueued steps") +
+                " inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------ reference arm / cpu baseline
@@ -245,18 +268,24 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
-    if rank == 0 and not args.no_clocks:
-        sampler.start(); time.sleep(0.15)
+    mode = "off" if args.no_clocks else args.clocks
+    if mode == "auto":
+        mode = "thread"
+    if rank == 0 and mode != "off":
+        sampler.start(poll=(mode == "thread")); time.sleep(0.15)
+    inline_at = {args.steps // 3, (2 * args.steps) // 3, args.steps - 1} if (rank == 0 and mode == "inline") else set()
+    if world > 1:
+        dist.barrier()      # AFTER the sampler start-up (rank 0 only): every rank enters the timed region together
     launches0 = lib.ts_launch_count()
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     start, end = ev(), ev()
     start.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         step(timed=True)
+        if i in inline_at:
+            sampler.sample_once()        # the GPU is still working through the queued steps
     end.record()
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
