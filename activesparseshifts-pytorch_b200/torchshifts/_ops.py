@@ -61,6 +61,19 @@ def _same_device_and_type(fn, input, weights, grad=None):
         raise RuntimeError(f'{fn}: "shiftnd_cuda" not implemented for {input.dtype}')
 
 
+_COPY_THRESHOLD = 1 << 16
+
+
+def _dense(input):
+    """Channels-last / sliced inputs: the stride-aware generic kernels read them in place, but their
+    per-element strided loads waste most of every 32-byte sector.  Above a few tens of thousands of
+    elements one extra coalesced pass (``.contiguous()``) plus the bandwidth kernels is several times
+    faster (native NHWC kernels are SURVEY 8f "next")."""
+    if input.numel() >= _COPY_THRESHOLD and not input.is_contiguous():
+        return input.contiguous()
+    return input
+
+
 def _stream(device):
     return ct.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -103,6 +116,7 @@ def _forward_cuda(dim, input, weights, borders, new_size, padding_mode, active_f
     lb, rb = _borders_lists(borders, dim)
     out = torch.empty(list(new_size), dtype=input.dtype, device=input.device)
     w = weights.contiguous()
+    input = _dense(input)
     geo = _geometry(dim, input, lb, rb)
     if list(out.shape[2:]) != [rb[a] - lb[a] for a in range(dim)]:
         raise RuntimeError(f'{fn}: new_size {list(new_size)} does not match the borders')
@@ -122,6 +136,7 @@ def _backward_cuda(dim, grad, weights, input, borders, padding_mode, active_flag
     w = weights.contiguous()
     out_grad = torch.empty(input.shape, dtype=input.dtype, device=input.device)
     weights_grad = torch.empty(w.shape, dtype=w.dtype, device=w.device)
+    input = _dense(input)
     geo = _geometry(dim, input, lb, rb)
     if list(grad.shape[2:]) != [rb[a] - lb[a] for a in range(dim)] or list(grad.shape[:2]) != list(input.shape[:2]):
         raise RuntimeError(f'{fn}: grad shape {list(grad.shape)} does not match the (cropped) output of input {list(input.shape)}')

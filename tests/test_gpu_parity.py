@@ -230,6 +230,28 @@ def test_strided_and_channels_last_inputs(dev, oracle_port, auto_path):
             assert np.allclose(wd.grad.cpu().numpy(), gw_ref, rtol=1e-4, atol=1e-4)
 
 
+def test_large_channels_last_input_takes_the_bandwidth_path(dev, lib, oracle_port, auto_path):
+    """Above the copy threshold a channels-last input is made dense once and served by the TMA / staged
+    kernels (values identical to the strided generic path and to the oracle)."""
+    from torchshifts.functional import shift2d_func
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((4, 32, 24, 32)).astype(np.float32)       # 98 304 elements
+    w = ((rng.random((32, 2)) * 2 - 1) * 2).astype(np.float32)
+    g = rng.standard_normal(x.shape).astype(np.float32)
+    for pad, active in ((0, False), (4, True)):
+        xd = torch.from_numpy(x).to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        wd = torch.from_numpy(w).to(dev).requires_grad_(True)
+        y = shift2d_func(xd, wd, pad, active)
+        assert lib.ts_last_kernel_path() in (STAGED, TMA)
+        y.backward(torch.from_numpy(g).to(dev))
+        assert lib.ts_last_kernel_path() in (STAGED, TMA)
+        assert np.array_equal(y.detach().cpu().numpy(), oracle_port.forward(x, w, pad, active))
+        gi_ref, _ = oracle_port.backward(g, x, w, pad, active)
+        assert np.array_equal(xd.grad.cpu().numpy(), gi_ref)
+        _, gw64 = oracle_port.backward(g.astype(np.float64), x.astype(np.float64), w.astype(np.float64), pad, active)
+        assert _gw_close(wd.grad.cpu().numpy(), gw64)
+
+
 def test_edge_cases(dev, lib, oracle_port, auto_path):
     from torchshifts.functional import shift2d_func
     # empty batch / empty channel set
@@ -529,3 +551,41 @@ def test_torch_compile_and_state_dict(dev, auto_path):
     got.sum().backward()
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
     assert torch.allclose(x.grad, gx, rtol=1e-5, atol=1e-6) and torch.allclose(sh.weight.grad, gw, rtol=1e-4, atol=1e-5)
+
+
+def test_cuda_graph_capture_and_replay(dev, lib, oracle_port, auto_path):
+    """The C ABI only enqueues work on the caller's stream (no sync, no allocation, tensor maps are
+    encoded on the host and passed by value), so forward + backward capture into a CUDA graph; the
+    replay on new data matches the oracle.  cfg1-sized layers are launch-bound without it."""
+    fwd = torch.ops.torchshifts._shift2d_forward
+    bwd = torch.ops.torchshifts._shift2d_backward
+    rng = np.random.default_rng(4)
+    shape = (8, 64, 32, 32)
+    borders = torch.tensor([0, 32, 0, 32, 0, 1], dtype=torch.int32)
+    x = torch.zeros(shape, device=dev)
+    g = torch.zeros(shape, device=dev)
+    w = torch.from_numpy(((rng.random((64, 2)) * 2 - 1) * 2).astype(np.float32)).to(dev)
+    for pad, active in ((0, False), (3, True)):
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                                   # warm-up outside the capture
+                y = fwd(x, w, borders, list(shape), pad, active)
+                gi, gw = bwd(g, w, x, borders, pad, active)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph), torch.no_grad():
+            y = fwd(x, w, borders, list(shape), pad, active)
+            gi, gw = bwd(g, w, x, borders, pad, active)
+        for seed in (1, 2):
+            xs = np.random.default_rng(seed).standard_normal(shape).astype(np.float32)
+            gs = np.random.default_rng(seed + 10).standard_normal(shape).astype(np.float32)
+            x.copy_(torch.from_numpy(xs)); g.copy_(torch.from_numpy(gs))
+            graph.replay()
+            torch.cuda.synchronize()
+            wn = w.cpu().numpy()
+            assert np.array_equal(y.cpu().numpy(), oracle_port.forward(xs, wn, pad, active))
+            gi_ref, _ = oracle_port.backward(gs, xs, wn, pad, active)
+            assert np.array_equal(gi.cpu().numpy(), gi_ref)
+            _, gw64 = oracle_port.backward(gs.astype(np.float64), xs.astype(np.float64), wn.astype(np.float64), pad, active)
+            assert _gw_close(gw.cpu().numpy(), gw64)
