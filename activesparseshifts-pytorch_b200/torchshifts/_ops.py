@@ -176,6 +176,11 @@ def _forward_qcuda(dim, input, weights, borders, new_size, padding_mode, active_
                                            x.data_ptr(), wq.data_ptr(), _QKINDS[weights.dtype], int(weights.q_zero_point()),
                                            out.data_ptr(), _stream(input.device))
     _NATIVE.check(st, 'ts_qshift_forward')
+    # the reference allocates the quantized output in the input's memory format
+    # (quantized/shifts_quantized.cpp:119-122): channels-last in, channels-last out
+    fmt = {2: torch.channels_last, 3: torch.channels_last_3d}.get(dim)
+    if fmt is not None and x is not input and input.is_contiguous(memory_format=fmt):
+        out = out.contiguous(memory_format=fmt)
     return out
 
 

@@ -589,3 +589,25 @@ def test_cuda_graph_capture_and_replay(dev, lib, oracle_port, auto_path):
             assert np.array_equal(gi.cpu().numpy(), gi_ref)
             _, gw64 = oracle_port.backward(gs.astype(np.float64), xs.astype(np.float64), wn.astype(np.float64), pad, active)
             assert _gw_close(gw.cpu().numpy(), gw64)
+
+
+def test_quantized_channels_last_keeps_its_memory_format(dev, oracle_port, auto_path):
+    """quantized/shifts_quantized.cpp:119-122: the output takes the input's memory format."""
+    from torchshifts.quantized.functional import shift2d_quantized
+    from oracle.oracle import quantize_shift_weights_np
+    rng = np.random.default_rng(31)
+    x = torch.from_numpy(rng.random((2, 8, 6, 16)).astype(np.float32)).to(dev)
+    w = ((rng.random((8, 2)) * 2 - 1) * 2).astype(np.float32)
+    wraw, wzp = quantize_shift_weights_np(w)
+    qw = torch._make_per_tensor_quantized_tensor(torch.from_numpy(wraw.astype(np.uint8)).to(dev), 1.0, int(wzp))
+    for qdtype, zp in ((torch.quint8, 3), (torch.qint8, -5)):
+        xq = torch.quantize_per_tensor(x, 0.01, zp, qdtype)
+        xcl = xq.contiguous(memory_format=torch.channels_last)
+        assert xcl.is_contiguous(memory_format=torch.channels_last) and not xcl.is_contiguous()
+        for pad in (0, 3):
+            y = shift2d_quantized(xcl, qw, pad)
+            assert y.is_contiguous(memory_format=torch.channels_last) and y.dtype == qdtype
+            assert y.q_scale() == xq.q_scale() and y.q_zero_point() == zp
+            want = oracle_port.qforward(xq.int_repr().cpu().numpy(), wraw, wzp, zp, pad)
+            assert np.array_equal(y.int_repr().cpu().numpy(), want)
+            assert shift2d_quantized(xq, qw, pad).is_contiguous()
