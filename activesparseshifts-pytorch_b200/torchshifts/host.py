@@ -22,7 +22,7 @@ _OPS = {1: ('_shift1d_forward', '_shift1d_backward'), 2: ('_shift2d_forward', '_
 
 
 class HostShiftPipeline:
-    def __init__(self, N, C, spatial, device, dtype=torch.float32, chunk=16, slots=3):
+    def __init__(self, N, C, spatial, device, dtype=torch.float32, chunk=16, slots=4):
         self.N, self.C, self.spatial = int(N), int(C), tuple(int(s) for s in spatial)
         self.dim = len(self.spatial)
         assert self.dim in (1, 2, 3)
@@ -102,5 +102,5 @@ class HostShiftPipeline:
 
 
 class HostShift2dPipeline(HostShiftPipeline):
-    def __init__(self, N, C, H, W, device, dtype=torch.float32, chunk=16, slots=3):
+    def __init__(self, N, C, H, W, device, dtype=torch.float32, chunk=16, slots=4):
         super().__init__(N, C, (H, W), device, dtype, chunk, slots)
