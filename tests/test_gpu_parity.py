@@ -611,3 +611,33 @@ def test_quantized_channels_last_keeps_its_memory_format(dev, oracle_port, auto_
             want = oracle_port.qforward(xq.int_repr().cpu().numpy(), wraw, wzp, zp, pad)
             assert np.array_equal(y.int_repr().cpu().numpy(), want)
             assert shift2d_quantized(xq, qw, pad).is_contiguous()
+
+
+def test_misaligned_dense_tensors_fall_back(dev, lib, oracle_port, auto_path):
+    """Dense NCHW tensors whose base pointer is not 16-byte aligned (a view into a larger buffer) cannot use
+    bulk / TMA copies: the planners must reject them and the generic family must give the same values."""
+    from torchshifts.functional import shift2d_func
+    rng = np.random.default_rng(41)
+    shape = (2, 3, 8, 16)
+    n = int(np.prod(shape))
+    x = rng.standard_normal(shape).astype(np.float32)
+    g = rng.standard_normal(shape).astype(np.float32)
+    w = ((rng.random((3, 2)) * 2 - 1) * 2).astype(np.float32)
+    for pad, active in ((0, False), (0, True), (2, True)):
+        buf = torch.zeros(n + 1, device=dev)
+        xd = buf[1:].view(shape)
+        xd.copy_(torch.from_numpy(x))
+        assert xd.data_ptr() % 16 != 0 and xd.is_contiguous()
+        xd.requires_grad_(True)
+        wd = torch.from_numpy(w).to(dev).requires_grad_(True)
+        gbuf = torch.zeros(n + 3, device=dev)
+        gd = gbuf[3:].view(shape)
+        gd.copy_(torch.from_numpy(g))
+        y = shift2d_func(xd, wd, pad, active)
+        assert lib.ts_last_kernel_path() == GENERIC
+        y.backward(gd)
+        assert np.array_equal(y.detach().cpu().numpy(), oracle_port.forward(x, w, pad, active))
+        gi_ref, _ = oracle_port.backward(g, x, w, pad, active)
+        assert np.array_equal(xd.grad.cpu().numpy(), gi_ref)
+        _, gw64 = oracle_port.backward(g.astype(np.float64), x.astype(np.float64), w.astype(np.float64), pad, active)
+        assert _gw_close(wd.grad.cpu().numpy(), gw64)
