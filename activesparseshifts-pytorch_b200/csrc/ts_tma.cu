@@ -155,7 +155,8 @@ struct alignas(64) TArgs {
     int stage_stride, stages, nw, n_per_unit, units;
     int GP, img_items;       // padded groups per row of the item index space; items per image = TA*TB*GP
     int img_stride16;        // output distance between consecutive images of one channel, in 16-byte units
-    FastDiv d_img, d_GP, d_TB, d_tg, d_tb;
+    int R, nchunk;           // strip-mined arithmetic kernels: rows per strip, strips per tile column
+    FastDiv d_img, d_GP, d_TB, d_tg, d_tb, d_TG, d_nchunk, d_TA;
 };
 
 TS_D int level_axis(int level, int dim) { return level - (3 - dim); }
@@ -254,6 +255,7 @@ TS_D void producer(const TArgs& a, unsigned char* smem, uint64_t* full, uint64_t
 struct Stage {
     const unsigned char* st;   // stage base in shared memory
     unsigned char* dst;        // output address of (first image of the stage, channel c, tile origin)
+    int npl;                   // images in this stage
     int total;                 // items of this stage in the padded index space: images * img_items
     int an, bn, gn;            // valid extents of this tile (slabs, rows, groups)
 };
@@ -271,7 +273,8 @@ TS_D void consumer_loop(const TArgs& a, unsigned char* smem, uint64_t* full, uin
         body.begin_unit(c);
         for (int nb = n0; nb < n1; nb += np) {
             Stage sg;
-            sg.total = (n1 - nb < np ? n1 - nb : np) * a.img_items;
+            sg.npl = n1 - nb < np ? n1 - nb : np;
+            sg.total = sg.npl * a.img_items;
             unsigned char* img = a.out + ((long long)nb * C + c) * plane_bytes;
             for (int t = 0; t < tiles; ++t) {
                 sg.an = a.TA; sg.bn = a.TB; sg.gn = a.TG;
@@ -460,12 +463,68 @@ struct ActiveFwdBody {
             __stcs((float4*)item_dst(a, sg, p), make_float4(o[0], o[1], o[2], o[3]));
         }
     }
+    // strip-mined variant, used for 3-D (see BackwardBody::run_strip)
+    template <int M>
+    TS_D void run_strip(const Stage& sg) const {
+        constexpr int NR = 1 << (DIM - 1);
+        constexpr int S = DIM == 3 ? 2 : 1;
+        const unsigned box = shared_addr(sg.st);
+        const int pitch = a.TG + 1, ximg = a.x_img_chunks, xb = a.xb;
+        const int xslab = xb * pitch;
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        const int R = a.R, nchunk = a.nchunk, TG = a.TG, TA = a.TA;
+        const int strips = sg.npl * TA * nchunk * TG;
+        const int orow = a.OGR * 16;
+        for (int sidx = tid; sidx < strips; sidx += nt) {
+            const int r = (int)fdiv((unsigned)sidx, a.d_TG), cg = sidx - r * TG;
+            const int r2 = (int)fdiv((unsigned)r, a.d_nchunk), kc = r - r2 * nchunk;
+            int pl = r2, ia = 0;
+            if (TA > 1) { pl = (int)fdiv((unsigned)r2, a.d_TA); ia = r2 - pl * TA; }
+            const int b0 = kc * R;
+            if (cg >= sg.gn || ia >= sg.an || b0 >= sg.bn) continue;
+            const int bend = b0 + R < sg.bn ? b0 + R : sg.bn;
+            Item p;
+            p.pl = pl; p.a = ia; p.b = b0; p.cg = cg;
+            int xch = pl * ximg + (ia * xb + b0) * pitch + cg;
+            unsigned char* dst = item_dst(a, sg, p);
+            float Xlo[S][5];
+#pragma unroll
+            for (int q = 0; q < S; ++q) load_win<M, 5>(box, xch + q * xslab, Xlo[q]);
+            for (int b = b0; b < bend; ++b) {
+                float X[NR][5];
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
+                    load_win<M, 5>(box, xch + pitch + q * xslab, X[S + q]);
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) X[q][t] = Xlo[q][t];
+                }
+                float o[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float v[8];
+                    neighbours_from_rows<DIM>(X, t, v);
+                    o[t] = interpolate<float, DIM>(v, d);
+                }
+                __stcs((float4*)dst, make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+                for (int q = 0; q < S; ++q)
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) Xlo[q][t] = X[S + q][t];
+                xch += pitch; dst += orow;
+            }
+        }
+    }
+    template <int M>
+    TS_D void run_any(const Stage& sg) const {
+        if constexpr (DIM == 3) run_strip<M>(sg); else run<M>(sg);   // 2-D is HBM-bound either way and the flat,
+                                                                     // padded index space is measurably faster there
+    }
     TS_D void step(const Stage& sg) const {
         switch (m) {
-        case 0: run<0>(sg); break;
-        case 1: run<1>(sg); break;
-        case 2: run<2>(sg); break;
-        default: run<3>(sg); break;
+        case 0: run_any<0>(sg); break;
+        case 1: run_any<1>(sg); break;
+        case 2: run_any<2>(sg); break;
+        default: run_any<3>(sg); break;
         }
     }
 };
@@ -547,12 +606,107 @@ struct BackwardBody {
 #pragma unroll
         for (int k = 0; k < DIM; ++k) acc[k] += (double)ts[k];   // fp32 inside a stage, fp64 across stages
     }
+    // Strip-mined variant (used for 3-D, where the kernels are instruction-bound): a thread owns (image, slab, group, chunk of R rows); the "+1 row"
+    // windows of one item are the "+0 row" windows of the next and stay in registers.
+    template <int M>
+    TS_D void run_strip(const Stage& sg) {
+        constexpr int NR = 1 << (DIM - 1);
+        constexpr int S = DIM == 3 ? 2 : 1;
+        constexpr int MG = ACTIVE ? M : ((4 - M) & 3);
+        const unsigned xbox = shared_addr(sg.st);
+        const unsigned gv_box = xbox + a.off_gv;
+        const unsigned g2_box = xbox + a.off_g2;
+        const int pitch = a.TG + 1, ximg = a.x_img_chunks, gimg = a.g_img_chunks, xb = a.xb, tb = a.TB;
+        const int xslab = xb * pitch;
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        float ts[DIM];
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) ts[k] = 0.f;
+        const int R = a.R, nchunk = a.nchunk, TG = a.TG, TA = a.TA;
+        const int strips = sg.npl * TA * nchunk * TG;
+        const int orow = a.OGR * 16;
+        for (int sidx = tid; sidx < strips; sidx += nt) {
+            const int r = (int)fdiv((unsigned)sidx, a.d_TG), cg = sidx - r * TG;
+            const int r2 = (int)fdiv((unsigned)r, a.d_nchunk), kc = r - r2 * nchunk;
+            int pl = r2, ia = 0;
+            if (TA > 1) { pl = (int)fdiv((unsigned)r2, a.d_TA); ia = r2 - pl * TA; }
+            const int b0 = kc * R;
+            if (cg >= sg.gn || ia >= sg.an || b0 >= sg.bn) continue;
+            const int bend = b0 + R < sg.bn ? b0 + R : sg.bn;
+            Item p;
+            p.pl = pl; p.a = ia; p.b = b0; p.cg = cg;
+            int gch = pl * gimg + (ia * tb + b0) * pitch + cg;
+            int xch = pl * ximg + (ia * xb + b0) * pitch + cg;
+            unsigned char* dst = item_dst(a, sg, p);
+            float Xlo[S][5], Glo[S][5];
+#pragma unroll
+            for (int q = 0; q < S; ++q) load_win<M, 5>(xbox, xch + q * xslab, Xlo[q]);
+            if (ACTIVE) {
+#pragma unroll
+                for (int q = 0; q < S; ++q) load_win<MG, 5>(g2_box, xch + q * xslab, Glo[q]);
+            }
+            for (int b = b0; b < bend; ++b) {
+                float gv[4];
+                load_win<0, 4>(gv_box, gch, gv);
+                float X[NR][5];
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
+                    load_win<M, 5>(xbox, xch + pitch + q * xslab, X[S + q]);
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) X[q][t] = Xlo[q][t];
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float v[8], wg[3];
+                    neighbours_from_rows<DIM>(X, t, v);
+                    weight_partials_fast<DIM>(v, d, wg);
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) ts[k] = fmaf(gv[t], wg[k], ts[k]);
+                }
+                float o[4];
+                if (ACTIVE) {
+                    float G[NR][5];
+#pragma unroll
+                    for (int q = 0; q < S; ++q) {
+                        load_win<MG, 5>(g2_box, xch + pitch + q * xslab, G[S + q]);
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) G[q][t] = Glo[q][t];
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        float v[8];
+                        neighbours_from_rows<DIM>(G, t, v);
+                        o[t] = interpolate<float, DIM>(v, d);
+                    }
+#pragma unroll
+                    for (int q = 0; q < S; ++q)
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) Glo[q][t] = G[S + q][t];
+                } else {
+                    load_win<MG, 4>(g2_box, gch, o);
+                }
+                __stcs((float4*)dst, make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+                for (int q = 0; q < S; ++q)
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) Xlo[q][t] = X[S + q][t];
+                xch += pitch; gch += pitch; dst += orow;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) acc[k] += (double)ts[k];
+    }
+    template <int M>
+    TS_D void run_any(const Stage& sg) {
+        if constexpr (DIM == 3) run_strip<M>(sg); else run<M>(sg);   // 2-D is HBM-bound either way and the flat,
+                                                                     // padded index space is measurably faster there
+    }
     TS_D void step(const Stage& sg) {
         switch (m) {
-        case 0: run<0>(sg); break;
-        case 1: run<1>(sg); break;
-        case 2: run<2>(sg); break;
-        default: run<3>(sg); break;
+        case 0: run_any<0>(sg); break;
+        case 1: run_any<1>(sg); break;
+        case 2: run_any<2>(sg); break;
+        default: run_any<3>(sg); break;
         }
     }
 };
@@ -644,6 +798,17 @@ bool make_args(const Geo& g, const TmaPlan& p, int mode, int active, int es, TAr
     a.GP = p.gp;
     a.img_items = a.TA * a.TB * a.GP;
     a.img_stride16 = (int)(g.C * (mode == 2 ? g.in_plane : g.out_plane) * es / 16);
+    {   // strips: about three per thread and stage, at least two rows each (the row reuse is the point)
+        const long long items = (long long)a.np * a.TA * a.TB * a.TG, nt = 32ll * p.warps;
+        long long R = (items + 3 * nt - 1) / (3 * nt);
+        if (R < 2) R = 2;
+        if (R > a.TB) R = a.TB;
+        a.R = (int)R;
+        a.nchunk = (a.TB + a.R - 1) / a.R;
+    }
+    a.d_TG = make_fastdiv((unsigned)a.TG);
+    a.d_nchunk = make_fastdiv((unsigned)a.nchunk);
+    a.d_TA = make_fastdiv((unsigned)a.TA);
     a.d_img = make_fastdiv((unsigned)a.img_items);
     a.d_GP = make_fastdiv((unsigned)a.GP);
     a.d_TB = make_fastdiv((unsigned)a.TB);
