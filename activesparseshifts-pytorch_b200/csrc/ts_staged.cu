@@ -781,8 +781,10 @@ struct ActiveFwdBody {
     EdgeSets es;
     EdgeRotor rotor;
     bool any_interior;
+    int R, nchunk;        // rows per strip / strips per column of the interior box (per unit)
+    UDiv d_nchunk;
 
-    TS_D ActiveFwdBody(const SArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), any_interior(false) {}
+    TS_D ActiveFwdBody(const SArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), any_interior(false), R(1), nchunk(1) {}
     TS_D void begin_unit(int c) {
         us = unit_shift(a, c);
         // rows: 0 <= ob + lbB - s1, ob + lbB - s1 + 1 <= B-1 ; groups: 0 <= cs, cs + V + 1 <= L
@@ -797,6 +799,7 @@ struct ActiveFwdBody {
         any_interior = a.L > 1 && (DIM < 2 || a.B > 1) && (DIM < 3 || a.A > 1);
         if (!any_interior) in.b_hi = in.b_lo = in.c_hi = in.c_lo = 0;
         es.init_unit(in, a.OB, a.gpr);
+        strip_plan(in, a.np * a.TA, nt, R, nchunk, d_nchunk);
     }
     TS_D void end_unit(int, int) {}
 
@@ -811,8 +814,67 @@ struct ActiveFwdBody {
         if (!any_interior) a_lo = a_hi = 0;
     }
 
+    // strip-mined interior (fp32, DIM >= 2): see BackwardBody::interior_strip
+    template <int WS>
+    TS_D void interior_strip(const Stage& sg, int a_lo, int a_hi) const {
+        constexpr int S = DIM == 3 ? 2 : 1;
+        const int ci = in.c_hi - in.c_lo, bi = in.b_hi - in.b_lo, ai = a_hi - a_lo;
+        if (ci <= 0 || bi <= 0 || ai <= 0) return;
+        const int img_bytes = a.xs * a.slab_x;
+        const int col0 = a.lbL - us.sx[2];
+        const int rsh = a.lbB - us.sx[1];
+        const unsigned sst = shared_addr(sg.st);
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        const int L = a.L, xslab = a.B * a.L, orowb = a.gpr * 16;
+        const int strips = sg.npl * ai * nchunk * ci;
+        const UDiv d_ai = make_udiv(ai);
+        for (int sidx = tid; sidx < strips; sidx += nt) {
+            const int r = udiv(sidx, es.d_ci), j = sidx - r * ci;
+            const int r2 = udiv(r, d_nchunk), k = r - r2 * nchunk;
+            int pl = r2, ia = 0;
+            if (ai > 1) { pl = udiv(r2, d_ai); ia = r2 - pl * ai; }
+            Item p;
+            p.pl = pl; p.a = a_lo + ia; p.b = in.b_lo + k * R; p.cg = in.c_lo + j;
+            const int bend = p.b + R < in.b_hi ? p.b + R : in.b_hi;
+            const unsigned img = sst + p.pl * img_bytes;
+            int xe = (p.a * a.B + p.b + rsh) * L + col0 + p.cg * V;
+            unsigned char* dst = item_dst(a, sg, p);
+            float Xlo[S][NVW];
+#pragma unroll
+            for (int q = 0; q < S; ++q) load_window<ST, WS, NVW>(img, xe + q * xslab, Xlo[q]);
+            for (int b = p.b; b < bend; ++b) {
+                float X[NR][NVW];
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
+                    load_window<ST, WS, NVW>(img, xe + L + q * xslab, X[S + q]);
+#pragma unroll
+                    for (int t = 0; t < NVW; ++t) X[q][t] = Xlo[q][t];
+                }
+                float o[V];
+#pragma unroll
+                for (int t = 0; t < V; ++t) {
+                    float v[8];
+                    neighbours_from_rows<DIM, NVW>(X, t, v);
+                    o[t] = interpolate<float, DIM>(v, d);
+                }
+                __stcs((uint4*)dst, Pack<ST>::pack(o));
+#pragma unroll
+                for (int q = 0; q < S; ++q)
+#pragma unroll
+                    for (int t = 0; t < NVW; ++t) Xlo[q][t] = X[S + q][t];
+                xe += L; dst += orowb;
+            }
+        }
+    }
+
     template <int WS>
     TS_D void interior(const Stage& sg, int a_lo, int a_hi) const {
+        if constexpr (sizeof(ST) == 4 && DIM >= 2) interior_strip<WS>(sg, a_lo, a_hi);
+        else interior_flat<WS>(sg, a_lo, a_hi);
+    }
+
+    template <int WS>
+    TS_D void interior_flat(const Stage& sg, int a_lo, int a_hi) const {
         const int total = sg.npl * a.img_items;
         const int img_bytes = a.xs * a.slab_x;
         const int col0 = a.lbL - us.sx[2];
