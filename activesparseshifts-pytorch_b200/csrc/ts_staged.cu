@@ -901,6 +901,8 @@ struct ActiveFwdBody {
         }
     }
 
+    // (an element-per-thread edge pass like the backward's was measured slower here: the forward gathers
+    // only the x windows, whole items amortise the remapping better)
     TS_D void edges(const Stage& sg, int a_lo, int a_hi) {
         es.init_stage(a_lo, a_hi, sg.an);
         const int per = es.per_image(), total = sg.npl * per;
@@ -1197,7 +1199,86 @@ struct BackwardBody {
         }
     }
 
+    // Edge pass, fp32: ONE ELEMENT per thread-iteration (4 per item).  An edge item's windows are gathered
+    // element by element anyway; with whole items per thread the lanes of a warp sit on consecutive ROWS at
+    // the same column, and a row pitch of 56 words puts them on 4 banks (8-way conflicts on ~44 scalar loads
+    // per item; measured: 10 % of the items cost 55 % of the 3-D backward).  With the element index fastest,
+    // 4 consecutive lanes read 4 consecutive words (2-way conflicts), four times as many threads share the
+    // edge work and the dependent chain per thread is one element instead of four.
+    TS_D void edges_elem(const Stage& sg, int a_lo, int a_hi, float* ts) {
+        es.init_stage(a_lo, a_hi, sg.an);
+        const int per = es.per_image(), total = sg.npl * per * V;
+        const int pad = a.g.pad;
+        const int ximg = a.xs * a.slab_x, gvimg = a.gvs * a.slab_g, giimg = (a.gis ? a.gis : a.gvs) * a.slab_g;
+        const unsigned char* gibase = sg.st + (a.gis ? a.off_gi : a.off_gv);
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        for (int task = rotor.first(tid, nt, total); task < total; task += nt) {
+            const int e = task / V, t = task - e * V;
+            Item p;
+            p.pl = a.np > 1 ? es.image_of(e) : 0;
+            es.decode(e - p.pl * per, p);
+            const ST* x_p = (const ST*)(sg.st + (size_t)p.pl * ximg);
+            const ST* gv_p = (const ST*)(sg.st + a.off_gv + (size_t)p.pl * gvimg);
+            const ST* gi_p = (const ST*)(gibase + (size_t)p.pl * giimg);
+            ST* dst = (ST*)item_dst(a, sg, p) + t;
+            const int col = p.cg * V + t;
+            const int oa = sg.a0 + p.a - a.lbA, ob = p.b - a.lbB, oj = col - a.lbL;
+            const bool pass = ob >= 0 && ob < a.OB && (DIM < 3 || (oa >= 0 && oa < a.OA)) && oj >= 0 && oj < a.OL;
+            if (!pass) { __stcs(dst, Elem<ST>::st(0.f)); continue; }
+            const float gvv = Elem<ST>::ld(gv_p[((DIM == 3 ? p.a * a.OB : 0) + ob) * a.OL + oj]);
+            // per-level index pairs (index, index of the +1 neighbour); -1 = outside (zeros padding)
+            int xs[3][2], gs[3][2];
+            xs[0][0] = xs[0][1] = gs[0][0] = gs[0][1] = 0;
+            xs[1][0] = xs[1][1] = gs[1][0] = gs[1][1] = 0;
+            if (DIM == 3) {
+                xs[0][0] = x_slot_slab(a, us, sg.a0, p.a) >= 0 ? p.a : -1;
+                xs[0][1] = x_slot_slab(a, us, sg.a0, p.a + 1) >= 0 ? p.a + 1 : -1;
+                gs[0][0] = gi_slot_slab(a, us, sg.a0, p.a) >= 0 ? p.a : -1;
+                gs[0][1] = ACTIVE ? (gi_slot_slab(a, us, sg.a0, p.a + 1) >= 0 ? p.a + 1 : -1) : -1;
+            }
+            if (DIM >= 2) {
+                xs[1][0] = axis_index(p.b - us.sx[1], a.B, pad);
+                xs[1][1] = axis_index(p.b - us.sx[1] + 1, a.B, pad);
+                gs[1][0] = axis_index(ACTIVE ? ob - us.sg[1] : ob + us.sg[1], a.OB, pad);
+                gs[1][1] = ACTIVE ? axis_index(ob - us.sg[1] + 1, a.OB, pad) : -1;
+            }
+            xs[2][0] = axis_index(col - us.sx[2], a.L, pad);
+            xs[2][1] = axis_index(col - us.sx[2] + 1, a.L, pad);
+            gs[2][0] = axis_index(ACTIVE ? oj - us.sg[2] : oj + us.sg[2], a.OL, pad);
+            gs[2][1] = ACTIVE ? axis_index(oj - us.sg[2] + 1, a.OL, pad) : -1;
+            // neighbour q: bit k = +1 on TENSOR axis k; tensor axis k lives on level k + (3 - DIM)
+            float v[8], wg[3];
+#pragma unroll
+            for (int q = 0; q < (1 << DIM); ++q) {
+                const int ia = DIM == 3 ? xs[0][q & 1] : 0;
+                const int ib = DIM == 3 ? xs[1][(q >> 1) & 1] : DIM == 2 ? xs[1][q & 1] : 0;
+                const int ic = xs[2][(q >> (DIM - 1)) & 1];
+                v[q] = (ia >= 0 && ib >= 0 && ic >= 0) ? Elem<ST>::ld(x_p[(ia * a.B + ib) * a.L + ic]) : 0.f;
+            }
+            weight_partials_fast<DIM>(v, d, wg);
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) ts[k] = fmaf(gvv, wg[k], ts[k]);
+            float o;
+            if (ACTIVE) {
+#pragma unroll
+                for (int q = 0; q < (1 << DIM); ++q) {
+                    const int ia = DIM == 3 ? gs[0][q & 1] : 0;
+                    const int ib = DIM == 3 ? gs[1][(q >> 1) & 1] : DIM == 2 ? gs[1][q & 1] : 0;
+                    const int ic = gs[2][(q >> (DIM - 1)) & 1];
+                    v[q] = (ia >= 0 && ib >= 0 && ic >= 0) ? Elem<ST>::ld(gi_p[(ia * a.OB + ib) * a.OL + ic]) : 0.f;
+                }
+                o = interpolate<float, DIM>(v, d);
+            } else {
+                const int ia = gs[0][0], ib = gs[1][0], ic = gs[2][0];
+                o = (ia >= 0 && ib >= 0 && ic >= 0) ? Elem<ST>::ld(gi_p[(ia * a.OB + ib) * a.OL + ic]) : 0.f;
+            }
+            __stcs(dst, Elem<ST>::st(o));
+        }
+    }
+
     TS_D void edges(const Stage& sg, int a_lo, int a_hi, float* ts) {
+        // 2-D / 1-D sparse items gather few words: whole items win there (measured on cfg3 with reflect padding)
+        if constexpr (sizeof(ST) == 4 && (ACTIVE || DIM == 3)) { edges_elem(sg, a_lo, a_hi, ts); return; }
         es.init_stage(a_lo, a_hi, sg.an);
         const int per = es.per_image(), total = sg.npl * per;
         const int pad = a.g.pad;

@@ -27,8 +27,10 @@ CASES = {
              ("cfg2 1d active periodic bf16", (64, 512, 4096), 2, True, torch.bfloat16)],
     "cfg3": [("cfg3 2d sparse zeros f32", (256, 256, 56, 56), 0, False, torch.float32),
              ("cfg3 2d active zeros f32", (256, 256, 56, 56), 0, True, torch.float32),
-             ("cfg3 2d sparse reflect f32", (256, 256, 56, 56), 3, False, torch.float32)],
-    "cfg4": [(f"cfg4 3d active {PADS[p]} f32", (32, 128, 16, 56, 56), p, True, torch.float32) for p in range(5)],
+             ("cfg3 2d sparse reflect f32", (256, 256, 56, 56), 3, False, torch.float32),
+             ("cfg3 2d active reflect f32", (256, 256, 56, 56), 3, True, torch.float32)],
+    "cfg4": [(f"cfg4 3d active {PADS[p]} f32", (32, 128, 16, 56, 56), p, True, torch.float32) for p in range(5)] +
+            [("cfg4 3d sparse reflect f32", (32, 128, 16, 56, 56), 3, False, torch.float32)],
     "cfg5": [("cfg5 2d qint8 zeros", (256, 256, 56, 56), 0, False, torch.qint8),
              ("cfg5 2d quint8 zeros", (256, 256, 56, 56), 0, False, torch.quint8)],
 }
