@@ -1506,7 +1506,8 @@ StagedPlan plan_staged(const Geo& g, int mode, int active, int esize, int dtype,
     const int IA = mode == 2 ? A : OA;
     const long long IB = mode == 2 ? B : OB;
     const int ex = mode != 0 ? 1 : 0;                       // +1 neighbour slab for the arithmetic kernels
-    const long long budget = SMEM_LIMIT - 1024;
+    const int ctas = (mode == 0 && t.ctas_per_sm > 1) ? t.ctas_per_sm : 1;     // byte mover only: several small pipelines per SM
+    const long long budget = SMEM_LIMIT / ctas - 1024;
     // bytes of one image's slots for a tile of `ta` slabs
     auto slots = [&](long long ta, int* xs, int* gvs, int* gis) {
         const int x_ = (int)(d == 3 ? ta + ex : 1);
@@ -1559,7 +1560,7 @@ StagedPlan plan_staged(const Geo& g, int mode, int active, int esize, int dtype,
     if ((long long)xs * slab_x * np >= 0x7fffffffLL) return p;
 
     const long long planes = g.N * g.C;
-    const long long grid_max = (long long)sm_count;
+    const long long grid_max = (long long)sm_count * ctas;
     // images per unit: the per-unit setup (shift split, interior box, magic divisors) is amortised over
     // >= 4 stages while every CTA still gets >= 8 units
     long long npu = t.chunk_planes > 0 ? t.chunk_planes : planes / (grid_max * 32);
@@ -1573,7 +1574,7 @@ StagedPlan plan_staged(const Geo& g, int mode, int active, int esize, int dtype,
     const long long chunks = (g.N + npu - 1) / npu;
     const long long units = chunks * g.C;
     int warps = t.warps;
-    const int max_warps = (mode == 0 ? MAXT_GATHER : MAXT_ARITH) / 32 - 1;
+    const int max_warps = ((mode == 0 ? MAXT_GATHER : MAXT_ARITH) / 32) / ctas - 1;
     if (warps > max_warps) warps = max_warps;
     if (units > 0x7fffffffLL || chunks * warps > 0x7fffffffLL) return p;
 

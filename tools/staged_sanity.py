@@ -82,7 +82,7 @@ for shape in shapes:
                     if not np.allclose(wd.grad.cpu().numpy(), gw64, rtol=1e-5, atol=1e-5 * np.abs(gw64).max() + 1e-30):
                         fails.append((tag, "grad_weight", float(np.abs(wd.grad.cpu().numpy() - gw64).max())))
 # raw element sizes through the sparse gather: f64, f16, int8 (quantized), int32 (quantized)
-for shape in [(2, 3, 8, 16), (3, 2, 64), (2, 2, 4, 4, 8), (4, 3, 6, 24)]:
+for shape in [(2, 3, 8, 16), (3, 2, 64), (2, 2, 4, 4, 8), (4, 3, 6, 24), (3, 4, 56, 56), (2, 2, 10, 40), (2, 3, 7, 24), (5, 2, 2, 24), (2, 2, 6, 20)]:
     dim = len(shape) - 2
     w = ((rng.random((shape[1], dim)) * 2 - 1) * 3).astype(np.float32)
     for pad in range(5):
