@@ -308,6 +308,23 @@ int ts_shift_backward(const ts_geometry* gin, int dtype, int padding, int active
     return generic_backward(g, dtype, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, s);
 }
 
+int ts_shift_backward_allreduce(const ts_geometry* gin, int dtype, int padding, int active, const void* grad, const void* x,
+                                const void* weights, void* grad_input, void* grad_weight, void* workspace, size_t workspace_bytes,
+                                const ts_peer_group* peers, void* stream) {
+    if (!peers || !gin) return TS_ERR_INVALID_ARGUMENT;
+    if (peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world || peers->epoch == 0)
+        return TS_ERR_INVALID_ARGUMENT;
+    if (dtype != TS_F32 && dtype != TS_F16 && dtype != TS_BF16) return TS_ERR_UNSUPPORTED;   // contributions travel as fp32
+    if (gin->C * gin->dim > peers->capacity || gin->N == 0 || gin->C == 0) return TS_ERR_INVALID_ARGUMENT;
+    for (int p = 0; p < peers->world; ++p)
+        if (!peers->bufs[p] || !peers->flags[p]) return TS_ERR_INVALID_ARGUMENT;
+    set_pending_peers(peers);
+    const int rc = ts_shift_backward(gin, dtype, padding, active, grad, x, weights, grad_input, grad_weight, workspace, workspace_bytes,
+                                     stream);
+    set_pending_peers(nullptr);
+    return rc;
+}
+
 int ts_qshift_forward(const ts_geometry* gin, int elem_bytes, int padding, int64_t zero_point, const void* xq,
                       const void* qweights, int qweight_kind, int64_t weight_zero_point, void* yq, void* stream) {
     Geo g;

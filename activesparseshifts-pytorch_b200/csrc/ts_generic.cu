@@ -200,8 +200,74 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int slots
     if (lane == 0) gw[warp] = Elem<ST>::st((typename Elem<ST>::CT)s);
 }
 
+// ---- pass 2 fused with the all-reduce of grad_weight over NVLink peer memory -----------------------
+// One CTA.  Thread i owns output i: (1) fixed-order sum of the partial slots -> this rank's value,
+// stored with plain P2P stores into slot `rank` of EVERY peer's exchange buffer (own included);
+// (2) system-scope fence, then one release-store of the epoch into each peer's flag word for this
+// rank; (3) acquire-poll of this rank's flag words until every peer has published the epoch;
+// (4) sum of the `world` slots in rank order -> grad_weight.  Buffers are double-buffered by epoch
+// parity: a rank can run at most one call ahead of the slowest peer (it needs that peer's flag for
+// the call in between), so the slot being read is never the one being overwritten.
+struct PeerArgs {
+    int world, rank, capacity;
+    unsigned epoch;
+    float* bufs[8];
+    unsigned* flags[8];
+};
+
+template <typename ST>
+__global__ void __launch_bounds__(1024, 1) k_reduce_partials_allreduce(const double* __restrict__ partials, int slots, int outputs,
+                                                                       ST* __restrict__ gw, const PeerArgs pa) {
+    const int par = (int)(pa.epoch & 1u);
+    const size_t slot_base = (size_t)par * pa.world * pa.capacity;
+    for (int i = threadIdx.x; i < outputs; i += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < slots; ++k) s += partials[(long long)k * outputs + i];
+        const float v = (float)s;
+        for (int p = 0; p < pa.world; ++p) pa.bufs[p][slot_base + (size_t)pa.rank * pa.capacity + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pa.world) {
+        unsigned* remote = pa.flags[threadIdx.x] + pa.rank;          // my word in peer threadIdx.x's flag array
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(pa.epoch) : "memory");
+        const unsigned* mine = pa.flags[pa.rank] + threadIdx.x;      // peer threadIdx.x's word in my flag array
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned f;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(mine) : "memory");
+            if ((int)(f - pa.epoch) >= 0) break;
+            if (clock64() - t0 > 8000000000LL) __trap();             // ~4 s: a peer never arrived -- fail loudly, do not hang
+        }
+    }
+    __syncthreads();
+    const float* my = pa.bufs[pa.rank] + slot_base;
+    for (int i = threadIdx.x; i < outputs; i += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < pa.world; ++p) s += __ldcg(my + (size_t)p * pa.capacity + i);   // L2: peer writes never pass through this SM's L1
+        gw[i] = Elem<ST>::st(s);
+    }
+}
+
+static thread_local const ts_peer_group* t_pending_peers = nullptr;
+void set_pending_peers(const ts_peer_group* peers) { t_pending_peers = peers; }
+
 template <typename ST>
 int launch_reduce_partials(const double* partials, int slots, int outputs, void* gw, cudaStream_t stream) {
+    if (t_pending_peers) {
+        const ts_peer_group* pg = t_pending_peers;
+        t_pending_peers = nullptr;
+        if constexpr (sizeof(ST) == 8) {
+            return TS_ERR_UNSUPPORTED;
+        } else {
+            PeerArgs pa;
+            pa.world = pg->world; pa.rank = pg->rank; pa.capacity = pg->capacity; pa.epoch = pg->epoch;
+            for (int p = 0; p < 8; ++p) { pa.bufs[p] = (float*)pg->bufs[p]; pa.flags[p] = (unsigned*)pg->flags[p]; }
+            k_reduce_partials_allreduce<ST><<<1, 1024, 0, stream>>>(partials, slots, outputs, (ST*)gw, pa);
+            note_launch();
+            return check_launch();
+        }
+    }
     const int threads = 128;
     const int blocks = (outputs * 32 + threads - 1) / threads;
     k_reduce_partials<ST><<<blocks, threads, 0, stream>>>(partials, slots, outputs, (ST*)gw);

@@ -37,6 +37,9 @@ int generic_backward(const Geo& g, int dtype, int active, const void* grad, cons
 
 template <typename ST>
 int launch_reduce_partials(const double* partials, int slots, int outputs, void* gw, cudaStream_t stream);
+// When set (by ts_shift_backward_allreduce, for the duration of one backward call on this thread) the next
+// pass-2 launch is the variant fused with the all-reduce over peer memory.
+void set_pending_peers(const ts_peer_group* peers);
 
 // ---- staged family (ts_staged.cu): bulk-async shared-memory staging ---------------------------
 struct Tuning {

@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = (
     'ts_abi_version', 'ts_cuda_version', 'ts_error_string', 'ts_last_cuda_error', 'ts_last_kernel_path',
     'ts_set_kernel_path', 'ts_launch_count', 'ts_set_tuning', 'ts_check_borders', 'ts_debug_remap',
     'ts_debug_remap_reduced', 'ts_debug_split_f32', 'ts_debug_split_f64', 'ts_shift_forward',
-    'ts_shift_backward_workspace_bytes', 'ts_shift_backward', 'ts_qshift_forward',
+    'ts_shift_backward_workspace_bytes', 'ts_shift_backward', 'ts_qshift_forward', 'ts_shift_backward_allreduce',
 )
 
 
@@ -28,6 +28,12 @@ class Geometry(ct.Structure):
     """struct ts_geometry."""
     _fields_ = [('dim', ct.c_int32), ('reserved', ct.c_int32), ('N', ct.c_int64), ('C', ct.c_int64),
                 ('size', ct.c_int64 * 3), ('x_stride', ct.c_int64 * 5), ('lb', ct.c_int64 * 3), ('rb', ct.c_int64 * 3)]
+
+
+class PeerGroup(ct.Structure):
+    """struct ts_peer_group."""
+    _fields_ = [('world', ct.c_int32), ('rank', ct.c_int32), ('epoch', ct.c_uint32), ('capacity', ct.c_int32),
+                ('bufs', ct.c_void_p * 8), ('flags', ct.c_void_p * 8)]
 
 
 def make_geometry(dim, shape, strides, lb, rb):
@@ -67,6 +73,7 @@ class NativeLibrary:
             'ts_shift_backward_workspace_bytes': (sz, [gp, i]),
             'ts_shift_backward': (i, [gp, i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]),
             'ts_qshift_forward': (i, [gp, i, i, i64, vp, vp, i, i64, vp, vp]),
+            'ts_shift_backward_allreduce': (i, [gp, i, i, i, vp, vp, vp, vp, vp, vp, sz, ct.POINTER(PeerGroup), vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)

@@ -22,6 +22,7 @@ import torch
 from ._cabi import QW_I8, QW_I32, QW_U8, make_geometry
 
 _LIB = None            # torch.library.Library handle (kept alive)
+_FUSED_ALLREDUCE = None   # torchshifts.sharded.FusedGradWeightAllReduce while enabled: grad_weight is summed over the ranks in-kernel
 _NATIVE = None         # NativeLibrary
 _DTYPES = {torch.float32: 0, torch.float64: 1, torch.float16: 2, torch.bfloat16: 3}
 _QKINDS = {torch.quint8: QW_U8, torch.qint8: QW_I8, torch.qint32: QW_I32}
@@ -146,6 +147,12 @@ def _backward_cuda(dim, grad, weights, input, borders, padding_mode, active_flag
         workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=input.device)
         args = (ct.byref(geo), code, int(padding_mode), int(bool(active_flag)), grad.data_ptr(), input.data_ptr(), w.data_ptr(),
                 out_grad.data_ptr(), weights_grad.data_ptr())
+        fused = _FUSED_ALLREDUCE
+        if fused is not None and fused.device == input.device and code != 1 and w.numel() <= fused.capacity and input.shape[0] > 0:
+            pg = fused.peer_group()
+            st = _NATIVE.lib.ts_shift_backward_allreduce(*args, workspace.data_ptr(), nbytes, ct.byref(pg), _stream(input.device))
+            _NATIVE.check(st, 'ts_shift_backward_allreduce')
+            return out_grad, weights_grad
         st = _NATIVE.lib.ts_shift_backward(*args, workspace.data_ptr(), nbytes, _stream(input.device))
         if st == 3:       # TS_ERR_WORKSPACE: the tuning knobs changed since the size was cached
             _WS_CACHE.clear()

@@ -8,6 +8,7 @@ collective in forward or grad_input, and exactly ONE all-reduce (sum) of the tin
 grad_weight per backward -- for all shift layers of a model coalesced into a single flat buffer.
 Works with any torch.distributed backend (NCCL over NVLink on the B200 box, gloo in the CPU tests).
 """
+import ctypes as ct
 from typing import Iterable, Optional, Tuple
 
 import torch
@@ -73,3 +74,80 @@ def broadcast_weights(module_or_params, src: int = 0, group=None) -> None:
         n = p.numel()
         p.data.copy_(flat[off:off + n].reshape(p.shape).to(p.dtype))
         off += n
+
+
+class FusedGradWeightAllReduce:
+    """grad_weight leaves the backward already summed over the ranks: the deterministic pass-2
+    reduction kernel exchanges the ``C x dim`` values over NVLink peer memory itself (P2P stores into
+    every peer's buffer + flags, ``ts_shift_backward_allreduce``), so the step has no separate
+    collective launch at all.
+
+    Usage (every rank, after ``init_process_group``)::
+
+        fused = torchshifts.sharded.FusedGradWeightAllReduce()      # allocates + rendezvous
+        with fused:                                                  # or fused.enable() / fused.disable()
+            loss.backward()          # shift layers' weight.grad are global sums; do NOT all-reduce them again
+
+    Every rank must run the same sequence of shift backward calls (true for replicated models).  The
+    exchange buffer is symmetric memory (``torch.distributed._symmetric_memory``); with a single rank a
+    plain device buffer is used and the protocol degenerates to a local copy."""
+
+    FLAG_WORDS = 64
+
+    def __init__(self, group=None, capacity: int = 4096, device=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        assert 1 <= self.world <= 8, 'one box: at most 8 ranks'
+        self.capacity = int(capacity)
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        floats = 2 * self.world * self.capacity + self.FLAG_WORDS
+        if self.world == 1:
+            self.buf = torch.zeros(floats, dtype=torch.float32, device=self.device)
+            ptrs = [self.buf.data_ptr()]
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+            pg = group if group is not None else dist.group.WORLD
+            try:
+                symm_mem.enable_symm_mem_for_group(pg.group_name)
+            except Exception:
+                pass
+            with torch.cuda.device(self.device):
+                self.buf = symm_mem.empty(floats, dtype=torch.float32, device=self.device)
+            self.buf.zero_()
+            self.handle = symm_mem.rendezvous(self.buf, pg.group_name)
+            ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)             # every buffer is zeroed before anybody's first exchange
+        self._ptrs = ptrs
+        self.epoch = 0
+        self._prev = None
+
+    def peer_group(self):
+        """ctypes ``ts_peer_group`` for the next backward call (bumps the epoch)."""
+        from ._cabi import PeerGroup
+        self.epoch += 1
+        pg = PeerGroup()
+        pg.world, pg.rank, pg.epoch, pg.capacity = self.world, self.rank, self.epoch, self.capacity
+        flag_off = 4 * 2 * self.world * self.capacity
+        for p in range(self.world):
+            pg.bufs[p] = self._ptrs[p]
+            pg.flags[p] = self._ptrs[p] + flag_off
+        return pg
+
+    def enable(self):
+        from . import _ops
+        self._prev = _ops._FUSED_ALLREDUCE
+        _ops._FUSED_ALLREDUCE = self
+        return self
+
+    def disable(self):
+        from . import _ops
+        _ops._FUSED_ALLREDUCE = self._prev
+        self._prev = None
+
+    __enter__ = enable
+
+    def __exit__(self, *exc):
+        self.disable()
+        return False

@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
                     help="weak (default): every rank owns a full BASELINE shard, N=256 images (global batch 256*G, batch-sharded); "
                          "strong: the global batch N=256 is split over the ranks")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="multi-GPU: all-reduce grad_weight with torch.distributed (NCCL) after the backward instead of the "
+                         "default in-kernel exchange over NVLink peer memory (ts_shift_backward_allreduce)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample clocks during the timed region")
     ap.add_argument("--clocks", default="auto", choices=["auto", "thread", "inline", "off"],
@@ -252,6 +255,10 @@ def run_ours(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     bwd_pairs = []
+    fused = None
+    if world > 1 and not args.nccl_allreduce:
+        from torchshifts.sharded import FusedGradWeightAllReduce
+        fused = FusedGradWeightAllReduce(capacity=4096, device=dev).enable()
 
     def step(timed=False):
         xr.grad = None; w.grad = None
@@ -261,9 +268,9 @@ def run_ours(args):
         y.backward(g)
         if timed:
             b.record(); bwd_pairs.append((a, b))
-        if world > 1:
+        if world > 1 and fused is None:
             dist.all_reduce(w.grad)          # the one collective of the path: C x 2 floats
-        return y
+        return y                             # (fused: w.grad is already the global sum)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -304,6 +311,8 @@ def run_ours(args):
 
     # ---- e2e: public API, host (pinned) buffers, copies inside the timed region -----------------
     e2e = None
+    if fused is not None:
+        fused.disable()       # the host pipeline reduces its per-chunk grad_weight once per step (NCCL below)
     if not args.no_e2e:
         from torchshifts.host import HostShift2dPipeline
         pipe = HostShift2dPipeline(N, C, H, W, device=dev)
@@ -354,7 +363,9 @@ def run_ours(args):
                    "l2": "inputs (822 MB per tensor at N=256) are larger than the 126 MB L2; no flush needed",
                    "kernel_path": {1: "generic", 2: "staged (cp.async.bulk + mbarrier)",
                                    3: "TMA tensor boxes (cp.async.bulk.tensor.5d, shift + zero pad by the copy engine)"}.get(path, str(path)),
-                   "collective": "torch.distributed all_reduce (NCCL) of grad_weight [C,2]" if world > 1 else "none"},
+                   "collective": ("none" if world == 1 else "torch.distributed all_reduce (NCCL) of grad_weight [C,2]" if fused is None else
+                                  "grad_weight [C,2] summed over the ranks inside the pass-2 reduction kernel (P2P stores + flags "
+                                  "over NVLink peer memory, ts_shift_backward_allreduce); no separate collective launch")},
         "elements_per_s": elems_job / (ms * 1e-3),
         "frac_of_hbm_peak": value / world / peak,
         "roofline": {"bound": "hbm", "kernel": "shift backward (grad_input + grad_weight partials) + pass-2 reduce",

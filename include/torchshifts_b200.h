@@ -121,6 +121,28 @@ int ts_shift_backward(const ts_geometry* g, int dtype, int padding, int active,
                       void* grad_input, void* grad_weight,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward fused with the path's one collective: the deterministic pass-2 reduction of grad_weight
+ * writes this rank's C x dim result into every peer's exchange buffer over NVLink peer memory
+ * (plain P2P stores), raises a flag on each peer, waits for the peers' flags and sums the `world`
+ * contributions in rank order -- grad_weight leaves the call already all-reduced (sum), no NCCL launch.
+ * `bufs[p]` / `flags[p]`: device pointers, valid on THIS device, to rank p's exchange buffer
+ * (>= 2 * world * capacity floats, double-buffered by epoch parity) and flag words (>= world uint32,
+ * zero before the first call).  Every rank must make the same sequence of calls with the same `epoch`
+ * (1, 2, 3, ...).  dtype: TS_F32 / TS_F16 / TS_BF16 (contributions travel as fp32). */
+typedef struct ts_peer_group {
+    int32_t  world, rank;          /* 1 <= world <= 8                                              */
+    uint32_t epoch;                /* call counter, identical on every rank, starts at 1           */
+    int32_t  capacity;             /* floats per rank slot; C * dim must not exceed it             */
+    void*    bufs[8];
+    void*    flags[8];
+} ts_peer_group;
+
+int ts_shift_backward_allreduce(const ts_geometry* g, int dtype, int padding, int active,
+                                const void* grad, const void* x, const void* weights,
+                                void* grad_input, void* grad_weight,
+                                void* workspace, size_t workspace_bytes,
+                                const ts_peer_group* peers, void* stream);
+
 /* Quantized forward on the raw integer representation.  elem_bytes: 1 (qint8/quint8) or
  * 4 (qint32).  zero_point: input zero point = pad value.  qweights: raw integer weights
  * [C,dim] of kind `qweight_kind`; effective shift = qweights - weight_zero_point. */

@@ -641,3 +641,34 @@ def test_misaligned_dense_tensors_fall_back(dev, lib, oracle_port, auto_path):
         assert np.array_equal(xd.grad.cpu().numpy(), gi_ref)
         _, gw64 = oracle_port.backward(g.astype(np.float64), x.astype(np.float64), w.astype(np.float64), pad, active)
         assert _gw_close(wd.grad.cpu().numpy(), gw64)
+
+
+def test_fused_allreduce_single_rank(dev, lib, oracle_port, auto_path):
+    """ts_shift_backward_allreduce with a one-rank peer group: the exchange protocol (P2P stores into the
+    own buffer, flag, acquire-poll, rank-ordered sum) must reproduce the plain backward; several calls in a
+    row exercise the epoch / double buffering.  (The multi-rank run is tools/fused_allreduce_probe.py.)"""
+    from torchshifts.functional import shift2d_func, shift3d_func
+    from torchshifts.sharded import FusedGradWeightAllReduce
+    rng = np.random.default_rng(51)
+    fused = FusedGradWeightAllReduce(capacity=512, device=dev)
+    for it, (fn, shape, pad, active) in enumerate([(shift2d_func, (4, 6, 16, 16), 0, False), (shift2d_func, (4, 6, 16, 16), 3, True),
+                                                   (shift3d_func, (2, 3, 4, 8, 8), 2, True), (shift2d_func, (3, 5, 7, 9), 4, False),
+                                                   (shift2d_func, (4, 6, 16, 16), 0, True)]):
+        dim = len(shape) - 2
+        x = rng.standard_normal(shape).astype(np.float32)
+        g = rng.standard_normal(shape).astype(np.float32)
+        w = ((rng.random((shape[1], dim)) * 2 - 1) * 2).astype(np.float32)
+        xd = torch.from_numpy(x).to(dev).requires_grad_(True)
+        wd = torch.from_numpy(w).to(dev).requires_grad_(True)
+        with fused:
+            fn(xd, wd, pad, active).backward(torch.from_numpy(g).to(dev))
+        assert fused.epoch == it + 1
+        gi_ref, _ = oracle_port.backward(g, x, w, pad, active)
+        _, gw64 = oracle_port.backward(g.astype(np.float64), x.astype(np.float64), w.astype(np.float64), pad, active)
+        assert np.array_equal(xd.grad.cpu().numpy(), gi_ref)
+        assert _gw_close(wd.grad.cpu().numpy(), gw64), (it, wd.grad.cpu().numpy(), gw64)
+    # outside the context the plain path runs again
+    xd = torch.from_numpy(x).to(dev).requires_grad_(True)
+    wd = torch.from_numpy(w).to(dev).requires_grad_(True)
+    shift2d_func(xd, wd, 0, True).backward(torch.from_numpy(g).to(dev))
+    assert fused.epoch == 5 and _gw_close(wd.grad.cpu().numpy(), gw64)
