@@ -315,7 +315,7 @@ int ts_shift_backward_allreduce(const ts_geometry* gin, int dtype, int padding, 
     if (peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world || peers->epoch == 0)
         return TS_ERR_INVALID_ARGUMENT;
     if (dtype != TS_F32 && dtype != TS_F16 && dtype != TS_BF16) return TS_ERR_UNSUPPORTED;   // contributions travel as fp32
-    if (gin->C * gin->dim > peers->capacity || gin->N == 0 || gin->C == 0) return TS_ERR_INVALID_ARGUMENT;
+    if (gin->C * gin->dim > peers->capacity || peers->capacity > 4096 || gin->N == 0 || gin->C == 0) return TS_ERR_INVALID_ARGUMENT;
     for (int p = 0; p < peers->world; ++p)
         if (!peers->bufs[p] || !peers->flags[p]) return TS_ERR_INVALID_ARGUMENT;
     set_pending_peers(peers);

@@ -201,37 +201,46 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int slots
 }
 
 // ---- pass 2 fused with the all-reduce of grad_weight over NVLink peer memory -----------------------
-// One CTA.  Thread i owns output i: (1) fixed-order sum of the partial slots -> this rank's value,
-// stored with plain P2P stores into slot `rank` of EVERY peer's exchange buffer (own included);
-// (2) system-scope fence, then one release-store of the epoch into each peer's flag word for this
-// rank; (3) acquire-poll of this rank's flag words until every peer has published the epoch;
-// (4) sum of the `world` slots in rank order -> grad_weight.  Buffers are double-buffered by epoch
-// parity: a rank can run at most one call ahead of the slowest peer (it needs that peer's flag for
-// the call in between), so the slot being read is never the one being overwritten.
+// Same decomposition as k_reduce_partials (one warp per output, lanes stride over the partial slots,
+// fixed shuffle tree -> the local value is bit-identical to the unfused pass 2); 32 outputs per CTA,
+// and every CTA runs the exchange for ITS outputs on its own flag words, so there is no inter-CTA
+// synchronisation: (1) lane 0 of each warp stores this rank's value with plain P2P stores into slot
+// `rank` of EVERY peer's exchange buffer (own included); (2) system-scope fence, then one
+// release-store of the epoch into each peer's flag word (rank, cta); (3) acquire-poll of this rank's
+// flag words (peer, cta) until every peer has published the epoch; (4) sum of the `world` slots in
+// rank order -> grad_weight.  Buffers are double-buffered by epoch parity: a rank can run at most one
+// call ahead of the slowest peer (it needs that peer's flag for the call in between), so the slot
+// being read is never the one being overwritten.
 struct PeerArgs {
     int world, rank, capacity;
     unsigned epoch;
     float* bufs[8];
     unsigned* flags[8];
 };
+constexpr int PEER_MAX_CTAS = 128;      // flag words per sender: capacity 4096 outputs / 32 per CTA
 
 template <typename ST>
 __global__ void __launch_bounds__(1024, 1) k_reduce_partials_allreduce(const double* __restrict__ partials, int slots, int outputs,
                                                                        ST* __restrict__ gw, const PeerArgs pa) {
-    const int par = (int)(pa.epoch & 1u);
-    const size_t slot_base = (size_t)par * pa.world * pa.capacity;
-    for (int i = threadIdx.x; i < outputs; i += blockDim.x) {
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 32 + wid;
+    const size_t slot_base = (size_t)(pa.epoch & 1u) * pa.world * pa.capacity;
+    if (o < outputs) {
         double s = 0.0;
-        for (int k = 0; k < slots; ++k) s += partials[(long long)k * outputs + i];
-        const float v = (float)s;
-        for (int p = 0; p < pa.world; ++p) pa.bufs[p][slot_base + (size_t)pa.rank * pa.capacity + i] = v;
+        for (int k = lane; k < slots; k += 32) s += partials[(long long)k * outputs + o];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+        if (lane == 0) {
+            const float v = (float)s;
+            for (int p = 0; p < pa.world; ++p) pa.bufs[p][slot_base + (size_t)pa.rank * pa.capacity + o] = v;
+            __threadfence_system();
+        }
     }
-    __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < pa.world) {
-        unsigned* remote = pa.flags[threadIdx.x] + pa.rank;          // my word in peer threadIdx.x's flag array
+        unsigned* remote = pa.flags[threadIdx.x] + pa.rank * PEER_MAX_CTAS + blockIdx.x;     // my word in that peer's flag array
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(pa.epoch) : "memory");
-        const unsigned* mine = pa.flags[pa.rank] + threadIdx.x;      // peer threadIdx.x's word in my flag array
+        const unsigned* mine = pa.flags[pa.rank] + threadIdx.x * PEER_MAX_CTAS + blockIdx.x; // that peer's word in my flag array
         const long long t0 = clock64();
         for (;;) {
             unsigned f;
@@ -241,11 +250,11 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_partials_allreduce(const dou
         }
     }
     __syncthreads();
-    const float* my = pa.bufs[pa.rank] + slot_base;
-    for (int i = threadIdx.x; i < outputs; i += blockDim.x) {
+    if (o < outputs && lane == 0) {
+        const float* my = pa.bufs[pa.rank] + slot_base;
         float s = 0.f;
-        for (int p = 0; p < pa.world; ++p) s += __ldcg(my + (size_t)p * pa.capacity + i);   // L2: peer writes never pass through this SM's L1
-        gw[i] = Elem<ST>::st(s);
+        for (int p = 0; p < pa.world; ++p) s += __ldcg(my + (size_t)p * pa.capacity + o);   // L2: peer writes never pass through this SM's L1
+        gw[o] = Elem<ST>::st(s);
     }
 }
 
@@ -263,7 +272,8 @@ int launch_reduce_partials(const double* partials, int slots, int outputs, void*
             PeerArgs pa;
             pa.world = pg->world; pa.rank = pg->rank; pa.capacity = pg->capacity; pa.epoch = pg->epoch;
             for (int p = 0; p < 8; ++p) { pa.bufs[p] = (float*)pg->bufs[p]; pa.flags[p] = (unsigned*)pg->flags[p]; }
-            k_reduce_partials_allreduce<ST><<<1, 1024, 0, stream>>>(partials, slots, outputs, (ST*)gw, pa);
+            if (outputs > 32 * PEER_MAX_CTAS) return TS_ERR_INVALID_ARGUMENT;
+            k_reduce_partials_allreduce<ST><<<(outputs + 31) / 32, 1024, 0, stream>>>(partials, slots, outputs, (ST*)gw, pa);
             note_launch();
             return check_launch();
         }

@@ -92,7 +92,7 @@ class FusedGradWeightAllReduce:
     exchange buffer is symmetric memory (``torch.distributed._symmetric_memory``); with a single rank a
     plain device buffer is used and the protocol degenerates to a local copy."""
 
-    FLAG_WORDS = 64
+    FLAG_WORDS = 8 * 128          # (sender, CTA) flag words: 8 ranks x 128 CTAs of 32 outputs
 
     def __init__(self, group=None, capacity: int = 4096, device=None):
         self.group = group
@@ -100,6 +100,7 @@ class FusedGradWeightAllReduce:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         assert 1 <= self.world <= 8, 'one box: at most 8 ranks'
         self.capacity = int(capacity)
+        assert self.capacity <= 4096, 'at most 4096 grad_weight elements per layer'
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         floats = 2 * self.world * self.capacity + self.FLAG_WORDS
         if self.world == 1:
@@ -108,10 +109,6 @@ class FusedGradWeightAllReduce:
         else:
             import torch.distributed._symmetric_memory as symm_mem
             pg = group if group is not None else dist.group.WORLD
-            try:
-                symm_mem.enable_symm_mem_for_group(pg.group_name)
-            except Exception:
-                pass
             with torch.cuda.device(self.device):
                 self.buf = symm_mem.empty(floats, dtype=torch.float32, device=self.device)
             self.buf.zero_()

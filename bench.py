@@ -255,10 +255,21 @@ def run_ours(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     bwd_pairs = []
-    fused = None
+    fused, fused_note = None, ""
     if world > 1 and not args.nccl_allreduce:
-        from torchshifts.sharded import FusedGradWeightAllReduce
-        fused = FusedGradWeightAllReduce(capacity=4096, device=dev).enable()
+        # every rank must take the same branch: agree on the outcome of the symmetric-memory set-up
+        try:
+            from torchshifts.sharded import FusedGradWeightAllReduce
+            fused = FusedGradWeightAllReduce(capacity=4096, device=dev)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:      # no symmetric memory on this box: NCCL all-reduce instead
+            fused, fused_note = None, f" (in-kernel exchange unavailable: {type(e).__name__}: {str(e)[:120]})"
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) < 1:
+            fused = None
+        else:
+            fused.enable()
 
     def step(timed=False):
         xr.grad = None; w.grad = None
@@ -363,7 +374,7 @@ def run_ours(args):
                    "l2": "inputs (822 MB per tensor at N=256) are larger than the 126 MB L2; no flush needed",
                    "kernel_path": {1: "generic", 2: "staged (cp.async.bulk + mbarrier)",
                                    3: "TMA tensor boxes (cp.async.bulk.tensor.5d, shift + zero pad by the copy engine)"}.get(path, str(path)),
-                   "collective": ("none" if world == 1 else "torch.distributed all_reduce (NCCL) of grad_weight [C,2]" if fused is None else
+                   "collective": ("none" if world == 1 else "torch.distributed all_reduce (NCCL) of grad_weight [C,2]" + fused_note if fused is None else
                                   "grad_weight [C,2] summed over the ranks inside the pass-2 reduction kernel (P2P stores + flags "
                                   "over NVLink peer memory, ts_shift_backward_allreduce); no separate collective launch")},
         "elements_per_s": elems_job / (ms * 1e-3),

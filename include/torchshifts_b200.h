@@ -126,8 +126,8 @@ int ts_shift_backward(const ts_geometry* g, int dtype, int padding, int active,
  * (plain P2P stores), raises a flag on each peer, waits for the peers' flags and sums the `world`
  * contributions in rank order -- grad_weight leaves the call already all-reduced (sum), no NCCL launch.
  * `bufs[p]` / `flags[p]`: device pointers, valid on THIS device, to rank p's exchange buffer
- * (>= 2 * world * capacity floats, double-buffered by epoch parity) and flag words (>= world uint32,
- * zero before the first call).  Every rank must make the same sequence of calls with the same `epoch`
+ * (>= 2 * world * capacity floats, double-buffered by epoch parity) and flag words (>= world * 128
+ * uint32, zero before the first call; capacity <= 4096).  Every rank must make the same sequence of calls with the same `epoch`
  * (1, 2, 3, ...).  dtype: TS_F32 / TS_F16 / TS_BF16 (contributions travel as fp32). */
 typedef struct ts_peer_group {
     int32_t  world, rank;          /* 1 <= world <= 8                                              */
