@@ -227,3 +227,35 @@ def test_product_never_imports_the_oracle():
     for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.h")):
         text = path.read_text()
         assert "oracle" not in text.lower() or path.name in ("ts_common.cuh",), f"{path} mentions the oracle"
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors of ts_geometry / ts_peer_group must have the C compiler's layout."""
+    import ctypes as ct
+    import shutil
+    import subprocess
+    from torchshifts._cabi import Geometry, PeerGroup
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    if not Path(gcc).exists():
+        pytest.skip("gcc not available")
+    src = tmp_path / "layout.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "torchshifts_b200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ts_geometry), offsetof(ts_geometry, N), offsetof(ts_geometry, size),
+           offsetof(ts_geometry, x_stride), offsetof(ts_geometry, lb), offsetof(ts_geometry, rb));
+    printf("%zu %zu %zu %zu %zu\n", sizeof(ts_peer_group), offsetof(ts_peer_group, epoch), offsetof(ts_peer_group, capacity),
+           offsetof(ts_peer_group, bufs), offsetof(ts_peer_group, flags));
+    return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", str(ROOT / "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    geo = [int(v) for v in out[0].split()]
+    assert geo == [ct.sizeof(Geometry), Geometry.N.offset, Geometry.size.offset, Geometry.x_stride.offset, Geometry.lb.offset,
+                   Geometry.rb.offset]
+    peer = [int(v) for v in out[1].split()]
+    assert peer == [ct.sizeof(PeerGroup), PeerGroup.epoch.offset, PeerGroup.capacity.offset, PeerGroup.bufs.offset, PeerGroup.flags.offset]
