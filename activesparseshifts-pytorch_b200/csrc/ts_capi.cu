@@ -360,4 +360,43 @@ int ts_qshift_forward(const ts_geometry* gin, int elem_bytes, int padding, int64
     return generic_gather(g, WK_QUANT, xq, yq, fill, elem_bytes, qweights, qweight_kind, weight_zero_point, s);
 }
 
+static int qshift_common(const ts_geometry* gin, int elem_bytes, int padding, int qweight_kind, Geo* g) {
+    const int rc = make_geo(gin, padding, g);
+    if (rc != TS_OK) return rc;
+    if (elem_bytes != 1 && elem_bytes != 4) return TS_ERR_UNSUPPORTED;
+    if (qweight_kind < TS_QW_U8 || qweight_kind > TS_QW_I32) return TS_ERR_INVALID_ARGUMENT;
+    return TS_OK;
+}
+
+static unsigned long long qfill(int elem_bytes, int64_t zero_point) {
+    return elem_bytes == 1 ? (unsigned long long)((unsigned)zero_point & 0xffu) : (unsigned long long)(uint32_t)(int32_t)zero_point;
+}
+
+int ts_qshift_forward_nhwc(const ts_geometry* gin, int elem_bytes, int padding, int64_t zero_point, const void* xq,
+                           const void* qweights, int qweight_kind, int64_t weight_zero_point, void* yq, void* stream) {
+    Geo g;
+    int rc = qshift_common(gin, elem_bytes, padding, qweight_kind, &g);
+    if (rc != TS_OK) return rc;
+    if (g.N * g.C == 0 || g.out_plane == 0) return TS_OK;
+    if (!xq || !qweights || !yq) return TS_ERR_INVALID_ARGUMENT;
+    int sms = 0;
+    if ((rc = sm_count(&sms)) != TS_OK) return rc;
+    t_last_path = TS_PATH_NHWC;
+    return nhwc_gather(g, xq, yq, qfill(elem_bytes, zero_point), elem_bytes, qweights, qweight_kind, weight_zero_point, sms, 0, false,
+                       (cudaStream_t)stream);
+}
+
+int ts_debug_nhwc_emulate(const ts_geometry* gin, int elem_bytes, int padding, int64_t zero_point, const void* xq_host,
+                          const void* qweights_host, int qweight_kind, int64_t weight_zero_point, void* yq_host, int sm_count_,
+                          int max_grid_x) {
+    Geo g;
+    const int rc = qshift_common(gin, elem_bytes, padding, qweight_kind, &g);
+    if (rc != TS_OK) return rc;
+    if (g.N * g.C == 0 || g.out_plane == 0) return TS_OK;
+    if (!xq_host || !qweights_host || !yq_host || sm_count_ < 1) return TS_ERR_INVALID_ARGUMENT;
+    if ((double)g.N * (double)g.C * (double)g.in_plane > 4194304.0) return TS_ERR_TOO_LARGE;   // a test aid, not a CPU path
+    return nhwc_gather(g, xq_host, yq_host, qfill(elem_bytes, zero_point), elem_bytes, qweights_host, qweight_kind, weight_zero_point,
+                       sm_count_, max_grid_x, true, nullptr);
+}
+
 }  // extern "C"

@@ -246,7 +246,7 @@ TS_D ShiftParams<typename Elem<ST>::CT, DIM> load_params(const ST* __restrict__ 
 // Integer shifts of the quantized path: raw integer weight minus its zero point
 // (quantized/shifts_quantized.cpp:113-114, kernels/shifts_kernels.h:553-555).
 template <int DIM>
-TS_D void load_qshifts(const void* __restrict__ qw, int kind, long long wzp, long long c, const Geo& g, int* sx) {
+TS_HD void load_qshifts(const void* __restrict__ qw, int kind, long long wzp, long long c, const Geo& g, int* sx) {
 #pragma unroll
     for (int a = 0; a < DIM; ++a) {
         long long raw;

@@ -41,6 +41,10 @@ int launch_reduce_partials(const double* partials, int slots, int outputs, void*
 // pass-2 launch is the variant fused with the all-reduce over peer memory.
 void set_pending_peers(const ts_peer_group* peers);
 
+// ---- channels-last gather (ts_nhwc.cu): input and output keep the channel axis innermost -------
+int nhwc_gather(const Geo& g, const void* x, void* y, unsigned long long fill, int esize, const void* w, int qkind,
+                long long wzp, int sm_count, int max_grid_x, bool emulate, cudaStream_t s);
+
 // ---- staged family (ts_staged.cu): bulk-async shared-memory staging ---------------------------
 struct Tuning {
     int stages;        // ring depth

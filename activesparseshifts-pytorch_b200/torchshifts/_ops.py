@@ -173,20 +173,36 @@ def _forward_qcuda(dim, input, weights, borders, new_size, padding_mode, active_
     if input.dtype not in _QBYTES or weights.dtype not in _QKINDS:
         raise RuntimeError(f'{fn}: unsupported quantized dtype {input.dtype} / {weights.dtype}')
     lb, rb = _borders_lists(borders, dim)
-    x = input if input.is_contiguous() else input.contiguous()
+    if list(new_size[2:]) != [rb[a] - lb[a] for a in range(dim)] or list(new_size[:2]) != list(input.shape[:2]):
+        raise RuntimeError(f'{fn}: new_size {list(new_size)} does not match the borders')
     wq = weights.int_repr().to(input.device).contiguous()
+    args = (_QBYTES[input.dtype], int(padding_mode), int(input.q_zero_point()))
+    wargs = (wq.data_ptr(), _QKINDS[weights.dtype], int(weights.q_zero_point()))
+    # the reference allocates the quantized output in the input's memory format
+    # (quantized/shifts_quantized.cpp:119-122): channels-last in, channels-last out -- served by the
+    # native NHWC kernel (one read + one write, no layout conversion on either side)
+    fmt = {2: torch.channels_last, 3: torch.channels_last_3d}.get(dim)
+    if fmt is not None and not input.is_contiguous() and input.is_contiguous(memory_format=fmt):
+        to_cl = (0,) + tuple(range(2, dim + 2)) + (1,)
+        to_nc = (0, dim + 1) + tuple(range(1, dim + 1))
+        out_cl = torch._empty_affine_quantized([new_size[i] for i in to_cl], scale=input.q_scale(),
+                                               zero_point=input.q_zero_point(), dtype=input.dtype, device=input.device)
+        geo = _geometry(dim, input, lb, rb)
+        with torch.cuda.device(input.device):
+            st = _NATIVE.lib.ts_qshift_forward_nhwc(ct.byref(geo), *args, input.data_ptr(), *wargs, out_cl.data_ptr(),
+                                                    _stream(input.device))
+        if st not in (2, 4):      # TS_ERR_UNSUPPORTED / TOO_LARGE (row offsets beyond 32 bits): planar kernels + conversions
+            _NATIVE.check(st, 'ts_qshift_forward_nhwc')
+            return out_cl.permute(*to_nc)
+        del out_cl
+    x = input if input.is_contiguous() else input.contiguous()
     out = torch._empty_affine_quantized(list(new_size), scale=input.q_scale(), zero_point=input.q_zero_point(),
                                         dtype=input.dtype, device=input.device)
     geo = _geometry(dim, x, lb, rb)
     with torch.cuda.device(input.device):
-        st = _NATIVE.lib.ts_qshift_forward(ct.byref(geo), _QBYTES[input.dtype], int(padding_mode), int(input.q_zero_point()),
-                                           x.data_ptr(), wq.data_ptr(), _QKINDS[weights.dtype], int(weights.q_zero_point()),
-                                           out.data_ptr(), _stream(input.device))
+        st = _NATIVE.lib.ts_qshift_forward(ct.byref(geo), *args, x.data_ptr(), *wargs, out.data_ptr(), _stream(input.device))
     _NATIVE.check(st, 'ts_qshift_forward')
-    # the reference allocates the quantized output in the input's memory format
-    # (quantized/shifts_quantized.cpp:119-122): channels-last in, channels-last out
-    fmt = {2: torch.channels_last, 3: torch.channels_last_3d}.get(dim)
-    if fmt is not None and x is not input and input.is_contiguous(memory_format=fmt):
+    if x is not input and fmt is not None and input.is_contiguous(memory_format=fmt):
         out = out.contiguous(memory_format=fmt)
     return out
 

@@ -67,7 +67,8 @@ typedef enum ts_kernel_path {      /* which kernel family served the last call (
     TS_PATH_NONE = 0,
     TS_PATH_GENERIC = 1,           /* stride-generic one-element-per-thread kernels               */
     TS_PATH_STAGED = 2,            /* bulk-async (cp.async.bulk + mbarrier) shared-memory staged  */
-    TS_PATH_TMA = 3                /* TMA tensor copies: the copy engine applies shift + zero pad  */
+    TS_PATH_TMA = 3,               /* TMA tensor copies: the copy engine applies shift + zero pad  */
+    TS_PATH_NHWC = 4               /* channels-last in, channels-last out (ts_qshift_forward_nhwc) */
 } ts_kernel_path;
 
 /* Geometry of one call.  Unused spatial axes: size 1, stride 0, lb 0, rb 1. */
@@ -149,6 +150,23 @@ int ts_shift_backward_allreduce(const ts_geometry* g, int dtype, int padding, in
 int ts_qshift_forward(const ts_geometry* g, int elem_bytes, int padding, int64_t zero_point,
                       const void* xq, const void* qweights, int qweight_kind,
                       int64_t weight_zero_point, void* yq, void* stream);
+
+/* Channels-last variant of ts_qshift_forward      <- shift_forward_kernel_nhwdc_q, ops/kernels/shifts_kernels.h:574-624,
+ * driven from ops/quantized/shifts_quantized.cpp:119-125 (the output takes the input's memory format).
+ * xq is read through g->x_stride (channel stride 1 for a channels-last tensor); yq is written DENSE
+ * channels-last: element (n, c, o0, o1, o2) lives at (((n*O0 + o0)*O1 + o1)*O2 + o2)*C + c.  One read and
+ * one write of the tensor, no layout conversion on either side. */
+int ts_qshift_forward_nhwc(const ts_geometry* g, int elem_bytes, int padding, int64_t zero_point,
+                           const void* xq, const void* qweights, int qweight_kind,
+                           int64_t weight_zero_point, void* yq, void* stream);
+
+/* Test aid (HOST pointers, no GPU work): walks every (block, thread) of the launch
+ * ts_qshift_forward_nhwc would make on a device with `sm_count` SMs and runs the kernel's own per-thread
+ * program on the host, so the CPU-side tests can pin its index logic against the oracle.  Refuses
+ * tensors above 2^22 elements; max_grid_x > 0 caps the grid to exercise the grid-stride loop. */
+int ts_debug_nhwc_emulate(const ts_geometry* g, int elem_bytes, int padding, int64_t zero_point,
+                          const void* xq_host, const void* qweights_host, int qweight_kind,
+                          int64_t weight_zero_point, void* yq_host, int sm_count, int max_grid_x);
 
 #ifdef __cplusplus
 }

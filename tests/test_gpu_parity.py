@@ -672,3 +672,68 @@ def test_fused_allreduce_single_rank(dev, lib, oracle_port, auto_path):
     wd = torch.from_numpy(w).to(dev).requires_grad_(True)
     shift2d_func(xd, wd, 0, True).backward(torch.from_numpy(g).to(dev))
     assert fused.epoch == 5 and _gw_close(wd.grad.cpu().numpy(), gw64)
+
+
+NHWC = 4
+
+
+def test_quantized_channels_last_native_kernel(dev, lib, oracle_port, auto_path):
+    """channels-last quantized tensors go through ts_qshift_forward_nhwc (NHWC in, NHWC out,
+    no layout conversion), bit-exact with the oracle for every padding, dtype, crop and channel count
+    (kernels/shifts_kernels.h:574-624)."""
+    from torchshifts.quantized.functional import shift2d_quantized, shift3d_quantized
+    rng = np.random.default_rng(41)
+    cases = [((2, 8, 6, 16), None), ((3, 3, 5, 7), None), ((2, 20, 9, 12), [[1, 0], [2, 1]]), ((1, 1028, 4, 6), None),
+             ((2, 64, 56, 56), None), ((2, 6, 3, 4, 5), None), ((1, 16, 6, 10, 12), [[0, 1], [1, 0], [2, 1]]),
+             ((4, 256, 1, 40), None)]
+    for shape, borders in cases:
+        dim = len(shape) - 2
+        fn = shift2d_quantized if dim == 2 else shift3d_quantized
+        fmt = torch.channels_last if dim == 2 else torch.channels_last_3d
+        wraw = (rng.integers(-5, 5, size=(shape[1], dim), endpoint=True) + 128).astype(np.uint8)
+        qw = torch._make_per_tensor_quantized_tensor(torch.from_numpy(wraw).to(dev), 1.0, 128)
+        cut = None if borders is None else torch.tensor(borders)
+        for qdtype, npdt, zp in ((torch.quint8, np.uint8, 3), (torch.qint8, np.int8, -5), (torch.qint32, np.int32, 70000)):
+            info = np.iinfo(npdt)
+            raw = rng.integers(max(info.min, -2 ** 20), min(info.max, 2 ** 20), size=shape, endpoint=True).astype(npdt)
+            xq = torch._make_per_tensor_quantized_tensor(torch.from_numpy(raw).to(dev), 0.02, zp)
+            to_cl = (0,) + tuple(range(2, dim + 2)) + (1,)
+            to_nc = (0, dim + 1) + tuple(range(1, dim + 1))
+            raw_cl = np.ascontiguousarray(raw.transpose(to_cl))
+            xcl = torch._make_per_tensor_quantized_tensor(torch.from_numpy(raw_cl).to(dev), 0.02, zp).permute(*to_nc)
+            assert xcl.is_contiguous(memory_format=fmt) and tuple(xcl.shape) == shape
+            if xcl.is_contiguous():
+                continue                          # degenerate shapes where both layouts coincide
+            for pad in range(5):
+                y = fn(xcl, qw, pad, cut)
+                assert lib.ts_last_kernel_path() == NHWC, (shape, pad)
+                assert y.is_contiguous(memory_format=fmt) and y.dtype == qdtype
+                assert y.q_scale() == xq.q_scale() and y.q_zero_point() == zp
+                got = y.permute(*to_cl).int_repr().cpu().numpy().transpose(to_nc)
+                want = oracle_port.qforward(raw, wraw.astype(np.int64), 128, zp, pad, borders)
+                assert np.array_equal(got, want), (shape, borders, qdtype, pad)
+                # the planar path on the same tensor gives the same integers
+                assert np.array_equal(fn(xq, qw, pad, cut).int_repr().cpu().numpy(), want)
+
+
+def test_full_size_cfg5_channels_last(dev, lib, oracle_port, auto_path):
+    """cfg5 in channels-last: N=256 C=256 56x56 qint8, native NHWC kernel == planar kernel on every byte,
+    == oracle on sampled images."""
+    from torchshifts.quantized.functional import shift2d_quantized
+    from torchshifts.quantized.modules.shifts import quantize_shift_weights
+    from oracle.oracle import quantize_shift_weights_np
+    torch.manual_seed(5)
+    x = torch.rand(256, 256, 56, 56, device=dev)
+    w = (torch.rand(256, 2, device=dev) * 2 - 1) * 3
+    raw, wzp = quantize_shift_weights_np(w.cpu().numpy())
+    qw = quantize_shift_weights(w)
+    xq = torch.quantize_per_tensor(x, 1 / 255., -128, torch.qint8)
+    del x
+    xcl = xq.contiguous(memory_format=torch.channels_last)
+    for pad in (0, 4):
+        y = shift2d_quantized(xcl, qw, pad)
+        assert lib.ts_last_kernel_path() == NHWC and y.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(y.int_repr(), shift2d_quantized(xq, qw, pad).int_repr())
+        idx = [0, 131, 255]
+        want = oracle_port.qforward(xq.int_repr()[idx].cpu().numpy(), raw, wzp, -128, pad)
+        assert np.array_equal(y.int_repr()[idx].cpu().numpy(), want)

@@ -259,3 +259,62 @@ int main(void) {
                    Geometry.rb.offset]
     peer = [int(v) for v in out[1].split()]
     assert peer == [ct.sizeof(PeerGroup), PeerGroup.epoch.offset, PeerGroup.capacity.offset, PeerGroup.bufs.offset, PeerGroup.flags.offset]
+
+
+def _nhwc_emulate(native, xraw, wraw, wkind, wzp, zp, pad, borders, sm_count=148, max_grid_x=0):
+    """Run the channels-last kernel's per-thread program on the host (ts_debug_nhwc_emulate) on a
+    channels-last copy of `xraw` (logical [N, C, *spatial]); returns the logical-NCHW result."""
+    from torchshifts._cabi import make_geometry
+    from oracle.oracle import check_borders
+    dim = xraw.ndim - 2
+    perm = (0,) + tuple(range(2, 2 + dim)) + (1,)                 # NCHW -> NHWC
+    inv = (0, dim + 1) + tuple(range(1, dim + 1))                 # NHWC -> NCHW
+    xcl = np.ascontiguousarray(xraw.transpose(perm))
+    strides_cl = [s // xraw.itemsize for s in xcl.strides]        # (N, spatial..., C) in elements
+    strides = [strides_cl[0], strides_cl[-1]] + strides_cl[1:-1]  # logical (N, C, spatial...) order
+    lb, rb = check_borders(dim, xraw.shape[2:], borders)
+    geo = make_geometry(dim, xraw.shape, strides, lb, rb)
+    out_sp = [rb[a] - lb[a] for a in range(dim)]
+    ycl = np.full([xraw.shape[0]] + out_sp + [xraw.shape[1]], 0x5A, dtype=xraw.dtype)
+    w = np.ascontiguousarray(wraw)
+    st = native.lib.ts_debug_nhwc_emulate(ct.byref(geo), xraw.itemsize, pad, zp, xcl.ctypes.data, w.ctypes.data, wkind, wzp,
+                                          ycl.ctypes.data, sm_count, max_grid_x)
+    assert st == 0, native.lib.ts_error_string(st)
+    return ycl.transpose(inv)
+
+
+def test_channels_last_kernel_program_matches_the_oracle(native, oracle_port):
+    """The NHWC gather (ts_nhwc.cu) is index arithmetic only; its per-thread program is host+device
+    code, so every (block, thread) of a real launch shape is walked here and compared, bit for bit,
+    with the oracle (kernels/shifts_kernels.h:574-624 semantics)."""
+    rng = np.random.default_rng(77)
+    cases = [
+        # shape (N, C, *spatial), borders
+        ((2, 8, 5, 7), None), ((1, 4, 1, 9), None), ((3, 3, 6, 4), None), ((2, 20, 4, 6), [[1, 0], [1, 2]]),
+        ((1, 1028, 3, 2), None), ((2, 16, 9), None), ((2, 6, 3, 4, 5), None), ((1, 8, 4, 3, 6), [[0, 1], [1, 0], [2, 1]]),
+        ((2, 12, 2, 2), None), ((1, 260, 2, 70), None), ((2, 8, 5, 1), None), ((1, 4, 1, 1, 6), None),
+    ]
+    kinds = {np.uint8: 0, np.int8: 1, np.int32: 2}
+    for shape, borders in cases:
+        dim = len(shape) - 2
+        for dt, zp in ((np.uint8, 7), (np.int8, -3), (np.int32, 100000)):
+            info = np.iinfo(dt)
+            x = rng.integers(max(info.min, -2 ** 20), min(info.max, 2 ** 20), size=shape, endpoint=True).astype(dt)
+            for wdt, wzp in ((np.uint8, 128), (np.int8, 0), (np.int32, -2)):
+                lo, hi = (-6, 6) if wdt is not np.int32 else (-40, 40)
+                wraw = (rng.integers(lo, hi, size=(shape[1], dim), endpoint=True) + wzp).astype(wdt)
+                for pad in range(5):
+                    want = oracle_port.qforward(x, wraw.astype(np.int64), wzp, zp, pad, borders)
+                    got = _nhwc_emulate(native, x, wraw, kinds[wdt], wzp, zp, pad, borders)
+                    assert np.array_equal(got, want), (shape, borders, dt, wdt, pad)
+    # launch-shape variations: few SMs (no last-axis split), many SMs (split), capped grid (grid-stride loop)
+    x = rng.integers(0, 255, size=(3, 8, 10, 33), endpoint=True).astype(np.uint8)
+    wraw = (rng.integers(-4, 4, size=(8, 2), endpoint=True) + 128).astype(np.uint8)
+    for pad in (0, 3):
+        want = oracle_port.qforward(x, wraw.astype(np.int64), 128, 9, pad, None)
+        for sms, cap in ((1, 0), (148, 0), (4096, 0), (148, 3), (2, 1)):
+            assert np.array_equal(_nhwc_emulate(native, x, wraw, 0, 128, 9, pad, None, sms, cap), want), (pad, sms, cap)
+    # the emulation is a test aid, not a CPU path: anything sizeable is refused
+    from torchshifts._cabi import make_geometry
+    geo = make_geometry(2, (64, 64, 64, 64), (64 * 64 * 64, 1, 64 * 64, 64), (0, 0), (64, 64))
+    assert native.lib.ts_debug_nhwc_emulate(ct.byref(geo), 1, 0, 0, 1, 1, 0, 0, 1, 148, 0) == 4

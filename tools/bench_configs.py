@@ -48,7 +48,7 @@ def timeit(fn, reps=10):
     return a.elapsed_time(b) / reps
 
 
-names = {0: "none", 1: "generic", 2: "staged", 3: "tma"}
+names = {0: "none", 1: "generic", 2: "staged", 3: "tma", 4: "nhwc"}
 want = [a for a in sys.argv[1:] if a in CASES] or list(CASES)
 for key in want:
     for label, shape, pad, active, dtype in CASES[key]:
@@ -69,6 +69,14 @@ for key in want:
                 tf = timeit(lambda: fwd(x, qw, borders, list(shape), pad, False))
                 pf = lib.ts_last_kernel_path()
                 print(f"{label:34s} fwd {tf:7.3f} ms {n * 2 / tf / 1e6:6.0f} GB/s ({n * 2 / tf / 1e6 / PEAK:4.0%}) [{names[pf]}]", flush=True)
+                # the same tensor in channels-last: native NHWC kernel vs the three-pass route it replaces
+                xcl = x.contiguous(memory_format=torch.channels_last)
+                tf = timeit(lambda: fwd(xcl, qw, borders, list(shape), pad, False))
+                pf = lib.ts_last_kernel_path()
+                print(f"{label + ' NHWC':34s} fwd {tf:7.3f} ms {n * 2 / tf / 1e6:6.0f} GB/s ({n * 2 / tf / 1e6 / PEAK:4.0%}) [{names[pf]}]", flush=True)
+                tc = timeit(lambda: fwd(xcl.contiguous(), qw, borders, list(shape), pad, False).contiguous(memory_format=torch.channels_last))
+                print(f"{label + ' NHWC via NCHW':34s} fwd {tc:7.3f} ms {n * 2 / tc / 1e6:6.0f} GB/s ({n * 2 / tc / 1e6 / PEAK:4.0%}) [3 passes]", flush=True)
+                del xcl
                 continue
             x = torch.randn(shape, device=dev).to(dtype)
             g = torch.randn(shape, device=dev).to(dtype)
