@@ -144,6 +144,8 @@ int ts_set_tuning(const char* spec) {
         else if (!strcmp(key, "tma_warps")) t.tma_warps = val;
         else if (!strcmp(key, "use_tma")) t.use_tma = val != 0;
         else if (!strcmp(key, "tma_stage_kb")) t.tma_stage_kb = val;
+        else if (!strcmp(key, "nhwc_variant")) t.nhwc_variant = val;
+        else if (!strcmp(key, "nhwc_ring_rows")) t.nhwc_ring_rows = val;
         else return TS_ERR_INVALID_ARGUMENT;
         p += n;
         while (*p == ',' || *p == ' ') ++p;
@@ -151,7 +153,7 @@ int ts_set_tuning(const char* spec) {
     if (t.stages < 0 || t.stages > 8 || t.stage_kb < 0 || t.stage_kb > 220 || t.warps < 1 || t.warps > 31 ||
         t.ctas_per_sm < 1 || t.ctas_per_sm > 8 || t.chunk_planes < 0 || t.tma_stages < 0 || t.tma_stages > 32 ||
         t.tma_ctas_per_sm < 0 || t.tma_ctas_per_sm > 8 || t.tma_warps < 0 || t.tma_warps > 31 || t.tma_stage_kb < 0 ||
-        t.tma_stage_kb > 220)
+        t.tma_stage_kb > 220 || t.nhwc_variant < 0 || t.nhwc_variant > 2 || t.nhwc_ring_rows < 0)
         return TS_ERR_INVALID_ARGUMENT;
     tuning() = t;
     g_tuning_epoch.fetch_add(1);
@@ -382,21 +384,22 @@ int ts_qshift_forward_nhwc(const ts_geometry* gin, int elem_bytes, int padding, 
     int sms = 0;
     if ((rc = sm_count(&sms)) != TS_OK) return rc;
     t_last_path = TS_PATH_NHWC;
-    return nhwc_gather(g, xq, yq, qfill(elem_bytes, zero_point), elem_bytes, qweights, qweight_kind, weight_zero_point, sms, 0, false,
-                       (cudaStream_t)stream);
+    return nhwc_gather(g, xq, yq, qfill(elem_bytes, zero_point), elem_bytes, qweights, qweight_kind, weight_zero_point, sms, 0,
+                       tuning().nhwc_variant, tuning().nhwc_ring_rows, false, (cudaStream_t)stream);
 }
 
 int ts_debug_nhwc_emulate(const ts_geometry* gin, int elem_bytes, int padding, int64_t zero_point, const void* xq_host,
                           const void* qweights_host, int qweight_kind, int64_t weight_zero_point, void* yq_host, int sm_count_,
-                          int max_grid_x) {
+                          int max_grid_x, int variant, int ring_rows) {
     Geo g;
     const int rc = qshift_common(gin, elem_bytes, padding, qweight_kind, &g);
     if (rc != TS_OK) return rc;
     if (g.N * g.C == 0 || g.out_plane == 0) return TS_OK;
-    if (!xq_host || !qweights_host || !yq_host || sm_count_ < 1) return TS_ERR_INVALID_ARGUMENT;
+    if (!xq_host || !qweights_host || !yq_host || sm_count_ < 1 || variant < 0 || variant > 2 || ring_rows < 0)
+        return TS_ERR_INVALID_ARGUMENT;
     if ((double)g.N * (double)g.C * (double)g.in_plane > 4194304.0) return TS_ERR_TOO_LARGE;   // a test aid, not a CPU path
     return nhwc_gather(g, xq_host, yq_host, qfill(elem_bytes, zero_point), elem_bytes, qweights_host, qweight_kind, weight_zero_point,
-                       sm_count_, max_grid_x, true, nullptr);
+                       sm_count_, max_grid_x, variant, ring_rows, true, nullptr);
 }
 
 }  // extern "C"

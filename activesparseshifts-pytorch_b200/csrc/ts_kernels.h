@@ -43,7 +43,7 @@ void set_pending_peers(const ts_peer_group* peers);
 
 // ---- channels-last gather (ts_nhwc.cu): input and output keep the channel axis innermost -------
 int nhwc_gather(const Geo& g, const void* x, void* y, unsigned long long fill, int esize, const void* w, int qkind,
-                long long wzp, int sm_count, int max_grid_x, bool emulate, cudaStream_t s);
+                long long wzp, int sm_count, int max_grid_x, int variant, int ring_rows, bool emulate, cudaStream_t s);
 
 // ---- staged family (ts_staged.cu): bulk-async shared-memory staging ---------------------------
 struct Tuning {
@@ -57,6 +57,8 @@ struct Tuning {
     int tma_warps;     // consumer warps of the TMA-tensor arithmetic kernels
     int use_tma;       // 0: the automatic path choice never picks the TMA-tensor family
     int tma_stage_kb;  // target bytes per stage of the TMA-tensor kernels (0 = auto)
+    int nhwc_variant;  // channels-last gather: 0 auto, 1 direct (L1) kernel only, 2 ring (shared-memory) kernel only
+    int nhwc_ring_rows;  // cap on the ring slots of the channels-last ring kernel (0 = as many as fit)
 };
 Tuning& tuning();
 

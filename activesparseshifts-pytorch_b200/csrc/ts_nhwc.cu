@@ -167,6 +167,358 @@ NhwcPlan make_plan(const Geo& g, int esize, const void* y, int sm_count, int max
     return pl;
 }
 
+// ------------------------------------------------------------------------------------------
+// Ring kernel (2-D, 1-byte elements): the same gather, fed from shared memory.
+//
+// Through L1 every gathered byte costs one 32-byte sector access (neighbouring channels have different
+// shifts, so the 32 lanes of a request land in ~28 different sectors: measured with ncu, 184 M sector
+// accesses for 205 M output bytes, L1 throughput-bound at 0.28 ms).  Shared memory serves 32 scattered
+// bytes per cycle as long as the lanes hit different banks, and with lane <-> word-of-the-channel-slice
+// the bank IS the lane whatever pixel each lane's shift selects.  So a CTA owns (image, slice of <= 128
+// channels, segment of output rows), walks down the rows and keeps the input rows the current group of
+// output rows can reach in a ring of K row slots: every input row slice is fetched from global memory
+// exactly once per unit, with 16-byte cp.async copies of whole sectors.  The ring is a software cache,
+// not a contract: a tap whose (remapped) row is not in the ring -- wrap-around paddings at the image
+// edges, shifts spread wider than the ring -- is read from global memory instead, so the choice of
+// window only ever affects speed.
+struct RingPlan {
+    int cs, slices;       // channels per slice (power of two, 32..128), C / cs
+    int k;                // ring slots (input rows of one slice)
+    int segs, seg_rows;   // output rows are split into segs segments of seg_rows rows
+    int tw, tp;           // threads along the words of a slice (cs / 4), along the pixels of a row
+    int chunk_shift;      // log2(cs / 16): 16-byte chunks per pixel slice
+    unsigned units, grid;
+    unsigned smem_bytes;  // ring + 16 (the last 16 bytes hold the fill byte)
+};
+constexpr int RING_THREADS = 256;
+constexpr int RING_MAX_CS = 128;
+
+struct RingUnit { unsigned n; int c_base, o_begin, o_end; };
+struct RingThread { int s0[4], s1[4], smin, smax; };   // lives in registers across the phases of a unit
+struct RingStep { int o_a, o_b, lo, hi, new_lo, slot_lo; };
+
+TS_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+TS_HD RingUnit ring_unit(const Geo& g, const RingPlan& pl, unsigned unit) {
+    RingUnit u;
+    const unsigned seg = unit % (unsigned)pl.segs;
+    const unsigned t = unit / (unsigned)pl.segs;
+    const unsigned k = t % (unsigned)pl.slices;
+    u.n = t / (unsigned)pl.slices;
+    u.c_base = (int)k * pl.cs;
+    u.o_begin = (int)seg * pl.seg_rows;
+    u.o_end = u.o_begin + pl.seg_rows < g.OS[0] ? u.o_begin + pl.seg_rows : g.OS[0];
+    return u;
+}
+
+// Phase 1: one thread per channel of the slice reduces its two shifts into sh[0..cs) / sh[128..128+cs).
+TS_HD void ring_phase_shifts(const Geo& g, const RingPlan& pl, const RingUnit& u, int tid, const void* __restrict__ w, int qkind,
+                             long long wzp, int* sh, uint8_t* ring, uint8_t fill) {
+    if (tid == 0) ring[pl.smem_bytes - 16u] = fill;      // the pad value, addressable like any ring byte
+    if (tid < pl.cs) {
+        int sx[2];
+        load_qshifts<2>(w, qkind, wzp, (long long)(u.c_base + tid), g, sx);
+        sh[tid] = sx[0];
+        sh[RING_MAX_CS + tid] = sx[1];
+    }
+}
+
+// Phase 2 (after a barrier): every thread picks up the shifts of its 4 channels and the slice-wide range
+// of the axis-0 shifts (identical in every thread: it sizes the groups of output rows).
+TS_HD void ring_phase_regs(const RingPlan& pl, int tid, const int* sh, RingThread& th) {
+    const int wi = tid % pl.tw;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        th.s0[v] = sh[4 * wi + v];
+        th.s1[v] = sh[RING_MAX_CS + 4 * wi + v];
+    }
+    int mn = sh[0], mx = sh[0];
+    for (int i = 1; i < pl.cs; ++i) {
+        const int s = sh[i];
+        mn = s < mn ? s : mn;
+        mx = s > mx ? s : mx;
+    }
+    th.smin = mn;
+    th.smax = mx;
+}
+
+// The walk down the output rows of a unit, identical in every thread.
+struct RingWalk {
+    int o_next, o_end, rb, phi, smin, smax, lb0, s0, k;
+    TS_HD RingWalk(const Geo& g, const RingPlan& pl, const RingUnit& u, const RingThread& th) {
+        o_next = u.o_begin;
+        o_end = u.o_end;
+        smin = th.smin;
+        smax = th.smax;
+        lb0 = g.lb[0];
+        s0 = g.S[0];
+        k = pl.k;
+        const int span = smax - smin;
+        rb = k - span > 1 ? k - span : 1;         // output rows per step: their reach, rb + span rows, fits the ring
+        phi = -1;                                  // highest input row fetched so far in this unit
+    }
+    TS_HD bool next(RingStep& s) {
+        if (o_next >= o_end) return false;
+        s.o_a = o_next;
+        s.o_b = o_next + rb < o_end ? o_next + rb : o_end;
+        o_next = s.o_b;
+        s.lo = clampi(s.o_a + lb0 - smax, 0, s0 - 1);
+        s.hi = clampi(s.o_b - 1 + lb0 - smin, 0, s0 - 1);
+        if (s.hi - s.lo + 1 > k) s.hi = s.lo + k - 1;
+        s.new_lo = s.lo > phi + 1 ? s.lo : phi + 1;
+        if (s.hi > phi) phi = s.hi;
+        s.slot_lo = s.lo % k;
+        return true;
+    }
+};
+
+TS_HD int ring_slot(const RingStep& st, int k, int row) {   // row in [st.lo, st.hi]
+    const int s = row - st.lo + st.slot_lo;
+    return s >= k ? s - k : s;
+}
+
+TS_HD void copy16(uint8_t* dst_ring, const uint8_t* src_global) {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(shared_addr(dst_ring)), "l"(src_global) : "memory");
+#else
+    for (int i = 0; i < 16; ++i) dst_ring[i] = src_global[i];
+#endif
+}
+
+// One byte of the ring.  On the device the ring is addressed through its 32-bit shared-window address and an
+// opaque ld.shared.u8 (written as `ring[off]` the compiler re-derives the window base, half a dozen
+// instructions, next to every load).
+TS_HD unsigned ring_base(const uint8_t* ring) {
+#ifdef __CUDA_ARCH__
+    return shared_addr(ring);
+#else
+    (void)ring;
+    return 0u;
+#endif
+}
+TS_HD uint8_t ring_byte(const uint8_t* ring, unsigned addr) {
+#ifdef __CUDA_ARCH__
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return (uint8_t)v;
+#else
+    return ring[addr];
+#endif
+}
+
+// Fetch the input rows [st.new_lo, st.hi] of this unit's channel slice into their ring slots.
+TS_HD void ring_load(const Geo& g, const RingPlan& pl, const RingUnit& u, const RingStep& st, int tid, int threads,
+                     const uint8_t* __restrict__ x, uint8_t* ring) {
+    const int rows = st.hi - st.new_lo + 1;
+    if (rows <= 0) return;
+    const int per_row = g.S[1] << pl.chunk_shift;
+    const int total = rows * per_row;
+    const uint8_t* src0 = x + (long long)u.n * g.xs[0] + u.c_base;
+    for (int i = tid; i < total; i += threads) {
+        const int rr = i / per_row;
+        const int j = i - rr * per_row;
+        const int q = j >> pl.chunk_shift;
+        const int part = j & ((1 << pl.chunk_shift) - 1);
+        const int row = st.new_lo + rr;
+        const uint8_t* src = src0 + (long long)row * g.xs[2] + (long long)q * g.xs[3] + part * 16;
+        uint8_t* dst = ring + ((size_t)(ring_slot(st, pl.k, row) * g.S[1] + q) * pl.cs + part * 16);
+        copy16(dst, src);
+    }
+}
+
+// Gather phase.  Per (output row, channel) the source is one of three: a ring row (the common case), the
+// fill byte (the whole source row is outside the image: zeros padding), or global memory (a valid row the
+// ring does not hold).  The fill byte lives in shared memory right behind the ring, so "outside" is just
+// another address and the inner loop has no select after the load; rows with a global-memory channel take a
+// separate, slower loop.
+template <int PAD>
+TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, const RingStep& st, const RingThread& th, int tid,
+                        const uint8_t* __restrict__ x, uint8_t* __restrict__ y, uint8_t fill, const uint8_t* ring) {
+    const int wi = tid % pl.tw;
+    const int pw = tid / pl.tw;
+    const int c0 = u.c_base + 4 * wi;
+    const int s1 = g.S[1], lb1 = g.lb[1], ow = g.OS[1];
+    const unsigned base = ring_base(ring);
+    const unsigned fill_addr = base + pl.smem_bytes - 16u;
+    const unsigned long long xs3 = (unsigned long long)g.xs[3];
+    const long long y_step = (long long)pl.tp * g.C;
+    for (int o = st.o_a; o < st.o_b; ++o) {
+        unsigned row_addr[4], pitch[4];     // ring address of pixel 0 of the source row, bytes between its pixels
+        bool from_global = false;
+        int t0s[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int t0 = axis_index_c<PAD>(o + g.lb[0] - th.s0[v], g.S[0]);
+            t0s[v] = t0;
+            const bool inw = t0 >= st.lo && t0 <= st.hi;           // implies t0 >= 0
+            row_addr[v] = inw ? base + (unsigned)(ring_slot(st, pl.k, t0) * s1) * (unsigned)pl.cs + (unsigned)(4 * wi + v) : fill_addr;
+            pitch[v] = inw ? (unsigned)pl.cs : 0u;
+            from_global = from_global || (t0 >= 0 && !inw);
+        }
+        uint8_t* yp = y + (((long long)u.n * g.OS[0] + o) * ow + pw) * g.C + c0;
+        if (!from_global) {
+#pragma unroll 2
+            for (int p = pw; p < ow; p += pl.tp, yp += y_step) {
+                uint8_t val[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int t1 = axis_index_c<PAD>(p + lb1 - th.s1[v], s1);
+                    val[v] = ring_byte(ring, t1 >= 0 ? row_addr[v] + (unsigned)t1 * pitch[v] : fill_addr);
+                }
+                PackOut<uint8_t, 4>::store(yp, val);
+            }
+        } else {
+            for (int p = pw; p < ow; p += pl.tp, yp += y_step) {
+                uint8_t val[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int t1 = axis_index_c<PAD>(p + lb1 - th.s1[v], s1);
+                    if (t0s[v] >= 0 && pitch[v] == 0u) {     // valid row, not in the ring
+                        const uint8_t* src = x + (long long)u.n * g.xs[0] + (long long)t0s[v] * g.xs[2] + (c0 + v);
+                        val[v] = t1 >= 0 ? load_ro(src + (unsigned long long)(unsigned)t1 * xs3) : fill;
+                    } else {
+                        val[v] = ring_byte(ring, t1 >= 0 ? row_addr[v] + (unsigned)t1 * pitch[v] : fill_addr);
+                    }
+                }
+                PackOut<uint8_t, 4>::store(yp, val);
+            }
+        }
+    }
+}
+
+template <int PAD>
+__global__ void __launch_bounds__(RING_THREADS) k_gather_nhwc_ring(Geo g, RingPlan pl, const uint8_t* __restrict__ x,
+                                                                   uint8_t* __restrict__ y, uint8_t fill,
+                                                                   const void* __restrict__ w, int qkind, long long wzp) {
+    extern __shared__ uint4 ring_store[];
+    __shared__ int sh[2 * RING_MAX_CS];
+    uint8_t* ring = reinterpret_cast<uint8_t*>(ring_store);
+    const int tid = (int)threadIdx.x;
+    for (unsigned unit = blockIdx.x; unit < pl.units; unit += gridDim.x) {
+        const RingUnit u = ring_unit(g, pl, unit);
+        ring_phase_shifts(g, pl, u, tid, w, qkind, wzp, sh, ring, fill);
+        __syncthreads();
+        RingThread th;
+        ring_phase_regs(pl, tid, sh, th);
+        RingWalk walk(g, pl, u, th);
+        RingStep st;
+        while (walk.next(st)) {
+            ring_load(g, pl, u, st, tid, RING_THREADS, x, ring);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();             // the new rows are visible to every thread
+            ring_compute<PAD>(g, pl, u, st, th, tid, x, y, fill, ring);
+            __syncthreads();             // every thread is done with the rows the next step overwrites (and with sh)
+        }
+    }
+}
+
+// Host walk of the same CTA program: phases separated by the kernel's barriers, threads in turn.
+template <int PAD>
+void ring_emulate(const Geo& g, const RingPlan& pl, const uint8_t* x, uint8_t* y, uint8_t fill, const void* w, int qkind,
+                  long long wzp) {
+    uint8_t* ring = new uint8_t[pl.smem_bytes];
+    RingThread* th = new RingThread[RING_THREADS];
+    int sh[2 * RING_MAX_CS];
+    for (unsigned b = 0; b < pl.grid; ++b) {
+        for (unsigned unit = b; unit < pl.units; unit += pl.grid) {
+            const RingUnit u = ring_unit(g, pl, unit);
+            for (unsigned i = 0; i < pl.smem_bytes; ++i) ring[i] = 0xEE;   // a slot read before it is fetched shows up as a mismatch
+            for (int tid = 0; tid < RING_THREADS; ++tid) ring_phase_shifts(g, pl, u, tid, w, qkind, wzp, sh, ring, fill);
+            for (int tid = 0; tid < RING_THREADS; ++tid) ring_phase_regs(pl, tid, sh, th[tid]);
+            RingWalk walk(g, pl, u, th[0]);
+            RingStep st;
+            while (walk.next(st)) {
+                for (int tid = 0; tid < RING_THREADS; ++tid) ring_load(g, pl, u, st, tid, RING_THREADS, x, ring);
+                for (int tid = 0; tid < RING_THREADS; ++tid) ring_compute<PAD>(g, pl, u, st, th[tid], tid, x, y, fill, ring);
+            }
+        }
+    }
+    delete[] th;
+    delete[] ring;
+}
+
+bool plan_ring(const Geo& g, int esize, const void* x, const void* y, int sm_count, int max_grid_x, int ring_rows, RingPlan* out) {
+    if (g.dim != 2 || esize != 1 || g.xs[1] != 1 || g.C % 32 != 0) return false;
+    if (((uintptr_t)x & 15u) || ((uintptr_t)y & 3u)) return false;
+    if ((g.xs[0] & 15) || (g.xs[2] & 15) || (g.xs[3] & 15) || g.xs[0] < 0 || g.xs[2] < 0 || g.xs[3] < 0) return false;
+    if (g.xs[3] * (long long)g.S[1] >= 0x7fffffffLL) return false;
+    RingPlan pl;
+    const int cs_first = g.C % 128 == 0 ? 128 : (g.C % 64 == 0 ? 64 : 32);
+    bool found = false;
+    int ctas = 2;
+    for (int cs = cs_first; cs >= 32 && !found; cs >>= 1) {
+        for (ctas = 2; ctas >= 1 && !found; --ctas) {
+            const long long avail = (227LL * 1024) / ctas - 1024 - 2048 - 16;   // reserved per CTA, static shared, fill tail
+            long long k = avail / ((long long)g.S[1] * cs);
+            if (k > g.S[0]) k = g.S[0];
+            if (ring_rows > 0 && k > ring_rows) k = ring_rows;        // tests: force a small ring
+            if (k >= 6 || (k >= 1 && (k == g.S[0] || ring_rows > 0))) {
+                pl.cs = cs;
+                pl.k = (int)k;
+                found = true;
+                break;
+            }
+        }
+    }
+    if (!found) return false;
+    pl.slices = (int)(g.C / pl.cs);
+    pl.tw = pl.cs / 4;
+    pl.tp = RING_THREADS / pl.tw;
+    pl.chunk_shift = pl.cs == 128 ? 3 : (pl.cs == 64 ? 2 : 1);
+    pl.smem_bytes = (unsigned)((long long)pl.k * g.S[1] * pl.cs) + 16u;   // + the fill byte's 16-byte tail
+    const long long base_units = g.N * pl.slices;
+    const long long slots = (long long)sm_count * ctas;
+    double best = -1.0;
+    int best_rows = g.OS[0];
+    for (int segs = 1; segs <= 8 && segs <= g.OS[0]; ++segs) {
+        const int rows = (g.OS[0] + segs - 1) / segs;
+        const int real_segs = (g.OS[0] + rows - 1) / rows;
+        const long long units = base_units * real_segs;
+        const long long waves = (units + slots - 1) / slots;
+        const double eff = (double)units / (double)(waves * slots) * (double)rows / (double)(rows + 2);
+        if (eff > best * 1.02) { best = eff; best_rows = rows; }
+    }
+    pl.seg_rows = best_rows;
+    pl.segs = (g.OS[0] + best_rows - 1) / best_rows;
+    const long long units = base_units * pl.segs;
+    if (units >= 0x7fffffffLL) return false;
+    pl.units = (unsigned)units;
+    long long grid = units < slots ? units : slots;
+    if (max_grid_x > 0 && grid > max_grid_x) grid = max_grid_x;
+    pl.grid = (unsigned)grid;
+    *out = pl;
+    return true;
+}
+
+template <int PAD>
+int ring_launch(const Geo& g, const RingPlan& pl, const void* x, void* y, uint8_t fill, const void* w, int qkind, long long wzp,
+                cudaStream_t s, bool emulate) {
+    if (emulate) {
+        ring_emulate<PAD>(g, pl, (const uint8_t*)x, (uint8_t*)y, fill, w, qkind, wzp);
+        return TS_OK;
+    }
+    static bool configured = false;      // per instantiation; racing threads set the same value
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_gather_nhwc_ring<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048) != cudaSuccess)
+            return check_launch();
+        configured = true;
+    }
+    k_gather_nhwc_ring<PAD><<<pl.grid, RING_THREADS, pl.smem_bytes, s>>>(g, pl, (const uint8_t*)x, (uint8_t*)y, fill, w, qkind, wzp);
+    note_launch();
+    return check_launch();
+}
+
+int ring_run(const Geo& g, const RingPlan& pl, const void* x, void* y, uint8_t fill, const void* w, int qkind, long long wzp,
+             cudaStream_t s, bool emulate) {
+    switch (g.pad) {
+    case TS_PAD_BORDER: return ring_launch<TS_PAD_BORDER>(g, pl, x, y, fill, w, qkind, wzp, s, emulate);
+    case TS_PAD_PERIODIC: return ring_launch<TS_PAD_PERIODIC>(g, pl, x, y, fill, w, qkind, wzp, s, emulate);
+    case TS_PAD_REFLECT: return ring_launch<TS_PAD_REFLECT>(g, pl, x, y, fill, w, qkind, wzp, s, emulate);
+    case TS_PAD_SYMMETRIC: return ring_launch<TS_PAD_SYMMETRIC>(g, pl, x, y, fill, w, qkind, wzp, s, emulate);
+    default: return ring_launch<TS_PAD_ZEROS>(g, pl, x, y, fill, w, qkind, wzp, s, emulate);
+    }
+}
+
 template <typename E, int DIM, int VEC, int PAD>
 void run_dim(const Geo& g, const NhwcPlan& pl, const void* x, void* y, E fill, const void* w, int qkind, long long wzp, cudaStream_t s,
              bool emulate) {
@@ -211,9 +563,16 @@ int run_type(const Geo& g, const NhwcPlan& pl, const void* x, void* y, E fill, c
 
 // x: any strides (g.xs), meant for channel stride 1; y: dense [N, OS0(,OS1(,OS2)), C].
 // emulate: x / y / w are HOST pointers and the launch is walked on the host (tests only, no GPU work).
+// variant: 0 automatic (ring kernel when it applies, else direct), 1 direct only, 2 ring only; ring_rows > 0 caps the ring.
 int nhwc_gather(const Geo& g, const void* x, void* y, unsigned long long fill, int esize, const void* w, int qkind,
-                long long wzp, int sm_count, int max_grid_x, bool emulate, cudaStream_t s) {
+                long long wzp, int sm_count, int max_grid_x, int variant, int ring_rows, bool emulate, cudaStream_t s) {
     if (g.N * g.C == 0 || g.out_plane == 0) return TS_OK;
+    if (variant != 1) {
+        RingPlan rp;
+        if (plan_ring(g, esize, x, y, sm_count, max_grid_x, ring_rows, &rp))
+            return ring_run(g, rp, x, y, (uint8_t)fill, w, qkind, wzp, s, emulate);
+        if (variant == 2) return TS_ERR_UNSUPPORTED;
+    }
     long long rows = g.N;
     for (int a = 0; a < g.dim - 1; ++a) rows *= g.OS[a];
     if (rows >= 0x7fffffffLL || g.C >= 0x7fffffffLL) return TS_ERR_TOO_LARGE;

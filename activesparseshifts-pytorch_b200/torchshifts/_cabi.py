@@ -75,7 +75,7 @@ class NativeLibrary:
             'ts_shift_backward': (i, [gp, i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]),
             'ts_qshift_forward': (i, [gp, i, i, i64, vp, vp, i, i64, vp, vp]),
             'ts_qshift_forward_nhwc': (i, [gp, i, i, i64, vp, vp, i, i64, vp, vp]),
-            'ts_debug_nhwc_emulate': (i, [gp, i, i, i64, vp, vp, i, i64, vp, i, i]),
+            'ts_debug_nhwc_emulate': (i, [gp, i, i, i64, vp, vp, i, i64, vp, i, i, i, i]),
             'ts_shift_backward_allreduce': (i, [gp, i, i, i, vp, vp, vp, vp, vp, vp, sz, ct.POINTER(PeerGroup), vp]),
         }
         for name, (res, args) in sig.items():

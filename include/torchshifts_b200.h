@@ -162,11 +162,15 @@ int ts_qshift_forward_nhwc(const ts_geometry* g, int elem_bytes, int padding, in
 
 /* Test aid (HOST pointers, no GPU work): walks every (block, thread) of the launch
  * ts_qshift_forward_nhwc would make on a device with `sm_count` SMs and runs the kernel's own per-thread
- * program on the host, so the CPU-side tests can pin its index logic against the oracle.  Refuses
- * tensors above 2^22 elements; max_grid_x > 0 caps the grid to exercise the grid-stride loop. */
+ * program on the host (barrier-separated phases in order, shared memory as a host buffer), so the
+ * CPU-side tests can pin its index logic against the oracle.  Refuses tensors above 2^22 elements;
+ * max_grid_x > 0 caps the grid to exercise the grid-stride loops; variant: 0 automatic choice, 1 the
+ * direct (L1) kernel, 2 the ring (shared-memory) kernel or TS_ERR_UNSUPPORTED; ring_rows > 0 caps the
+ * ring so small cases exercise its wrap-around and the global-memory fall-back. */
 int ts_debug_nhwc_emulate(const ts_geometry* g, int elem_bytes, int padding, int64_t zero_point,
                           const void* xq_host, const void* qweights_host, int qweight_kind,
-                          int64_t weight_zero_point, void* yq_host, int sm_count, int max_grid_x);
+                          int64_t weight_zero_point, void* yq_host, int sm_count, int max_grid_x,
+                          int variant, int ring_rows);
 
 #ifdef __cplusplus
 }

@@ -34,10 +34,10 @@ def lib():
 @pytest.fixture()
 def auto_path(lib):
     lib.ts_set_kernel_path(0)
-    lib.ts_set_tuning(b"use_tma=1")
+    lib.ts_set_tuning(b"use_tma=1,nhwc_variant=0,nhwc_ring_rows=0")
     yield
     lib.ts_set_kernel_path(0)
-    lib.ts_set_tuning(b"use_tma=1")
+    lib.ts_set_tuning(b"use_tma=1,nhwc_variant=0,nhwc_ring_rows=0")
 
 
 # kernel-family selection modes exercised by the sweeps: the automatic choice (TMA-tensor family for
@@ -685,7 +685,8 @@ def test_quantized_channels_last_native_kernel(dev, lib, oracle_port, auto_path)
     rng = np.random.default_rng(41)
     cases = [((2, 8, 6, 16), None), ((3, 3, 5, 7), None), ((2, 20, 9, 12), [[1, 0], [2, 1]]), ((1, 1028, 4, 6), None),
              ((2, 64, 56, 56), None), ((2, 6, 3, 4, 5), None), ((1, 16, 6, 10, 12), [[0, 1], [1, 0], [2, 1]]),
-             ((4, 256, 1, 40), None)]
+             ((4, 256, 1, 40), None), ((2, 128, 20, 24), [[2, 1], [0, 3]]), ((1, 96, 33, 17), None), ((3, 32, 8, 8), None),
+             ((300, 128, 9, 5), None)]
     for shape, borders in cases:
         dim = len(shape) - 2
         fn = shift2d_quantized if dim == 2 else shift3d_quantized
@@ -704,14 +705,22 @@ def test_quantized_channels_last_native_kernel(dev, lib, oracle_port, auto_path)
             assert xcl.is_contiguous(memory_format=fmt) and tuple(xcl.shape) == shape
             if xcl.is_contiguous():
                 continue                          # degenerate shapes where both layouts coincide
+            # kernel variants: automatic choice, the direct (L1) kernel, and -- where it applies (2-D, 1-byte
+            # elements, C % 32 == 0) -- the shared-memory ring kernel, also with a ring too small for the shifts
+            variants = [b"nhwc_variant=0,nhwc_ring_rows=0", b"nhwc_variant=1,nhwc_ring_rows=0"]
+            if dim == 2 and npdt is not np.int32 and shape[1] % 32 == 0:
+                variants += [b"nhwc_variant=2,nhwc_ring_rows=0", b"nhwc_variant=2,nhwc_ring_rows=3"]
             for pad in range(5):
-                y = fn(xcl, qw, pad, cut)
-                assert lib.ts_last_kernel_path() == NHWC, (shape, pad)
-                assert y.is_contiguous(memory_format=fmt) and y.dtype == qdtype
-                assert y.q_scale() == xq.q_scale() and y.q_zero_point() == zp
-                got = y.permute(*to_cl).int_repr().cpu().numpy().transpose(to_nc)
                 want = oracle_port.qforward(raw, wraw.astype(np.int64), 128, zp, pad, borders)
-                assert np.array_equal(got, want), (shape, borders, qdtype, pad)
+                for variant in variants:
+                    assert lib.ts_set_tuning(variant) == 0
+                    y = fn(xcl, qw, pad, cut)
+                    assert lib.ts_last_kernel_path() == NHWC, (shape, pad, variant)
+                    assert y.is_contiguous(memory_format=fmt) and y.dtype == qdtype
+                    assert y.q_scale() == xq.q_scale() and y.q_zero_point() == zp
+                    got = y.permute(*to_cl).int_repr().cpu().numpy().transpose(to_nc)
+                    assert np.array_equal(got, want), (shape, borders, qdtype, pad, variant)
+                lib.ts_set_tuning(b"nhwc_variant=0,nhwc_ring_rows=0")
                 # the planar path on the same tensor gives the same integers
                 assert np.array_equal(fn(xq, qw, pad, cut).int_repr().cpu().numpy(), want)
 
@@ -731,9 +740,12 @@ def test_full_size_cfg5_channels_last(dev, lib, oracle_port, auto_path):
     del x
     xcl = xq.contiguous(memory_format=torch.channels_last)
     for pad in (0, 4):
-        y = shift2d_quantized(xcl, qw, pad)
-        assert lib.ts_last_kernel_path() == NHWC and y.is_contiguous(memory_format=torch.channels_last)
-        assert torch.equal(y.int_repr(), shift2d_quantized(xq, qw, pad).int_repr())
+        planar = shift2d_quantized(xq, qw, pad).int_repr()
         idx = [0, 131, 255]
         want = oracle_port.qforward(xq.int_repr()[idx].cpu().numpy(), raw, wzp, -128, pad)
-        assert np.array_equal(y.int_repr()[idx].cpu().numpy(), want)
+        for variant in (b"nhwc_variant=2", b"nhwc_variant=1", b"nhwc_variant=0"):       # ring, direct, automatic
+            assert lib.ts_set_tuning(variant) == 0
+            y = shift2d_quantized(xcl, qw, pad)
+            assert lib.ts_last_kernel_path() == NHWC and y.is_contiguous(memory_format=torch.channels_last)
+            assert torch.equal(y.int_repr(), planar), (pad, variant)
+            assert np.array_equal(y.int_repr()[idx].cpu().numpy(), want)

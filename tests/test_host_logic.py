@@ -261,7 +261,7 @@ int main(void) {
     assert peer == [ct.sizeof(PeerGroup), PeerGroup.epoch.offset, PeerGroup.capacity.offset, PeerGroup.bufs.offset, PeerGroup.flags.offset]
 
 
-def _nhwc_emulate(native, xraw, wraw, wkind, wzp, zp, pad, borders, sm_count=148, max_grid_x=0):
+def _nhwc_emulate(native, xraw, wraw, wkind, wzp, zp, pad, borders, sm_count=148, max_grid_x=0, variant=0, ring_rows=0):
     """Run the channels-last kernel's per-thread program on the host (ts_debug_nhwc_emulate) on a
     channels-last copy of `xraw` (logical [N, C, *spatial]); returns the logical-NCHW result."""
     from torchshifts._cabi import make_geometry
@@ -278,7 +278,9 @@ def _nhwc_emulate(native, xraw, wraw, wkind, wzp, zp, pad, borders, sm_count=148
     ycl = np.full([xraw.shape[0]] + out_sp + [xraw.shape[1]], 0x5A, dtype=xraw.dtype)
     w = np.ascontiguousarray(wraw)
     st = native.lib.ts_debug_nhwc_emulate(ct.byref(geo), xraw.itemsize, pad, zp, xcl.ctypes.data, w.ctypes.data, wkind, wzp,
-                                          ycl.ctypes.data, sm_count, max_grid_x)
+                                          ycl.ctypes.data, sm_count, max_grid_x, variant, ring_rows)
+    if st == 2 and variant == 2:
+        return None                                                # the ring kernel does not apply to this case
     assert st == 0, native.lib.ts_error_string(st)
     return ycl.transpose(inv)
 
@@ -305,7 +307,7 @@ def test_channels_last_kernel_program_matches_the_oracle(native, oracle_port):
                 wraw = (rng.integers(lo, hi, size=(shape[1], dim), endpoint=True) + wzp).astype(wdt)
                 for pad in range(5):
                     want = oracle_port.qforward(x, wraw.astype(np.int64), wzp, zp, pad, borders)
-                    got = _nhwc_emulate(native, x, wraw, kinds[wdt], wzp, zp, pad, borders)
+                    got = _nhwc_emulate(native, x, wraw, kinds[wdt], wzp, zp, pad, borders, variant=1)
                     assert np.array_equal(got, want), (shape, borders, dt, wdt, pad)
     # launch-shape variations: few SMs (no last-axis split), many SMs (split), capped grid (grid-stride loop)
     x = rng.integers(0, 255, size=(3, 8, 10, 33), endpoint=True).astype(np.uint8)
@@ -313,8 +315,39 @@ def test_channels_last_kernel_program_matches_the_oracle(native, oracle_port):
     for pad in (0, 3):
         want = oracle_port.qforward(x, wraw.astype(np.int64), 128, 9, pad, None)
         for sms, cap in ((1, 0), (148, 0), (4096, 0), (148, 3), (2, 1)):
-            assert np.array_equal(_nhwc_emulate(native, x, wraw, 0, 128, 9, pad, None, sms, cap), want), (pad, sms, cap)
+            assert np.array_equal(_nhwc_emulate(native, x, wraw, 0, 128, 9, pad, None, sms, cap, variant=1), want), (pad, sms, cap)
     # the emulation is a test aid, not a CPU path: anything sizeable is refused
     from torchshifts._cabi import make_geometry
     geo = make_geometry(2, (64, 64, 64, 64), (64 * 64 * 64, 1, 64 * 64, 64), (0, 0), (64, 64))
-    assert native.lib.ts_debug_nhwc_emulate(ct.byref(geo), 1, 0, 0, 1, 1, 0, 0, 1, 148, 0) == 4
+    assert native.lib.ts_debug_nhwc_emulate(ct.byref(geo), 1, 0, 0, 1, 1, 0, 0, 1, 148, 0, 0, 0) == 4
+
+
+def test_channels_last_ring_kernel_program_matches_the_oracle(native, oracle_port):
+    """The shared-memory ring variant of the NHWC gather (2-D, 1-byte elements, C % 32 == 0): its CTA
+    program (shift phase, row walk, ring loads, gather with the global-memory fall-back) is walked on the
+    host phase by phase and compared with the oracle.  Small rings force slot wrap-around, windows
+    narrower than the shifts' spread and, with the wrap-around paddings, taps outside the ring."""
+    rng = np.random.default_rng(78)
+    cases = [((2, 32, 9, 6), None), ((1, 64, 12, 5), None), ((2, 128, 7, 9), None), ((1, 256, 6, 4), [[1, 1], [0, 1]]),
+             ((3, 96, 10, 3), [[2, 0], [0, 0]]), ((1, 32, 1, 8), None), ((2, 32, 16, 1), None)]
+    applied = 0
+    for shape, borders in cases:
+        for dt, zp in ((np.uint8, 7), (np.int8, -3)):
+            x = rng.integers(np.iinfo(dt).min, np.iinfo(dt).max, size=shape, endpoint=True).astype(dt)
+            for spread in (1, 3, 20):
+                wraw = (rng.integers(-spread, spread, size=(shape[1], 2), endpoint=True) + 128).astype(np.uint8)
+                for pad in range(5):
+                    want = oracle_port.qforward(x, wraw.astype(np.int64), 128, zp, pad, borders)
+                    for sms, cap, rows in ((148, 0, 0), (148, 0, 4), (2, 3, 2), (1, 1, 1), (148, 0, 7)):
+                        got = _nhwc_emulate(native, x, wraw, 0, 128, zp, pad, borders, sms, cap, variant=2, ring_rows=rows)
+                        assert got is not None, (shape, "ring kernel should apply")
+                        assert np.array_equal(got, want), (shape, borders, dt, spread, pad, sms, cap, rows)
+                        applied += 1
+    assert applied > 1000
+    # shapes the ring kernel declines (3-D, 4-byte elements, C not a multiple of 32) go to the direct kernel
+    x3 = rng.integers(0, 255, size=(1, 32, 3, 4, 5), endpoint=True).astype(np.uint8)
+    w3 = np.full((32, 3), 128, np.uint8)
+    assert _nhwc_emulate(native, x3, w3, 0, 128, 0, 0, None, variant=2) is None
+    x4 = rng.integers(0, 255, size=(1, 20, 4, 5), endpoint=True).astype(np.uint8)
+    assert _nhwc_emulate(native, x4, np.full((20, 2), 128, np.uint8), 0, 128, 0, 0, None, variant=2) is None
+    assert _nhwc_emulate(native, x4, np.full((20, 2), 128, np.uint8), 0, 128, 0, 0, None, variant=0) is not None

@@ -1,5 +1,5 @@
 """cfg5 in channels-last through the native NHWC kernel: a few launches for ncu / timing.
-Usage: python tools/nhwc_probe.py [reps]"""
+Usage: python tools/nhwc_probe.py [reps] [shift spread]"""
 import sys
 from pathlib import Path
 
@@ -17,8 +17,11 @@ torch.manual_seed(0)
 x = torch.quantize_per_tensor(torch.rand(256, 256, 56, 56, device=dev), 1 / 255., -128, torch.qint8)
 xcl = x.contiguous(memory_format=torch.channels_last)
 del x
-qw = quantize_shift_weights((torch.rand(256, 2, device=dev) * 2 - 1) * 3)
-for pad in (0, 3):
+spread = float(sys.argv[2]) if len(sys.argv) > 2 else 3.0
+qw = quantize_shift_weights((torch.rand(256, 2, device=dev) * 2 - 1) * spread)
+lib = torchshifts.extension.native().lib
+for variant, pad in ((2, 0), (2, 3), (1, 0)):
+    assert lib.ts_set_tuning(b"nhwc_variant=%d" % variant) == 0
     for _ in range(reps):
         y = shift2d_quantized(xcl, qw, pad)
     torch.cuda.synchronize()
@@ -29,4 +32,4 @@ for pad in (0, 3):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 10
-    print(f"pad {pad}: {ms:.3f} ms  {2 * xcl.numel() / ms / 1e6:.0f} GB/s  path {torchshifts.extension.native().lib.ts_last_kernel_path()}")
+    print(f"variant {variant} pad {pad}: {ms:.3f} ms  {2 * xcl.numel() / ms / 1e6:.0f} GB/s  path {torchshifts.extension.native().lib.ts_last_kernel_path()}")
