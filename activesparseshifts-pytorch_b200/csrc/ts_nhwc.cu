@@ -296,33 +296,38 @@ TS_HD unsigned ring_base(const uint8_t* ring) {
     return 0u;
 #endif
 }
-TS_HD uint8_t ring_byte(const uint8_t* ring, unsigned addr) {
+TS_HD unsigned ring_byte(const uint8_t* ring, unsigned addr) {      // zero-extended
 #ifdef __CUDA_ARCH__
     unsigned v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-    return (uint8_t)v;
+    return v;
 #else
     return ring[addr];
+#endif
+}
+// Four zero-extended bytes -> one little-endian word (three PRMTs on the device).
+TS_HD void store4(uint8_t* p, const unsigned* v) {
+#ifdef __CUDA_ARCH__
+    const unsigned lo = __byte_perm(v[0], v[1], 0x0040), hi = __byte_perm(v[2], v[3], 0x0040);
+    *reinterpret_cast<uint32_t*>(p) = __byte_perm(lo, hi, 0x5410);
+#else
+    *reinterpret_cast<uint32_t*>(p) = (v[0] & 0xffu) | ((v[1] & 0xffu) << 8) | ((v[2] & 0xffu) << 16) | ((v[3] & 0xffu) << 24);
 #endif
 }
 
 // Fetch the input rows [st.new_lo, st.hi] of this unit's channel slice into their ring slots.
 TS_HD void ring_load(const Geo& g, const RingPlan& pl, const RingUnit& u, const RingStep& st, int tid, int threads,
                      const uint8_t* __restrict__ x, uint8_t* ring) {
-    const int rows = st.hi - st.new_lo + 1;
-    if (rows <= 0) return;
-    const int per_row = g.S[1] << pl.chunk_shift;
-    const int total = rows * per_row;
+    const int per_row = g.S[1] << pl.chunk_shift;       // 16-byte chunks of one row slice
     const uint8_t* src0 = x + (long long)u.n * g.xs[0] + u.c_base;
-    for (int i = tid; i < total; i += threads) {
-        const int rr = i / per_row;
-        const int j = i - rr * per_row;
-        const int q = j >> pl.chunk_shift;
-        const int part = j & ((1 << pl.chunk_shift) - 1);
-        const int row = st.new_lo + rr;
-        const uint8_t* src = src0 + (long long)row * g.xs[2] + (long long)q * g.xs[3] + part * 16;
-        uint8_t* dst = ring + ((size_t)(ring_slot(st, pl.k, row) * g.S[1] + q) * pl.cs + part * 16);
-        copy16(dst, src);
+    for (int row = st.new_lo; row <= st.hi; ++row) {
+        const uint8_t* src_row = src0 + (long long)row * g.xs[2];
+        uint8_t* dst_row = ring + (size_t)(ring_slot(st, pl.k, row) * g.S[1]) * pl.cs;
+        for (int j = tid; j < per_row; j += threads) {
+            const int q = j >> pl.chunk_shift;
+            const int part = j & ((1 << pl.chunk_shift) - 1);
+            copy16(dst_row + (size_t)q * pl.cs + part * 16, src_row + (long long)q * g.xs[3] + part * 16);
+        }
     }
 }
 
@@ -342,6 +347,15 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
     const unsigned fill_addr = base + pl.smem_bytes - 16u;
     const unsigned long long xs3 = (unsigned long long)g.xs[3];
     const long long y_step = (long long)pl.tp * g.C;
+    // output pixels [p_lo, p_hi] whose taps p + lb1 - s1[v] fall inside the source row for all 4 channels
+    int s1_max = th.s1[0], s1_min = th.s1[0];
+#pragma unroll
+    for (int v = 1; v < 4; ++v) {
+        s1_max = th.s1[v] > s1_max ? th.s1[v] : s1_max;
+        s1_min = th.s1[v] < s1_min ? th.s1[v] : s1_min;
+    }
+    const int p_lo = s1_max - lb1 > 0 ? s1_max - lb1 : 0;
+    const int p_hi = s1 - 1 - lb1 + s1_min < ow - 1 ? s1 - 1 - lb1 + s1_min : ow - 1;
     for (int o = st.o_a; o < st.o_b; ++o) {
         unsigned row_addr[4], pitch[4];     // ring address of pixel 0 of the source row, bytes between its pixels
         bool from_global = false;
@@ -357,30 +371,56 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
         }
         uint8_t* yp = y + (((long long)u.n * g.OS[0] + o) * ow + pw) * g.C + c0;
         if (!from_global) {
-#pragma unroll 2
-            for (int p = pw; p < ow; p += pl.tp, yp += y_step) {
-                uint8_t val[4];
+            int p = pw;
+            for (; p < p_lo && p < ow; p += pl.tp, yp += y_step) {          // leading pixels: some tap is left of the row
+                unsigned val[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     const int t1 = axis_index_c<PAD>(p + lb1 - th.s1[v], s1);
                     val[v] = ring_byte(ring, t1 >= 0 ? row_addr[v] + (unsigned)t1 * pitch[v] : fill_addr);
                 }
-                PackOut<uint8_t, 4>::store(yp, val);
+                store4(yp, val);
+            }
+            // interior: every tap of the 4 channels is inside the row, the addresses just advance
+            unsigned addr[4], step[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                addr[v] = row_addr[v] + (unsigned)(p + lb1 - th.s1[v]) * pitch[v];
+                step[v] = (unsigned)pl.tp * pitch[v];
+            }
+#pragma unroll 4
+            for (; p <= p_hi; p += pl.tp, yp += y_step) {
+                unsigned val[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    val[v] = ring_byte(ring, addr[v]);
+                    addr[v] += step[v];
+                }
+                store4(yp, val);
+            }
+            for (; p < ow; p += pl.tp, yp += y_step) {                      // trailing pixels
+                unsigned val[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int t1 = axis_index_c<PAD>(p + lb1 - th.s1[v], s1);
+                    val[v] = ring_byte(ring, t1 >= 0 ? row_addr[v] + (unsigned)t1 * pitch[v] : fill_addr);
+                }
+                store4(yp, val);
             }
         } else {
             for (int p = pw; p < ow; p += pl.tp, yp += y_step) {
-                uint8_t val[4];
+                unsigned val[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     const int t1 = axis_index_c<PAD>(p + lb1 - th.s1[v], s1);
                     if (t0s[v] >= 0 && pitch[v] == 0u) {     // valid row, not in the ring
                         const uint8_t* src = x + (long long)u.n * g.xs[0] + (long long)t0s[v] * g.xs[2] + (c0 + v);
-                        val[v] = t1 >= 0 ? load_ro(src + (unsigned long long)(unsigned)t1 * xs3) : fill;
+                        val[v] = t1 >= 0 ? (unsigned)load_ro(src + (unsigned long long)(unsigned)t1 * xs3) : (unsigned)fill;
                     } else {
                         val[v] = ring_byte(ring, t1 >= 0 ? row_addr[v] + (unsigned)t1 * pitch[v] : fill_addr);
                     }
                 }
-                PackOut<uint8_t, 4>::store(yp, val);
+                store4(yp, val);
             }
         }
     }
