@@ -192,6 +192,7 @@ struct RingPlan {
 };
 constexpr int RING_THREADS = 256;
 constexpr int RING_MAX_CS = 128;
+constexpr int RING_WARPS = RING_THREADS / 32;
 
 struct RingUnit { unsigned n; int c_base, o_begin, o_end; };
 struct RingThread { int s0[4], s1[4], smin, smax; };   // lives in registers across the phases of a unit
@@ -226,7 +227,7 @@ TS_HD void ring_phase_shifts(const Geo& g, const RingPlan& pl, const RingUnit& u
 // Phase 2 (after a barrier): every thread picks up the shifts of its 4 channels and the slice-wide range
 // of the axis-0 shifts (identical in every thread: it sizes the groups of output rows).
 TS_HD void ring_phase_regs(const RingPlan& pl, int tid, const int* sh, RingThread& th) {
-    const int wi = tid % pl.tw;
+    const int wi = (tid & 31) % pl.tw;
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
         th.s0[v] = sh[4 * wi + v];
@@ -244,7 +245,7 @@ TS_HD void ring_phase_regs(const RingPlan& pl, int tid, const int* sh, RingThrea
 
 // The walk down the output rows of a unit, identical in every thread.
 struct RingWalk {
-    int o_next, o_end, rb, phi, smin, smax, lb0, s0, k;
+    int o_next, o_end, rb, phi, smin, smax, lb0, s0, k, prev_lo, prev_slot;
     TS_HD RingWalk(const Geo& g, const RingPlan& pl, const RingUnit& u, const RingThread& th) {
         o_next = u.o_begin;
         o_end = u.o_end;
@@ -255,7 +256,10 @@ struct RingWalk {
         k = pl.k;
         const int span = smax - smin;
         rb = k - span > 1 ? k - span : 1;         // output rows per step: their reach, rb + span rows, fits the ring
+        if (rb > RING_WARPS) rb -= rb % RING_WARPS;   // one output row per warp at a time: keep the warps level
         phi = -1;                                  // highest input row fetched so far in this unit
+        prev_lo = 0;                               // row 0 lives in slot 0: slot(row) = row mod k
+        prev_slot = 0;
     }
     TS_HD bool next(RingStep& s) {
         if (o_next >= o_end) return false;
@@ -267,7 +271,12 @@ struct RingWalk {
         if (s.hi - s.lo + 1 > k) s.hi = s.lo + k - 1;
         s.new_lo = s.lo > phi + 1 ? s.lo : phi + 1;
         if (s.hi > phi) phi = s.hi;
-        s.slot_lo = s.lo % k;
+        // lo only moves forward: one division for the first step, a short catch-up afterwards
+        const int adv = s.lo - prev_lo;
+        if (adv >= 2 * k) prev_slot = s.lo % k;
+        else { prev_slot += adv; if (prev_slot >= k) prev_slot -= k; if (prev_slot >= k) prev_slot -= k; }
+        prev_lo = s.lo;
+        s.slot_lo = prev_slot;
         return true;
     }
 };
@@ -331,22 +340,52 @@ TS_HD void ring_load(const Geo& g, const RingPlan& pl, const RingUnit& u, const 
     }
 }
 
-// Gather phase.  Per (output row, channel) the source is one of three: a ring row (the common case), the
-// fill byte (the whole source row is outside the image: zeros padding), or global memory (a valid row the
-// ring does not hold).  The fill byte lives in shared memory right behind the ring, so "outside" is just
-// another address and the inner loop has no select after the load; rows with a global-memory channel take a
-// separate, slower loop.
+template <int OFF> TS_HD unsigned ring_byte_at(const uint8_t* ring, unsigned addr) {   // ring_byte with an immediate offset
+#ifdef __CUDA_ARCH__
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+#else
+    return ring[addr + OFF];
+#endif
+}
+
+// 8 consecutive pixel steps of a warp (one step = 32 words = 128 ring bytes whatever the slice width) with
+// the ring offsets as immediates: 4 loads, 3 PRMTs and one store per 4 output bytes.
+template <int I> struct Span8 {
+    static TS_HD void run(const uint8_t* ring, const unsigned* a, uint8_t* yp, long long y_step) {
+        unsigned val[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) val[v] = ring_byte_at<I * 128>(ring, a[v]);
+        store4(yp, val);
+        Span8<I + 1>::run(ring, a, yp + y_step, y_step);
+    }
+};
+template <> struct Span8<8> {
+    static TS_HD void run(const uint8_t*, const unsigned*, uint8_t*, long long) {}
+};
+
+// Gather phase.  A warp owns one output row at a time: its lanes are the words of the channel slice (and,
+// for slices narrower than 128 channels, 2 or 4 neighbouring pixels), so the per-row work -- remapping the
+// source row of each of the thread's 4 channels, locating it in the ring -- is paid once per 56-pixel row,
+// not once per handful of pixels.  Per (output row, channel) the source is one of three: a ring row (the
+// common case), the fill byte (the whole source row is outside the image: zeros padding), or global memory
+// (a valid row the ring does not hold).  The fill byte lives in shared memory right behind the ring, so
+// "outside" is just another address; rows with a global-memory channel take a separate, slower loop.
 template <int PAD>
 TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, const RingStep& st, const RingThread& th, int tid,
                         const uint8_t* __restrict__ x, uint8_t* __restrict__ y, uint8_t fill, const uint8_t* ring) {
-    const int wi = tid % pl.tw;
-    const int pw = tid / pl.tw;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wi = lane % pl.tw;              // word of the slice
+    const int pw = lane / pl.tw;              // pixel lane inside the warp
+    const int ppw = 32 / pl.tw;               // pixels a warp covers per step; ppw * cs == 128
     const int c0 = u.c_base + 4 * wi;
     const int s1 = g.S[1], lb1 = g.lb[1], ow = g.OS[1];
     const unsigned base = ring_base(ring);
     const unsigned fill_addr = base + pl.smem_bytes - 16u;
+    const unsigned cs = (unsigned)pl.cs;
     const unsigned long long xs3 = (unsigned long long)g.xs[3];
-    const long long y_step = (long long)pl.tp * g.C;
+    const long long y_step = (long long)ppw * g.C;
     // output pixels [p_lo, p_hi] whose taps p + lb1 - s1[v] fall inside the source row for all 4 channels
     int s1_max = th.s1[0], s1_min = th.s1[0];
 #pragma unroll
@@ -356,23 +395,24 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
     }
     const int p_lo = s1_max - lb1 > 0 ? s1_max - lb1 : 0;
     const int p_hi = s1 - 1 - lb1 + s1_min < ow - 1 ? s1 - 1 - lb1 + s1_min : ow - 1;
-    for (int o = st.o_a; o < st.o_b; ++o) {
+    for (int o = st.o_a + warp; o < st.o_b; o += RING_WARPS) {
         unsigned row_addr[4], pitch[4];     // ring address of pixel 0 of the source row, bytes between its pixels
-        bool from_global = false;
+        bool from_global = false, all_ring = true;
         int t0s[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             const int t0 = axis_index_c<PAD>(o + g.lb[0] - th.s0[v], g.S[0]);
             t0s[v] = t0;
             const bool inw = t0 >= st.lo && t0 <= st.hi;           // implies t0 >= 0
-            row_addr[v] = inw ? base + (unsigned)(ring_slot(st, pl.k, t0) * s1) * (unsigned)pl.cs + (unsigned)(4 * wi + v) : fill_addr;
-            pitch[v] = inw ? (unsigned)pl.cs : 0u;
+            row_addr[v] = inw ? base + (unsigned)(ring_slot(st, pl.k, t0) * s1) * cs + (unsigned)(4 * wi + v) : fill_addr;
+            pitch[v] = inw ? cs : 0u;
             from_global = from_global || (t0 >= 0 && !inw);
+            all_ring = all_ring && inw;
         }
         uint8_t* yp = y + (((long long)u.n * g.OS[0] + o) * ow + pw) * g.C + c0;
+        int p = pw;
         if (!from_global) {
-            int p = pw;
-            for (; p < p_lo && p < ow; p += pl.tp, yp += y_step) {          // leading pixels: some tap is left of the row
+            for (; p < p_lo && p < ow; p += ppw, yp += y_step) {            // leading pixels: some tap is left of the row
                 unsigned val[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -381,15 +421,21 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
                 }
                 store4(yp, val);
             }
-            // interior: every tap of the 4 channels is inside the row, the addresses just advance
+            // interior: every tap of the 4 channels is inside its source row, the addresses just advance
             unsigned addr[4], step[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
                 addr[v] = row_addr[v] + (unsigned)(p + lb1 - th.s1[v]) * pitch[v];
-                step[v] = (unsigned)pl.tp * pitch[v];
+                step[v] = (unsigned)ppw * pitch[v];
             }
-#pragma unroll 4
-            for (; p <= p_hi; p += pl.tp, yp += y_step) {
+            if (all_ring) {
+                for (; p + 7 * ppw <= p_hi; p += 8 * ppw, yp += 8 * y_step) {
+                    Span8<0>::run(ring, addr, yp, y_step);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) addr[v] += 8u * 128u;
+                }
+            }
+            for (; p <= p_hi; p += ppw, yp += y_step) {
                 unsigned val[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -398,7 +444,7 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
                 }
                 store4(yp, val);
             }
-            for (; p < ow; p += pl.tp, yp += y_step) {                      // trailing pixels
+            for (; p < ow; p += ppw, yp += y_step) {                        // trailing pixels
                 unsigned val[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -408,7 +454,7 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
                 store4(yp, val);
             }
         } else {
-            for (int p = pw; p < ow; p += pl.tp, yp += y_step) {
+            for (; p < ow; p += ppw, yp += y_step) {
                 unsigned val[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -511,11 +557,12 @@ bool plan_ring(const Geo& g, int esize, const void* x, const void* y, int sm_cou
     double best = -1.0;
     int best_rows = g.OS[0];
     for (int segs = 1; segs <= 8 && segs <= g.OS[0]; ++segs) {
-        const int rows = (g.OS[0] + segs - 1) / segs;
+        int rows = (g.OS[0] + segs - 1) / segs;
+        if (segs > 1 && rows > RING_WARPS) rows = (rows + RING_WARPS - 1) / RING_WARPS * RING_WARPS;   // whole rounds of the warps
         const int real_segs = (g.OS[0] + rows - 1) / rows;
         const long long units = base_units * real_segs;
         const long long waves = (units + slots - 1) / slots;
-        const double eff = (double)units / (double)(waves * slots) * (double)rows / (double)(rows + 2);
+        const double eff = (double)units / (double)(waves * slots) * (double)rows / (double)(rows + 2);   // wave tail x halo re-reads
         if (eff > best * 1.02) { best = eff; best_rows = rows; }
     }
     pl.seg_rows = best_rows;

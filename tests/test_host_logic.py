@@ -329,7 +329,8 @@ def test_channels_last_ring_kernel_program_matches_the_oracle(native, oracle_por
     narrower than the shifts' spread and, with the wrap-around paddings, taps outside the ring."""
     rng = np.random.default_rng(78)
     cases = [((2, 32, 9, 6), None), ((1, 64, 12, 5), None), ((2, 128, 7, 9), None), ((1, 256, 6, 4), [[1, 1], [0, 1]]),
-             ((3, 96, 10, 3), [[2, 0], [0, 0]]), ((1, 32, 1, 8), None), ((2, 32, 16, 1), None)]
+             ((3, 96, 10, 3), [[2, 0], [0, 0]]), ((1, 32, 1, 8), None), ((2, 32, 16, 1), None),
+             ((1, 128, 6, 40), None), ((1, 32, 5, 70), [[0, 0], [3, 2]]), ((1, 64, 19, 41), None)]   # wide rows: the unrolled interior
     applied = 0
     for shape, borders in cases:
         for dt, zp in ((np.uint8, 7), (np.int8, -3)):
