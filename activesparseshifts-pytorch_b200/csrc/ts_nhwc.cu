@@ -351,18 +351,17 @@ template <int OFF> TS_HD unsigned ring_byte_at(const uint8_t* ring, unsigned add
 }
 
 // 8 consecutive pixel steps of a warp (one step = 32 words = 128 ring bytes whatever the slice width) with
-// the ring offsets as immediates: 4 loads, 3 PRMTs and one store per 4 output bytes.
+// the ring offsets as immediates: 4 loads, 3 PRMTs and one store per 4 output bytes.  All 32 loads are
+// issued before the first pack, so the warp waits for the shared-memory latency once per 8 pixels.
 template <int I> struct Span8 {
-    static TS_HD void run(const uint8_t* ring, const unsigned* a, uint8_t* yp, long long y_step) {
-        unsigned val[4];
+    static TS_HD void load(const uint8_t* ring, const unsigned* a, unsigned (*val)[4]) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) val[v] = ring_byte_at<I * 128>(ring, a[v]);
-        store4(yp, val);
-        Span8<I + 1>::run(ring, a, yp + y_step, y_step);
+        for (int v = 0; v < 4; ++v) val[I][v] = ring_byte_at<I * 128>(ring, a[v]);
+        Span8<I + 1>::load(ring, a, val);
     }
 };
 template <> struct Span8<8> {
-    static TS_HD void run(const uint8_t*, const unsigned*, uint8_t*, long long) {}
+    static TS_HD void load(const uint8_t*, const unsigned*, unsigned (*)[4]) {}
 };
 
 // Gather phase.  A warp owns one output row at a time: its lanes are the words of the channel slice (and,
@@ -429,8 +428,11 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
                 step[v] = (unsigned)ppw * pitch[v];
             }
             if (all_ring) {
-                for (; p + 7 * ppw <= p_hi; p += 8 * ppw, yp += 8 * y_step) {
-                    Span8<0>::run(ring, addr, yp, y_step);
+                for (; p + 7 * ppw <= p_hi; p += 8 * ppw) {
+                    unsigned val[8][4];
+                    Span8<0>::load(ring, addr, val);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i, yp += y_step) store4(yp, val[i]);
 #pragma unroll
                     for (int v = 0; v < 4; ++v) addr[v] += 8u * 128u;
                 }
@@ -553,7 +555,9 @@ bool plan_ring(const Geo& g, int esize, const void* x, const void* y, int sm_cou
     pl.chunk_shift = pl.cs == 128 ? 3 : (pl.cs == 64 ? 2 : 1);
     pl.smem_bytes = (unsigned)((long long)pl.k * g.S[1] * pl.cs) + 16u;   // + the fill byte's 16-byte tail
     const long long base_units = g.N * pl.slices;
-    const long long slots = (long long)sm_count * ctas;
+    long long fit = (228LL * 1024) / ((long long)pl.smem_bytes + 2048 + 1024);       // CTAs of this size one SM holds
+    fit = fit < 1 ? 1 : (fit > 8 ? 8 : fit);
+    const long long slots = (long long)sm_count * fit;
     double best = -1.0;
     int best_rows = g.OS[0];
     for (int segs = 1; segs <= 8 && segs <= g.OS[0]; ++segs) {

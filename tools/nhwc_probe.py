@@ -20,8 +20,9 @@ del x
 spread = float(sys.argv[2]) if len(sys.argv) > 2 else 3.0
 qw = quantize_shift_weights((torch.rand(256, 2, device=dev) * 2 - 1) * spread)
 lib = torchshifts.extension.native().lib
-for variant, pad in ((2, 0), (2, 3), (1, 0)):
-    assert lib.ts_set_tuning(b"nhwc_variant=%d" % variant) == 0
+rows_sweep = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
+for variant, pad, rows in [(2, 0, r) for r in rows_sweep] + [(2, 3, 0), (1, 0, 0)]:
+    assert lib.ts_set_tuning(b"nhwc_variant=%d,nhwc_ring_rows=%d" % (variant, rows)) == 0
     for _ in range(reps):
         y = shift2d_quantized(xcl, qw, pad)
     torch.cuda.synchronize()
@@ -32,4 +33,4 @@ for variant, pad in ((2, 0), (2, 3), (1, 0)):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 10
-    print(f"variant {variant} pad {pad}: {ms:.3f} ms  {2 * xcl.numel() / ms / 1e6:.0f} GB/s  path {torchshifts.extension.native().lib.ts_last_kernel_path()}")
+    print(f"variant {variant} ring_rows {rows} pad {pad}: {ms:.3f} ms  {2 * xcl.numel() / ms / 1e6:.0f} GB/s  path {torchshifts.extension.native().lib.ts_last_kernel_path()}")
