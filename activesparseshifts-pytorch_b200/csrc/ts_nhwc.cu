@@ -196,7 +196,7 @@ constexpr int RING_WARPS = RING_THREADS / 32;
 
 struct RingUnit { unsigned n; int c_base, o_begin, o_end; };
 struct RingThread { int s0[4], s1[4], smin, smax; };   // lives in registers across the phases of a unit
-struct RingStep { int o_a, o_b, lo, hi, new_lo, slot_lo; };
+struct RingStep { int o_a, o_b, lo, hi, new_lo, slot_lo, rb; };
 
 TS_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -256,7 +256,8 @@ struct RingWalk {
         k = pl.k;
         const int span = smax - smin;
         rb = k - span > 1 ? k - span : 1;         // output rows per step: their reach, rb + span rows, fits the ring
-        if (rb > RING_WARPS) rb -= rb % RING_WARPS;   // one output row per warp at a time: keep the warps level
+        if (rb >= RING_WARPS) rb -= rb % RING_WARPS;  // a warp owns one output row at a time: keep the warps level
+        else rb = rb >= 4 ? 4 : (rb >= 2 ? 2 : 1);    // fewer rows than warps: 2 / 4 / 8 warps share a row (ring_compute)
         phi = -1;                                  // highest input row fetched so far in this unit
         prev_lo = 0;                               // row 0 lives in slot 0: slot(row) = row mod k
         prev_slot = 0;
@@ -264,6 +265,7 @@ struct RingWalk {
     TS_HD bool next(RingStep& s) {
         if (o_next >= o_end) return false;
         s.o_a = o_next;
+        s.rb = rb;
         s.o_b = o_next + rb < o_end ? o_next + rb : o_end;
         o_next = s.o_b;
         s.lo = clampi(s.o_a + lb0 - smax, 0, s0 - 1);
@@ -394,7 +396,15 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
     }
     const int p_lo = s1_max - lb1 > 0 ? s1_max - lb1 : 0;
     const int p_hi = s1 - 1 - lb1 + s1_min < ow - 1 ? s1 - 1 - lb1 + s1_min : ow - 1;
-    for (int o = st.o_a + warp; o < st.o_b; o += RING_WARPS) {
+    // rows of the step over the warps; with fewer rows than warps, `parts` warps share a row (pixel ranges)
+    const int parts = st.rb >= RING_WARPS ? 1 : RING_WARPS / st.rb;
+    const int rows_in_flight = RING_WARPS / parts;
+    const int part = warp / rows_in_flight;
+    const int part_len = (ow + parts - 1) / parts;
+    const int pa = part * part_len;
+    const int pb = pa + part_len < ow ? pa + part_len : ow;
+    const int p_hi_w = p_hi < pb - 1 ? p_hi : pb - 1;
+    for (int o = st.o_a + warp % rows_in_flight; o < st.o_b; o += rows_in_flight) {
         unsigned row_addr[4], pitch[4];     // ring address of pixel 0 of the source row, bytes between its pixels
         bool from_global = false, all_ring = true;
         int t0s[4];
@@ -408,10 +418,10 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
             from_global = from_global || (t0 >= 0 && !inw);
             all_ring = all_ring && inw;
         }
-        uint8_t* yp = y + (((long long)u.n * g.OS[0] + o) * ow + pw) * g.C + c0;
-        int p = pw;
+        int p = pa + pw;
+        uint8_t* yp = y + (((long long)u.n * g.OS[0] + o) * ow + p) * g.C + c0;
         if (!from_global) {
-            for (; p < p_lo && p < ow; p += ppw, yp += y_step) {            // leading pixels: some tap is left of the row
+            for (; p < p_lo && p < pb; p += ppw, yp += y_step) {            // leading pixels: some tap is left of the row
                 unsigned val[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -428,7 +438,7 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
                 step[v] = (unsigned)ppw * pitch[v];
             }
             if (all_ring) {
-                for (; p + 7 * ppw <= p_hi; p += 8 * ppw) {
+                for (; p + 7 * ppw <= p_hi_w; p += 8 * ppw) {
                     unsigned val[8][4];
                     Span8<0>::load(ring, addr, val);
 #pragma unroll
@@ -437,7 +447,7 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
                     for (int v = 0; v < 4; ++v) addr[v] += 8u * 128u;
                 }
             }
-            for (; p <= p_hi; p += ppw, yp += y_step) {
+            for (; p <= p_hi_w; p += ppw, yp += y_step) {
                 unsigned val[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -446,7 +456,7 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
                 }
                 store4(yp, val);
             }
-            for (; p < ow; p += ppw, yp += y_step) {                        // trailing pixels
+            for (; p < pb; p += ppw, yp += y_step) {                        // trailing pixels
                 unsigned val[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -456,7 +466,7 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
                 store4(yp, val);
             }
         } else {
-            for (; p < ow; p += ppw, yp += y_step) {
+            for (; p < pb; p += ppw, yp += y_step) {
                 unsigned val[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -475,7 +485,7 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
 }
 
 template <int PAD>
-__global__ void __launch_bounds__(RING_THREADS) k_gather_nhwc_ring(Geo g, RingPlan pl, const uint8_t* __restrict__ x,
+__global__ void __launch_bounds__(RING_THREADS, 3) k_gather_nhwc_ring(Geo g, RingPlan pl, const uint8_t* __restrict__ x,
                                                                    uint8_t* __restrict__ y, uint8_t fill,
                                                                    const void* __restrict__ w, int qkind, long long wzp) {
     extern __shared__ uint4 ring_store[];
@@ -532,19 +542,21 @@ bool plan_ring(const Geo& g, int esize, const void* x, const void* y, int sm_cou
     if (g.xs[3] * (long long)g.S[1] >= 0x7fffffffLL) return false;
     RingPlan pl;
     const int cs_first = g.C % 128 == 0 ? 128 : (g.C % 64 == 0 ? 64 : 32);
+    // Ring size: several CTAs per SM overlap one CTA's fetch phase with the others' gather phase (measured on
+    // cfg5: 3 CTAs x 10 rows beat 2 x 15), but the ring must still hold the rows a group of output rows can reach.
     bool found = false;
-    int ctas = 2;
-    for (int cs = cs_first; cs >= 32 && !found; cs >>= 1) {
-        for (ctas = 2; ctas >= 1 && !found; --ctas) {
-            const long long avail = (227LL * 1024) / ctas - 1024 - 2048 - 16;   // reserved per CTA, static shared, fill tail
-            long long k = avail / ((long long)g.S[1] * cs);
-            if (k > g.S[0]) k = g.S[0];
-            if (ring_rows > 0 && k > ring_rows) k = ring_rows;        // tests: force a small ring
-            if (k >= 6 || (k >= 1 && (k == g.S[0] || ring_rows > 0))) {
-                pl.cs = cs;
-                pl.k = (int)k;
-                found = true;
-                break;
+    for (int min_k = 8; min_k >= 4 && !found; min_k -= 4) {
+        for (int cs = cs_first; cs >= 32 && !found; cs >>= 1) {
+            for (int ctas = 3; ctas >= 1 && !found; --ctas) {
+                const long long avail = (227LL * 1024) / ctas - 1024 - 2048 - 16;   // reserved per CTA, static shared, fill tail
+                long long k = avail / ((long long)g.S[1] * cs);
+                if (k > g.S[0]) k = g.S[0];
+                if (ring_rows > 0 && k > ring_rows) k = ring_rows;        // tuning / tests: force a small ring
+                if (k >= min_k || (k >= 1 && (k == g.S[0] || ring_rows > 0))) {
+                    pl.cs = cs;
+                    pl.k = (int)k;
+                    found = true;
+                }
             }
         }
     }
