@@ -193,6 +193,7 @@ struct RingPlan {
 constexpr int RING_THREADS = 256;
 constexpr int RING_MAX_CS = 128;
 constexpr int RING_WARPS = RING_THREADS / 32;
+static_assert(RING_WARPS == 8, "ring_compute splits rows across 8 warps with shifts");
 
 struct RingUnit { unsigned n; int c_base, o_begin, o_end; };
 struct RingThread { int s0[4], s1[4], smin, smax; };   // lives in registers across the phases of a unit
@@ -329,15 +330,25 @@ TS_HD void store4(uint8_t* p, const unsigned* v) {
 // Fetch the input rows [st.new_lo, st.hi] of this unit's channel slice into their ring slots.
 TS_HD void ring_load(const Geo& g, const RingPlan& pl, const RingUnit& u, const RingStep& st, int tid, int threads,
                      const uint8_t* __restrict__ x, uint8_t* ring) {
+    const int nrows = st.hi - st.new_lo + 1;
+    if (nrows <= 0) return;
+    // A thread keeps its chunk position(s) inside the row slice and walks down the rows: per copy one
+    // 64-bit add for the source and an add-with-wrap for the ring slot.
     const int per_row = g.S[1] << pl.chunk_shift;       // 16-byte chunks of one row slice
-    const uint8_t* src0 = x + (long long)u.n * g.xs[0] + u.c_base;
-    for (int row = st.new_lo; row <= st.hi; ++row) {
-        const uint8_t* src_row = src0 + (long long)row * g.xs[2];
-        uint8_t* dst_row = ring + (size_t)(ring_slot(st, pl.k, row) * g.S[1]) * pl.cs;
-        for (int j = tid; j < per_row; j += threads) {
-            const int q = j >> pl.chunk_shift;
-            const int part = j & ((1 << pl.chunk_shift) - 1);
-            copy16(dst_row + (size_t)q * pl.cs + part * 16, src_row + (long long)q * g.xs[3] + part * 16);
+    const unsigned row_bytes = (unsigned)g.S[1] * (unsigned)pl.cs;
+    const unsigned ring_bytes = (unsigned)pl.k * row_bytes;
+    const int slot0 = ring_slot(st, pl.k, st.new_lo);
+    const uint8_t* src0 = x + (long long)u.n * g.xs[0] + u.c_base + (long long)st.new_lo * g.xs[2];
+    for (int j = tid; j < per_row; j += threads) {
+        const int q = j >> pl.chunk_shift;
+        const int part = j & ((1 << pl.chunk_shift) - 1);
+        const uint8_t* src = src0 + (long long)q * g.xs[3] + part * 16;
+        unsigned d = (unsigned)slot0 * row_bytes + (unsigned)q * (unsigned)pl.cs + (unsigned)part * 16u;
+        for (int r = 0; r < nrows; ++r) {
+            copy16(ring + d, src);
+            src += g.xs[2];
+            d += row_bytes;
+            if (d >= ring_bytes) d -= ring_bytes;
         }
     }
 }
@@ -397,14 +408,15 @@ TS_HD void ring_compute(const Geo& g, const RingPlan& pl, const RingUnit& u, con
     const int p_lo = s1_max - lb1 > 0 ? s1_max - lb1 : 0;
     const int p_hi = s1 - 1 - lb1 + s1_min < ow - 1 ? s1 - 1 - lb1 + s1_min : ow - 1;
     // rows of the step over the warps; with fewer rows than warps, `parts` warps share a row (pixel ranges)
-    const int parts = st.rb >= RING_WARPS ? 1 : RING_WARPS / st.rb;
-    const int rows_in_flight = RING_WARPS / parts;
-    const int part = warp / rows_in_flight;
-    const int part_len = (ow + parts - 1) / parts;
-    const int pa = part * part_len;
+    // (st.rb is a multiple of the warp count, or 4 / 2 / 1: everything here is a shift)
+    const int part_shift = st.rb >= RING_WARPS ? 0 : (st.rb == 4 ? 1 : (st.rb == 2 ? 2 : 3));
+    const int rows_in_flight = RING_WARPS >> part_shift;
+    const int part = warp >> (3 - part_shift);
+    const int part_len = (ow + (1 << part_shift) - 1) >> part_shift;
+    const int pa = part * part_len < ow ? part * part_len : ow;
     const int pb = pa + part_len < ow ? pa + part_len : ow;
     const int p_hi_w = p_hi < pb - 1 ? p_hi : pb - 1;
-    for (int o = st.o_a + warp % rows_in_flight; o < st.o_b; o += rows_in_flight) {
+    for (int o = st.o_a + (warp & (rows_in_flight - 1)); o < st.o_b; o += rows_in_flight) {
         unsigned row_addr[4], pitch[4];     // ring address of pixel 0 of the source row, bytes between its pixels
         bool from_global = false, all_ring = true;
         int t0s[4];
