@@ -247,7 +247,6 @@ TS_HD void ring_phase_regs(const RingPlan& pl, int tid, const int* sh, RingThrea
 // The walk down the output rows of a unit, identical in every thread.
 struct RingWalk {
     int o_next, o_end, rb, phi, smin, smax, lb0, s0, k, prev_lo, prev_slot;
-    bool first;
     TS_HD RingWalk(const Geo& g, const RingPlan& pl, const RingUnit& u, const RingThread& th) {
         o_next = u.o_begin;
         o_end = u.o_end;
@@ -256,16 +255,13 @@ struct RingWalk {
         lb0 = g.lb[0];
         s0 = g.S[0];
         k = pl.k;
-        // The rows of step i+1 are fetched while step i is gathered, so the ring holds the reach of two
-        // consecutive groups of rb output rows: 2 * rb + span input rows.
         const int span = smax - smin;
-        rb = (k - span) / 2 > 1 ? (k - span) / 2 : 1;
+        rb = k - span > 1 ? k - span : 1;         // output rows per step: their reach, rb + span rows, fits the ring
         if (rb >= RING_WARPS) rb -= rb % RING_WARPS;  // a warp owns one output row at a time: keep the warps level
         else rb = rb >= 4 ? 4 : (rb >= 2 ? 2 : 1);    // fewer rows than warps: 2 / 4 / 8 warps share a row (ring_compute)
         phi = -1;                                  // highest input row fetched so far in this unit
         prev_lo = 0;                               // row 0 lives in slot 0: slot(row) = row mod k
         prev_slot = 0;
-        first = true;
     }
     TS_HD bool next(RingStep& s) {
         if (o_next >= o_end) return false;
@@ -275,11 +271,7 @@ struct RingWalk {
         o_next = s.o_b;
         s.lo = clampi(s.o_a + lb0 - smax, 0, s0 - 1);
         s.hi = clampi(s.o_b - 1 + lb0 - smin, 0, s0 - 1);
-        // this step's rows are fetched while the previous step still reads its window [prev_lo, ..]: they may
-        // only take slots of rows below prev_lo.  Rows cut off here are served from global memory.
-        const int cap_from = first ? s.lo : prev_lo;
-        if (s.hi - cap_from + 1 > k) s.hi = cap_from + k - 1;
-        if (s.hi < s.lo) s.hi = s.lo - 1;          // (empty window: nothing of this step's reach fits)
+        if (s.hi - s.lo + 1 > k) s.hi = s.lo + k - 1;
         s.new_lo = s.lo > phi + 1 ? s.lo : phi + 1;
         if (s.hi > phi) phi = s.hi;
         // lo only moves forward: one division for the first step, a short catch-up afterwards
@@ -288,7 +280,6 @@ struct RingWalk {
         else { prev_slot += adv; if (prev_slot >= k) prev_slot -= k; if (prev_slot >= k) prev_slot -= k; }
         prev_lo = s.lo;
         s.slot_lo = prev_slot;
-        first = false;
         return true;
     }
 };
@@ -520,19 +511,13 @@ __global__ void __launch_bounds__(RING_THREADS, 3) k_gather_nhwc_ring(Geo g, Rin
         RingThread th;
         ring_phase_regs(pl, tid, sh, th);
         RingWalk walk(g, pl, u, th);
-        RingStep cur, nxt;
-        bool have = walk.next(cur);
-        ring_load(g, pl, u, cur, tid, RING_THREADS, x, ring);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();                 // the first window is in place
-        while (have) {
-            const bool more = walk.next(nxt);
-            if (more) ring_load(g, pl, u, nxt, tid, RING_THREADS, x, ring);   // in flight during the gather below
-            ring_compute<PAD>(g, pl, u, cur, th, tid, x, y, fill, ring);
+        RingStep st;
+        while (walk.next(st)) {
+            ring_load(g, pl, u, st, tid, RING_THREADS, x, ring);
             asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncthreads();             // next window visible; everyone is done with the rows (and sh) the step after may replace
-            cur = nxt;
-            have = more;
+            __syncthreads();             // the new rows are visible to every thread
+            ring_compute<PAD>(g, pl, u, st, th, tid, x, y, fill, ring);
+            __syncthreads();             // every thread is done with the rows the next step overwrites (and with sh)
         }
     }
 }
@@ -551,16 +536,10 @@ void ring_emulate(const Geo& g, const RingPlan& pl, const uint8_t* x, uint8_t* y
             for (int tid = 0; tid < RING_THREADS; ++tid) ring_phase_shifts(g, pl, u, tid, w, qkind, wzp, sh, ring, fill);
             for (int tid = 0; tid < RING_THREADS; ++tid) ring_phase_regs(pl, tid, sh, th[tid]);
             RingWalk walk(g, pl, u, th[0]);
-            RingStep cur, nxt;
-            bool have = walk.next(cur);
-            for (int tid = 0; tid < RING_THREADS; ++tid) ring_load(g, pl, u, cur, tid, RING_THREADS, x, ring);
-            while (have) {
-                const bool more = walk.next(nxt);
-                // worst-case order of the asynchronous copies: all of them land before the gather starts
-                if (more) for (int tid = 0; tid < RING_THREADS; ++tid) ring_load(g, pl, u, nxt, tid, RING_THREADS, x, ring);
-                for (int tid = 0; tid < RING_THREADS; ++tid) ring_compute<PAD>(g, pl, u, cur, th[tid], tid, x, y, fill, ring);
-                cur = nxt;
-                have = more;
+            RingStep st;
+            while (walk.next(st)) {
+                for (int tid = 0; tid < RING_THREADS; ++tid) ring_load(g, pl, u, st, tid, RING_THREADS, x, ring);
+                for (int tid = 0; tid < RING_THREADS; ++tid) ring_compute<PAD>(g, pl, u, st, th[tid], tid, x, y, fill, ring);
             }
         }
     }
