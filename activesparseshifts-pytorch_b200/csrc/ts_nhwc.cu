@@ -612,12 +612,9 @@ int ring_launch(const Geo& g, const RingPlan& pl, const void* x, void* y, uint8_
         ring_emulate<PAD>(g, pl, (const uint8_t*)x, (uint8_t*)y, fill, w, qkind, wzp);
         return TS_OK;
     }
-    static bool configured = false;      // per instantiation; racing threads set the same value
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_gather_nhwc_ring<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048) != cudaSuccess)
-            return check_launch();
-        configured = true;
-    }
+    // per launch, like the other families: the attribute belongs to the current device's copy of the kernel
+    if (cudaFuncSetAttribute(k_gather_nhwc_ring<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes) != cudaSuccess)
+        return check_launch();
     k_gather_nhwc_ring<PAD><<<pl.grid, RING_THREADS, pl.smem_bytes, s>>>(g, pl, (const uint8_t*)x, (uint8_t*)y, fill, w, qkind, wzp);
     note_launch();
     return check_launch();
