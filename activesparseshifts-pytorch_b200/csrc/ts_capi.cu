@@ -388,6 +388,16 @@ int ts_qshift_forward_nhwc(const ts_geometry* gin, int elem_bytes, int padding, 
                        tuning().nhwc_variant, tuning().nhwc_ring_rows, false, (cudaStream_t)stream);
 }
 
+int ts_nhwc_to_nchw(const void* x, void* y, int64_t N, int64_t C, int64_t P, int elem_bytes, void* stream) {
+    if (N < 0 || C < 0 || P < 0) return TS_ERR_INVALID_ARGUMENT;
+    if (N == 0 || C == 0 || P == 0) return TS_OK;
+    if (!x || !y) return TS_ERR_INVALID_ARGUMENT;
+    int sms = 0;
+    const int rc = sm_count(&sms);      // fails loudly without a device
+    if (rc != TS_OK) return rc;
+    return nhwc_to_planar(x, y, N, C, P, elem_bytes, (cudaStream_t)stream);
+}
+
 int ts_debug_nhwc_emulate(const ts_geometry* gin, int elem_bytes, int padding, int64_t zero_point, const void* xq_host,
                           const void* qweights_host, int qweight_kind, int64_t weight_zero_point, void* yq_host, int sm_count_,
                           int max_grid_x, int variant, int ring_rows) {

@@ -45,6 +45,8 @@ void set_pending_peers(const ts_peer_group* peers);
 int nhwc_gather(const Geo& g, const void* x, void* y, unsigned long long fill, int esize, const void* w, int qkind,
                 long long wzp, int sm_count, int max_grid_x, int variant, int ring_rows, bool emulate, cudaStream_t s);
 
+int nhwc_to_planar(const void* x, void* y, long long N, long long C, long long P, int esize, cudaStream_t s);
+
 // ---- staged family (ts_staged.cu): bulk-async shared-memory staging ---------------------------
 struct Tuning {
     int stages;        // ring depth

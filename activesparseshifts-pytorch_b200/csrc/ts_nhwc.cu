@@ -671,7 +671,55 @@ int run_type(const Geo& g, const NhwcPlan& pl, const void* x, void* y, E fill, c
     return check_launch();
 }
 
+// ------------------------------------------------------------------------------------------
+// Layout adapter for the float path: dense channels-last -> dense planar (per image a [P, C] -> [C, P]
+// transpose through a padded shared-memory tile; both sides move whole 128-byte lines).  The reference
+// returns planar tensors for channels-last float inputs (cpu/shifts_cpu.cpp:221), so the planar bandwidth
+// kernels serve them after this one pass; torch's own .contiguous() does the same job at 1.9 TB/s.
+template <typename E>
+__global__ void __launch_bounds__(256) k_nhwc_to_nchw(const E* __restrict__ x, E* __restrict__ y, int C, int P, unsigned ptiles) {
+    __shared__ E tile[32][33];
+    const unsigned n = blockIdx.x / ptiles;
+    const int p0 = (int)(blockIdx.x - n * ptiles) * 32;
+    const int c0 = (int)blockIdx.y * 32;
+    const E* xi = x + (long long)n * P * C;
+    E* yo = y + (long long)n * P * C;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int p = p0 + j, c = c0 + tx;
+        if (p < P && c < C) tile[j][tx] = xi[(long long)p * C + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, p = p0 + tx;
+        if (c < C && p < P) yo[(long long)c * P + p] = tile[tx][j];
+    }
+}
+
+template <typename E>
+int to_planar_t(const void* x, void* y, long long N, long long C, long long P, cudaStream_t s) {
+    const long long ptiles = (P + 31) / 32, ctiles = (C + 31) / 32;
+    if (N * ptiles >= 0x7fffffffLL || ctiles > 65535) return TS_ERR_TOO_LARGE;
+    const dim3 grid((unsigned)(N * ptiles), (unsigned)ctiles, 1), block(32, 8, 1);
+    k_nhwc_to_nchw<E><<<grid, block, 0, s>>>((const E*)x, (E*)y, (int)C, (int)P, (unsigned)ptiles);
+    note_launch();
+    return check_launch();
+}
+
 }  // namespace
+
+int nhwc_to_planar(const void* x, void* y, long long N, long long C, long long P, int esize, cudaStream_t s) {
+    if (N == 0 || C == 0 || P == 0) return TS_OK;
+    if (C >= 0x7fffffffLL || P >= 0x7fffffffLL) return TS_ERR_TOO_LARGE;
+    switch (esize) {
+    case 2: return to_planar_t<uint16_t>(x, y, N, C, P, s);
+    case 4: return to_planar_t<uint32_t>(x, y, N, C, P, s);
+    case 8: return to_planar_t<unsigned long long>(x, y, N, C, P, s);
+    }
+    return TS_ERR_UNSUPPORTED;
+}
 
 // x: any strides (g.xs), meant for channel stride 1; y: dense [N, OS0(,OS1(,OS2)), C].
 // emulate: x / y / w are HOST pointers and the launch is walked on the host (tests only, no GPU work).

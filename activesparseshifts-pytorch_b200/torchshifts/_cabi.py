@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = (
     'ts_set_kernel_path', 'ts_launch_count', 'ts_set_tuning', 'ts_check_borders', 'ts_debug_remap',
     'ts_debug_remap_reduced', 'ts_debug_split_f32', 'ts_debug_split_f64', 'ts_shift_forward',
     'ts_shift_backward_workspace_bytes', 'ts_shift_backward', 'ts_qshift_forward', 'ts_shift_backward_allreduce',
-    'ts_qshift_forward_nhwc', 'ts_debug_nhwc_emulate',
+    'ts_qshift_forward_nhwc', 'ts_debug_nhwc_emulate', 'ts_nhwc_to_nchw',
 )
 
 
@@ -76,6 +76,7 @@ class NativeLibrary:
             'ts_qshift_forward': (i, [gp, i, i, i64, vp, vp, i, i64, vp, vp]),
             'ts_qshift_forward_nhwc': (i, [gp, i, i, i64, vp, vp, i, i64, vp, vp]),
             'ts_debug_nhwc_emulate': (i, [gp, i, i, i64, vp, vp, i, i64, vp, i, i, i, i]),
+            'ts_nhwc_to_nchw': (i, [vp, vp, i64, i64, i64, i, vp]),
             'ts_shift_backward_allreduce': (i, [gp, i, i, i, vp, vp, vp, vp, vp, vp, sz, ct.POINTER(PeerGroup), vp]),
         }
         for name, (res, args) in sig.items():

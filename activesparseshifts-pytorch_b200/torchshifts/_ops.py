@@ -65,14 +65,27 @@ def _same_device_and_type(fn, input, weights, grad=None):
 _COPY_THRESHOLD = 1 << 16
 
 
+_CL_FORMATS = {4: torch.channels_last, 5: torch.channels_last_3d}
+
+
 def _dense(input):
     """Channels-last / sliced inputs: the stride-aware generic kernels read them in place, but their
     per-element strided loads waste most of every 32-byte sector.  Above a few tens of thousands of
-    elements one extra coalesced pass (``.contiguous()``) plus the bandwidth kernels is several times
-    faster (native NHWC kernels are SURVEY 8f "next")."""
-    if input.numel() >= _COPY_THRESHOLD and not input.is_contiguous():
-        return input.contiguous()
-    return input
+    elements one extra coalesced pass plus the bandwidth kernels is several times faster: a dense
+    channels-last tensor goes through the library's own tiled transpose (``ts_nhwc_to_nchw``), anything
+    else through ``.contiguous()``."""
+    if input.numel() < _COPY_THRESHOLD or input.is_contiguous():
+        return input
+    fmt = _CL_FORMATS.get(input.dim())
+    if fmt is not None and input.is_contiguous(memory_format=fmt) and input.element_size() in (2, 4, 8):
+        out = torch.empty(input.shape, dtype=input.dtype, device=input.device)
+        n, c = input.shape[0], input.shape[1]
+        with torch.cuda.device(input.device):
+            st = _NATIVE.lib.ts_nhwc_to_nchw(input.data_ptr(), out.data_ptr(), n, c, input.numel() // max(n * c, 1),
+                                             input.element_size(), _stream(input.device))
+        _NATIVE.check(st, 'ts_nhwc_to_nchw')
+        return out
+    return input.contiguous()
 
 
 def _stream(device):

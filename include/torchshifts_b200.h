@@ -160,6 +160,12 @@ int ts_qshift_forward_nhwc(const ts_geometry* g, int elem_bytes, int padding, in
                            const void* xq, const void* qweights, int qweight_kind,
                            int64_t weight_zero_point, void* yq, void* stream);
 
+/* Layout adapter of the float path: x dense channels-last ([N, P, C] in memory, P = product of the spatial
+ * sizes) -> y dense planar ([N, C, P]).  The reference hands channels-last float inputs to its nhwdc bodies
+ * and returns planar tensors (ops/cpu/shifts_cpu.cpp:55-75, :221); here the planar bandwidth kernels serve
+ * them after this one pass.  elem_bytes: 2, 4 or 8. */
+int ts_nhwc_to_nchw(const void* x, void* y, int64_t N, int64_t C, int64_t P, int elem_bytes, void* stream);
+
 /* Test aid (HOST pointers, no GPU work): walks every (block, thread) of the launch
  * ts_qshift_forward_nhwc would make on a device with `sm_count` SMs and runs the kernel's own per-thread
  * program on the host (barrier-separated phases in order, shared memory as a host buffer), so the

@@ -749,3 +749,28 @@ def test_full_size_cfg5_channels_last(dev, lib, oracle_port, auto_path):
             assert lib.ts_last_kernel_path() == NHWC and y.is_contiguous(memory_format=torch.channels_last)
             assert torch.equal(y.int_repr(), planar), (pad, variant)
             assert np.array_equal(y.int_repr()[idx].cpu().numpy(), want)
+
+
+def test_channels_last_to_planar_adapter(dev, lib, oracle_port, auto_path):
+    """ts_nhwc_to_nchw (the float path's layout pass for channels-last inputs) == torch's .contiguous(), bit for bit,
+    for ragged tile edges and every element size; and a channels-last float input gives the oracle's result through it."""
+    import ctypes as ct
+    from torchshifts.functional import shift2d_func
+    torch.manual_seed(11)
+    stream = ct.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for dtype in (torch.float32, torch.bfloat16, torch.float16, torch.float64):
+        for shape in ((2, 5, 7, 9), (3, 64, 56, 56), (1, 33, 3, 4, 5), (2, 256, 1, 40), (1, 1, 6, 6), (2, 70, 31, 1)):
+            fmt = torch.channels_last if len(shape) == 4 else torch.channels_last_3d
+            x = torch.randn(shape, device=dev).to(dtype).contiguous(memory_format=fmt)
+            out = torch.full(shape, 7, dtype=dtype, device=dev)
+            n, c = shape[0], shape[1]
+            assert lib.ts_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), n, c, x.numel() // (n * c), x.element_size(), stream) == 0
+            assert out.is_contiguous() and torch.equal(out, x.contiguous()), (dtype, shape)
+    assert lib.ts_nhwc_to_nchw(0, 0, 1, 1, 1, 3, stream) != 0            # null pointers / odd element size are refused
+    x = torch.randn(4, 96, 40, 40, device=dev)                              # above the copy threshold: _dense() uses the adapter
+    w = (torch.rand(96, 2, device=dev) * 2 - 1) * 2
+    before = lib.ts_launch_count()
+    y = shift2d_func(x.contiguous(memory_format=torch.channels_last), w, 3, True)
+    assert lib.ts_launch_count() - before == 2 and lib.ts_last_kernel_path() in (STAGED, TMA)
+    assert y.is_contiguous()
+    assert np.array_equal(y.cpu().numpy(), oracle_port.forward(x.cpu().numpy(), w.cpu().numpy(), 3, True))
