@@ -1,16 +1,24 @@
-// ts_nhwc.cu -- channels-last (NHWC / NDHWC) integer gather: input AND output keep the channel axis
-// innermost, so a quantized channels-last pipeline pays one read and one write of the tensor instead
-// of the three passes (to-NCHW copy, NCHW kernel, to-NHWC copy) the planar families would need.
+// ts_nhwc.cu -- channels-last (NHWC / NDHWC) support.
 //
-// Semantics: reference body  ops/kernels/shifts_kernels.h:574-624 (shift_forward_kernel_nhwdc_q),
-//            driver          ops/quantized/shifts_quantized.cpp:107-130 (output allocated in the
-//                            input's memory format, :119-122).
+//  * Quantized gather with input AND output channels-last (ts_qshift_forward_nhwc), so a quantized
+//    channels-last pipeline pays one read and one write of the tensor instead of the three passes
+//    (to-NCHW copy, NCHW kernel, to-NHWC copy) the planar families would need.  Two kernels:
+//      k_gather_nhwc_ring  2-D, 1-byte elements, C % 32 == 0: input rows staged in a shared-memory ring,
+//      k_gather_nhwc       everything else (3-D, 4-byte elements, odd channel counts): direct global loads.
+//    Semantics: reference body  ops/kernels/shifts_kernels.h:574-624 (shift_forward_kernel_nhwdc_q),
+//               driver          ops/quantized/shifts_quantized.cpp:107-130 (output allocated in the
+//                               input's memory format, :119-122).
+//  * k_nhwc_to_nchw (ts_nhwc_to_nchw): the layout pass of the FLOAT path, whose outputs are planar in the
+//    reference too (ops/cpu/shifts_cpu.cpp:55-75 reads NHWC, :221 returns NCHW).
 //
-// Layout of the work.  In NHWC the per-channel shift is a per-lane gather: the channel vector of one
-// output pixel takes each of its channels from a different input pixel.  Consecutive lanes own
+// Both gather kernels' thread programs are host+device code: ts_debug_nhwc_emulate walks them on the host,
+// barrier phase by barrier phase, so the CPU-side tests can check the index logic without a GPU.
+//
+// Direct kernel, layout of the work.  In NHWC the per-channel shift is a per-lane gather: the channel vector
+// of one output pixel takes each of its channels from a different input pixel.  Consecutive lanes own
 // consecutive 4-byte words of the channel vector (4 channels of a 1-byte type, 1 channel of a 4-byte
-// type), so every warp store is one contiguous 128-byte line and every warp load touches at most
-// (distinct shifts) x 4 sectors, all of them re-used by the neighbouring pixels through L1/L2.
+// type), so every warp store is one contiguous 128-byte line; the loads are one byte each and land in
+// (nearly) as many 32-byte sectors as there are lanes, re-used by the neighbouring pixels through L1/L2.
 // A CTA owns a few consecutive output rows of one image and its threads keep their channel group for
 // the whole CTA lifetime: the shifts, the remapped outer-axis offsets and the validity flags are
 // registers, and the inner loop over the pixels of a row is one remap + one byte load per channel.
@@ -185,7 +193,7 @@ struct RingPlan {
     int cs, slices;       // channels per slice (power of two, 32..128), C / cs
     int k;                // ring slots (input rows of one slice)
     int segs, seg_rows;   // output rows are split into segs segments of seg_rows rows
-    int tw, tp;           // threads along the words of a slice (cs / 4), along the pixels of a row
+    int tw;               // lanes along the words of a slice (cs / 4); a warp covers 32 / tw pixels at a time
     int chunk_shift;      // log2(cs / 16): 16-byte chunks per pixel slice
     unsigned units, grid;
     unsigned smem_bytes;  // ring + 16 (the last 16 bytes hold the fill byte)
@@ -575,7 +583,6 @@ bool plan_ring(const Geo& g, int esize, const void* x, const void* y, int sm_cou
     if (!found) return false;
     pl.slices = (int)(g.C / pl.cs);
     pl.tw = pl.cs / 4;
-    pl.tp = RING_THREADS / pl.tw;
     pl.chunk_shift = pl.cs == 128 ? 3 : (pl.cs == 64 ? 2 : 1);
     pl.smem_bytes = (unsigned)((long long)pl.k * g.S[1] * pl.cs) + 16u;   // + the fill byte's 16-byte tail
     const long long base_units = g.N * pl.slices;
