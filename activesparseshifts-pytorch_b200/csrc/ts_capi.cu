@@ -26,6 +26,25 @@ int check_launch() {
     return TS_ERR_CUDA;
 }
 
+bool ensure_dynamic_smem(const void* func, size_t bytes) {
+    struct Slot { const void* func; int dev; size_t bytes; };
+    static thread_local Slot seen[64];
+    static thread_local int used = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    int i = 0;
+    for (; i < used; ++i)
+        if (seen[i].func == func && seen[i].dev == dev) break;
+    if (i < used && seen[i].bytes >= bytes) return true;
+    if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
+    if (i == used) {
+        if (used == 64) return true;          // table full: keep setting the attribute per launch for the rest
+        ++used;
+    }
+    seen[i] = Slot{func, dev, bytes};
+    return true;
+}
+
 static int cuda_fail(cudaError_t e) {
     snprintf(t_cuda_error, sizeof(t_cuda_error), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
     return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? TS_ERR_NO_DEVICE : TS_ERR_CUDA;
@@ -269,9 +288,9 @@ size_t ts_shift_backward_workspace_bytes(const ts_geometry* gin, int dtype) {
     return bytes;
 }
 
-int ts_shift_backward(const ts_geometry* gin, int dtype, int padding, int active, const void* grad, const void* x,
-                      const void* weights, void* grad_input, void* grad_weight, void* workspace, size_t workspace_bytes,
-                      void* stream) {
+static int backward_impl(const ts_geometry* gin, int dtype, int padding, int active, const void* grad, const void* x,
+                         const void* weights, void* grad_input, void* grad_weight, void* workspace, size_t workspace_bytes,
+                         const ts_peer_group* peers, void* stream) {
     Geo g;
     int rc = make_geo(gin, padding, &g);
     if (rc != TS_OK) return rc;
@@ -281,6 +300,14 @@ int ts_shift_backward(const ts_geometry* gin, int dtype, int padding, int active
     if (g.C * g.dim == 0) return TS_OK;
     if (!grad_weight) return TS_ERR_INVALID_ARGUMENT;
     if (g.N == 0 || g.in_plane == 0) {
+        if (peers) {      // an empty shard still takes part in the exchange: it contributes zeros
+            const int outputs = (int)(g.C * g.dim);
+            switch (dtype) {
+            case TS_F32: return launch_reduce_partials<float>(nullptr, 0, outputs, grad_weight, peers, s);
+            case TS_F16: return launch_reduce_partials<__half>(nullptr, 0, outputs, grad_weight, peers, s);
+            default: return launch_reduce_partials<__nv_bfloat16>(nullptr, 0, outputs, grad_weight, peers, s);
+            }
+        }
         const cudaError_t e = cudaMemsetAsync(grad_weight, 0, (size_t)(g.C * g.dim) * es, s);
         return e == cudaSuccess ? TS_OK : cuda_fail(e);
     }
@@ -294,7 +321,7 @@ int ts_shift_backward(const ts_geometry* gin, int dtype, int padding, int active
         const TmaPlan tp = plan_tma(g, 2, active, es, dtype, x_is_dense(g), 0ull, x, grad_input, grad, sms);
         if (tp.ok) {
             t_last_path = TS_PATH_TMA;
-            return tma_backward(g, tp, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, s);
+            return tma_backward(g, tp, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, peers, s);
         }
     }
     if (forced == TS_PATH_TMA) return TS_ERR_UNSUPPORTED;
@@ -304,27 +331,31 @@ int ts_shift_backward(const ts_geometry* gin, int dtype, int padding, int active
     if (forced == TS_PATH_STAGED && !plan.ok) return TS_ERR_UNSUPPORTED;
     if (plan.ok) {
         t_last_path = TS_PATH_STAGED;
-        return staged_backward(g, plan, dtype, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, s);
+        return staged_backward(g, plan, dtype, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, peers, s);
     }
     t_last_path = TS_PATH_GENERIC;
-    return generic_backward(g, dtype, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, s);
+    return generic_backward(g, dtype, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, peers, s);
+}
+
+int ts_shift_backward(const ts_geometry* gin, int dtype, int padding, int active, const void* grad, const void* x,
+                      const void* weights, void* grad_input, void* grad_weight, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    return backward_impl(gin, dtype, padding, active, grad, x, weights, grad_input, grad_weight, workspace, workspace_bytes, nullptr,
+                         stream);
 }
 
 int ts_shift_backward_allreduce(const ts_geometry* gin, int dtype, int padding, int active, const void* grad, const void* x,
                                 const void* weights, void* grad_input, void* grad_weight, void* workspace, size_t workspace_bytes,
                                 const ts_peer_group* peers, void* stream) {
     if (!peers || !gin) return TS_ERR_INVALID_ARGUMENT;
-    if (peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world || peers->epoch == 0)
+    if (peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world || !peers->state)
         return TS_ERR_INVALID_ARGUMENT;
     if (dtype != TS_F32 && dtype != TS_F16 && dtype != TS_BF16) return TS_ERR_UNSUPPORTED;   // contributions travel as fp32
-    if (gin->C * gin->dim > peers->capacity || peers->capacity > 4096 || gin->N == 0 || gin->C == 0) return TS_ERR_INVALID_ARGUMENT;
+    if (gin->C * gin->dim > peers->capacity || peers->capacity > 4096 || gin->C == 0) return TS_ERR_INVALID_ARGUMENT;
     for (int p = 0; p < peers->world; ++p)
-        if (!peers->bufs[p] || !peers->flags[p]) return TS_ERR_INVALID_ARGUMENT;
-    set_pending_peers(peers);
-    const int rc = ts_shift_backward(gin, dtype, padding, active, grad, x, weights, grad_input, grad_weight, workspace, workspace_bytes,
-                                     stream);
-    set_pending_peers(nullptr);
-    return rc;
+        if (!peers->bufs[p] || ((uintptr_t)peers->bufs[p] & 7)) return TS_ERR_INVALID_ARGUMENT;
+    return backward_impl(gin, dtype, padding, active, grad, x, weights, grad_input, grad_weight, workspace, workspace_bytes, peers,
+                         stream);
 }
 
 int ts_qshift_forward(const ts_geometry* gin, int elem_bytes, int padding, int64_t zero_point, const void* xq,

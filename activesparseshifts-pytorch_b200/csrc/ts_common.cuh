@@ -291,5 +291,8 @@ struct LaunchCtx {
 void note_launch(int n = 1);
 void note_error(const char* text);  // text returned by ts_last_cuda_error() for non-CUDA-runtime failures
 int check_launch();               // cudaGetLastError -> ts_status
+// cudaFuncAttributeMaxDynamicSharedMemorySize >= bytes for `func` on the current device; the attribute call is
+// made only when a kernel needs more than it was last given (not on every launch)
+bool ensure_dynamic_smem(const void* func, size_t bytes);
 
 }  // namespace ts

@@ -202,77 +202,86 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int slots
 
 // ---- pass 2 fused with the all-reduce of grad_weight over NVLink peer memory -----------------------
 // Same decomposition as k_reduce_partials (one warp per output, lanes stride over the partial slots,
-// fixed shuffle tree -> the local value is bit-identical to the unfused pass 2); 32 outputs per CTA,
-// and every CTA runs the exchange for ITS outputs on its own flag words, so there is no inter-CTA
-// synchronisation: (1) lane 0 of each warp stores this rank's value with plain P2P stores into slot
-// `rank` of EVERY peer's exchange buffer (own included); (2) system-scope fence, then one
-// release-store of the epoch into each peer's flag word (rank, cta); (3) acquire-poll of this rank's
-// flag words (peer, cta) until every peer has published the epoch; (4) sum of the `world` slots in
-// rank order -> grad_weight.  Buffers are double-buffered by epoch parity: a rank can run at most one
-// call ahead of the slowest peer (it needs that peer's flag for the call in between), so the slot
-// being read is never the one being overwritten.
+// fixed shuffle tree -> the local value is bit-identical to the unfused pass 2); 32 outputs per CTA.
+// Exchange = the "LL" scheme: a contribution travels as ONE 64-bit word {epoch : value}, written with a
+// single 8-byte store (single-copy atomic) into slot [parity][sender][output] of EVERY peer's buffer,
+// so there is no separate flag, no fence and no second NVLink round trip: lane p of the output's warp
+// stores this rank's word to peer p and then polls peer p's word in this rank's own buffer until it
+// carries the call's epoch.  The `world` values are summed in rank order -> identical on every rank.
+//   * The epoch lives in DEVICE memory (`state[cta]`, bumped by the kernel): nothing call-specific is
+//     passed from the host, so the launch can be captured in a CUDA graph and replayed.  Every rank makes
+//     the same sequence of calls (replicated layers), so the per-CTA counters agree across ranks.
+//   * Buffers are double-buffered by epoch parity: a rank can run at most one call ahead of the slowest
+//     peer (it needs that peer's word of the call in between), so the word being polled is never the one
+//     being overwritten.
+//   * A peer that does not arrive within `timeout_ns` (0 = wait for ever, like a collective without a
+//     watchdog) makes the kernel record the call's epoch in state[PEER_MAX_CTAS] and trap.
 struct PeerArgs {
     int world, rank, capacity;
-    unsigned epoch;
-    float* bufs[8];
-    unsigned* flags[8];
+    unsigned long long timeout_ns;
+    unsigned long long* bufs[8];
+    unsigned* state;
 };
-constexpr int PEER_MAX_CTAS = 128;      // flag words per sender: capacity 4096 outputs / 32 per CTA
+constexpr int PEER_MAX_CTAS = 128;      // capacity 4096 outputs / 32 per CTA
+
+TS_D unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <typename ST>
 __global__ void __launch_bounds__(1024, 1) k_reduce_partials_allreduce(const double* __restrict__ partials, int slots, int outputs,
                                                                        ST* __restrict__ gw, const PeerArgs pa) {
+    __shared__ unsigned s_epoch;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int o = blockIdx.x * 32 + wid;
-    const size_t slot_base = (size_t)(pa.epoch & 1u) * pa.world * pa.capacity;
-    if (o < outputs) {
-        double s = 0.0;
-        for (int k = lane; k < slots; k += 32) s += partials[(long long)k * outputs + o];
+    if (threadIdx.x == 0) { const unsigned e = pa.state[blockIdx.x] + 1u; pa.state[blockIdx.x] = e; s_epoch = e; }
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    if (o >= outputs) return;
+    double s = 0.0;
+    for (int k = lane; k < slots; k += 32) s += partials[(long long)k * outputs + o];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
-        if (lane == 0) {
-            const float v = (float)s;
-            for (int p = 0; p < pa.world; ++p) pa.bufs[p][slot_base + (size_t)pa.rank * pa.capacity + o] = v;
-            __threadfence_system();
-        }
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < pa.world) {
-        unsigned* remote = pa.flags[threadIdx.x] + pa.rank * PEER_MAX_CTAS + blockIdx.x;     // my word in that peer's flag array
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(pa.epoch) : "memory");
-        const unsigned* mine = pa.flags[pa.rank] + threadIdx.x * PEER_MAX_CTAS + blockIdx.x; // that peer's word in my flag array
-        const long long t0 = clock64();
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+    const float mine = __shfl_sync(0xffffffffu, (float)s, 0);
+    const size_t half = (size_t)(epoch & 1u) * pa.world * pa.capacity;
+    float v = 0.f;
+    if (lane < pa.world) {
+        const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(mine);
+        unsigned long long* remote = pa.bufs[lane] + half + (size_t)pa.rank * pa.capacity + o;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(word) : "memory");
+        const unsigned long long* local = pa.bufs[pa.rank] + half + (size_t)lane * pa.capacity + o;
+        const unsigned long long t0 = pa.timeout_ns ? global_ns() : 0ull;
+        unsigned spins = 0;
         for (;;) {
-            unsigned f;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(mine) : "memory");
-            if ((int)(f - pa.epoch) >= 0) break;
-            if (clock64() - t0 > 8000000000LL) __trap();             // ~4 s: a peer never arrived -- fail loudly, do not hang
+            unsigned long long got;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(local) : "memory");
+            if ((unsigned)(got >> 32) == epoch) { v = __uint_as_float((unsigned)got); break; }
+            if (pa.timeout_ns && (++spins & 1023u) == 0 && global_ns() - t0 > pa.timeout_ns) {
+                pa.state[PEER_MAX_CTAS] = epoch;        // which call gave up (host-readable after the failure)
+                __threadfence_system();
+                __trap();
+            }
         }
     }
-    __syncthreads();
-    if (o < outputs && lane == 0) {
-        const float* my = pa.bufs[pa.rank] + slot_base;
-        float s = 0.f;
-        for (int p = 0; p < pa.world; ++p) s += __ldcg(my + (size_t)p * pa.capacity + o);   // L2: peer writes never pass through this SM's L1
-        gw[o] = Elem<ST>::st(s);
-    }
+    // sum in rank order (fixed): every rank computes the same bits
+    float total = 0.f;
+    for (int p = 0; p < pa.world; ++p) total += __shfl_sync(0xffffffffu, v, p);
+    if (lane == 0) gw[o] = Elem<ST>::st(total);
 }
 
-static thread_local const ts_peer_group* t_pending_peers = nullptr;
-void set_pending_peers(const ts_peer_group* peers) { t_pending_peers = peers; }
-
 template <typename ST>
-int launch_reduce_partials(const double* partials, int slots, int outputs, void* gw, cudaStream_t stream) {
-    if (t_pending_peers) {
-        const ts_peer_group* pg = t_pending_peers;
-        t_pending_peers = nullptr;
+int launch_reduce_partials(const double* partials, int slots, int outputs, void* gw, const ts_peer_group* pg, cudaStream_t stream) {
+    if (pg) {
         if constexpr (sizeof(ST) == 8) {
             return TS_ERR_UNSUPPORTED;
         } else {
             PeerArgs pa;
-            pa.world = pg->world; pa.rank = pg->rank; pa.capacity = pg->capacity; pa.epoch = pg->epoch;
-            for (int p = 0; p < 8; ++p) { pa.bufs[p] = (float*)pg->bufs[p]; pa.flags[p] = (unsigned*)pg->flags[p]; }
-            if (outputs > 32 * PEER_MAX_CTAS) return TS_ERR_INVALID_ARGUMENT;
+            pa.world = pg->world; pa.rank = pg->rank; pa.capacity = pg->capacity; pa.timeout_ns = pg->timeout_ns;
+            for (int p = 0; p < 8; ++p) pa.bufs[p] = (unsigned long long*)pg->bufs[p];
+            pa.state = (unsigned*)pg->state;
+            if (outputs > 32 * PEER_MAX_CTAS || outputs > pg->capacity) return TS_ERR_INVALID_ARGUMENT;
             k_reduce_partials_allreduce<ST><<<(outputs + 31) / 32, 1024, 0, stream>>>(partials, slots, outputs, (ST*)gw, pa);
             note_launch();
             return check_launch();
@@ -284,10 +293,10 @@ int launch_reduce_partials(const double* partials, int slots, int outputs, void*
     note_launch();
     return check_launch();
 }
-template int launch_reduce_partials<float>(const double*, int, int, void*, cudaStream_t);
-template int launch_reduce_partials<double>(const double*, int, int, void*, cudaStream_t);
-template int launch_reduce_partials<__half>(const double*, int, int, void*, cudaStream_t);
-template int launch_reduce_partials<__nv_bfloat16>(const double*, int, int, void*, cudaStream_t);
+template int launch_reduce_partials<float>(const double*, int, int, void*, const ts_peer_group*, cudaStream_t);
+template int launch_reduce_partials<double>(const double*, int, int, void*, const ts_peer_group*, cudaStream_t);
+template int launch_reduce_partials<__half>(const double*, int, int, void*, const ts_peer_group*, cudaStream_t);
+template int launch_reduce_partials<__nv_bfloat16>(const double*, int, int, void*, const ts_peer_group*, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------
 // Host launchers.
@@ -394,20 +403,20 @@ static int bwd_dim(const Geo& g, const GenericBwdPlan& p, const void* grad, cons
 
 template <typename ST>
 static int bwd_t(const Geo& g, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
-                 double* partials, cudaStream_t s) {
+                 double* partials, const ts_peer_group* peers, cudaStream_t s) {
     const GenericBwdPlan p = plan_generic_backward(g);
     int rc = active ? bwd_dim<ST, true>(g, p, grad, x, w, gi, partials, s) : bwd_dim<ST, false>(g, p, grad, x, w, gi, partials, s);
     if (rc != TS_OK) return rc;
-    return launch_reduce_partials<ST>(partials, p.units, (int)(g.C * g.dim), gw, s);
+    return launch_reduce_partials<ST>(partials, p.units, (int)(g.C * g.dim), gw, peers, s);
 }
 
 int generic_backward(const Geo& g, int dtype, int active, const void* grad, const void* x, const void* w, void* gi,
-                     void* gw, double* partials, cudaStream_t s) {
+                     void* gw, double* partials, const ts_peer_group* peers, cudaStream_t s) {
     switch (dtype) {
-    case TS_F32: return bwd_t<float>(g, active, grad, x, w, gi, gw, partials, s);
-    case TS_F64: return bwd_t<double>(g, active, grad, x, w, gi, gw, partials, s);
-    case TS_F16: return bwd_t<__half>(g, active, grad, x, w, gi, gw, partials, s);
-    case TS_BF16: return bwd_t<__nv_bfloat16>(g, active, grad, x, w, gi, gw, partials, s);
+    case TS_F32: return bwd_t<float>(g, active, grad, x, w, gi, gw, partials, peers, s);
+    case TS_F64: return bwd_t<double>(g, active, grad, x, w, gi, gw, partials, peers, s);
+    case TS_F16: return bwd_t<__half>(g, active, grad, x, w, gi, gw, partials, peers, s);
+    case TS_BF16: return bwd_t<__nv_bfloat16>(g, active, grad, x, w, gi, gw, partials, peers, s);
     }
     return TS_ERR_INVALID_ARGUMENT;
 }

@@ -33,13 +33,12 @@ int generic_gather(const Geo& g, int wk, const void* x, void* y, unsigned long l
                    int qkind, long long wzp, cudaStream_t s);
 int generic_active_forward(const Geo& g, int dtype, const void* x, const void* w, void* y, cudaStream_t s);
 int generic_backward(const Geo& g, int dtype, int active, const void* grad, const void* x, const void* w, void* gi,
-                     void* gw, double* partials, cudaStream_t s);
+                     void* gw, double* partials, const ts_peer_group* peers, cudaStream_t s);
 
+// peers != nullptr: the pass-2 launch is the variant fused with the all-reduce over peer memory
+// (ts_shift_backward_allreduce); slots may be 0 (a rank with an empty shard contributes zeros).
 template <typename ST>
-int launch_reduce_partials(const double* partials, int slots, int outputs, void* gw, cudaStream_t stream);
-// When set (by ts_shift_backward_allreduce, for the duration of one backward call on this thread) the next
-// pass-2 launch is the variant fused with the all-reduce over peer memory.
-void set_pending_peers(const ts_peer_group* peers);
+int launch_reduce_partials(const double* partials, int slots, int outputs, void* gw, const ts_peer_group* peers, cudaStream_t stream);
 
 // ---- channels-last gather (ts_nhwc.cu): input and output keep the channel axis innermost -------
 int nhwc_gather(const Geo& g, const void* x, void* y, unsigned long long fill, int esize, const void* w, int qkind,
@@ -82,7 +81,7 @@ int staged_gather(const Geo& g, const StagedPlan& p, int wk, const void* x, void
                   const void* w, int qkind, long long wzp, cudaStream_t s);
 int staged_active_forward(const Geo& g, const StagedPlan& p, int dtype, const void* x, const void* w, void* y, cudaStream_t s);
 int staged_backward(const Geo& g, const StagedPlan& p, int dtype, int active, const void* grad, const void* x, const void* w,
-                    void* gi, void* gw, double* partials, cudaStream_t s);
+                    void* gi, void* gw, double* partials, const ts_peer_group* peers, cudaStream_t s);
 
 // ---- TMA-tensor family (ts_tma.cu): zeros padding done by the copy engine ----------------------
 struct TmaPlan {
@@ -101,6 +100,6 @@ int tma_gather(const Geo& g, const TmaPlan& p, int wk, const void* x, void* y, i
                cudaStream_t s);
 int tma_active_forward(const Geo& g, const TmaPlan& p, const void* x, const void* w, void* y, cudaStream_t s);
 int tma_backward(const Geo& g, const TmaPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
-                 double* partials, cudaStream_t s);
+                 double* partials, const ts_peer_group* peers, cudaStream_t s);
 
 }  // namespace ts

@@ -1426,8 +1426,7 @@ __global__ void __launch_bounds__(MAXT_ARITH, 1) k_staged_backward(const __grid_
 
 template <class K>
 int launch(K kernel, const SArgs& a, const StagedPlan& p, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
-    if (e != cudaSuccess) return check_launch();
+    if (!ensure_dynamic_smem((const void*)kernel, p.smem_bytes)) return check_launch();
     kernel<<<p.grid, (p.warps + 1) * 32, p.smem_bytes, s>>>(a);
     note_launch();
     return check_launch();
@@ -1654,7 +1653,7 @@ static int backward_t(const Geo& g, const SArgs& a, const StagedPlan& p, int act
 }
 
 int staged_backward(const Geo& g, const StagedPlan& p, int dtype, int active, const void* grad, const void* x, const void* w,
-                    void* gi, void* gw, double* partials, cudaStream_t s) {
+                    void* gi, void* gw, double* partials, const ts_peer_group* peers, cudaStream_t s) {
     SArgs a = make_args(g, p, 2, active ? 1 : 0, dtype == TS_F32 ? 4 : 2);
     a.x = (const unsigned char*)x;
     a.grad = (const unsigned char*)grad;
@@ -1671,9 +1670,9 @@ int staged_backward(const Geo& g, const StagedPlan& p, int dtype, int active, co
     if (rc != TS_OK) return rc;
     const int outputs = (int)(g.C * g.dim);
     switch (dtype) {
-    case TS_F32: return launch_reduce_partials<float>(partials, p.slots, outputs, gw, s);
-    case TS_F16: return launch_reduce_partials<__half>(partials, p.slots, outputs, gw, s);
-    default: return launch_reduce_partials<__nv_bfloat16>(partials, p.slots, outputs, gw, s);
+    case TS_F32: return launch_reduce_partials<float>(partials, p.slots, outputs, gw, peers, s);
+    case TS_F16: return launch_reduce_partials<__half>(partials, p.slots, outputs, gw, peers, s);
+    default: return launch_reduce_partials<__nv_bfloat16>(partials, p.slots, outputs, gw, peers, s);
     }
 }
 

@@ -66,9 +66,26 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// rank-5 map over a dense [N][C][A][B][L] tensor of `es`-byte elements, box {bl, bb, ba, 1, bn}
+// rank-5 map over a dense [N][C][A][B][L] tensor of `es`-byte elements, box {bl, bb, ba, 1, bn}.
+// Encoded maps are memoised per thread (a training loop presents the same few (pointer, geometry) pairs every
+// step; the descriptor is a pure function of these arguments).
+struct MapKey {
+    const void* base;
+    long long N, C;
+    int es, A, B, L, bl, bb, ba, bn;
+};
+struct MapSlot { MapKey key; CUtensorMap map; bool used; };
+constexpr int MAP_CACHE = 32;
+
 bool make_map(CUtensorMap* map, const void* base, int es, long long N, long long C, int A, int B, int L, int bl, int bb, int ba,
               int bn) {
+    static thread_local MapSlot cache[MAP_CACHE];
+    static thread_local int next_victim = 0;
+    MapKey key;
+    memset(&key, 0, sizeof(key));
+    key.base = base; key.N = N; key.C = C; key.es = es; key.A = A; key.B = B; key.L = L; key.bl = bl; key.bb = bb; key.ba = ba; key.bn = bn;
+    for (int i = 0; i < MAP_CACHE; ++i)
+        if (cache[i].used && !memcmp(&cache[i].key, &key, sizeof(key))) { *map = cache[i].map; return true; }
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
     // cuTensorMapEncodeTiled is a DRIVER call: it needs the primary context current on the calling
@@ -90,8 +107,12 @@ bool make_map(CUtensorMap* map, const void* base, int es, long long N, long long
         snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled -> %d: es %d dims {%d,%d,%d,%lld,%lld} box {%d,%d,%d,1,%d} base %p", (int)r, es, L, B,
                  A, C, N, bl, bb, ba, bn, base);
         note_error(msg);
+        return false;
     }
-    return r == CUDA_SUCCESS;
+    MapSlot& slot = cache[next_victim];
+    next_victim = (next_victim + 1) % MAP_CACHE;
+    slot.key = key; slot.map = *map; slot.used = true;
+    return true;
 }
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -757,8 +778,7 @@ __global__ void __launch_bounds__(MAXT_TMA_ARITH, 1) k_tma_backward(const __grid
 
 template <class K>
 int launch(K kernel, const TArgs& a, const TmaPlan& p, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
-    if (e != cudaSuccess) return check_launch();
+    if (!ensure_dynamic_smem((const void*)kernel, p.smem_bytes)) return check_launch();
     kernel<<<p.grid, (p.warps + 1) * 32, p.smem_bytes, s>>>(a);
     note_launch();
     return check_launch();
@@ -991,7 +1011,7 @@ int tma_active_forward(const Geo& g, const TmaPlan& p, const void* x, const void
 }
 
 int tma_backward(const Geo& g, const TmaPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
-                 double* partials, cudaStream_t s) {
+                 double* partials, const ts_peer_group* peers, cudaStream_t s) {
     TArgs a;
     make_args(g, p, 2, active ? 1 : 0, 4, &a);
     const int d = g.dim;
@@ -1012,7 +1032,7 @@ int tma_backward(const Geo& g, const TmaPlan& p, int active, const void* grad, c
     default: rc = launch(k_tma_backward<3, true>, a, p, s); break;
     }
     if (rc != TS_OK) return rc;
-    return launch_reduce_partials<float>(partials, p.slots, (int)(g.C * g.dim), gw, s);
+    return launch_reduce_partials<float>(partials, p.slots, (int)(g.C * g.dim), gw, peers, s);
 }
 
 }  // namespace ts

@@ -10,6 +10,7 @@ from pathlib import Path
 LIB_NAME = 'libtorchshifts_b200.so'
 
 TS_OK = 0
+ABI_VERSION = 2
 STATUS_NAMES = {0: 'TS_OK', 1: 'TS_ERR_INVALID_ARGUMENT', 2: 'TS_ERR_UNSUPPORTED', 3: 'TS_ERR_WORKSPACE',
                 4: 'TS_ERR_TOO_LARGE', 5: 'TS_ERR_BORDERS', 6: 'TS_ERR_CUDA', 7: 'TS_ERR_NO_DEVICE'}
 PATH_NONE, PATH_GENERIC, PATH_STAGED, PATH_TMA = 0, 1, 2, 3
@@ -33,8 +34,8 @@ class Geometry(ct.Structure):
 
 class PeerGroup(ct.Structure):
     """struct ts_peer_group."""
-    _fields_ = [('world', ct.c_int32), ('rank', ct.c_int32), ('epoch', ct.c_uint32), ('capacity', ct.c_int32),
-                ('bufs', ct.c_void_p * 8), ('flags', ct.c_void_p * 8)]
+    _fields_ = [('world', ct.c_int32), ('rank', ct.c_int32), ('capacity', ct.c_int32), ('reserved', ct.c_int32),
+                ('timeout_ns', ct.c_uint64), ('bufs', ct.c_void_p * 8), ('state', ct.c_void_p)]
 
 
 def make_geometry(dim, shape, strides, lb, rb):
@@ -82,8 +83,8 @@ class NativeLibrary:
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.ts_abi_version() != 1:
-            raise ImportError(f'{self.path}: ABI version {lib.ts_abi_version()} != 1')
+        if lib.ts_abi_version() != ABI_VERSION:
+            raise ImportError(f'{self.path}: ABI version {lib.ts_abi_version()} != {ABI_VERSION}')
         spec = os.environ.get('TS_TUNING')          # e.g. TS_TUNING="stages=3,use_tma=0"
         if spec and lib.ts_set_tuning(spec.encode()) != TS_OK:
             raise ImportError(f'TS_TUNING={spec!r} is not a valid tuning spec (see ts_set_tuning in include/torchshifts_b200.h)')

@@ -15,7 +15,9 @@ Dispatch keys: ``shiftNd`` is CompositeImplicitAutograd (border validation, then
 ``CUDA`` and ``QuantizedCUDA`` kernels that call the sm_100a library, fake kernels for tracing,
 and ``CPU`` / ``QuantizedCPU`` kernels that raise: this build has NO CPU compute path.
 """
+import contextlib
 import ctypes as ct
+import weakref
 
 import torch
 
@@ -80,7 +82,7 @@ def _dense(input):
     if fmt is not None and input.is_contiguous(memory_format=fmt) and input.element_size() in (2, 4, 8):
         out = torch.empty(input.shape, dtype=input.dtype, device=input.device)
         n, c = input.shape[0], input.shape[1]
-        with torch.cuda.device(input.device):
+        with _guard(input.device):
             st = _NATIVE.lib.ts_nhwc_to_nchw(input.data_ptr(), out.data_ptr(), n, c, input.numel() // max(n * c, 1),
                                              input.element_size(), _stream(input.device))
         _NATIVE.check(st, 'ts_nhwc_to_nchw')
@@ -89,32 +91,41 @@ def _dense(input):
 
 
 def _stream(device):
-    return ct.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return ct.c_void_p(torch._C._cuda_getCurrentRawStream(device.index))
+
+
+_NO_GUARD = contextlib.nullcontext()
+
+
+def _guard(device):
+    """CUDAGuard of cuda/shifts_cuda.cu:215, :284 -- skipped (it costs ~10 us in Python) when the tensor's device
+    already is the current one."""
+    return _NO_GUARD if device.index == torch._C._cuda_getDevice() else torch.cuda.device(device)
 
 
 _GEO_CACHE = {}        # (dim, shape, strides, lb, rb) -> ts_geometry; shift layers see the same few shapes every step
+_WS_CACHE = {}         # (geometry key, dtype code, device index) -> backward workspace bytes
 
 
 def _geometry(dim, input, lb, rb):
+    """-> (ts_geometry, its cache key)"""
     key = (dim, tuple(input.shape), tuple(input.stride()), tuple(lb), tuple(rb))
     geo = _GEO_CACHE.get(key)
     if geo is None:
         if len(_GEO_CACHE) > 256:
             _GEO_CACHE.clear()
+            _WS_CACHE.clear()
         geo = _GEO_CACHE[key] = make_geometry(dim, input.shape, input.stride(), lb, rb)
-    return geo
+    return geo, key
 
 
-_WS_CACHE = {}         # (id(geometry), dtype code) -> backward workspace bytes
-
-
-def _workspace_bytes(geo, code):
-    key = (id(geo), code)
-    n = _WS_CACHE.get(key)
+def _workspace_bytes(geo, key, code, device):
+    wkey = (key, code, device.index)
+    n = _WS_CACHE.get(wkey)
     if n is None:
         if len(_WS_CACHE) > 256:
             _WS_CACHE.clear()
-        n = _WS_CACHE[key] = int(_NATIVE.lib.ts_shift_backward_workspace_bytes(ct.byref(geo), code))
+        n = _WS_CACHE[wkey] = int(_NATIVE.lib.ts_shift_backward_workspace_bytes(ct.byref(geo), code))
     return n
 
 
@@ -131,13 +142,14 @@ def _forward_cuda(dim, input, weights, borders, new_size, padding_mode, active_f
     out = torch.empty(list(new_size), dtype=input.dtype, device=input.device)
     w = weights.contiguous()
     input = _dense(input)
-    geo = _geometry(dim, input, lb, rb)
+    geo, _ = _geometry(dim, input, lb, rb)
     if list(out.shape[2:]) != [rb[a] - lb[a] for a in range(dim)]:
         raise RuntimeError(f'{fn}: new_size {list(new_size)} does not match the borders')
-    with torch.cuda.device(input.device):
+    with _guard(input.device):
         st = _NATIVE.lib.ts_shift_forward(ct.byref(geo), _DTYPES[input.dtype], int(padding_mode), int(bool(active_flag)),
                                           input.data_ptr(), w.data_ptr(), out.data_ptr(), _stream(input.device))
-    _NATIVE.check(st, 'ts_shift_forward')
+    if st:
+        _NATIVE.check(st, 'ts_shift_forward')
     return out
 
 
@@ -151,29 +163,56 @@ def _backward_cuda(dim, grad, weights, input, borders, padding_mode, active_flag
     out_grad = torch.empty(input.shape, dtype=input.dtype, device=input.device)
     weights_grad = torch.empty(w.shape, dtype=w.dtype, device=w.device)
     input = _dense(input)
-    geo = _geometry(dim, input, lb, rb)
+    geo, key = _geometry(dim, input, lb, rb)
     if list(grad.shape[2:]) != [rb[a] - lb[a] for a in range(dim)] or list(grad.shape[:2]) != list(input.shape[:2]):
         raise RuntimeError(f'{fn}: grad shape {list(grad.shape)} does not match the (cropped) output of input {list(input.shape)}')
     code = _DTYPES[input.dtype]
-    with torch.cuda.device(input.device):
-        nbytes = _workspace_bytes(geo, code)
-        workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=input.device)
-        args = (ct.byref(geo), code, int(padding_mode), int(bool(active_flag)), grad.data_ptr(), input.data_ptr(), w.data_ptr(),
-                out_grad.data_ptr(), weights_grad.data_ptr())
-        fused = _FUSED_ALLREDUCE
-        if fused is not None and fused.device == input.device and code != 1 and w.numel() <= fused.capacity and input.shape[0] > 0:
-            pg = fused.peer_group()
-            st = _NATIVE.lib.ts_shift_backward_allreduce(*args, workspace.data_ptr(), nbytes, ct.byref(pg), _stream(input.device))
-            _NATIVE.check(st, 'ts_shift_backward_allreduce')
-            return out_grad, weights_grad
-        st = _NATIVE.lib.ts_shift_backward(*args, workspace.data_ptr(), nbytes, _stream(input.device))
-        if st == 3:       # TS_ERR_WORKSPACE: the tuning knobs changed since the size was cached
+    dev = input.device
+    fused = _FUSED_ALLREDUCE
+    if fused is not None:
+        # Taking part in the in-kernel exchange must never depend on rank-local data (an empty shard, a ragged last
+        # batch): a rank that skipped it would leave its peers waiting.  What cannot be served raises on EVERY rank
+        # (dtype, weight count and device are the same everywhere for replicated layers).
+        if fused.device != dev:
+            raise RuntimeError(f'{fn}: FusedGradWeightAllReduce was created for {fused.device} but the tensors live on {dev}')
+        if code == 1:
+            raise RuntimeError(f'{fn}: the fused grad_weight all-reduce carries fp32 contributions; float64 layers must use '
+                               'torchshifts.sharded.allreduce_grad_weights (disable() the fused mode around them)')
+        if w.numel() > fused.capacity:
+            raise RuntimeError(f'{fn}: {w.numel()} weight elements exceed the exchange capacity {fused.capacity} '
+                               '(FusedGradWeightAllReduce(capacity=...), at most 4096)')
+    with _guard(dev):
+        for attempt in (0, 1):
+            nbytes = _workspace_bytes(geo, key, code, dev)
+            workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+            args = (ct.byref(geo), code, int(padding_mode), int(bool(active_flag)), grad.data_ptr(), input.data_ptr(), w.data_ptr(),
+                    out_grad.data_ptr(), weights_grad.data_ptr(), workspace.data_ptr(), nbytes)
+            if fused is not None:
+                st = _NATIVE.lib.ts_shift_backward_allreduce(*args, ct.byref(fused.peer_group()), _stream(dev))
+            else:
+                st = _NATIVE.lib.ts_shift_backward(*args, _stream(dev))
+            if st != 3:       # TS_ERR_WORKSPACE (nothing was launched): the tuning knobs changed since the size was cached
+                break
             _WS_CACHE.clear()
-            nbytes = _workspace_bytes(geo, code)
-            workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=input.device)
-            st = _NATIVE.lib.ts_shift_backward(*args, workspace.data_ptr(), nbytes, _stream(input.device))
-    _NATIVE.check(st, 'ts_shift_backward')
+    if st:
+        _NATIVE.check(st, 'ts_shift_backward_allreduce' if fused is not None else 'ts_shift_backward')
     return out_grad, weights_grad
+
+
+_QW_CACHE = {}         # id(quantized weight) -> (weakref, version, device, raw integer weights on that device)
+
+
+def _raw_qweights(weights, device):
+    """``weights.int_repr()`` on ``device``, memoised per weight tensor (a quantized layer presents the same
+    tensor on every forward; int_repr + copy are two ATen launches otherwise)."""
+    hit = _QW_CACHE.get(id(weights))
+    if hit is not None and hit[0]() is weights and hit[1] == weights._version and hit[2] == device:
+        return hit[3]
+    wq = weights.int_repr().to(device).contiguous()
+    if len(_QW_CACHE) > 64:
+        _QW_CACHE.clear()
+    _QW_CACHE[id(weights)] = (weakref.ref(weights), weights._version, device, wq)
+    return wq
 
 
 def _forward_qcuda(dim, input, weights, borders, new_size, padding_mode, active_flag):
@@ -188,7 +227,7 @@ def _forward_qcuda(dim, input, weights, borders, new_size, padding_mode, active_
     lb, rb = _borders_lists(borders, dim)
     if list(new_size[2:]) != [rb[a] - lb[a] for a in range(dim)] or list(new_size[:2]) != list(input.shape[:2]):
         raise RuntimeError(f'{fn}: new_size {list(new_size)} does not match the borders')
-    wq = weights.int_repr().to(input.device).contiguous()
+    wq = _raw_qweights(weights, input.device)
     args = (_QBYTES[input.dtype], int(padding_mode), int(input.q_zero_point()))
     wargs = (wq.data_ptr(), _QKINDS[weights.dtype], int(weights.q_zero_point()))
     # the reference allocates the quantized output in the input's memory format
@@ -200,8 +239,8 @@ def _forward_qcuda(dim, input, weights, borders, new_size, padding_mode, active_
         to_nc = (0, dim + 1) + tuple(range(1, dim + 1))
         out_cl = torch._empty_affine_quantized([new_size[i] for i in to_cl], scale=input.q_scale(),
                                                zero_point=input.q_zero_point(), dtype=input.dtype, device=input.device)
-        geo = _geometry(dim, input, lb, rb)
-        with torch.cuda.device(input.device):
+        geo, _ = _geometry(dim, input, lb, rb)
+        with _guard(input.device):
             st = _NATIVE.lib.ts_qshift_forward_nhwc(ct.byref(geo), *args, input.data_ptr(), *wargs, out_cl.data_ptr(),
                                                     _stream(input.device))
         if st not in (2, 4):      # TS_ERR_UNSUPPORTED / TOO_LARGE (row offsets beyond 32 bits): planar kernels + conversions
@@ -211,8 +250,8 @@ def _forward_qcuda(dim, input, weights, borders, new_size, padding_mode, active_
     x = input if input.is_contiguous() else input.contiguous()
     out = torch._empty_affine_quantized(list(new_size), scale=input.q_scale(), zero_point=input.q_zero_point(),
                                         dtype=input.dtype, device=input.device)
-    geo = _geometry(dim, x, lb, rb)
-    with torch.cuda.device(input.device):
+    geo, _ = _geometry(dim, x, lb, rb)
+    with _guard(input.device):
         st = _NATIVE.lib.ts_qshift_forward(ct.byref(geo), *args, x.data_ptr(), *wargs, out.data_ptr(), _stream(input.device))
     _NATIVE.check(st, 'ts_qshift_forward')
     if x is not input and fmt is not None and input.is_contiguous(memory_format=fmt):

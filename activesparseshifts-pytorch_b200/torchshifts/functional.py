@@ -15,8 +15,32 @@ _AXES = {1: 'H', 2: 'H and W', 3: 'H,W and D'}
 _MODES = '0 - zeros, 1 - border, 2 - periodic, 3 - reflect, 4 - symmetric'
 
 
+def _resolve_borders(dim, sizes, cuts):
+    """Pure-Python twin of ``ts_check_borders`` (csrc/ops/shifts.cpp:111-127): ``cuts`` = ``dim`` pairs
+    (left_cut, right_cut) -> (lb, rb) lists of 3.  Used only while ``torch.compile`` traces a layer that crops
+    its output: there the border tensor is a traced (fake) tensor whose values cannot be read, while the
+    module's cached Python integers can (tests pin this function against the C one)."""
+    lb, rb = [0, 0, 0], [int(sizes[a]) if a < dim else 1 for a in range(3)]
+    for a in range(dim):
+        size = int(sizes[a])
+        r, l = size - int(cuts[a][1]), int(cuts[a][0])
+        if r - l < 1:
+            r = l + 1
+        if l == size:
+            l, r = size - 1, size
+        if r == 0:
+            l, r = 0, 1
+        l = max(l, 0)
+        r = min(r, size)
+        if r - l < 0:
+            raise RuntimeError('torchshifts-b200: borders give a negative output dimension '
+                               '(the reference fails here with "Trying to create tensor with negative dimension")')
+        lb[a], rb[a] = l, r
+    return lb, rb
+
+
 def _shift_func(dim: int, input: Tensor, weights: Tensor, padding_mode: int, active_flag: bool,
-                borders: Optional[Tensor]) -> Tensor:
+                borders: Optional[Tensor], _border_ints=None) -> Tensor:
     name = f'shift{dim}d_func()'
     _assert_has_ops()
     assert padding_mode in [0, 1, 2, 3, 4], f'{name} expected padding_mode can be {_MODES}'
@@ -28,6 +52,13 @@ def _shift_func(dim: int, input: Tensor, weights: Tensor, padding_mode: int, act
                                             f'but input is  on {input.device} and weights is on {weights.device}')
     if borders is not None:
         assert (len(borders.shape) == 2) and (borders.shape[1] == 2) and (borders.shape[0] == dim), f'borders must have shape [{dim}, 2]'
+        if _border_ints is not None and torch.compiler.is_compiling():
+            # torch.compile: resolve the crop from Python integers (constants of the trace) and call the inner
+            # operator, which has a fake kernel and a registered autograd formula
+            lb, rb = _resolve_borders(dim, input.shape[2:], _border_ints)
+            std = torch.tensor([lb[0], rb[0], lb[1], rb[1], lb[2], rb[2]], dtype=torch.int32)
+            new_size = [input.shape[0], input.shape[1]] + [rb[a] - lb[a] for a in range(dim)]
+            return getattr(torch.ops.torchshifts, f'_shift{dim}d_forward')(input, weights, std, new_size, padding_mode, active_flag)
     else:
         borders = torch.Tensor()
     op = getattr(torch.ops.torchshifts, f'shift{dim}d')
@@ -35,7 +66,7 @@ def _shift_func(dim: int, input: Tensor, weights: Tensor, padding_mode: int, act
 
 
 def shift1d_func(input: Tensor, weights: Tensor, padding_mode: int, active_flag: bool,
-                 borders: Optional[Tensor] = None) -> Tensor:
+                 borders: Optional[Tensor] = None, _border_ints=None) -> Tensor:
     """Shift every channel of ``input [N, C, H]`` along H by its own learnable amount.
 
     ``weights [C, 1]`` holds sign and magnitude of the per-channel shift; ``padding_mode`` selects
@@ -43,21 +74,21 @@ def shift1d_func(input: Tensor, weights: Tensor, padding_mode: int, active_flag:
     ``active_flag`` switches from the rounded (sparse) shift to linear interpolation (ignored for
     quantized inputs); ``borders [1, 2]`` = (left_cut, right_cut) crops the output.
     """
-    return _shift_func(1, input, weights, padding_mode, active_flag, borders)
+    return _shift_func(1, input, weights, padding_mode, active_flag, borders, _border_ints)
 
 
 def shift2d_func(input: Tensor, weights: Tensor, padding_mode: int, active_flag: bool,
-                 borders: Optional[Tensor] = None) -> Tensor:
+                 borders: Optional[Tensor] = None, _border_ints=None) -> Tensor:
     """2-D version: ``input [N, C, H, W]``, ``weights [C, 2]`` (H and W shifts), ``borders [2, 2]``;
     the active shift is bilinear."""
-    return _shift_func(2, input, weights, padding_mode, active_flag, borders)
+    return _shift_func(2, input, weights, padding_mode, active_flag, borders, _border_ints)
 
 
 def shift3d_func(input: Tensor, weights: Tensor, padding_mode: int, active_flag: bool,
-                 borders: Optional[Tensor] = None) -> Tensor:
+                 borders: Optional[Tensor] = None, _border_ints=None) -> Tensor:
     """3-D version: ``input [N, C, H, W, D]``, ``weights [C, 3]``, ``borders [3, 2]``; the active
     shift is trilinear."""
-    return _shift_func(3, input, weights, padding_mode, active_flag, borders)
+    return _shift_func(3, input, weights, padding_mode, active_flag, borders, _border_ints)
 
 
 # BASELINE.json names these "functional.shift1d/2d/3d"; keep the real names and add the aliases.

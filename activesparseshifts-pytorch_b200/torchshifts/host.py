@@ -36,6 +36,8 @@ class HostShiftPipeline:
         self.g_host = torch.empty(shape, **pin)
         self.y_host = torch.empty(shape, **pin)
         self.gi_host = torch.empty(shape, **pin)
+        self.gw_host = torch.empty((self.C, self.dim), **pin)
+        self.gw_device = None
         cshape = (self.chunk, self.C) + self.spatial
         self._xd = [torch.empty(cshape, dtype=dtype, device=self.device) for _ in range(slots)]
         self._gd = [torch.empty(cshape, dtype=dtype, device=self.device) for _ in range(slots)]
@@ -52,7 +54,8 @@ class HostShiftPipeline:
     def describe(self):
         return (f"HostShiftPipeline: pinned host x/grad -> device in chunks of {self.chunk} images on a copy-in stream, "
                 f"torchshifts::_shift{self.dim}d_forward/_backward on a compute stream, y/grad_input -> pinned host on a "
-                f"copy-out stream ({self.slots}-slot ring); grad_weight summed on device and read back")
+                f"copy-out stream ({self.slots}-slot ring); grad_weight summed on device and copied to pinned host "
+                f"(read_back_grad_weight)")
 
     @torch.no_grad()
     def forward_backward(self, weight, padding_mode=0, active_flag=False):
@@ -65,6 +68,7 @@ class HostShiftPipeline:
         for s in (self._s_in, self._s_comp, self._s_out):
             s.wait_stream(cur)
         gw_total = torch.zeros(self.C, self.dim, dtype=self.dtype, device=self.device)
+        self.gw_device = gw_total
         self._s_comp.wait_stream(cur)
         free = [None] * self.slots           # event: slot's device inputs may be overwritten
         nchunks = (self.N + self.chunk - 1) // self.chunk
@@ -100,7 +104,72 @@ class HostShiftPipeline:
         cur.wait_stream(self._s_in)
         return gw_total
 
+    def read_back_grad_weight(self, gw=None):
+        """grad_weight [C, dim] -> pinned host (``gw_host``), ordered on the current stream; this is the
+        ``C*dim*esize`` bytes ``d2h_bytes`` counts.  ``gw``: the tensor to read back (default: the device sum of
+        the last ``forward_backward``; multi-GPU callers pass the all-reduced one)."""
+        self.gw_host.copy_(self.gw_device if gw is None else gw, non_blocking=True)
+        return self.gw_host
+
 
 class HostShift2dPipeline(HostShiftPipeline):
     def __init__(self, N, C, H, W, device, dtype=torch.float32, chunk=16, slots=4):
         super().__init__(N, C, (H, W), device, dtype, chunk, slots)
+
+
+class GraphedShiftStep:
+    """Forward + backward of one shift layer captured ONCE into CUDA graphs and replayed: the whole step costs
+    one (``split=False``) or two (``split=True``: forward graph, backward graph -- so the two can be timed
+    separately) graph launches instead of ~270 us of Python / dispatcher / launch work per step, which is what
+    bounds small per-GPU batches (cfg1; cfg3 split over 8 GPUs = 32 images per GPU).
+
+    The C ABI only enqueues kernels on the caller's stream, tensor maps are encoded on the host and passed by
+    value, and the in-kernel grad_weight exchange keeps its call counter on the device, so the capture includes
+    the fused all-reduce when a :class:`torchshifts.sharded.FusedGradWeightAllReduce` is enabled around the
+    construction AND the replays (every rank must then construct and replay in lock-step).
+
+    ``x``, ``weight`` and ``grad_out`` are the static buffers: overwrite them in place (``copy_``) between
+    replays; ``y``, ``grad_input`` and ``grad_weight`` are static outputs, valid after ``replay()`` in stream
+    order."""
+
+    def __init__(self, x, weight, grad_out, padding_mode=0, active_flag=False, borders=None, split=False, warmup=3):
+        dim = x.dim() - 2
+        func = {1: shift1d_func, 2: shift2d_func, 3: shift3d_func}[dim]
+        self.x = x.detach().requires_grad_(True)
+        self.weight = weight.detach().requires_grad_(True)
+        self.grad_out = grad_out
+        dev = x.device
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):       # also settles allocator state and lazy initialisation
+                y = func(self.x, self.weight, padding_mode, active_flag, borders)
+                torch.autograd.grad(y, (self.x, self.weight), grad_out)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.forward_graph = torch.cuda.CUDAGraph()
+        self.backward_graph = None
+        if split:
+            with torch.cuda.graph(self.forward_graph):
+                self.y = func(self.x, self.weight, padding_mode, active_flag, borders)
+            self.backward_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.backward_graph, pool=self.forward_graph.pool()):
+                self.grad_input, self.grad_weight = torch.autograd.grad(self.y, (self.x, self.weight), grad_out)
+        else:
+            with torch.cuda.graph(self.forward_graph):
+                self.y = func(self.x, self.weight, padding_mode, active_flag, borders)
+                self.grad_input, self.grad_weight = torch.autograd.grad(self.y, (self.x, self.weight), grad_out)
+
+    def replay_forward(self):
+        self.forward_graph.replay()
+
+    def replay_backward(self):
+        if self.backward_graph is not None:
+            self.backward_graph.replay()
+
+    def replay(self):
+        self.forward_graph.replay()
+        if self.backward_graph is not None:
+            self.backward_graph.replay()
+        return self.y, self.grad_input, self.grad_weight

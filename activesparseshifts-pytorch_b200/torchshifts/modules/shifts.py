@@ -124,6 +124,8 @@ class _Shiftnd(nn.Module):
             self.init_shift, self._w_post_init_scale, self.cut_borders, _ = _create_dw_emulation(emulate_dw, self.dim)
             if not (self._w_post_init_scale == 1).all():
                 self._reduction_fn = self._pooling(self._w_post_init_scale, self.dim)
+        self._cut_cache = None
+        self._border_ints()
         self._init_weights()
 
     def _init_shift_fn(self):
@@ -141,9 +143,26 @@ class _Shiftnd(nn.Module):
     def _compute_weight_loss(self):
         return self.sparsity_term * torch.sum(torch.abs(self.weight))
 
+    def _border_ints(self):
+        """``cut_borders`` as Python integers, read once per distinct tensor (and never while torch.compile traces,
+        where the tensor's values are not available)."""
+        cb = self.cut_borders
+        if cb is None:
+            return None
+        cached = getattr(self, '_cut_cache', None)
+        if cached is None or cached[0] is not cb:
+            if torch.compiler.is_compiling():
+                return cached[1] if cached is not None else None
+            cached = self._cut_cache = (cb, [[int(v) for v in row] for row in cb.tolist()])
+        return cached[1]
+
     def forward(self, input):
         loss = self._compute_weight_loss() if bool(self.sparsity_term) else None
-        out = self._shift_func(input, self.weight, self.padding, self._active_flag, self.cut_borders)
+        if self.cut_borders is None:
+            out = self._shift_func(input, self.weight, self.padding, self._active_flag, None)
+        else:
+            out = self._shift_func(input, self.weight, self.padding, self._active_flag, self.cut_borders,
+                                   _border_ints=self._border_ints())
         return self._reduction_fn(out), loss
 
     def extra_repr(self):

@@ -78,9 +78,9 @@ def broadcast_weights(module_or_params, src: int = 0, group=None) -> None:
 
 class FusedGradWeightAllReduce:
     """grad_weight leaves the backward already summed over the ranks: the deterministic pass-2
-    reduction kernel exchanges the ``C x dim`` values over NVLink peer memory itself (P2P stores into
-    every peer's buffer + flags, ``ts_shift_backward_allreduce``), so the step has no separate
-    collective launch at all.
+    reduction kernel exchanges the ``C x dim`` values over NVLink peer memory itself (one 8-byte
+    {epoch : value} peer store per contribution, ``ts_shift_backward_allreduce``), so the step has no
+    separate collective launch at all.
 
     Usage (every rank, after ``init_process_group``)::
 
@@ -88,49 +88,69 @@ class FusedGradWeightAllReduce:
         with fused:                                                  # or fused.enable() / fused.disable()
             loss.backward()          # shift layers' weight.grad are global sums; do NOT all-reduce them again
 
-    Every rank must run the same sequence of shift backward calls (true for replicated models).  The
-    exchange buffer is symmetric memory (``torch.distributed._symmetric_memory``); with a single rank a
+    Contract (checked where it can be, see ``_ops._backward_cuda``):
+
+    * every rank runs the same sequence of shift backward calls with the same ``C x dim`` while the mode
+      is enabled (true for replicated models); a rank whose batch shard is EMPTY still takes part and
+      contributes zeros (``shard_batch`` hands empty slices to ranks beyond a ragged last batch);
+    * fp64 weights, more than ``capacity`` weight elements or tensors on another device raise instead of
+      silently skipping the exchange (a rank-local skip would leave the peers waiting);
+    * the call counter lives in device memory, so a step that contains the exchange can be captured in a
+      CUDA graph and replayed (``torchshifts.host.GraphedShiftStep``);
+    * ``timeout_s``: how long a rank waits inside the kernel for its peers.  Default 1800 s (three times the
+      NCCL watchdog default): a data-loader stall, a checkpoint on rank 0 or a first-step compile must not
+      kill the job.  On expiry the kernel records the call in ``self.state[128]`` and traps (the CUDA context is
+      lost, like an NCCL watchdog abort); 0 waits for ever.
+    * with ``DistributedDataParallel`` call :meth:`exclude_from_ddp` BEFORE wrapping the model so DDP does
+      not all-reduce (and average) the shift weights a second time.
+
+    The exchange buffer is symmetric memory (``torch.distributed._symmetric_memory``); with a single rank a
     plain device buffer is used and the protocol degenerates to a local copy."""
 
-    FLAG_WORDS = 8 * 128          # (sender, CTA) flag words: 8 ranks x 128 CTAs of 32 outputs
+    STATE_WORDS = 129             # per-CTA call counters (128 CTAs of 32 outputs) + the timed-out epoch
 
-    def __init__(self, group=None, capacity: int = 4096, device=None):
+    def __init__(self, group=None, capacity: int = 4096, device=None, timeout_s: float = 1800.0):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         assert 1 <= self.world <= 8, 'one box: at most 8 ranks'
         self.capacity = int(capacity)
-        assert self.capacity <= 4096, 'at most 4096 grad_weight elements per layer'
+        assert 1 <= self.capacity <= 4096, 'at most 4096 grad_weight elements per layer'
+        self.timeout_s = float(timeout_s)
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
-        floats = 2 * self.world * self.capacity + self.FLAG_WORDS
+        words = 2 * self.world * self.capacity          # uint64 {epoch : value} words, double-buffered by epoch parity
         if self.world == 1:
-            self.buf = torch.zeros(floats, dtype=torch.float32, device=self.device)
+            self.buf = torch.zeros(words, dtype=torch.int64, device=self.device)
             ptrs = [self.buf.data_ptr()]
         else:
             import torch.distributed._symmetric_memory as symm_mem
             pg = group if group is not None else dist.group.WORLD
             with torch.cuda.device(self.device):
-                self.buf = symm_mem.empty(floats, dtype=torch.float32, device=self.device)
+                self.buf = symm_mem.empty(words, dtype=torch.int64, device=self.device)
             self.buf.zero_()
             self.handle = symm_mem.rendezvous(self.buf, pg.group_name)
             ptrs = [int(p) for p in self.handle.buffer_ptrs]
             torch.cuda.synchronize(self.device)
             dist.barrier(group=group)             # every buffer is zeroed before anybody's first exchange
+        self.state = torch.zeros(self.STATE_WORDS, dtype=torch.int32, device=self.device)
         self._ptrs = ptrs
-        self.epoch = 0
         self._prev = None
-
-    def peer_group(self):
-        """ctypes ``ts_peer_group`` for the next backward call (bumps the epoch)."""
         from ._cabi import PeerGroup
-        self.epoch += 1
         pg = PeerGroup()
-        pg.world, pg.rank, pg.epoch, pg.capacity = self.world, self.rank, self.epoch, self.capacity
-        flag_off = 4 * 2 * self.world * self.capacity
+        pg.world, pg.rank, pg.capacity, pg.reserved = self.world, self.rank, self.capacity, 0
+        pg.timeout_ns = int(self.timeout_s * 1e9)
         for p in range(self.world):
             pg.bufs[p] = self._ptrs[p]
-            pg.flags[p] = self._ptrs[p] + flag_off
-        return pg
+        pg.state = self.state.data_ptr()
+        self._pg = pg
+
+    def peer_group(self):
+        """ctypes ``ts_peer_group`` (constant: the call counter lives on the device)."""
+        return self._pg
+
+    def calls(self) -> int:
+        """Number of exchanges this rank has run so far (reads the device counter of CTA 0)."""
+        return int(self.state[0].item())
 
     def enable(self):
         from . import _ops
@@ -148,3 +168,29 @@ class FusedGradWeightAllReduce:
     def __exit__(self, *exc):
         self.disable()
         return False
+
+    @staticmethod
+    def exclude_from_ddp(module: torch.nn.Module) -> list:
+        """Tell ``DistributedDataParallel`` (call BEFORE wrapping ``module``) to leave the shift weights out of
+        its gradient buckets: with the fused exchange their ``.grad`` is already the global SUM when the
+        backward returns, a second bucketed all-reduce would double-count (and average) it.  Returns the
+        excluded parameter names.  DDP averages, this exchange sums: divide by the world size in the
+        optimiser step (or scale the loss) if the mean is wanted -- see ``ddp_sum_to_mean_hook``."""
+        from torchshifts.modules.shifts import _Shiftnd
+        names = [f'{name}.weight' if name else 'weight' for name, m in module.named_modules() if isinstance(m, _Shiftnd)]
+        prev = list(getattr(module, '_ddp_params_and_buffers_to_ignore', []))
+        torch.nn.parallel.DistributedDataParallel._set_params_and_buffers_to_ignore_for_model(module, prev + names)
+        return names
+
+
+def ddp_sum_to_mean_hook(module_or_params, world: Optional[int] = None):
+    """Register ``post_accumulate_grad`` hooks that turn the fused exchange's SUM into DDP's MEAN for the shift
+    weights (``grad /= world``), so a model whose shift weights were excluded from DDP with
+    :meth:`FusedGradWeightAllReduce.exclude_from_ddp` sees the same gradients as under stock DDP.  Returns the
+    hook handles."""
+    world = dist.get_world_size() if world is None else int(world)
+    scale = 1.0 / world
+
+    def hook(p):
+        p.grad.mul_(scale)
+    return [p.register_post_accumulate_grad_hook(hook) for p in _shift_weights(module_or_params)]

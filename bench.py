@@ -44,20 +44,29 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
-                    help="weak (default): every rank owns a full BASELINE shard, N=256 images (global batch 256*G, batch-sharded); "
-                         "strong: the global batch N=256 is split over the ranks")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
+                    help="strong (default for --gpus > 1, BASELINE.json configs[2] / SURVEY 8e): the global batch N=256 is split "
+                         "256/G images per GPU; weak: every rank owns a full N=256 shard (global batch 256*G).  With more than "
+                         "one GPU the other variant is measured as well and reported under the extra key `other_scaling`")
+    ap.add_argument("--graph", default="on", choices=["on", "off"],
+                    help="on (default): the step (forward, backward, in-kernel exchange) is captured once with "
+                         "torchshifts.host.GraphedShiftStep and replayed (two graph launches per step); off: eager public API")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="multi-GPU: all-reduce grad_weight with torch.distributed (NCCL) after the backward instead of the "
-                         "default in-kernel exchange over NVLink peer memory (ts_shift_backward_allreduce)")
+                         "default in-kernel exchange over NVLink peer memory (ts_shift_backward_allreduce); implies --graph off")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-scaling", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA kernels (N=1 only)")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample clocks during the timed region")
     ap.add_argument("--clocks", default="auto", choices=["auto", "thread", "inline", "off"],
                     help="how the SM clock / throttle reasons are sampled during the timed region: a 4 ms NVML polling "
                          "thread (default), or three NVML reads from the launching thread while the GPU works through the "
                          "queued steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-n", type=int, default=16)
+    ap.add_argument("--cpu-sample-n", type=int, default=0,
+                    help="images of the N=256 batch the CPU arm runs per step (0 = the full configuration, shrunk only if the "
+                         "run would not finish within a few minutes)")
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0)
     return ap.parse_args()
 
 
@@ -146,8 +155,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference arm / cpu baseline
-def cpu_reference_run(sample_n, steps, warmup, threads=None):
-    """Time the reference's CPU implementation of the path on a bounded sample of the workload.
+def cpu_reference_run(sample_n, steps, warmup, threads=None, budget_s=240.0):
+    """Time the reference's CPU implementation of the path: cfg3 at FULL size (N=256) for exactly `steps` steps after
+    `warmup` warm-up steps.  Only if that would not finish within `budget_s` (estimated from the first step) the
+    batch is cut to a bounded sample of the same workload, and the line says so.
 
     Preference order: (1) the reference's own torch extension (oracle/_ref/torchshifts_ref/_C.so,
     its registered op + autograd, at::parallel_for over all host threads) -- only in a process that
@@ -155,68 +166,88 @@ def cpu_reference_run(sample_n, steps, warmup, threads=None):
     per-element headers behind OpenMP (oracle/_ref/libref_shifts.so); (3) the oracle port."""
     import numpy as np
     cores = threads or os.cpu_count() or 1
-    N, C, H, W = sample_n, CFG["C"], CFG["H"], CFG["W"]
-    elems = N * C * H * W
-    rng = np.random.default_rng(0)
-    x = rng.standard_normal((N, C, H, W), dtype=np.float32)
-    g = rng.standard_normal((N, C, H, W), dtype=np.float32)
-    w = (rng.random((C, 2), dtype=np.float32) * 2 - 1)
+    C, H, W = CFG["C"], CFG["H"], CFG["W"]
     full = ROOT / "oracle" / "_ref" / "torchshifts_ref" / "_C.so"
-    kind, how = "port", ""
-    step = None
+    state = {"kind": "port", "how": "", "orc": None, "torch": None}
     if full.exists() and "torchshifts" not in sys.modules:
         try:
             import torch
             torch.ops.load_library(str(full))
             torch.set_num_threads(cores)
-            xt, gt = torch.from_numpy(x), torch.from_numpy(g)
+            state.update(kind="reference", torch=torch,
+                         how="reference torch extension (unmodified csrc, op torchshifts::shift2d + its autograd), at::parallel_for")
+        except Exception as e:  # fall through to the header build
+            state["how"] = f"(extension unusable: {e}) "
+    if state["torch"] is None:
+        from oracle.oracle import Oracle
+        if Oracle.available("reference"):
+            state["orc"] = Oracle("reference", threads=cores)
+            state.update(kind="reference", how=state["how"] + "reference per-element headers (kernels/shifts_kernels.h) behind OpenMP, "
+                                                             "oracle/_ref/libref_shifts.so")
+        else:
+            state["orc"] = Oracle("port", threads=1)
+            cores = 1
+            state.update(kind="port", how=state["how"] + "oracle/shift_oracle.c (scalar C restatement)")
+
+    def make_step(N):
+        rng = np.random.default_rng(0)
+        x = rng.standard_normal((N, C, H, W), dtype=np.float32)
+        g = rng.standard_normal((N, C, H, W), dtype=np.float32)
+        w = (rng.random((C, 2), dtype=np.float32) * 2 - 1)
+        if state["torch"] is not None:
+            torch = state["torch"]
+            xt, gt = torch.from_numpy(x).requires_grad_(True), torch.from_numpy(g)
             wt = torch.from_numpy(w).requires_grad_(True)
-            xt.requires_grad_(True)
             empty = torch.Tensor()
 
             def step():
                 xt.grad = None; wt.grad = None
                 y = torch.ops.torchshifts.shift2d(xt, wt, empty, 0, False)
                 y.backward(gt)
-            kind, how = "reference", "reference torch extension (unmodified csrc, op torchshifts::shift2d + its autograd), at::parallel_for"
-        except Exception as e:  # fall through to the header build
-            step, how = None, f"(extension unusable: {e}) "
-    if step is None:
-        from oracle.oracle import Oracle
-        if Oracle.available("reference"):
-            orc = Oracle("reference", threads=cores)
-            kind, how = "reference", how + "reference per-element headers (kernels/shifts_kernels.h) behind OpenMP, oracle/_ref/libref_shifts.so"
         else:
-            orc = Oracle("port", threads=1)
-            cores = 1
-            kind, how = "port", how + "oracle/shift_oracle.c (scalar C restatement)"
+            orc = state["orc"]
 
-        def step():
-            orc.forward(x, w, 0, False)
-            orc.backward(g, x, w, 0, False)
-    for _ in range(max(1, warmup)):
+            def step():
+                orc.forward(x, w, 0, False)
+                orc.backward(g, x, w, 0, False)
+        return step
+
+    N = sample_n if sample_n > 0 else CFG["N"]
+    step = make_step(N)
+    t0 = time.perf_counter(); step(); first = time.perf_counter() - t0
+    done_warm = 1
+    note = ""
+    if sample_n <= 0 and first * (steps + warmup) > budget_s:
+        N = max(16, int(CFG["N"] * budget_s / (first * (steps + warmup))) // 16 * 16)
+        note = f" (the full batch takes {first:.2f} s per step here: cut to fit {budget_s:.0f} s)"
+        step = make_step(N)
+        done_warm = 0
+    for _ in range(max(0, warmup - done_warm)):
         step()
     times = []
     for _ in range(max(1, steps)):
         t0 = time.perf_counter(); step(); times.append(time.perf_counter() - t0)
     t = statistics.median(times)
+    elems = N * C * H * W
     gbs = elems * (BYTES_PER_ELEM_FWD + BYTES_PER_ELEM_BWD) / t / 1e9
-    sample = f"Shift2d SSL zeros fwd+bwd on N={N} of 256 images (C=256, 56x56, fp32), median of {len(times)} runs; {how}"
-    return {"value": gbs, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "ms_per_step": t * 1e3,
-            "elements_per_s": elems / t}
+    sample = (f"Shift2d SSL zeros fwd+bwd on N={N} of 256 images (C=256, 56x56, fp32){note}, median of {len(times)} steps after "
+              f"{warmup} warm-up; {state['how']}")
+    return {"value": gbs, "unit": UNIT, "cores": cores, "kind": state["kind"], "sample": sample, "ms_per_step": t * 1e3,
+            "elements_per_s": elems / t, "sample_n": N}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded: at most ~25 steps of a 16-image sample, whatever --steps says (a few minutes at worst)
-    steps, warmup = min(args.steps, 25), min(max(args.warmup, 1), 3)
-    r = cpu_reference_run(args.cpu_sample_n, steps, warmup)
+    r = cpu_reference_run(args.cpu_sample_n, args.steps, args.warmup, budget_s=args.cpu_budget_s)
+    full = r["sample_n"] == CFG["N"]
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg3 Shift2d SSL zeros fwd+bwd N=256 C=256 56x56 fp32 (bounded sample, see cpu_baseline.sample)"},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": resolve_scaling(args), "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg3 Shift2d SSL zeros fwd+bwd N=256 C=256 56x56 fp32" +
+                                   ("" if full else f" (bounded sample: {r['sample_n']} images per step, see cpu_baseline.sample)"),
+                       "per_step_images": r["sample_n"]},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "elements_per_s": r["elements_per_s"],
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -224,78 +255,101 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def resolve_scaling(args):
+    if args.scaling != "auto":
+        return args.scaling
+    return "strong"       # BASELINE.json configs[2]: global N=256 split over the GPUs (one GPU: the two variants coincide)
+
+
 # ------------------------------------------------------------------------------------------ our arm
-def run_ours(args):
+def measure_device_resident(args, N, dev, world, rank, fused, lib, sampler=None, collect_clocks=False):
+    """K timed steps of fwd+bwd (+ exchange) on this rank's N images, inputs resident in HBM.
+    -> dict(ms, bwd_ms, launches_per_step, checks..., clocks)"""
     import torch
     import torch.distributed as dist
-    import torchshifts  # noqa: F401
-    from torchshifts.extension import native
     from torchshifts.functional import shift2d_func
+    from torchshifts.host import GraphedShiftStep
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = native().lib
-
-    N = CFG["N"] if args.scaling == "weak" else CFG["N"] // world
     C, H, W = CFG["C"], CFG["H"], CFG["W"]
-    elems_rank = N * C * H * W
-    elems_job = elems_rank * world
-    torch.manual_seed(rank)
+    torch.manual_seed(1000 + rank)
     x = torch.randn(N, C, H, W, device=dev)
     g = torch.randn(N, C, H, W, device=dev)
     torch.manual_seed(0)
-    w = (torch.rand(C, 2, device=dev) * 2 - 1).requires_grad_(True)   # module default init U(-1,1), same on every rank
-    xr = x.requires_grad_(True)
-
+    w = (torch.rand(C, 2, device=dev) * 2 - 1)          # module default init U(-1,1), same on every rank
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    bwd_pairs = []
-    fused, fused_note = None, ""
-    if world > 1 and not args.nccl_allreduce:
-        # every rank must take the same branch: agree on the outcome of the symmetric-memory set-up
-        try:
-            from torchshifts.sharded import FusedGradWeightAllReduce
-            fused = FusedGradWeightAllReduce(capacity=4096, device=dev)
-            ok = torch.ones(1, device=dev)
-        except Exception as e:      # no symmetric memory on this box: NCCL all-reduce instead
-            fused, fused_note = None, f" (in-kernel exchange unavailable: {type(e).__name__}: {str(e)[:120]})"
-            ok = torch.zeros(1, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if float(ok.item()) < 1:
-            fused = None
+    res = {}
+
+    # ---- the collective, checked before anything is timed (every rank, same sequence of calls) ----
+    if world > 1:
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        shift2d_func(xr, wr, 0, False).backward(g)             # plain backward: local grad_weight
+        ref = wr.grad.clone()
+        dist.all_reduce(ref)                                     # NCCL sum = what the exchange must produce
+        check = {"reference": "torch.distributed.all_reduce (NCCL, sum) of the per-rank grad_weight"}
+        if fused is not None:
+            xr.grad = None; wr.grad = None
+            with fused:
+                shift2d_func(xr, wr, 0, False).backward(g)
+            got = wr.grad.clone()
+            rel = float(((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item())
+            gathered = [torch.empty_like(got) for _ in range(world)]
+            dist.all_gather(gathered, got)
+            same = all(torch.equal(gathered[0], t) for t in gathered[1:])
+            check.update(max_rel_err=rel, tolerance=1e-5, identical_across_ranks=bool(same), ok=bool(rel < 1e-5 and same),
+                         what="eager step through ts_shift_backward_allreduce vs the NCCL all-reduce of the plain backward")
         else:
+            check.update(ok=True, what="NCCL path (no in-kernel exchange in this run)")
+        res["collective_check"] = check
+        res["_gw_ref"] = ref
+        del xr, wr
+
+    use_graph = args.graph == "on" and (world == 1 or fused is not None)
+    bwd_pairs = []
+    launches0 = lib.ts_launch_count()
+    if use_graph:
+        if fused is not None:
+            fused.enable()
+        stepper = GraphedShiftStep(x, w, g, 0, False, split=True, warmup=max(args.warmup, 3))
+        if fused is not None:
+            fused.disable()
+        per_step = (lib.ts_launch_count() - launches0) // (max(args.warmup, 3) + 1)    # warm-up steps + the capture pass
+
+        def step(timed=False):
+            stepper.replay_forward()
+            if timed:
+                a, b = ev(), ev(); a.record()
+            stepper.replay_backward()
+            if timed:
+                b.record(); bwd_pairs.append((a, b))
+    else:
+        xr = x.requires_grad_(True)
+        wr = w.requires_grad_(True)
+        if fused is not None:
             fused.enable()
 
-    def step(timed=False):
-        xr.grad = None; w.grad = None
-        y = shift2d_func(xr, w, 0, False)
-        if timed:
-            a, b = ev(), ev(); a.record()
-        y.backward(g)
-        if timed:
-            b.record(); bwd_pairs.append((a, b))
-        if world > 1 and fused is None:
-            dist.all_reduce(w.grad)          # the one collective of the path: C x 2 floats
-        return y                             # (fused: w.grad is already the global sum)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
+        def step(timed=False):
+            xr.grad = None; wr.grad = None
+            y = shift2d_func(xr, wr, 0, False)
+            if timed:
+                a, b = ev(), ev(); a.record()
+            y.backward(g)
+            if timed:
+                b.record(); bwd_pairs.append((a, b))
+            if world > 1 and fused is None:
+                dist.all_reduce(wr.grad)         # the one collective of the path: C x 2 floats
+        for _ in range(max(args.warmup, 3)):
+            step()
+        per_step = (lib.ts_launch_count() - launches0) // max(args.warmup, 3)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    mode = "off" if args.no_clocks else args.clocks
+
+    mode = "off" if (args.no_clocks or not collect_clocks) else args.clocks
     if mode == "auto":
         mode = "thread"
-    if rank == 0 and mode != "off":
+    if rank == 0 and mode != "off" and sampler is not None:
         sampler.start(poll=(mode == "thread")); time.sleep(0.15)
     inline_at = {args.steps // 3, (2 * args.steps) // 3, args.steps - 1} if (rank == 0 and mode == "inline") else set()
     if world > 1:
         dist.barrier()      # AFTER the sampler start-up (rank 0 only): every rank enters the timed region together
-    launches0 = lib.ts_launch_count()
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     start, end = ev(), ev()
@@ -309,21 +363,72 @@ def run_ours(args):
     t_wall1 = time.perf_counter()
     if world > 1:
         dist.barrier()
-    launches = lib.ts_launch_count() - launches0
+    if not use_graph and fused is not None:
+        fused.disable()
     ms = start.elapsed_time(end) / args.steps
     bwd_ms = statistics.mean(a.elapsed_time(b) for a, b in bwd_pairs)
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    path = lib.ts_last_kernel_path()
+    res["clocks"] = sampler.stop(t_wall0, t_wall1) if (rank == 0 and sampler is not None and collect_clocks) else None
     if world > 1:
         t = torch.tensor([ms, bwd_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, bwd_ms = t.tolist()
+        # the LAST timed step's grad_weight (graph replay included) must still be the cross-rank sum
+        got = stepper.grad_weight if use_graph else wr.grad
+        ref = res.pop("_gw_ref")
+        rel = float(((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item())
+        res["collective_check"]["after_timed_steps_max_rel_err"] = rel
+        res["collective_check"]["ok"] = bool(res["collective_check"]["ok"] and rel < 1e-5)
+    res.update(ms=ms, bwd_ms=bwd_ms, launches=int(per_step) * args.steps, launches_per_step=int(per_step), graph=use_graph,
+               path=lib.ts_last_kernel_path(), x=x, g=g, w=w)
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import torchshifts  # noqa: F401
+    from torchshifts.extension import native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = native().lib
+    scaling = resolve_scaling(args)
+    C, H, W = CFG["C"], CFG["H"], CFG["W"]
+
+    fused, fused_note = None, ""
+    if world > 1 and not args.nccl_allreduce:
+        # every rank must take the same branch: agree on the outcome of the symmetric-memory set-up
+        try:
+            from torchshifts.sharded import FusedGradWeightAllReduce
+            fused = FusedGradWeightAllReduce(capacity=4096, device=dev)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:      # no symmetric memory on this box: NCCL all-reduce instead
+            fused, fused_note = None, f" (in-kernel exchange unavailable: {type(e).__name__}: {str(e)[:120]})"
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) < 1:
+            fused = None
+
+    def batch_of(kind):
+        return CFG["N"] if kind == "weak" else max(1, CFG["N"] // world)
+
+    N = batch_of(scaling)
+    elems_rank = N * C * H * W
+    elems_job = elems_rank * world
+    sampler = ClockSampler(local)
+    main = measure_device_resident(args, N, dev, world, rank, fused, lib, sampler=sampler, collect_clocks=True)
+    ms, bwd_ms = main["ms"], main["bwd_ms"]
     value = elems_job * (BYTES_PER_ELEM_FWD + BYTES_PER_ELEM_BWD) / (ms * 1e-3) / 1e9
+    x, g, w = main.pop("x"), main.pop("g"), main.pop("w")
 
     # ---- e2e: public API, host (pinned) buffers, copies inside the timed region -----------------
     e2e = None
-    if fused is not None:
-        fused.disable()       # the host pipeline reduces its per-chunk grad_weight once per step (NCCL below)
     if not args.no_e2e:
         from torchshifts.host import HostShift2dPipeline
         pipe = HostShift2dPipeline(N, C, H, W, device=dev)
@@ -339,7 +444,8 @@ def run_ours(args):
         for _ in range(k):
             gw = pipe.forward_backward(wh, 0, False)
             if world > 1:
-                dist.all_reduce(gw)
+                dist.all_reduce(gw)                 # the host pipeline reduces its per-chunk grad_weight once per step
+            pipe.read_back_grad_weight(gw)          # the C x 2 result goes back to the host as well
         torch.cuda.synchronize()
         e_ms = (time.perf_counter() - t0) / k * 1e3
         if world > 1:
@@ -350,6 +456,21 @@ def run_ours(args):
                "h2d_bytes_per_step": pipe.h2d_bytes * world, "d2h_bytes_per_step": pipe.d2h_bytes * world,
                "how": pipe.describe()}
         del pipe
+    del x, g
+    torch.cuda.empty_cache()
+
+    # ---- the other scaling variant (extra key; N > 1 only) ---------------------------------------
+    other = None
+    if world > 1 and not args.no_other_scaling:
+        kind = "weak" if scaling == "strong" else "strong"
+        No = batch_of(kind)
+        o = measure_device_resident(args, No, dev, world, rank, fused, lib)
+        for k_ in ("x", "g", "w"):
+            o.pop(k_)
+        torch.cuda.empty_cache()
+        other = {"scaling": kind, "per_gpu_batch": No, "global_batch": No * world, "ms_per_step": o["ms"],
+                 "value": No * world * C * H * W * 20 / (o["ms"] * 1e-3) / 1e9, "unit": UNIT,
+                 "collective_check_ok": o.get("collective_check", {}).get("ok")}
 
     if rank != 0:
         if world > 1:
@@ -358,40 +479,73 @@ def run_ours(args):
     peak, peak_src = peaks()
     bwd_bytes = elems_rank * BYTES_PER_ELEM_BWD
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get("backward_dram_bytes_per_launch")
+            tj = json.loads(tf.read_text())
+            traffic = tj.get("backward_dram_bytes_per_launch")
+            traffic_src = {k_: tj.get(k_) for k_ in ("captured_at_commit", "kernel", "source", "per_gpu_batch")}
         except Exception:
             pass
+    if traffic is not None and N != CFG["N"]:
+        traffic = traffic * N / CFG["N"]          # the capture is of the N=256 launch; DRAM traffic scales with the batch
+    path = main["path"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"cfg3 Shift2d SSL zeros fwd+bwd, global N={N * world} C={C} {H}x{W} fp32, batch-sharded over {world} GPU(s)",
+        "config": {"workload": f"cfg3 Shift2d SSL zeros fwd+bwd, global N={N * world} C={C} {H}x{W} fp32, batch-sharded over {world} GPU(s)"
+                               f" ({scaling} scaling: {N} images per GPU)",
                    "per_gpu_batch": N, "padding": "zeros", "active": False, "weights": "U(-1,1)",
-                   "l2": "inputs (822 MB per tensor at N=256) are larger than the 126 MB L2; no flush needed",
+                   "l2": f"per-step working set per GPU (x, grad, y, grad_input: {4 * elems_rank * 4 / 1e6:.0f} MB) is larger than the "
+                         "126 MB L2 and every tensor is streamed once per pass; no flush needed",
+                   "launch": ("step captured once (torchshifts.host.GraphedShiftStep) and replayed: one graph launch for the forward, one "
+                              "for the backward + pass 2 (+ exchange)" if main["graph"] else "eager public API (shift2d_func + autograd)"),
                    "kernel_path": {1: "generic", 2: "staged (cp.async.bulk + mbarrier)",
                                    3: "TMA tensor boxes (cp.async.bulk.tensor.5d, shift + zero pad by the copy engine)"}.get(path, str(path)),
                    "collective": ("none" if world == 1 else "torch.distributed all_reduce (NCCL) of grad_weight [C,2]" + fused_note if fused is None else
-                                  "grad_weight [C,2] summed over the ranks inside the pass-2 reduction kernel (P2P stores + flags "
-                                  "over NVLink peer memory, ts_shift_backward_allreduce); no separate collective launch")},
+                                  "grad_weight [C,2] summed over the ranks inside the pass-2 reduction kernel (one 8-byte {epoch:value} "
+                                  "peer store per contribution over NVLink, ts_shift_backward_allreduce); no separate collective launch")},
         "elements_per_s": elems_job / (ms * 1e-3),
         "frac_of_hbm_peak": value / world / peak,
-        "roofline": {"bound": "hbm", "kernel": "shift backward (grad_input + grad_weight partials) + pass-2 reduce",
+        "roofline": {"bound": "hbm", "kernel": "shift backward (grad_input + grad_weight partials) + pass-2 reduce" +
+                                               (" + in-kernel exchange" if fused is not None else ""),
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                     "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_ms": bwd_ms, "traffic": traffic},
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                     "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_ms": bwd_ms, "traffic": traffic,
+                     "traffic_source": traffic_src},
+        "e2e": e2e, "gpu_launches": main["launches"],
+        "gpu_launches_how": f"{main['launches_per_step']} kernels of libtorchshifts_b200.so per step (ts_launch_count over the warm-up "
+                            f"steps" + (" and the capture; the timed steps replay them from the graph)" if main["graph"] else ")") + f" x {args.steps} steps",
+        "clocks": main["clocks"],
     }
+    if "collective_check" in main:
+        line["collective_check"] = main["collective_check"]
+    if other is not None:
+        line["other_scaling"] = other
     if not args.no_cpu_baseline and world == 1:
         try:
-            out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "5", "--warmup", "1",
-                                  "--cpu-sample-n", str(args.cpu_sample_n)], capture_output=True, text=True, timeout=600)
+            out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "10", "--warmup", "3",
+                                  "--cpu-sample-n", str(args.cpu_sample_n), "--cpu-budget-s", "60"],
+                                 capture_output=True, text=True, timeout=900)
             ref = json.loads(out.stdout.strip().splitlines()[-1])
             line["cpu_baseline"] = ref["cpu_baseline"]
         except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    if not args.no_gpu_reference and world == 1:
+        # the reference's OWN CUDA kernels (unmodified, sm_100 build) on this GPU, separate process: the GPU kernel to beat
+        try:
+            out = subprocess.run([sys.executable, str(ROOT / "tools" / "ref_cuda_bench.py"), "cfg3", "--json"],
+                                 capture_output=True, text=True, timeout=600)
+            gj = json.loads(out.stdout.strip().splitlines()[-1])
+            c3 = gj.get("cases", {}).get("cfg3")
+            if c3 and "error" not in c3:
+                line["gpu_reference"] = {"value": c3["fwd_bwd_gbs"], "unit": UNIT, "ms_per_step": c3["fwd_bwd_ms"], "fwd_ms": c3["fwd_ms"],
+                                         "bwd_ms": c3["bwd_ms"], "what": gj["what"], "speedup_device_resident": value / c3["fwd_bwd_gbs"]}
+            else:
+                line["gpu_reference"] = {"value": None, "why": gj.get("unavailable") or (c3 or {}).get("error")}
+        except Exception as e:
+            line["gpu_reference"] = {"value": None, "why": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define TS_ABI_VERSION 1
+#define TS_ABI_VERSION 2
 
 typedef enum ts_status {
     TS_OK = 0,
@@ -123,19 +123,27 @@ int ts_shift_backward(const ts_geometry* g, int dtype, int padding, int active,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward fused with the path's one collective: the deterministic pass-2 reduction of grad_weight
- * writes this rank's C x dim result into every peer's exchange buffer over NVLink peer memory
- * (plain P2P stores), raises a flag on each peer, waits for the peers' flags and sums the `world`
- * contributions in rank order -- grad_weight leaves the call already all-reduced (sum), no NCCL launch.
- * `bufs[p]` / `flags[p]`: device pointers, valid on THIS device, to rank p's exchange buffer
- * (>= 2 * world * capacity floats, double-buffered by epoch parity) and flag words (>= world * 128
- * uint32, zero before the first call; capacity <= 4096).  Every rank must make the same sequence of calls with the same `epoch`
- * (1, 2, 3, ...).  dtype: TS_F32 / TS_F16 / TS_BF16 (contributions travel as fp32). */
+ * publishes this rank's C x dim result to every peer over NVLink peer memory and sums the `world`
+ * contributions in rank order -- grad_weight leaves the call already all-reduced (sum), identical on
+ * every rank, with no NCCL launch.  A contribution travels as one 64-bit word {call epoch : fp32 value}
+ * written with a single 8-byte peer store; the receiver polls that word (no separate flag, no fence).
+ *   bufs[p]   device pointer, valid on THIS device, to rank p's exchange buffer:
+ *             2 (epoch parity) x world x capacity uint64 words, zero before the first call;
+ *   state     THIS rank's private device words: 129 uint32, zero before the first call (per-CTA call
+ *             counters; word 128 receives the epoch of a call that timed out).  The call counter lives on
+ *             the device, so nothing call-specific crosses the ABI and the launch can be captured in a CUDA
+ *             graph and replayed;
+ *   timeout_ns  how long a rank waits for its peers before it records the failure and traps (0 = for ever).
+ * Every rank must make the same sequence of calls with the same C x dim (replicated layers), one stream at
+ * a time per peer group.  A rank whose shard is empty (N == 0) must still call: it contributes zeros.
+ * dtype: TS_F32 / TS_F16 / TS_BF16 (contributions travel as fp32); capacity <= 4096. */
 typedef struct ts_peer_group {
     int32_t  world, rank;          /* 1 <= world <= 8                                              */
-    uint32_t epoch;                /* call counter, identical on every rank, starts at 1           */
-    int32_t  capacity;             /* floats per rank slot; C * dim must not exceed it             */
+    int32_t  capacity;             /* words per rank slot; C * dim must not exceed it              */
+    int32_t  reserved;
+    uint64_t timeout_ns;
     void*    bufs[8];
-    void*    flags[8];
+    void*    state;
 } ts_peer_group;
 
 int ts_shift_backward_allreduce(const ts_geometry* g, int dtype, int padding, int active,

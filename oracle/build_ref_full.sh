@@ -11,7 +11,15 @@
 set -euo pipefail
 REPO="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 SRC="${TS_REFERENCE_DIR:-/root/reference}"
-OUT="$REPO/oracle/_ref/torchshifts_ref"
+# `build_ref_full.sh cuda` builds the reference WITH its own CUDA kernels for sm_100 (csrc/ops/cuda/shifts_cuda.cu,
+# FORCE_CUDA=1 TORCH_CUDA_ARCH_LIST=10.0): the "existing GPU kernel" comparator that tools/ref_cuda_bench.py
+# times on the B200 box in a separate process.  It is never loaded next to the product library.
+VARIANT="${1:-cpu}"
+if [ "$VARIANT" = "cuda" ]; then
+    OUT="$REPO/oracle/_ref/torchshifts_ref_cuda"; export FORCE_CUDA=1 TORCH_CUDA_ARCH_LIST="10.0"
+else
+    OUT="$REPO/oracle/_ref/torchshifts_ref"; export FORCE_CUDA=0
+fi
 [ -d "$SRC/torchshifts/csrc" ] || { echo "reference tree not found at $SRC" >&2; exit 3; }
 WORK="$(mktemp -d /tmp/tsref.XXXXXX)"
 trap 'rm -rf "$WORK"' EXIT
@@ -20,7 +28,7 @@ chmod -R u+w "$WORK"
 cd "$WORK"
 sed -i 's/AT_DISPATCH_QINT_TYPES(input.scalar_type(), name,/AT_DISPATCH_QINT_TYPES(input.scalar_type(), "q_shiftnd_cpu",/' \
     torchshifts/csrc/ops/quantized/shifts_quantized.cpp
-FORCE_CUDA=0 python setup.py build_ext --inplace > "$WORK/build.log" 2>&1 || { tail -50 "$WORK/build.log" >&2; exit 4; }
+python setup.py build_ext --inplace > "$WORK/build.log" 2>&1 || { tail -50 "$WORK/build.log" >&2; exit 4; }
 mkdir -p "$OUT"
 cp torchshifts/_C*.so "$OUT/_C.so"
 echo "built $OUT/_C.so"

@@ -9,9 +9,15 @@ Tolerances (BASELINE.json north_star):
     serial sum is less accurate than that, SURVEY.md 7);
   * fp16 / bf16 (no CPU oracle exists): fp32 oracle on the rounded inputs, rtol 1e-2.
 """
+import subprocess
+import sys
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
+
+ROOT = Path(__file__).resolve().parents[1]
 
 pytestmark = pytest.mark.gpu
 
@@ -553,6 +559,34 @@ def test_torch_compile_and_state_dict(dev, auto_path):
     assert torch.allclose(x.grad, gx, rtol=1e-5, atol=1e-6) and torch.allclose(sh.weight.grad, gw, rtol=1e-4, atol=1e-5)
 
 
+def test_torch_compile_cropping_layer_and_inductor(dev, auto_path):
+    """A layer built with emulate_dw that CROPS its output (kernel_size > 2*padding+1) and average-pools it
+    (stride 2) compiles as one graph: the crop is resolved from Python integers while tracing (the border tensor's
+    values cannot be read there).  Backends: aot_eager (always) and inductor (Triton for the pointwise / pooling
+    ops around the custom operator)."""
+    import torchshifts
+    torch.manual_seed(0)
+    sh = torchshifts.Shift2d(8, padding='reflect', active_flag=True, emulate_dw={'kernel_size': 3, 'padding': 0, 'stride': 2}).to(dev)
+    assert sh.cut_borders is not None
+
+    def f(x):
+        y, loss = sh(x * 2.0)
+        return torch.relu(y).sum() + loss
+
+    x = torch.randn(2, 8, 16, 16, device=dev, requires_grad=True)
+    want = f(x)
+    want.backward()
+    gx, gw = x.grad.clone(), sh.weight.grad.clone()
+    for backend in ("aot_eager", "inductor"):
+        x.grad = None; sh.weight.grad = None
+        torch._dynamo.reset()
+        got = torch.compile(f, dynamic=False, backend=backend, fullgraph=True)(x)
+        got.backward()
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), backend
+        assert torch.allclose(x.grad, gx, rtol=1e-5, atol=1e-6), backend
+        assert torch.allclose(sh.weight.grad, gw, rtol=1e-4, atol=1e-5), backend
+
+
 def test_cuda_graph_capture_and_replay(dev, lib, oracle_port, auto_path):
     """The C ABI only enqueues work on the caller's stream (no sync, no allocation, tensor maps are
     encoded on the host and passed by value), so forward + backward capture into a CUDA graph; the
@@ -644,9 +678,9 @@ def test_misaligned_dense_tensors_fall_back(dev, lib, oracle_port, auto_path):
 
 
 def test_fused_allreduce_single_rank(dev, lib, oracle_port, auto_path):
-    """ts_shift_backward_allreduce with a one-rank peer group: the exchange protocol (P2P stores into the
-    own buffer, flag, acquire-poll, rank-ordered sum) must reproduce the plain backward; several calls in a
-    row exercise the epoch / double buffering.  (The multi-rank run is tools/fused_allreduce_probe.py.)"""
+    """ts_shift_backward_allreduce with a one-rank peer group: the exchange protocol ({epoch:value} words stored
+    into the own buffer, poll, rank-ordered sum) must reproduce the plain backward; several calls in a row
+    exercise the device-side call counter / double buffering.  (Multi-rank: test_fused_allreduce_two_ranks.)"""
     from torchshifts.functional import shift2d_func, shift3d_func
     from torchshifts.sharded import FusedGradWeightAllReduce
     rng = np.random.default_rng(51)
@@ -662,7 +696,7 @@ def test_fused_allreduce_single_rank(dev, lib, oracle_port, auto_path):
         wd = torch.from_numpy(w).to(dev).requires_grad_(True)
         with fused:
             fn(xd, wd, pad, active).backward(torch.from_numpy(g).to(dev))
-        assert fused.epoch == it + 1
+        assert fused.calls() == it + 1
         gi_ref, _ = oracle_port.backward(g, x, w, pad, active)
         _, gw64 = oracle_port.backward(g.astype(np.float64), x.astype(np.float64), w.astype(np.float64), pad, active)
         assert np.array_equal(xd.grad.cpu().numpy(), gi_ref)
@@ -671,7 +705,23 @@ def test_fused_allreduce_single_rank(dev, lib, oracle_port, auto_path):
     xd = torch.from_numpy(x).to(dev).requires_grad_(True)
     wd = torch.from_numpy(w).to(dev).requires_grad_(True)
     shift2d_func(xd, wd, 0, True).backward(torch.from_numpy(g).to(dev))
-    assert fused.epoch == 5 and _gw_close(wd.grad.cpu().numpy(), gw64)
+    assert fused.calls() == 5 and _gw_close(wd.grad.cpu().numpy(), gw64)
+
+
+def test_fused_allreduce_two_ranks():
+    """The in-kernel exchange on TWO ranks (needs >= 2 visible GPUs, skipped otherwise): tools/fused_allreduce_probe.py
+    under torchrun -- eager mixed layers, a ragged batch with an empty shard, CUDA-graph replay; every result against
+    NCCL's all-reduce of the plain backward (rtol 1e-5) and bit-identical across the ranks."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run on the box with: gpurun --gpus 2 -- python -m pytest tests -m gpu -k two_ranks)")
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "tools" / "fused_allreduce_probe.py"), "--quick"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "PROBE OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
 NHWC = 4

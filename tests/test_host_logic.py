@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(native):
     raw = ct.CDLL(str(native.path))
     for name in declared:
         assert hasattr(raw, name), f"{name} is declared in include/torchshifts_b200.h but not exported"
-    assert native.lib.ts_abi_version() == 1
+    assert native.lib.ts_abi_version() == 2
     assert native.lib.ts_cuda_version() >= 12080
     assert native.lib.ts_error_string(7).decode().startswith("no CUDA device")
 
@@ -246,8 +246,8 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
 int main(void) {
     printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ts_geometry), offsetof(ts_geometry, N), offsetof(ts_geometry, size),
            offsetof(ts_geometry, x_stride), offsetof(ts_geometry, lb), offsetof(ts_geometry, rb));
-    printf("%zu %zu %zu %zu %zu\n", sizeof(ts_peer_group), offsetof(ts_peer_group, epoch), offsetof(ts_peer_group, capacity),
-           offsetof(ts_peer_group, bufs), offsetof(ts_peer_group, flags));
+    printf("%zu %zu %zu %zu %zu\n", sizeof(ts_peer_group), offsetof(ts_peer_group, timeout_ns), offsetof(ts_peer_group, capacity),
+           offsetof(ts_peer_group, bufs), offsetof(ts_peer_group, state));
     return 0;
 }
 """)
@@ -258,7 +258,7 @@ int main(void) {
     assert geo == [ct.sizeof(Geometry), Geometry.N.offset, Geometry.size.offset, Geometry.x_stride.offset, Geometry.lb.offset,
                    Geometry.rb.offset]
     peer = [int(v) for v in out[1].split()]
-    assert peer == [ct.sizeof(PeerGroup), PeerGroup.epoch.offset, PeerGroup.capacity.offset, PeerGroup.bufs.offset, PeerGroup.flags.offset]
+    assert peer == [ct.sizeof(PeerGroup), PeerGroup.timeout_ns.offset, PeerGroup.capacity.offset, PeerGroup.bufs.offset, PeerGroup.state.offset]
 
 
 def _nhwc_emulate(native, xraw, wraw, wkind, wzp, zp, pad, borders, sm_count=148, max_grid_x=0, variant=0, ring_rows=0):
@@ -352,3 +352,35 @@ def test_channels_last_ring_kernel_program_matches_the_oracle(native, oracle_por
     x4 = rng.integers(0, 255, size=(1, 20, 4, 5), endpoint=True).astype(np.uint8)
     assert _nhwc_emulate(native, x4, np.full((20, 2), 128, np.uint8), 0, 128, 0, 0, None, variant=2) is None
     assert _nhwc_emulate(native, x4, np.full((20, 2), 128, np.uint8), 0, 128, 0, 0, None, variant=0) is not None
+
+
+def test_python_border_twin_matches_the_c_function():
+    """functional._resolve_borders (used only while torch.compile traces a cropping layer) against ts_check_borders."""
+    import random
+    import torchshifts  # noqa: F401
+    from torchshifts.extension import native
+    from torchshifts.functional import _resolve_borders
+    nat = native()
+    rnd = random.Random(0)
+    for _ in range(5000):
+        dim = rnd.randint(1, 3)
+        sizes = [rnd.randint(1, 12) for _ in range(dim)]
+        cuts = [[rnd.randint(-2, 14), rnd.randint(-2, 14)] for _ in range(dim)]
+        try:
+            want = tuple(list(v) for v in nat.check_borders(dim, sizes, [v for c in cuts for v in c]))
+        except RuntimeError:
+            want = "error"
+        try:
+            got = tuple(_resolve_borders(dim, sizes, cuts))
+        except RuntimeError:
+            got = "error"
+        assert got == want, (dim, sizes, cuts, got, want)
+
+
+def test_module_caches_its_crop_as_python_integers():
+    from torchshifts import Shift2d
+    m = Shift2d(4, emulate_dw={'kernel_size': 3, 'padding': 0, 'stride': 2})
+    assert m._border_ints() == [[1, 1], [1, 1]]
+    m.cut_borders = torch.tensor([[2, 0], [0, 1]])
+    assert m._border_ints() == [[2, 0], [0, 1]]
+    assert Shift2d(4)._border_ints() is None
