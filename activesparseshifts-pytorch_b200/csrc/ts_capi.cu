@@ -140,7 +140,7 @@ const char* ts_error_string(int status) {
 const char* ts_last_cuda_error(void) { return t_cuda_error; }
 int ts_last_kernel_path(void) { return t_last_path; }
 int ts_set_kernel_path(int path) {
-    if (path < 0 || path > 3) return -1;
+    if (path < 0 || path > 5 || path == TS_PATH_NHWC) return -1;
     return g_forced_path.exchange(path);
 }
 uint64_t ts_launch_count(void) { return (uint64_t)g_launches.load(); }
@@ -165,6 +165,10 @@ int ts_set_tuning(const char* spec) {
         else if (!strcmp(key, "tma_stage_kb")) t.tma_stage_kb = val;
         else if (!strcmp(key, "nhwc_variant")) t.nhwc_variant = val;
         else if (!strcmp(key, "nhwc_ring_rows")) t.nhwc_ring_rows = val;
+        else if (!strcmp(key, "use_halo")) t.use_halo = val != 0;
+        else if (!strcmp(key, "halo")) t.halo = val;
+        else if (!strcmp(key, "halo_stages")) t.halo_stages = val;
+        else if (!strcmp(key, "halo_warps")) t.halo_warps = val;
         else return TS_ERR_INVALID_ARGUMENT;
         p += n;
         while (*p == ',' || *p == ' ') ++p;
@@ -172,7 +176,8 @@ int ts_set_tuning(const char* spec) {
     if (t.stages < 0 || t.stages > 8 || t.stage_kb < 0 || t.stage_kb > 220 || t.warps < 1 || t.warps > 31 ||
         t.ctas_per_sm < 1 || t.ctas_per_sm > 8 || t.chunk_planes < 0 || t.tma_stages < 0 || t.tma_stages > 32 ||
         t.tma_ctas_per_sm < 0 || t.tma_ctas_per_sm > 8 || t.tma_warps < 0 || t.tma_warps > 31 || t.tma_stage_kb < 0 ||
-        t.tma_stage_kb > 220 || t.nhwc_variant < 0 || t.nhwc_variant > 2 || t.nhwc_ring_rows < 0)
+        t.tma_stage_kb > 220 || t.nhwc_variant < 0 || t.nhwc_variant > 2 || t.nhwc_ring_rows < 0 || t.halo < 0 || t.halo > 16 ||
+        t.halo_stages < 0 || t.halo_stages > 32 || t.halo_warps < 0 || t.halo_warps > 15)
         return TS_ERR_INVALID_ARGUMENT;
     tuning() = t;
     g_tuning_epoch.fetch_add(1);
@@ -240,6 +245,14 @@ int ts_shift_forward(const ts_geometry* gin, int dtype, int padding, int active,
         }
     }
     if (forced == TS_PATH_TMA) return TS_ERR_UNSUPPORTED;
+    if (active && ((forced == TS_PATH_NONE && tuning().use_halo) || forced == TS_PATH_HALO)) {
+        const HaloPlan hp = plan_halo(g, 1, 1, dtype, x_is_dense(g), x, y, nullptr, sms, forced == TS_PATH_HALO);
+        if (hp.ok) {
+            t_last_path = TS_PATH_HALO;
+            return halo_active_forward(g, hp, x, weights, y, s);
+        }
+    }
+    if (forced == TS_PATH_HALO) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
     if (forced != TS_PATH_GENERIC) plan = plan_staged(g, active ? 1 : 0, active, es, dtype, x_is_dense(g), x, y, nullptr, sms);
@@ -282,6 +295,13 @@ size_t ts_shift_backward_workspace_bytes(const ts_geometry* gin, int dtype) {
             const TmaPlan tp = plan_tma(gz, 2, active, elem_size(dtype), dtype, true, 0ull, nullptr, nullptr, nullptr, sms);
             if (tp.ok && (size_t)tp.slots > slots) slots = (size_t)tp.slots;
         }
+        for (int pad = 0; pad < 2; ++pad)
+            for (int active = 0; active < 2; ++active) {
+                Geo gh = g;
+                gh.pad = pad;
+                const HaloPlan hp = plan_halo(gh, 2, active, dtype, true, nullptr, nullptr, nullptr, sms, true);
+                if (hp.ok && (size_t)hp.slots > slots) slots = (size_t)hp.slots;
+            }
         bytes = slots * (size_t)(g.C * g.dim) * sizeof(double) + 16;
     }
     last_geo = *gin; last_dtype = dtype; last_epoch = epoch; last_bytes = bytes;
@@ -325,6 +345,14 @@ static int backward_impl(const ts_geometry* gin, int dtype, int padding, int act
         }
     }
     if (forced == TS_PATH_TMA) return TS_ERR_UNSUPPORTED;
+    if ((forced == TS_PATH_NONE && tuning().use_halo) || forced == TS_PATH_HALO) {
+        const HaloPlan hp = plan_halo(g, 2, active, dtype, x_is_dense(g), x, grad_input, grad, sms, forced == TS_PATH_HALO);
+        if (hp.ok) {
+            t_last_path = TS_PATH_HALO;
+            return halo_backward(g, hp, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, peers, s);
+        }
+    }
+    if (forced == TS_PATH_HALO) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
     if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 2, active, es, dtype, x_is_dense(g), x, grad_input, grad, sms);
@@ -380,7 +408,7 @@ int ts_qshift_forward(const ts_geometry* gin, int elem_bytes, int padding, int64
             return tma_gather(g, tp, WK_QUANT, xq, yq, elem_bytes, qweights, qweight_kind, weight_zero_point, s);
         }
     }
-    if (forced == TS_PATH_TMA) return TS_ERR_UNSUPPORTED;
+    if (forced == TS_PATH_TMA || forced == TS_PATH_HALO) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
     if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 0, 0, elem_bytes, -1, x_is_dense(g), xq, yq, nullptr, sms);

@@ -106,6 +106,8 @@ TS_HD int remap_bounded(int idx, int len, int pad) {
 
 // One axis of get_shifted_value: a size-1 axis always maps to 0.
 TS_HD int axis_index(int idx, int len, int pad) { return len == 1 ? 0 : remap_bounded(idx, len, pad); }
+// same with the literal (division) formula: valid for ANY index, not only idx = pos - reduce_shift(..) (+1)
+TS_HD int axis_index_literal(int idx, int len, int pad) { return len == 1 ? 0 : remap_literal(idx, len, pad); }
 
 // ------------------------------------------------------------------------------------------
 // Unfused arithmetic (the oracle is compiled without FMA; active forward / grad_input must be

@@ -1,0 +1,873 @@
+// ts_halo.cu -- the fp32 arithmetic kernels (active forward, backward) for EVERY padding mode and border crop on
+// 2-D planes and 3-D volumes: whole slabs are staged in shared memory WITH a halo, the halo is filled according to
+// the padding rule, and after that every item is an interior item -- no index remapping, no validity masks, no
+// edge pass in the arithmetic loop.
+//
+// Layout of a staged slab ("tile"): (hr + rows + hr) x pitch fp32, the slab's rows at [hr, hr + rows), its columns at
+// [hc, hc + cols).  ONE TMA tensor load (cp.async.bulk.tensor.5d, box {pitch, hr + rows + hr, 1, 1, 1} at coordinates
+// (-hc, -hr, slab, c, n)) delivers it: the copy engine lays the rows out at the padded pitch and fills everything
+// outside the tensor with zeros -- which IS the halo under zeros padding.  For border / periodic / reflect /
+// symmetric the consumer warps overwrite the halo cells the unit's shift can reach with tile[P(r)][P(c)]
+// (reference index remap, ops/kernels/shifts_kernels.h:10-29; ~3 % of the cells for |shift| <= 1) and meet at a
+// named barrier; the slab axis of 3-D volumes is resolved by the PRODUCER, which loads slab P(a - s) into the stage
+// of iteration a (a slab coordinate outside the tensor makes the copy engine deliver a zero tile).
+//
+// 3-D volumes stream slab by slab through the ring: stage k of an image holds source slab k of x and of grad (plus
+// the unshifted grad slab k-1); a thread owns one (row pair, 16-byte column group) of the slab for the whole image,
+// keeps the windows of slab k-1 in REGISTERS and combines them with the windows of slab k: every slab is fetched
+// from L2/HBM once (the round-1 kernels re-read the +1 neighbour slab per tile) and read from shared memory once.
+// The trilinear arithmetic is evaluated separably per column of the 5-wide window (slab lerp, row lerp, then the
+// column lerp between adjacent columns): the reference's operations in the reference's order for forward /
+// grad_input (bit-exact, unfused: ops/kernels/interpolation.h:3-38), an FMA form for the tolerance-checked
+// grad_weight factors (interpolation.h:9-61, shifts_kernels.h:132-154).
+//
+// A channel whose shift reaches beyond the halo (|shift| > hr/hc, default 4) is served by an element-wise routine
+// inside the same kernel (global loads with the literal remap): always correct, fast for the shifts layers learn.
+//
+// CTA = nw consumer warps + 1 producer warp, persistent, one per SM; unit = (channel, chunk of images); grad_weight
+// partials per (chunk, warp) in fp64, fixed shuffle tree, pass 2 in ts_generic.cu -> deterministic, no atomics.
+#include <cuda.h>
+
+#include <cstring>
+
+#include "ts_kernels.h"
+#include "ts_ptx.cuh"
+
+namespace ts {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int SMEM_LIMIT = 232448;
+constexpr int MAXT = 512;
+constexpr int GUARD = 128;          // readable slack before / after the tiles of a stage (window pairs may start 16 bytes early)
+
+struct alignas(64) HArgs {
+    CUtensorMap map_x;       // x,    box {px, bpx, 1, 1, 1}
+    CUtensorMap map_g;       // grad, box {pg, bpg, 1, 1, 1}
+    CUtensorMap map_v;       // grad, box {OL, OB, 1, 1, 1}   (dense slab: unshifted grad of the 3-D backward)
+    Geo g;
+    const float* x;
+    const float* grad;
+    float* out;
+    const float* w;
+    double* partials;
+    int mode, active, dim;
+    int A, B, L, OA, OB, OL, lbA, lbB, lbL;   // per level (0 slab, 1 row, 2 column); 2-D: A = OA = 1
+    int IA, IB, IG, GP;                       // iteration space (output space forward, input space backward): slabs, rows, groups; padded groups
+    int RP;                                   // row pairs per slab = ceil(IB / 2)
+    int hr, hc;
+    int px, bpx, pg, bpg;
+    int tile_x, tile_g, tile_v;               // bytes between consecutive tiles (128-byte multiples)
+    int box_x, box_g, box_v;                  // bytes one TMA box delivers
+    int off_g, off_v;                         // byte offsets of the grad tiles / dense grad tiles inside a stage (after GUARD)
+    int stage_stride, stages, nw, nt, np;
+    int img_pairs, pairs;                     // RP * GP, np * RP * GP
+    int n_per_unit, units;
+    int need_fix;
+    FastDivU d_GP, d_img;
+};
+
+TS_D int level_axis(int level, int dim) { return level - (3 - dim); }
+
+struct UnitShift {
+    int sx[3], sg[3];      // per level; absent levels 0
+    float d[3];            // per TENSOR axis
+};
+
+TS_D UnitShift unit_shift(const HArgs& a, long long c) {
+    UnitShift u;
+    u.d[0] = u.d[1] = u.d[2] = 0.f;
+#pragma unroll
+    for (int lev = 0; lev < 3; ++lev) {
+        const int ax = level_axis(lev, a.dim);
+        u.sx[lev] = u.sg[lev] = 0;
+        if (ax < 0) continue;
+        long long iw;
+        float d;
+        const float wv = a.w[c * a.dim + ax];
+        if (a.mode == 1) split_forward<float>(wv, true, iw, d);
+        else split_backward<float>(wv, a.active != 0, iw, d);
+        u.d[ax] = d;
+        u.sx[lev] = reduce_shift(iw, a.g.S[ax], a.g.pad);
+        u.sg[lev] = reduce_shift(iw, a.g.OS[ax], a.g.pad);
+    }
+    return u;
+}
+
+// Where a unit's windows sit inside the tiles, and whether they fit the halo.
+struct UnitGeom {
+    int xr0, xc0;          // tile row / column of the x window of iteration (row 0, column 0)
+    int gr0, gc0;          // same for the grad window that feeds grad_input (backward)
+    int vr0, vc0;          // same for the unshifted grad window (2-D: inside the grad tile; 3-D: inside the dense tile)
+    bool fits;
+};
+
+TS_D UnitGeom unit_geom(const HArgs& a, const UnitShift& us) {
+    UnitGeom u;
+    const bool bwd = a.mode == 2;
+    u.xr0 = (bwd ? 0 : a.lbB) - us.sx[1] + a.hr;
+    u.xc0 = (bwd ? 0 : a.lbL) - us.sx[2] + a.hc;
+    // rows r .. r+1 for r in [0, IB), columns xc0 .. xc0 + 4*IG (the +1 neighbour of the last element)
+    bool ok = u.xr0 >= 0 && u.xr0 + a.IB <= a.bpx - 1 && u.xc0 >= 0 && u.xc0 + 4 * a.IG <= a.px - 1;
+    u.gr0 = u.gc0 = u.vr0 = u.vc0 = 0;
+    if (bwd) {
+        const int sgr = a.active ? -us.sg[1] : us.sg[1], sgc = a.active ? -us.sg[2] : us.sg[2];
+        const int ex = a.active ? 1 : 0;
+        u.gr0 = -a.lbB + sgr + a.hr;          // + input row b
+        u.gc0 = -a.lbL + sgc + a.hc;          // + input column
+        // only rows / columns inside the crop read the tile: ob in [0, OB), oj in [0, OL)
+        ok = ok && sgr + a.hr >= 0 && a.OB - 1 + sgr + a.hr + ex <= a.bpg - 1 && sgc + a.hc >= 0 && a.OL - 1 + sgc + a.hc + ex <= a.pg - 1;
+        if (a.dim == 3) { u.vr0 = -a.lbB; u.vc0 = -a.lbL; }
+        else { u.vr0 = -a.lbB + a.hr; u.vc0 = -a.lbL + a.hc; }
+    }
+    u.fits = ok;
+    return u;
+}
+
+// ---- window loads -----------------------------------------------------------------------------
+// 5 (or 4) consecutive fp32 starting `ws` words into the aligned 16-byte group at shared address `addr`.
+// WS >= 0: compile-time misalignment (free register renaming); WS = -1: run-time, a two-level select network.
+template <int WS>
+TS_D void load5(unsigned addr, int ws, float* out) {
+    const uint4 A = lds128(addr), B = lds128(addr + 16);
+    const float W[8] = {__uint_as_float(A.x), __uint_as_float(A.y), __uint_as_float(A.z), __uint_as_float(A.w),
+                        __uint_as_float(B.x), __uint_as_float(B.y), __uint_as_float(B.z), __uint_as_float(B.w)};
+    if constexpr (WS >= 0) {
+#pragma unroll
+        for (int t = 0; t < 5; ++t) out[t] = W[t + WS];
+    } else {
+        float U[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) U[i] = (ws & 1) ? W[i + 1] : W[i];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) out[t] = (ws & 2) ? U[t + 2] : U[t];
+    }
+}
+template <int WS>
+TS_D void load4(unsigned addr, int ws, float* out) {
+    if constexpr (WS == 0) {
+        const uint4 A = lds128(addr);
+        out[0] = __uint_as_float(A.x); out[1] = __uint_as_float(A.y); out[2] = __uint_as_float(A.z); out[3] = __uint_as_float(A.w);
+    } else {
+        float t5[5];
+        load5<WS>(addr, ws, t5);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) out[t] = t5[t];
+    }
+}
+
+// ---- halo fill --------------------------------------------------------------------------------
+// Cells of the needed extended range [rn_lo, rn_hi] x [cn_lo, cn_hi] that lie outside [0, rows) x [0, cols) take
+// tile[P(r)][P(c)].  Writers touch halo cells only, readers interior cells only: one pass, no ordering inside.
+TS_D void fill_halo(float* tile, int pitch, int rows, int cols, int hr, int hc, int pad, int rn_lo, int rn_hi, int cn_lo, int cn_hi,
+                    int tid, int nt) {
+    const int nrt = rn_lo < 0 ? -rn_lo : 0, nrb = rn_hi > rows - 1 ? rn_hi - (rows - 1) : 0;
+    const int nct = cn_lo < 0 ? -cn_lo : 0, ncb = cn_hi > cols - 1 ? cn_hi - (cols - 1) : 0;
+    const int wc = cn_hi - cn_lo + 1, nch = nct + ncb;
+    const int nA = (nrt + nrb) * wc, total = nA + rows * nch;
+    for (int idx = tid; idx < total; idx += nt) {
+        int r, c;
+        if (idx < nA) {
+            const int ri = idx / wc, ci = idx - ri * wc;
+            r = ri < nrt ? rn_lo + ri : rows + (ri - nrt);
+            c = cn_lo + ci;
+        } else {
+            const int j = idx - nA;
+            r = j / nch;
+            const int k = j - r * nch;
+            c = k < nct ? cn_lo + k : cols + (k - nct);
+        }
+        const int sr = axis_index_literal(r, rows, pad), sc = axis_index_literal(c, cols, pad);
+        tile[(r + hr) * pitch + c + hc] = tile[(sr + hr) * pitch + sc + hc];
+    }
+}
+
+// ---- arithmetic -------------------------------------------------------------------------------
+// exact (unfused) column values of the reference's interpolation nest: rows / slabs first, columns last.
+// 3-D: V00 (slab a, row r), V10 (slab a+1, row r), V01 (slab a, row r+1), V11 (slab a+1, row r+1)
+TS_D float col3(float v00, float v10, float v01, float v11, float d0, float d1) {
+    return lerp<float>(lerp<float>(v00, v10, d0), lerp<float>(v01, v11, d0), d1);
+}
+
+// grad_weight terms of one item, 3-D, FMA form (tolerance-checked): windows of x over 5 columns, gv over 4
+TS_D void wp3(const float* x00, const float* x10, const float* x01, const float* x11, const float* gv, const float* d, float* ts) {
+    float hv[5], kv[5];
+    const float omd2 = 1.f - d[2];
+    hv[0] = omd2 * gv[0]; kv[0] = -gv[0];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) { hv[c] = fmaf(d[2], gv[c - 1], omd2 * gv[c]); kv[c] = gv[c - 1] - gv[c]; }
+    hv[4] = d[2] * gv[3]; kv[4] = gv[3];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const float a0 = fmaf(d[0], x10[c] - x00[c], x00[c]), a1 = fmaf(d[0], x11[c] - x01[c], x01[c]);
+        const float g1c = a1 - a0, pc = fmaf(d[1], g1c, a0);
+        const float e0 = x01[c] - x00[c], e1 = x11[c] - x10[c];
+        const float g0c = fmaf(d[1], e1 - e0, e0);
+        ts[0] = fmaf(g0c, hv[c], ts[0]);
+        ts[1] = fmaf(g1c, hv[c], ts[1]);
+        ts[2] = fmaf(pc, kv[c], ts[2]);
+    }
+}
+// 2-D: x0 (row r), x1 (row r+1)
+TS_D void wp2(const float* x0, const float* x1, const float* gv, const float* d, float* ts) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float p = x0[t + 1] - x0[t], q = (x1[t + 1] - x1[t]) - p;
+        ts[0] = fmaf(gv[t], fmaf(d[1], q, p), ts[0]);
+        ts[1] = fmaf(gv[t], fmaf(d[0], q, p), ts[1]);
+    }
+}
+
+// ---- element-wise routine for channels whose shift does not fit the halo ------------------------
+// (global loads, literal remap; mirrors ts_generic.cu.  All consumer threads of the CTA share the unit.)
+template <int DIM>
+TS_D void fetch8(const float* __restrict__ vol, const int* idx, const int* sizes, int pad, float* v) {
+    int t[DIM][2];
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) {
+        t[ax][0] = axis_index_literal(idx[ax], sizes[ax], pad);
+        t[ax][1] = axis_index_literal(idx[ax] + 1, sizes[ax], pad);
+    }
+#pragma unroll
+    for (int q = 0; q < (1 << DIM); ++q) {
+        bool ok = true;
+        long long off = 0;
+#pragma unroll
+        for (int ax = 0; ax < DIM; ++ax) {
+            const int i = t[ax][(q >> ax) & 1];
+            ok = ok && i >= 0;
+            off = off * sizes[ax] + i;
+        }
+        v[q] = ok ? vol[off] : 0.f;
+    }
+}
+
+template <int DIM>
+TS_D void slow_forward(const HArgs& a, int c, int n0, int n1, const UnitShift& us, int tid, int nt) {
+    const Geo& g = a.g;
+    const int plane = (int)g.out_plane;
+    int sx[DIM];
+    float d[3] = {us.d[0], us.d[1], us.d[2]};
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) sx[ax] = us.sx[ax + 3 - DIM];
+    for (int n = n0; n < n1; ++n) {
+        const float* xp = a.x + ((long long)n * g.C + c) * g.in_plane;
+        float* yp = a.out + ((long long)n * g.C + c) * g.out_plane;
+        for (int e = tid; e < plane; e += nt) {
+            int o[DIM], rem = e, idx[DIM];
+#pragma unroll
+            for (int ax = DIM - 1; ax >= 0; --ax) { o[ax] = rem % g.OS[ax]; rem /= g.OS[ax]; }
+#pragma unroll
+            for (int ax = 0; ax < DIM; ++ax) idx[ax] = o[ax] + g.lb[ax] - sx[ax];
+            float v[8];
+            fetch8<DIM>(xp, idx, g.S, g.pad, v);
+            yp[e] = interpolate<float, DIM>(v, d);
+        }
+    }
+}
+
+template <int DIM, bool ACTIVE>
+TS_D void slow_backward(const HArgs& a, int c, int n0, int n1, const UnitShift& us, int tid, int nt, double* acc) {
+    const Geo& g = a.g;
+    const int plane = (int)g.in_plane;
+    int sx[DIM], sg[DIM];
+    float d[3] = {us.d[0], us.d[1], us.d[2]};
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) { sx[ax] = us.sx[ax + 3 - DIM]; sg[ax] = us.sg[ax + 3 - DIM]; }
+    for (int n = n0; n < n1; ++n) {
+        const float* xp = a.x + ((long long)n * g.C + c) * g.in_plane;
+        const float* gp = a.grad + ((long long)n * g.C + c) * g.out_plane;
+        float* gip = a.out + ((long long)n * g.C + c) * g.in_plane;
+        for (int e = tid; e < plane; e += nt) {
+            int pos[DIM], rem = e, o[DIM];
+#pragma unroll
+            for (int ax = DIM - 1; ax >= 0; --ax) { pos[ax] = rem % g.S[ax]; rem /= g.S[ax]; }
+            bool pass = true;
+            long long goff = 0;
+#pragma unroll
+            for (int ax = 0; ax < DIM; ++ax) {
+                o[ax] = pos[ax] - g.lb[ax];
+                pass = pass && o[ax] >= 0 && o[ax] < g.OS[ax];
+                goff = goff * g.OS[ax] + o[ax];
+            }
+            float r = 0.f;
+            if (pass) {
+                const float gv = gp[goff];
+                int idx[DIM];
+#pragma unroll
+                for (int ax = 0; ax < DIM; ++ax) idx[ax] = pos[ax] - sx[ax];
+                float v[8], wg[3];
+                fetch8<DIM>(xp, idx, g.S, g.pad, v);
+                weight_partials<float, DIM>(v, d, wg);
+#pragma unroll
+                for (int ax = 0; ax < DIM; ++ax) acc[ax] += (double)(gv * wg[ax]);
+                if (ACTIVE) {
+#pragma unroll
+                    for (int ax = 0; ax < DIM; ++ax) idx[ax] = o[ax] - sg[ax];
+                    fetch8<DIM>(gp, idx, g.OS, g.pad, v);
+                    r = interpolate<float, DIM>(v, d);
+                } else {
+                    bool in = true;
+                    long long off = 0;
+#pragma unroll
+                    for (int ax = 0; ax < DIM; ++ax) {
+                        const int t = axis_index_literal(o[ax] + sg[ax], g.OS[ax], g.pad);
+                        in = in && t >= 0;
+                        off = off * g.OS[ax] + t;
+                    }
+                    r = in ? gp[off] : 0.f;
+                }
+            }
+            gip[e] = r;
+        }
+    }
+}
+
+// ---- producer ---------------------------------------------------------------------------------
+TS_D int slab_coord(int idx, int len, int pad) {
+    const int t = axis_index_literal(idx, len, pad);
+    return t < 0 ? -1 : t;                 // outside under zeros padding: the copy engine delivers a zero tile
+}
+
+TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty) {
+    int s = 0, kk = 0;
+    const int C = (int)a.g.C, N = (int)a.g.N;
+    const bool bwd = a.mode == 2;
+    const int steps = a.dim == 3 ? a.IA + 1 : 1;
+    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
+        const int chunk = u / C, c = u - chunk * C;
+        const int n0 = chunk * a.n_per_unit;
+        const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
+        const UnitShift us = unit_shift(a, c);
+        if (!unit_geom(a, us).fits) continue;              // consumers take the element-wise routine for this unit
+        for (int nb = n0; nb < n1; nb += a.np) {
+            const int npl = n1 - nb < a.np ? n1 - nb : a.np;
+            for (int k = 0; k < steps; ++k) {
+                if (kk > 0) mbar_wait(&empty[s], (unsigned)((kk - 1) & 1));
+                unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
+                const bool has_g = bwd && (a.dim == 2 || a.active || k >= 1);
+                const bool has_v = bwd && a.dim == 3 && k >= 1;
+                mbar_expect_tx(&full[s], (unsigned)npl * (unsigned)(a.box_x + (has_g ? a.box_g : 0) + (has_v ? a.box_v : 0)));
+                int xs = 0, gs = 0, vs = 0;
+                if (a.dim == 3) {
+                    xs = slab_coord((bwd ? k : k + a.lbA) - us.sx[0], a.A, a.g.pad);
+                    if (bwd) {
+                        gs = a.active ? slab_coord(k - a.lbA - us.sg[0], a.OA, a.g.pad) : slab_coord(k - 1 - a.lbA + us.sg[0], a.OA, a.g.pad);
+                        const int oa = k - 1 - a.lbA;
+                        vs = (oa >= 0 && oa < a.OA) ? oa : -1;
+                    }
+                }
+                for (int pl = 0; pl < npl; ++pl) {
+                    tma_load_5d(st + (size_t)pl * a.tile_x, &a.map_x, -a.hc, -a.hr, xs, c, nb + pl, &full[s]);
+                    if (has_g) tma_load_5d(st + a.off_g + (size_t)pl * a.tile_g, &a.map_g, -a.hc, -a.hr, gs, c, nb + pl, &full[s]);
+                    if (has_v) tma_load_5d(st + a.off_v + (size_t)pl * a.tile_v, &a.map_v, 0, 0, vs, c, nb + pl, &full[s]);
+                }
+                if (++s == a.stages) { s = 0; ++kk; }
+            }
+        }
+    }
+}
+
+// ---- consumers ----------------------------------------------------------------------------------
+// pair index -> (image of the stage, first row of the pair, column group); false = padding lane
+struct Pair { int pl, r, cg; };
+TS_D bool decode_pair(const HArgs& a, int p, Pair& q) {
+    q.pl = 0;
+    int rem = p;
+    if (a.np > 1) { q.pl = (int)fdivu((unsigned)p, a.d_img); rem = p - q.pl * a.img_pairs; }
+    const int rp = (int)fdivu((unsigned)rem, a.d_GP);
+    q.cg = rem - rp * a.GP;
+    q.r = 2 * rp;
+    return q.cg < a.IG;
+}
+
+// Everything about one pair that does not change from stage to stage of a unit.
+struct PairCtx {
+    unsigned xo, go, vo;       // byte offsets (inside one image's tile) of the aligned group of the pair's FIRST row
+    unsigned out_off;          // byte offset of the first row's 16-byte output inside the (image, slab 0) output
+    int rows;                  // rows of the pair that exist (1 or 2), 0: padding lane
+    unsigned cmask;            // bit t of nibble j: element t of row j takes part (inside the crop)
+};
+
+template <int MODE>
+TS_D PairCtx pair_ctx(const HArgs& a, const UnitGeom& ug, const Pair& q, bool valid) {
+    PairCtx p;
+    p.rows = !valid ? 0 : (q.r + 1 < a.IB ? 2 : 1);
+    p.xo = (unsigned)(((q.r + ug.xr0) * a.px + ((4 * q.cg + ug.xc0) & ~3)) * 4);
+    p.out_off = (unsigned)((q.r * a.IG + q.cg) * 16);
+    p.go = p.vo = 0;
+    p.cmask = 0xffu;
+    if (MODE == 2) {
+        unsigned m = 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int ob = q.r + j - a.lbB;
+            if (ob < 0 || ob >= a.OB) continue;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int oj = 4 * q.cg + t - a.lbL;
+                if (oj >= 0 && oj < a.OL) m |= 1u << (4 * j + t);
+            }
+        }
+        p.cmask = m;
+        // A pair with no row inside the crop never reads the grad tiles.  Otherwise the addresses are exact: a row of
+        // the pair outside the crop (masked) may then lie one row before / after its tile -- still inside the stage
+        // (tiles are preceded by other tiles or the head guard and followed by a tail of one row pitch).
+        if (m) {
+            const int vp = a.dim == 3 ? a.OL : a.pg;
+            p.go = (unsigned)(((q.r + ug.gr0) * a.pg + ((4 * q.cg + ug.gc0) & ~3)) * 4);
+            p.vo = (unsigned)(((q.r + ug.vr0) * vp + ((4 * q.cg + ug.vc0) & ~3)) * 4);
+        }
+    }
+    return p;
+}
+
+struct Ring {
+    int s;
+    unsigned phase;
+};
+
+template <int DIM, int MODE, bool ACTIVE>
+struct Body {
+    const HArgs& a;
+    const int tid, nt, wid, lane;
+    UnitShift us;
+    UnitGeom ug;
+    int wsx, wsg, wsv;
+    double acc[3];
+
+    TS_D Body(const HArgs& a_, int tid_, int nt_, int wid_, int lane_) : a(a_), tid(tid_), nt(nt_), wid(wid_), lane(lane_) {}
+
+    TS_D void begin_unit(int c) {
+        us = unit_shift(a, c);
+        ug = unit_geom(a, us);
+        wsx = ug.xc0 & 3; wsg = ug.gc0 & 3; wsv = ug.vc0 & 3;
+        acc[0] = acc[1] = acc[2] = 0.0;
+    }
+    TS_D void end_unit(int c, int chunk) {
+        if (MODE != 2) return;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) a.partials[((long long)chunk * a.nw + wid) * (a.g.C * DIM) + (long long)c * DIM + k] = v;
+        }
+    }
+
+    // halo cells of every tile of the stage (padding != zeros), then a barrier among the consumer warps
+    TS_D void fix_stage(unsigned char* st, int npl, bool has_g) const {
+        if (!a.need_fix) return;
+        const bool bwd = MODE == 2;
+        const int xr_lo = (bwd ? 0 : a.lbB) - us.sx[1], xc_lo = (bwd ? 0 : a.lbL) - us.sx[2];
+        for (int pl = 0; pl < npl; ++pl) {
+            fill_halo((float*)(st + (size_t)pl * a.tile_x), a.px, a.B, a.L, a.hr, a.hc, a.g.pad, xr_lo, xr_lo + a.IB, xc_lo, xc_lo + 4 * a.IG,
+                      tid, nt);
+            if (bwd && has_g) {
+                const int sgr = ACTIVE ? -us.sg[1] : us.sg[1], sgc = ACTIVE ? -us.sg[2] : us.sg[2], ex = ACTIVE ? 1 : 0;
+                fill_halo((float*)(st + a.off_g + (size_t)pl * a.tile_g), a.pg, a.OB, a.OL, a.hr, a.hc, a.g.pad, sgr, a.OB - 1 + sgr + ex,
+                          sgc, a.OL - 1 + sgc + ex, tid, nt);
+            }
+        }
+        fence_proxy_async();                 // the next TMA load of this stage must not overtake these generic-proxy writes
+        named_barrier(1, nt);
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // 2-D: a stage = np images, every pair is independent
+    template <int WSX, int WSG, int WSV>
+    TS_D void step2(const unsigned char* st, unsigned char* dst, int npl, float* ts) const {
+        const unsigned sx = shared_addr(st), sgb = sx + a.off_g;
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        const int total = npl * a.img_pairs;
+        const long long img_out = a.g.C * (MODE == 2 ? a.g.in_plane : a.g.out_plane) * 4;
+        for (int p = tid; p < total; p += nt) {
+            Pair q;
+            if (!decode_pair(a, p, q)) continue;
+            const PairCtx pc = pair_ctx<MODE>(a, ug, q, true);
+            unsigned char* o = dst + (long long)q.pl * img_out + pc.out_off;
+            const unsigned xa = sx + q.pl * a.tile_x + pc.xo;
+            float X[3][5];
+            load5<WSX>(xa, wsx, X[0]);
+            load5<WSX>(xa + a.px * 4, wsx, X[1]);
+            if (pc.rows == 2) load5<WSX>(xa + 2 * a.px * 4, wsx, X[2]);
+            if (MODE == 1) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j < pc.rows) {
+                        float R[5], y[4];
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) R[t] = lerp<float>(X[j][t], X[j + 1][t], d[0]);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) y[t] = lerp<float>(R[t], R[t + 1], d[1]);
+                        __stcs((float4*)(o + j * a.IG * 16), make_float4(y[0], y[1], y[2], y[3]));
+                    }
+                }
+                continue;
+            }
+            const unsigned ga = sgb + q.pl * a.tile_g + pc.go, va = sgb + q.pl * a.tile_g + pc.vo;
+            float G[3][5];
+            if (ACTIVE && pc.cmask) {
+                load5<WSG>(ga, wsg, G[0]);
+                load5<WSG>(ga + a.pg * 4, wsg, G[1]);
+                if (pc.rows == 2) load5<WSG>(ga + 2 * a.pg * 4, wsg, G[2]);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j >= pc.rows) continue;
+                const unsigned m = (pc.cmask >> (4 * j)) & 15u;
+                float y[4] = {0.f, 0.f, 0.f, 0.f};
+                if (m) {
+                    float gv[4];
+                    load4<WSV>(va + j * a.pg * 4, wsv, gv);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) gv[t] = (m >> t) & 1u ? gv[t] : 0.f;
+                    wp2(X[j], X[j + 1], gv, d, ts);
+                    if (ACTIVE) {
+                        float R[5];
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) R[t] = lerp<float>(G[j][t], G[j + 1][t], d[0]);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) y[t] = lerp<float>(R[t], R[t + 1], d[1]);
+                    } else {
+                        load4<WSG>(ga + j * a.pg * 4, wsg, y);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) y[t] = (m >> t) & 1u ? y[t] : 0.f;
+                }
+                __stcs((float4*)(o + j * a.IG * 16), make_float4(y[0], y[1], y[2], y[3]));
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // 3-D: one pair per thread for the whole image; windows of the previous slab stay in registers
+    struct Carry {
+        float X[3][5], G[3][5];
+    };
+
+    template <int WSX, int WSG>
+    TS_D void load_slab(const unsigned char* st, const Pair& q, const PairCtx& pc, bool has_g, float (*Xn)[5], float (*Gn)[5]) const {
+        const unsigned xa = shared_addr(st) + q.pl * a.tile_x + pc.xo;
+        load5<WSX>(xa, wsx, Xn[0]);
+        load5<WSX>(xa + a.px * 4, wsx, Xn[1]);
+        if (pc.rows == 2) load5<WSX>(xa + 2 * a.px * 4, wsx, Xn[2]);
+        if (MODE == 2 && ACTIVE && has_g && pc.cmask) {
+            const unsigned ga = shared_addr(st) + a.off_g + q.pl * a.tile_g + pc.go;
+            load5<WSG>(ga, wsg, Gn[0]);
+            load5<WSG>(ga + a.pg * 4, wsg, Gn[1]);
+            if (pc.rows == 2) load5<WSG>(ga + 2 * a.pg * 4, wsg, Gn[2]);
+        }
+    }
+
+    // iteration slab `it` (= k - 1) of the image: carry = slab it, stage = slab it + 1
+    template <int WSX, int WSG, int WSV>
+    TS_D void step3(const unsigned char* st, unsigned char* dst_img, int k, const Pair& q, const PairCtx& pc, Carry& cy, float* ts) const {
+        if (pc.rows == 0) return;
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        float Xn[3][5], Gn[3][5];
+        load_slab<WSX, WSG>(st, q, pc, true, Xn, Gn);
+        if (k >= 1) {
+            const int it = k - 1;
+            const long long img_out = a.g.C * (MODE == 2 ? a.g.in_plane : a.g.out_plane) * 4;
+            unsigned char* o = dst_img + (long long)q.pl * img_out + (long long)it * a.IB * a.IG * 16 + pc.out_off;
+            if (MODE == 1) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j < pc.rows) {
+                        float P[5], y[4];
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) P[t] = col3(cy.X[j][t], Xn[j][t], cy.X[j + 1][t], Xn[j + 1][t], d[0], d[1]);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
+                        __stcs((float4*)(o + j * a.IG * 16), make_float4(y[0], y[1], y[2], y[3]));
+                    }
+                }
+            } else {
+                const int oa = it - a.lbA;
+                const bool slab_pass = oa >= 0 && oa < a.OA;
+                const unsigned sb = shared_addr(st);
+                const unsigned va = sb + a.off_v + q.pl * a.tile_v + pc.vo;
+                const unsigned ga = sb + a.off_g + q.pl * a.tile_g + pc.go;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j >= pc.rows) continue;
+                    const unsigned m = slab_pass ? (pc.cmask >> (4 * j)) & 15u : 0u;
+                    float y[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (m) {
+                        float gv[4];
+                        load4<WSV>(va + j * a.OL * 4, wsv, gv);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) gv[t] = (m >> t) & 1u ? gv[t] : 0.f;
+                        wp3(cy.X[j], Xn[j], cy.X[j + 1], Xn[j + 1], gv, d, ts);
+                        if (ACTIVE) {
+                            float P[5];
+#pragma unroll
+                            for (int t = 0; t < 5; ++t) P[t] = col3(cy.G[j][t], Gn[j][t], cy.G[j + 1][t], Gn[j + 1][t], d[0], d[1]);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
+                        } else {
+                            load4<WSG>(ga + j * a.pg * 4, wsg, y);
+                        }
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) y[t] = (m >> t) & 1u ? y[t] : 0.f;
+                    }
+                    __stcs((float4*)(o + j * a.IG * 16), make_float4(y[0], y[1], y[2], y[3]));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                cy.X[j][t] = Xn[j][t];
+                if (MODE == 2 && ACTIVE) cy.G[j][t] = Gn[j][t];
+            }
+    }
+
+    // one image group (np images) of the unit, all its stages; WS* < 0: run-time window misalignment
+    template <int WSX, int WSG, int WSV>
+    TS_D void run_images(unsigned char* smem, uint64_t* full, uint64_t* empty, Ring& ring, unsigned char* dst_img, int npl, float* ts) {
+        if constexpr (DIM == 2) {
+            unsigned char* st = smem + (size_t)ring.s * a.stage_stride + GUARD;
+            mbar_wait(&full[ring.s], ring.phase);
+            fix_stage(st, npl, true);
+            step2<WSX, WSG, WSV>(st, dst_img, npl, ts);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[ring.s]);
+            if (++ring.s == a.stages) { ring.s = 0; ring.phase ^= 1u; }
+        } else {
+            Pair q;
+            const bool valid = tid < npl * a.img_pairs && decode_pair(a, tid, q);
+            if (!valid) { q.pl = 0; q.r = 0; q.cg = 0; }
+            const PairCtx pc = pair_ctx<MODE>(a, ug, q, valid);
+            Carry cy;
+            for (int k = 0; k <= a.IA; ++k) {
+                unsigned char* st = smem + (size_t)ring.s * a.stage_stride + GUARD;
+                mbar_wait(&full[ring.s], ring.phase);
+                fix_stage(st, npl, MODE == 2 && (ACTIVE || k >= 1));
+                step3<WSX, WSG, WSV>(st, dst_img, k, q, pc, cy, ts);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[ring.s]);
+                if (++ring.s == a.stages) { ring.s = 0; ring.phase ^= 1u; }
+            }
+        }
+    }
+
+    TS_D void run_unit(unsigned char* smem, uint64_t* full, uint64_t* empty, Ring& ring, int c, int n0, int n1) {
+        if (!ug.fits) {
+            if (MODE == 1) slow_forward<DIM>(a, c, n0, n1, us, tid, nt);
+            else slow_backward<DIM, ACTIVE>(a, c, n0, n1, us, tid, nt, acc);
+            return;
+        }
+        const long long plane_bytes = (MODE == 2 ? a.g.in_plane : a.g.out_plane) * 4;
+        // fast instantiations: every window misalignment known at compile time from the x window's
+        const bool derived = MODE == 1 || (wsv == 0 && wsg == (ACTIVE ? wsx : ((4 - wsx) & 3)));
+        for (int nb = n0; nb < n1; nb += a.np) {
+            const int npl = n1 - nb < a.np ? n1 - nb : a.np;
+            unsigned char* dst = (unsigned char*)a.out + ((long long)nb * a.g.C + c) * plane_bytes;
+            float ts[3] = {0.f, 0.f, 0.f};
+            if (derived) {
+                switch (wsx) {
+                case 0: run_images<0, 0, 0>(smem, full, empty, ring, dst, npl, ts); break;
+                case 1: run_images<1, ACTIVE ? 1 : 3, 0>(smem, full, empty, ring, dst, npl, ts); break;
+                case 2: run_images<2, 2, 0>(smem, full, empty, ring, dst, npl, ts); break;
+                default: run_images<3, ACTIVE ? 3 : 1, 0>(smem, full, empty, ring, dst, npl, ts); break;
+                }
+            } else {
+                run_images<-1, -1, -1>(smem, full, empty, ring, dst, npl, ts);
+            }
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) acc[k] += (double)ts[k];     // fp32 inside an image group, fp64 across
+        }
+    }
+};
+
+template <int DIM, int MODE, bool ACTIVE>
+__global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
+    uint64_t* empty = full + a.stages;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)a.nw); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
+    Body<DIM, MODE, ACTIVE> body(a, threadIdx.x, a.nt, wid, lane);
+    Ring ring = {0, 0u};
+    const int C = (int)a.g.C, N = (int)a.g.N;
+    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
+        const int chunk = u / C, c = u - chunk * C;
+        const int n0 = chunk * a.n_per_unit;
+        const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
+        body.begin_unit(c);
+        body.run_unit(smem, full, empty, ring, c, n0, n1);
+        body.end_unit(c, chunk);
+    }
+}
+
+long long round_up(long long v, long long q) { return (v + q - 1) / q * q; }
+
+template <class K>
+int launch(K kernel, const HArgs& a, const HaloPlan& p, cudaStream_t s) {
+    if (!ensure_dynamic_smem((const void*)kernel, p.smem_bytes)) return check_launch();
+    kernel<<<p.grid, (p.warps + 1) * 32, p.smem_bytes, s>>>(a);
+    note_launch();
+    return check_launch();
+}
+
+bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, const void* x, const void* grad, void* out, const void* w,
+               double* partials, HArgs* o) {
+    HArgs& a = *o;
+    memset(&a, 0, sizeof(a));
+    const int d = g.dim;
+    a.g = g;
+    a.x = (const float*)x; a.grad = (const float*)grad; a.out = (float*)out; a.w = (const float*)w; a.partials = partials;
+    a.mode = mode; a.active = active; a.dim = d;
+    a.A = d == 3 ? g.S[0] : 1;   a.OA = d == 3 ? g.OS[0] : 1;   a.lbA = d == 3 ? g.lb[0] : 0;
+    a.B = g.S[d - 2];            a.OB = g.OS[d - 2];            a.lbB = g.lb[d - 2];
+    a.L = g.S[d - 1];            a.OL = g.OS[d - 1];            a.lbL = g.lb[d - 1];
+    a.IA = mode == 2 ? a.A : a.OA;
+    a.IB = mode == 2 ? a.B : a.OB;
+    a.IG = (mode == 2 ? a.L : a.OL) / 4;
+    a.GP = p.GP;
+    a.RP = (a.IB + 1) / 2;
+    a.hr = p.hr; a.hc = p.hc;
+    a.px = p.px; a.bpx = p.bpx; a.pg = p.pg; a.bpg = p.bpg;
+    a.tile_x = p.tile_x; a.tile_g = p.tile_g; a.tile_v = p.tile_v;
+    a.box_x = p.px * p.bpx * 4; a.box_g = p.pg * p.bpg * 4; a.box_v = a.OL * a.OB * 4;
+    a.np = p.np;
+    a.off_g = p.np * p.tile_x;
+    a.off_v = a.off_g + p.np * p.tile_g;
+    a.stage_stride = p.stage_stride; a.stages = p.stages; a.nw = p.warps; a.nt = p.warps * 32;
+    a.img_pairs = a.RP * a.GP;
+    a.pairs = a.np * a.img_pairs;
+    a.n_per_unit = p.n_per_unit; a.units = p.units;
+    a.need_fix = g.pad != TS_PAD_ZEROS;
+    a.d_GP = make_fastdivu((unsigned)a.GP);
+    a.d_img = make_fastdivu((unsigned)a.img_pairs);
+    if (!make_tensor_map5(&a.map_x, x, 4, g.N, g.C, a.A, a.B, a.L, a.px, a.bpx, 1, 1)) return false;
+    if (mode == 2) {
+        if (!make_tensor_map5(&a.map_g, grad, 4, g.N, g.C, a.OA, a.OB, a.OL, a.pg, a.bpg, 1, 1)) return false;
+        if (d == 3 && !make_tensor_map5(&a.map_v, grad, 4, g.N, g.C, a.OA, a.OB, a.OL, a.OL, a.OB, 1, 1)) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+// ---- planning -----------------------------------------------------------------------------------
+HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, const void* x, const void* out, const void* grad,
+                   int sm_count, bool forced) {
+    HaloPlan p;
+    memset(&p, 0, sizeof(p));
+    p.ok = false;
+    if (!tma_available() || !dense_x || dtype != TS_F32 || (mode != 1 && mode != 2)) return p;
+    const int d = g.dim;
+    if (d != 2 && d != 3) return p;
+    if (g.N * g.C == 0 || g.in_plane == 0 || g.out_plane == 0) return p;
+    for (int ax = 0; ax < d; ++ax)
+        if (g.S[ax] < 2 || g.OS[ax] < 2) return p;        // a size-1 axis ignores its shift (shifts_kernels.h:40-50): other families
+    const int B = g.S[d - 2], L = g.S[d - 1];
+    const int OB = g.OS[d - 2], OL = g.OS[d - 1];
+    if (L % 4 || OL % 4) return p;
+    if (((uintptr_t)x & 15) || ((uintptr_t)out & 15) || ((uintptr_t)grad & 15)) return p;
+    if (g.N >= (1ll << 31) || g.C >= (1ll << 31)) return p;
+    if (g.in_plane * 4 >= (1ll << 40) / (g.C > 0 ? g.C : 1)) return p;
+    const Tuning& t = tuning();
+    const int halo = t.halo > 0 ? t.halo : 4;
+    p.hr = halo;
+    p.hc = (halo + 3) / 4 * 4;
+    p.px = L + 2 * p.hc;   p.bpx = B + 2 * p.hr;
+    p.pg = OL + 2 * p.hc;  p.bpg = OB + 2 * p.hr;
+    if (p.px > 256 || p.bpx > 256 || p.pg > 256 || p.bpg > 256) return p;           // TMA box extents
+    p.tile_x = (int)round_up((long long)p.px * p.bpx * 4, 128);
+    p.tile_g = mode == 2 ? (int)round_up((long long)p.pg * p.bpg * 4, 128) : 0;
+    p.tile_v = (mode == 2 && d == 3) ? (int)round_up((long long)OL * OB * 4, 128) : 0;
+    const long long per_image = (long long)p.tile_x + p.tile_g + p.tile_v;
+    const int IB = mode == 2 ? B : OB, IG = (mode == 2 ? L : OL) / 4;
+    int GP = IG;
+    if (IG % 8 != 0 && (double)IG / (double)((IG + 7) / 8 * 8) >= 0.85) GP = (IG + 7) / 8 * 8;
+    const int img_pairs = (IB + 1) / 2 * GP;
+    const int max_nt = MAXT - 32;
+    const long long budget = SMEM_LIMIT - 1024;
+    long long np;
+    if (d == 3) {
+        if (img_pairs > max_nt) return p;                  // one (row pair, group) per thread for the whole image
+        np = max_nt / img_pairs;
+    } else {
+        np = (48 * 1024) / per_image;                      // ~48 KB per stage
+    }
+    if (np < 1) np = 1;
+    if (np > g.N) np = g.N;
+    const long long tail = 4ll * (p.px > p.pg ? p.px : p.pg) + 256;       // a masked row may be read one row past the last tile
+    auto stride_of = [&](long long n) { return round_up(n * per_image + GUARD + tail, 1024); };
+    const int min_stages = d == 3 ? 3 : 2;
+    while (np > 1 && budget / (stride_of(np) + 16) < min_stages + 1) --np;
+    long long stages = budget / (stride_of(np) + 16);
+    if (stages < min_stages) return p;
+    const int want = t.halo_stages > 0 ? t.halo_stages : (d == 3 ? 6 : 5);
+    if (stages > want) stages = want;
+    if (np * per_image >= (1 << 20)) return p;             // mbarrier tx-count range
+    const long long pairs = np * img_pairs;
+    if (!forced && pairs < 128) return p;                  // tiny planes: too little work per stage hand-off
+    if (np * g.C * (mode == 2 ? g.in_plane : g.out_plane) * 4 >= 0x7fffffffLL) return p;
+    // consumer warps: 3-D needs one thread per pair; 2-D picks the count that fills the last pass best
+    int warps;
+    if (d == 3) {
+        warps = (int)((pairs + 31) / 32);
+    } else {
+        auto eff = [&](int w) {
+            const long long nt = 32ll * w, passes = (pairs + nt - 1) / nt;
+            return (double)pairs / (double)(passes * nt);
+        };
+        warps = 8;
+        for (int w = 8; w <= max_nt / 32; ++w)
+            if (eff(w) > eff(warps) + 1e-9) warps = w;
+    }
+    if (t.halo_warps > 0 && d != 3) warps = t.halo_warps < max_nt / 32 ? t.halo_warps : max_nt / 32;
+    if (warps < 1) warps = 1;
+    const long long planes = g.N * g.C;
+    long long npu = t.chunk_planes > 0 ? t.chunk_planes : planes / ((long long)sm_count * 32);
+    npu = (npu / np) * np;
+    if (npu < np) npu = np;
+    if (npu > g.N) npu = g.N;
+    const long long chunks = (g.N + npu - 1) / npu;
+    const long long units = chunks * g.C;
+    if (units > 0x7fffffffLL || chunks * warps > 0x7fffffffLL) return p;
+    p.ok = true;
+    p.np = (int)np; p.GP = GP; p.positions = (int)pairs; p.ncol = 1;
+    p.stages = (int)stages; p.stage_stride = (int)stride_of(np); p.warps = warps;
+    p.n_per_unit = (int)npu; p.units = (int)units;
+    p.grid = (int)(units < sm_count ? units : sm_count);
+    p.slots = (int)(chunks * warps);
+    p.smem_bytes = (size_t)(stages * stride_of(np) + 16 * stages + 64);
+    return p;
+}
+
+int halo_active_forward(const Geo& g, const HaloPlan& p, const void* x, const void* w, void* y, cudaStream_t s) {
+    HArgs a;
+    if (!make_args(g, p, 1, 1, x, nullptr, y, w, nullptr, &a)) return TS_ERR_UNSUPPORTED;
+    return g.dim == 3 ? launch(k_halo<3, 1, true>, a, p, s) : launch(k_halo<2, 1, true>, a, p, s);
+}
+
+int halo_backward(const Geo& g, const HaloPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
+                  double* partials, const ts_peer_group* peers, cudaStream_t s) {
+    HArgs a;
+    if (!make_args(g, p, 2, active ? 1 : 0, x, grad, gi, w, partials, &a)) return TS_ERR_UNSUPPORTED;
+    int rc;
+    switch (g.dim * 2 + (active ? 1 : 0)) {
+    case 4: rc = launch(k_halo<2, 2, false>, a, p, s); break;
+    case 5: rc = launch(k_halo<2, 2, true>, a, p, s); break;
+    case 6: rc = launch(k_halo<3, 2, false>, a, p, s); break;
+    default: rc = launch(k_halo<3, 2, true>, a, p, s); break;
+    }
+    if (rc != TS_OK) return rc;
+    return launch_reduce_partials<float>(partials, p.slots, (int)(g.C * g.dim), gw, peers, s);
+}
+
+}  // namespace ts

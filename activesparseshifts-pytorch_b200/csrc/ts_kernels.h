@@ -60,6 +60,10 @@ struct Tuning {
     int tma_stage_kb;  // target bytes per stage of the TMA-tensor kernels (0 = auto)
     int nhwc_variant;  // channels-last gather: 0 auto, 1 direct (L1) kernel only, 2 ring (shared-memory) kernel only
     int nhwc_ring_rows;  // cap on the ring slots of the channels-last ring kernel (0 = as many as fit)
+    int use_halo;      // 0: the automatic path choice never picks the halo family
+    int halo;          // halo rows / columns of the halo family (0 = 4)
+    int halo_stages;   // ring depth of the halo family (0 = auto)
+    int halo_warps;    // consumer warps of the 2-D halo kernels (0 = auto)
 };
 Tuning& tuning();
 
@@ -101,5 +105,27 @@ int tma_gather(const Geo& g, const TmaPlan& p, int wk, const void* x, void* y, i
 int tma_active_forward(const Geo& g, const TmaPlan& p, const void* x, const void* w, void* y, cudaStream_t s);
 int tma_backward(const Geo& g, const TmaPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
                  double* partials, const ts_peer_group* peers, cudaStream_t s);
+
+// rank-5 tensor map over a dense [N][C][A][B][L] tensor, box {bl, bb, ba, 1, bn} (memoised per thread); `map` points to a
+// CUtensorMap (128 bytes, 64-byte aligned)
+bool tma_available();
+bool make_tensor_map5(void* map, const void* base, int es, long long N, long long C, int A, int B, int L, int bl, int bb, int ba, int bn);
+
+// ---- halo family (ts_halo.cu): whole slabs staged WITH a padded halo, every item is interior ----
+struct HaloPlan {
+    bool ok;
+    int hr, hc;                 // halo rows / columns on each side of a staged slab
+    int px, bpx, pg, bpg;       // row pitch (elements) and rows of the x / grad tiles in shared memory
+    int tile_x, tile_g, tile_v; // bytes per tile (128-byte multiples); tile_v: dense grad slab (3-D backward)
+    int np, GP, positions, ncol;
+    int stages, stage_stride, warps, n_per_unit, units, grid, slots;
+    size_t smem_bytes;
+};
+// mode: 1 active forward, 2 backward (active = interpolating backward).  fp32, dims 2 and 3, every padding, border crops.
+HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, const void* x, const void* out, const void* grad,
+                   int sm_count, bool forced);
+int halo_active_forward(const Geo& g, const HaloPlan& p, const void* x, const void* w, void* y, cudaStream_t s);
+int halo_backward(const Geo& g, const HaloPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
+                  double* partials, const ts_peer_group* peers, cudaStream_t s);
 
 }  // namespace ts

@@ -31,7 +31,7 @@
 namespace ts {
 
 Tuning& tuning() {
-    static Tuning t = {0, 0, 15, 1, 0, 0, 0, 0, 1, 0};   // 0 = automatic (per-mode defaults in the planners)
+    static Tuning t = {0, 0, 15, 1, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};   // 0 = automatic (per-mode defaults in the planners)
     return t;
 }
 

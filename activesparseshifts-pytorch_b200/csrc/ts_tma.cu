@@ -839,6 +839,11 @@ bool make_args(const Geo& g, const TmaPlan& p, int mode, int active, int es, TAr
 
 }  // namespace
 
+bool tma_available() { return encode_tiled() != nullptr; }
+bool make_tensor_map5(void* map, const void* base, int es, long long N, long long C, int A, int B, int L, int bl, int bb, int ba, int bn) {
+    return make_map((CUtensorMap*)map, base, es, N, C, A, B, L, bl, bb, ba, bn);
+}
+
 // ---- planning -----------------------------------------------------------------------------------
 TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool dense_x, unsigned long long fill, const void* x,
                  const void* out, const void* grad, int sm_count) {

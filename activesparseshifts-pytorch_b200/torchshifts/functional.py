@@ -39,6 +39,12 @@ def _resolve_borders(dim, sizes, cuts):
     return lb, rb
 
 
+@torch.compiler.assume_constant_result
+def _std_borders(vals):
+    """int32[6] host tensor {l0,r0,l1,r1,l2,r2}; a constant of the compiled graph (no CPU code is generated for it)"""
+    return torch.tensor(list(vals), dtype=torch.int32)
+
+
 def _shift_func(dim: int, input: Tensor, weights: Tensor, padding_mode: int, active_flag: bool,
                 borders: Optional[Tensor], _border_ints=None) -> Tensor:
     name = f'shift{dim}d_func()'
@@ -56,7 +62,7 @@ def _shift_func(dim: int, input: Tensor, weights: Tensor, padding_mode: int, act
             # torch.compile: resolve the crop from Python integers (constants of the trace) and call the inner
             # operator, which has a fake kernel and a registered autograd formula
             lb, rb = _resolve_borders(dim, input.shape[2:], _border_ints)
-            std = torch.tensor([lb[0], rb[0], lb[1], rb[1], lb[2], rb[2]], dtype=torch.int32)
+            std = _std_borders((lb[0], rb[0], lb[1], rb[1], lb[2], rb[2]))
             new_size = [input.shape[0], input.shape[1]] + [rb[a] - lb[a] for a in range(dim)]
             return getattr(torch.ops.torchshifts, f'_shift{dim}d_forward')(input, weights, std, new_size, padding_mode, active_flag)
     else:

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small staged-path (bulk-async kernels) parity run, meant to be executed under compute-sanitizer
 on the GPU box:   compute-sanitizer --tool memcheck python tools/staged_sanity.py
-Every case forces the staged kernel family (ts_set_kernel_path(2)) and compares with the CPU oracle;
+Every case forces one kernel family (--path=2 staged (default), 3 TMA, 5 halo, 1 generic) and compares with the CPU oracle;
 failures are listed, not raised one by one, so a single GPU call reports everything."""
 import sys
 from pathlib import Path
@@ -29,7 +29,7 @@ if TUNING:
 FORCED = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--path=")), 2)
 
 shapes = [(3, 5, 64), (2, 4, 40), (2, 3, 12, 16), (3, 4, 8, 8), (2, 6, 28, 28), (2, 3, 4, 6, 8), (1, 2, 3, 5, 4), (5, 7, 1, 16), (9, 2, 4, 12), (37, 3, 8, 8),
-          (2, 3, 7, 6, 16), (1, 2, 1, 6, 8), (2, 2, 5, 1, 8), (3, 2, 1040)]
+          (2, 3, 7, 6, 16), (1, 2, 1, 6, 8), (2, 2, 5, 1, 8), (3, 2, 1040), (3, 5, 5, 9, 12), (2, 3, 9, 20), (5, 2, 3, 7, 8)]
 if quick:
     shapes = shapes[:5]
 rng = np.random.default_rng(0)
@@ -39,7 +39,12 @@ for shape in shapes:
     for wr in (2.5, 40.0):
         x = rng.standard_normal(shape).astype(np.float32)
         w = ((rng.random((shape[1], dim)) * 2 - 1) * wr).astype(np.float32)
-        for borders in (None, [[0, 4]] * dim if min(shape[2:]) > 4 else None):
+        seen_b = set()
+        for borders in (None, [[0, 4]] * dim if min(shape[2:]) > 4 else None, [[1, 2], [2, 1], [1, 1]][:dim] if min(shape[2:]) > 5 else None,
+                        [[0, 0]] * (dim - 1) + [[4, 0]] if shape[-1] > 8 else None):
+            if str(borders) in seen_b:
+                continue
+            seen_b.add(str(borders))
             for pad in range(5):
                 for active in (False, True):
                     tag = (shape, wr, borders, pad, active)
