@@ -140,7 +140,7 @@ const char* ts_error_string(int status) {
 const char* ts_last_cuda_error(void) { return t_cuda_error; }
 int ts_last_kernel_path(void) { return t_last_path; }
 int ts_set_kernel_path(int path) {
-    if (path < 0 || path > 5 || path == TS_PATH_NHWC) return -1;
+    if (path < 0 || path > 6 || path == TS_PATH_NHWC) return -1;
     return g_forced_path.exchange(path);
 }
 uint64_t ts_launch_count(void) { return (uint64_t)g_launches.load(); }
@@ -169,6 +169,12 @@ int ts_set_tuning(const char* spec) {
         else if (!strcmp(key, "halo")) t.halo = val;
         else if (!strcmp(key, "halo_stages")) t.halo_stages = val;
         else if (!strcmp(key, "halo_warps")) t.halo_warps = val;
+        else if (!strcmp(key, "unit_order")) t.unit_order = val != 0;
+        else if (!strcmp(key, "use_flat")) t.use_flat = val != 0;
+        else if (!strcmp(key, "flat_ctas")) t.flat_ctas = val;
+        else if (!strcmp(key, "flat_stage_kb")) t.flat_stage_kb = val;
+        else if (!strcmp(key, "flat_stages")) t.flat_stages = val;
+        else if (!strcmp(key, "flat_warps")) t.flat_warps = val;
         else return TS_ERR_INVALID_ARGUMENT;
         p += n;
         while (*p == ',' || *p == ' ') ++p;
@@ -177,7 +183,8 @@ int ts_set_tuning(const char* spec) {
         t.ctas_per_sm < 1 || t.ctas_per_sm > 8 || t.chunk_planes < 0 || t.tma_stages < 0 || t.tma_stages > 32 ||
         t.tma_ctas_per_sm < 0 || t.tma_ctas_per_sm > 8 || t.tma_warps < 0 || t.tma_warps > 31 || t.tma_stage_kb < 0 ||
         t.tma_stage_kb > 220 || t.nhwc_variant < 0 || t.nhwc_variant > 2 || t.nhwc_ring_rows < 0 || t.halo < 0 || t.halo > 16 ||
-        t.halo_stages < 0 || t.halo_stages > 32 || t.halo_warps < 0 || t.halo_warps > 15)
+        t.halo_stages < 0 || t.halo_stages > 32 || t.halo_warps < 0 || t.halo_warps > 15 || t.flat_ctas < 0 || t.flat_ctas > 8 ||
+        t.flat_stage_kb < 0 || t.flat_stage_kb > 100 || t.flat_stages < 0 || t.flat_stages > 16 || t.flat_warps < 0 || t.flat_warps > 15)
         return TS_ERR_INVALID_ARGUMENT;
     tuning() = t;
     g_tuning_epoch.fetch_add(1);
@@ -253,6 +260,14 @@ int ts_shift_forward(const ts_geometry* gin, int dtype, int padding, int active,
         }
     }
     if (forced == TS_PATH_HALO) return TS_ERR_UNSUPPORTED;
+    if (!active && ((forced == TS_PATH_NONE && tuning().use_flat) || forced == TS_PATH_FLAT)) {
+        const FlatPlan fp = plan_flat(g, es, x_is_dense(g), x, y, sms, forced == TS_PATH_FLAT);
+        if (fp.ok) {
+            t_last_path = TS_PATH_FLAT;
+            return flat_gather(g, fp, dtype, x, y, 0ull, es, weights, 0, 0, s);
+        }
+    }
+    if (forced == TS_PATH_FLAT) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
     if (forced != TS_PATH_GENERIC) plan = plan_staged(g, active ? 1 : 0, active, es, dtype, x_is_dense(g), x, y, nullptr, sms);
@@ -352,7 +367,7 @@ static int backward_impl(const ts_geometry* gin, int dtype, int padding, int act
             return halo_backward(g, hp, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, peers, s);
         }
     }
-    if (forced == TS_PATH_HALO) return TS_ERR_UNSUPPORTED;
+    if (forced == TS_PATH_HALO || forced == TS_PATH_FLAT) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
     if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 2, active, es, dtype, x_is_dense(g), x, grad_input, grad, sms);
@@ -409,6 +424,14 @@ int ts_qshift_forward(const ts_geometry* gin, int elem_bytes, int padding, int64
         }
     }
     if (forced == TS_PATH_TMA || forced == TS_PATH_HALO) return TS_ERR_UNSUPPORTED;
+    if ((forced == TS_PATH_NONE && tuning().use_flat) || forced == TS_PATH_FLAT) {
+        const FlatPlan fp = plan_flat(g, elem_bytes, x_is_dense(g), xq, yq, sms, forced == TS_PATH_FLAT);
+        if (fp.ok) {
+            t_last_path = TS_PATH_FLAT;
+            return flat_gather(g, fp, WK_QUANT, xq, yq, fill, elem_bytes, qweights, qweight_kind, weight_zero_point, s);
+        }
+    }
+    if (forced == TS_PATH_FLAT) return TS_ERR_UNSUPPORTED;
     StagedPlan plan;
     plan.ok = false;
     if (forced != TS_PATH_GENERIC) plan = plan_staged(g, 0, 0, elem_bytes, -1, x_is_dense(g), xq, yq, nullptr, sms);

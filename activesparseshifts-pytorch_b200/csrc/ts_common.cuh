@@ -285,6 +285,28 @@ TS_D unsigned lds32(unsigned addr) {
 #endif
 
 // ------------------------------------------------------------------------------------------
+// Which work units (channel, chunk of the batch) a persistent CTA processes, shared by the producer and the
+// consumers of a CTA.  order 1 (default): round-robin over (chunk, channel) -- the CTAs of one wave stream
+// neighbouring planes.  order 0: the CTA owns a CONTIGUOUS range of the channel-major unit list, so consecutive units
+// share the channel (same unrolled code variant, warm weights); tuning knob `unit_order`.
+#ifdef __CUDACC__
+struct UnitRange { int u, end, step; };
+TS_D UnitRange unit_range(int units, int order) {
+    UnitRange r;
+    if (order) { r.u = (int)blockIdx.x; r.end = units; r.step = (int)gridDim.x; return r; }
+    const long long b = blockIdx.x, G = gridDim.x;
+    r.u = (int)((long long)units * b / G);
+    r.end = (int)((long long)units * (b + 1) / G);
+    r.step = 1;
+    return r;
+}
+TS_D void unit_decode(int u, int C, int chunks, int order, int& c, int& chunk) {
+    if (order) { chunk = u / C; c = u - chunk * C; }
+    else { c = u / chunks; chunk = u - c * chunks; }
+}
+#endif
+
+// ------------------------------------------------------------------------------------------
 // Launch bookkeeping shared by the translation units.
 struct LaunchCtx {
     cudaStream_t stream;

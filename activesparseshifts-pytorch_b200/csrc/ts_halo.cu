@@ -64,7 +64,7 @@ struct alignas(64) HArgs {
     int off_g, off_v;                         // byte offsets of the grad tiles / dense grad tiles inside a stage (after GUARD)
     int stage_stride, stages, nw, nt, np;
     int img_pairs, pairs;                     // RP * GP, np * RP * GP
-    int n_per_unit, units;
+    int n_per_unit, units, chunks, unit_order;
     int need_fix;
     FastDivU d_GP, d_img;
 };
@@ -336,8 +336,10 @@ TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t
     const int C = (int)a.g.C, N = (int)a.g.N;
     const bool bwd = a.mode == 2;
     const int steps = a.dim == 3 ? a.IA + 1 : 1;
-    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
-        const int chunk = u / C, c = u - chunk * C;
+    const UnitRange ur = unit_range(a.units, a.unit_order);
+    for (int u = ur.u; u < ur.end; u += ur.step) {
+        int chunk, c;
+        unit_decode(u, C, a.chunks, a.unit_order, c, chunk);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         const UnitShift us = unit_shift(a, c);
@@ -700,8 +702,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs 
     Body<DIM, MODE, ACTIVE> body(a, threadIdx.x, a.nt, wid, lane);
     Ring ring = {0, 0u};
     const int C = (int)a.g.C, N = (int)a.g.N;
-    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
-        const int chunk = u / C, c = u - chunk * C;
+    const UnitRange ur = unit_range(a.units, a.unit_order);
+    for (int u = ur.u; u < ur.end; u += ur.step) {
+        int chunk, c;
+        unit_decode(u, C, a.chunks, a.unit_order, c, chunk);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         body.begin_unit(c);
@@ -747,6 +751,8 @@ bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, const void
     a.img_pairs = a.RP * a.GP;
     a.pairs = a.np * a.img_pairs;
     a.n_per_unit = p.n_per_unit; a.units = p.units;
+    a.chunks = (int)(p.units / (g.C > 0 ? g.C : 1));
+    a.unit_order = tuning().unit_order;
     a.need_fix = g.pad != TS_PAD_ZEROS;
     a.d_GP = make_fastdivu((unsigned)a.GP);
     a.d_img = make_fastdivu((unsigned)a.img_pairs);

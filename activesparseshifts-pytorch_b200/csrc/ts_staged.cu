@@ -31,7 +31,7 @@
 namespace ts {
 
 Tuning& tuning() {
-    static Tuning t = {0, 0, 15, 1, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};   // 0 = automatic (per-mode defaults in the planners)
+    static Tuning t = {0, 0, 15, 1, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0};   // 0 = automatic (per-mode defaults in the planners)
     return t;
 }
 
@@ -105,7 +105,7 @@ struct SArgs {
     int TA, tiles;                            // slabs per tile, tiles per image
     int xs, gvs, gis;                         // slab slots per image: x, grad at the output position, grad for grad_input (0: shares gvs)
     int slab_x, slab_g;                       // bytes of one slab of x / of grad
-    int np, stages, stage_stride, nw, n_per_unit, units;
+    int np, stages, stage_stride, nw, n_per_unit, units, chunks, unit_order;
     int off_gv, off_gi;                       // byte offsets of the grad regions inside a stage (after GUARD)
     int img_items;                            // TA * IB * GP
     long long img_stride;                     // output bytes between consecutive images of one channel
@@ -181,8 +181,10 @@ TS_D int gi_slot_slab(const SArgs& a, const UnitShift& us, int a0, int k) {
 TS_D void producer(const SArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty) {
     int s = 0, k = 0;
     const int C = (int)a.g.C, N = (int)a.g.N;
-    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
-        const int chunk = u / C, c = u - chunk * C;
+    const UnitRange ur = unit_range(a.units, a.unit_order);
+    for (int u = ur.u; u < ur.end; u += ur.step) {
+        int chunk, c;
+        unit_decode(u, C, a.chunks, a.unit_order, c, chunk);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         const UnitShift us = unit_shift(a, c);
@@ -243,8 +245,10 @@ TS_D void consumer_loop(const SArgs& a, unsigned char* smem, uint64_t* full, uin
     const int C = (int)a.g.C, N = (int)a.g.N;
     const long long plane_bytes = a.img_stride / C;
     const long long out_slab = (long long)a.IB * a.gpr * a.VB;
-    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
-        const int chunk = u / C, c = u - chunk * C;
+    const UnitRange ur = unit_range(a.units, a.unit_order);
+    for (int u = ur.u; u < ur.end; u += ur.step) {
+        int chunk, c;
+        unit_decode(u, C, a.chunks, a.unit_order, c, chunk);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         body.begin_unit(c);
@@ -1462,6 +1466,8 @@ SArgs make_args(const Geo& g, const StagedPlan& p, int mode, int active, int es)
     a.nw = p.warps;
     a.n_per_unit = p.n_per_unit;
     a.units = p.units;
+    a.chunks = (int)(p.units / (g.C > 0 ? g.C : 1));
+    a.unit_order = tuning().unit_order;
     a.off_gv = p.off_gv;
     a.off_gi = p.off_gi;
     a.img_items = a.TA * a.IB * a.GP;

@@ -173,7 +173,7 @@ struct alignas(64) TArgs {
     int g_img_chunks;        // 16-byte groups of one image's small grad box
     int off_gv, off_g2;      // byte offsets of the grad boxes inside a stage
     int tx_bytes;            // bytes landing per stage
-    int stage_stride, stages, nw, n_per_unit, units;
+    int stage_stride, stages, nw, n_per_unit, units, chunks, unit_order;
     int GP, img_items;       // padded groups per row of the item index space; items per image = TA*TB*GP
     int img_stride16;        // output distance between consecutive images of one channel, in 16-byte units
     int R, nchunk;           // strip-mined arithmetic kernels: rows per strip, strips per tile column
@@ -239,8 +239,11 @@ TS_D void producer(const TArgs& a, unsigned char* smem, uint64_t* full, uint64_t
     int s = 0, k = 0;
     const long long C = a.g.C, N = a.g.N;
     const int dim = a.g.dim;
-    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
-        const long long c = u % C, chunk = u / C;
+    const UnitRange ur = unit_range(a.units, a.unit_order);
+    for (int u = ur.u; u < ur.end; u += ur.step) {
+        int ci, chunki;
+        unit_decode(u, (int)C, a.chunks, a.unit_order, ci, chunki);
+        const long long c = ci, chunk = chunki;
         const long long n0 = chunk * a.n_per_unit;
         const long long n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         const UnitShift us = unit_shift(a, c);
@@ -287,8 +290,10 @@ TS_D void consumer_loop(const TArgs& a, unsigned char* smem, uint64_t* full, uin
     unsigned phase = 0;
     const int C = (int)a.g.C, N = (int)a.g.N, np = a.np, tiles = a.tiles, stages = a.stages;
     const long long plane_bytes = (a.mode == 2 ? a.g.in_plane : a.g.out_plane) * a.es;
-    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
-        const int chunk = u / C, c = u - chunk * C;
+    const UnitRange ur = unit_range(a.units, a.unit_order);
+    for (int u = ur.u; u < ur.end; u += ur.step) {
+        int chunk, c;
+        unit_decode(u, C, a.chunks, a.unit_order, c, chunk);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         body.begin_unit(c);
@@ -815,6 +820,8 @@ bool make_args(const Geo& g, const TmaPlan& p, int mode, int active, int es, TAr
     a.nw = p.warps;
     a.n_per_unit = p.n_per_unit;
     a.units = p.units;
+    a.chunks = (int)(p.units / (g.C > 0 ? g.C : 1));
+    a.unit_order = tuning().unit_order;
     a.GP = p.gp;
     a.img_items = a.TA * a.TB * a.GP;
     a.img_stride16 = (int)(g.C * (mode == 2 ? g.in_plane : g.out_plane) * es / 16);

@@ -69,8 +69,10 @@ typedef enum ts_kernel_path {      /* which kernel family served the last call (
     TS_PATH_STAGED = 2,            /* bulk-async (cp.async.bulk + mbarrier) shared-memory staged  */
     TS_PATH_TMA = 3,               /* TMA tensor copies: the copy engine applies shift + zero pad  */
     TS_PATH_NHWC = 4,              /* channels-last in, channels-last out (ts_qshift_forward_nhwc) */
-    TS_PATH_HALO = 5               /* slabs staged with a padded halo (TMA tensor loads), all-interior
+    TS_PATH_HALO = 5,              /* slabs staged with a padded halo (TMA tensor loads), all-interior
                                       arithmetic: fp32 active forward / backward, every padding, crops  */
+    TS_PATH_FLAT = 6               /* zeros padding, no crop: linear shifted copy of each dense slab with
+                                      byte masks (sparse / quantized forward, any row length)           */
 } ts_kernel_path;
 
 /* Geometry of one call.  Unused spatial axes: size 1, stride 0, lb 0, rb 1. */
@@ -90,7 +92,7 @@ const char*  ts_error_string(int status);
 const char*  ts_last_cuda_error(void);         /* text of the last CUDA error seen by this thread */
 int          ts_last_kernel_path(void);        /* ts_kernel_path of this thread's last launch     */
 int          ts_set_kernel_path(int path);     /* 0 auto (default), 1 force generic, 2 force staged,
-                                                  3 force TMA, 5 force halo (calls fail with TS_ERR_UNSUPPORTED
+                                                  3 force TMA, 5 force halo, 6 force flat (calls fail with TS_ERR_UNSUPPORTED
                                                   when the forced family does not apply); returns
                                                   the old value                                   */
 uint64_t     ts_launch_count(void);            /* kernels launched by this library so far         */

@@ -48,7 +48,7 @@ def timeit(fn, reps=10):
     return a.elapsed_time(b) / reps
 
 
-names = {0: "none", 1: "generic", 2: "staged", 3: "tma", 4: "nhwc"}
+names = {0: "none", 1: "generic", 2: "staged", 3: "tma", 4: "nhwc", 5: "halo", 6: "flat"}
 want = [a for a in sys.argv[1:] if a in CASES] or list(CASES)
 for key in want:
     for label, shape, pad, active, dtype in CASES[key]:

@@ -17,7 +17,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 shape, dim, pad, active = {"cfg3": ((256, 256, 56, 56), 2, 0, False), "cfg2": ((64, 512, 4096), 1, 2, True),
                            "cfg4": ((32, 128, 16, 56, 56), 3, 0, True), "cfg1": ((8, 64, 32, 32), 2, 0, False),
                            "cfg4r": ((32, 128, 16, 56, 56), 3, 3, True), "cfg3r": ((256, 256, 56, 56), 2, 3, False),
-                           "cfg2z": ((64, 512, 4096), 1, 0, True)}[cfg]
+                           "cfg2z": ((64, 512, 4096), 1, 0, True), "cfg3n32": ((32, 256, 56, 56), 2, 0, False),
+                           "cfg3ra": ((256, 256, 56, 56), 2, 3, True), "cfg4b": ((32, 128, 16, 56, 56), 3, 1, True)}[cfg]
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 x = torch.randn(shape, device=dev)
