@@ -41,6 +41,7 @@ using namespace ptx;
 
 constexpr int SMEM_LIMIT = 232448;
 constexpr int MAXT = 512;
+constexpr int TABLE_MAX_C = 512;    // channels whose shift parameters are tabulated in shared memory (36 bytes each)
 constexpr int GUARD = 128;          // readable slack before / after the tiles of a stage (window pairs may start 16 bytes early)
 
 struct alignas(64) HArgs {
@@ -65,8 +66,10 @@ struct alignas(64) HArgs {
     int stage_stride, stages, nw, nt, np;
     int img_pairs, pairs;                     // RP * GP, np * RP * GP
     int n_per_unit, units, chunks, unit_order;
-    int need_fix;
-    FastDivU d_GP, d_img;
+    int need_fix;                             // padding != zeros: a fixer warp patches the halo of every stage
+    int split;                                // 3-D interpolating backward: x-window warps and grad-window warps (two pairs per thread)
+    FastDivU d_GP, d_img, d_C, d_chunks;
+    int table;                                // per-channel shift table in shared memory (C <= TABLE_MAX_C)
 };
 
 TS_D int level_axis(int level, int dim) { return level - (3 - dim); }
@@ -76,7 +79,7 @@ struct UnitShift {
     float d[3];            // per TENSOR axis
 };
 
-TS_D UnitShift unit_shift(const HArgs& a, long long c) {
+TS_D UnitShift compute_unit_shift(const HArgs& a, long long c) {
     UnitShift u;
     u.d[0] = u.d[1] = u.d[2] = 0.f;
 #pragma unroll
@@ -94,6 +97,14 @@ TS_D UnitShift unit_shift(const HArgs& a, long long c) {
         u.sg[lev] = reduce_shift(iw, a.g.OS[ax], a.g.pad);
     }
     return u;
+}
+
+// computed once per CTA into shared memory (a few hundred dependent instructions per channel otherwise paid per unit by
+// the single producer thread); a unit then costs one 36-byte read
+TS_D UnitShift unit_shift(const HArgs& a, const UnitShift* tbl, long long c) { return a.table ? tbl[c] : compute_unit_shift(a, c); }
+TS_D void decode_unit(const HArgs& a, int u, int& c, int& chunk) {
+    if (a.unit_order) { chunk = (int)fdivu((unsigned)u, a.d_C); c = u - chunk * (int)a.g.C; }
+    else { c = (int)fdivu((unsigned)u, a.d_chunks); chunk = u - c * a.chunks; }
 }
 
 // Where a unit's windows sit inside the tiles, and whether they fit the halo.
@@ -161,26 +172,27 @@ TS_D void load4(unsigned addr, int ws, float* out) {
 // ---- halo fill --------------------------------------------------------------------------------
 // Cells of the needed extended range [rn_lo, rn_hi] x [cn_lo, cn_hi] that lie outside [0, rows) x [0, cols) take
 // tile[P(r)][P(c)].  Writers touch halo cells only, readers interior cells only: one pass, no ordering inside.
+// Run by ONE warp (the fixer): halo rows with the lanes along the columns (consecutive words), then the halo columns
+// of the interior rows with the lanes down the rows (the pitch is 4 mod 8 words: 4-way bank conflicts at worst).
+TS_D int remap_any(int idx, int len, int pad, bool bounded) { return bounded ? axis_index(idx, len, pad) : axis_index_literal(idx, len, pad); }
+
 TS_D void fill_halo(float* tile, int pitch, int rows, int cols, int hr, int hc, int pad, int rn_lo, int rn_hi, int cn_lo, int cn_hi,
-                    int tid, int nt) {
+                    int lane) {
     const int nrt = rn_lo < 0 ? -rn_lo : 0, nrb = rn_hi > rows - 1 ? rn_hi - (rows - 1) : 0;
     const int nct = cn_lo < 0 ? -cn_lo : 0, ncb = cn_hi > cols - 1 ? cn_hi - (cols - 1) : 0;
-    const int wc = cn_hi - cn_lo + 1, nch = nct + ncb;
-    const int nA = (nrt + nrb) * wc, total = nA + rows * nch;
-    for (int idx = tid; idx < total; idx += nt) {
-        int r, c;
-        if (idx < nA) {
-            const int ri = idx / wc, ci = idx - ri * wc;
-            r = ri < nrt ? rn_lo + ri : rows + (ri - nrt);
-            c = cn_lo + ci;
-        } else {
-            const int j = idx - nA;
-            r = j / nch;
-            const int k = j - r * nch;
-            c = k < nct ? cn_lo + k : cols + (k - nct);
-        }
-        const int sr = axis_index_literal(r, rows, pad), sc = axis_index_literal(c, cols, pad);
-        tile[(r + hr) * pitch + c + hc] = tile[(sr + hr) * pitch + sc + hc];
+    // the division-free remap is valid for indices within one period of the axis: halo <= hr (hc) < len
+    const bool rb = rows > hr + 1, cb = cols > hc + 1;
+    for (int ri = 0; ri < nrt + nrb; ++ri) {
+        const int r = ri < nrt ? rn_lo + ri : rows + (ri - nrt);
+        const int sr = remap_any(r, rows, pad, rb);
+        float* dst = tile + (r + hr) * pitch + hc;
+        const float* src = tile + (sr + hr) * pitch + hc;
+        for (int c = cn_lo + lane; c <= cn_hi; c += 32) dst[c] = src[remap_any(c, cols, pad, cb)];
+    }
+    for (int k = 0; k < nct + ncb; ++k) {
+        const int c = k < nct ? cn_lo + k : cols + (k - nct);
+        const int sc = remap_any(c, cols, pad, cb);
+        for (int r = lane; r < rows; r += 32) tile[(r + hr) * pitch + c + hc] = tile[(r + hr) * pitch + sc + hc];
     }
 }
 
@@ -331,7 +343,7 @@ TS_D int slab_coord(int idx, int len, int pad) {
     return t < 0 ? -1 : t;                 // outside under zeros padding: the copy engine delivers a zero tile
 }
 
-TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty) {
+TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, const UnitShift* tbl) {
     int s = 0, kk = 0;
     const int C = (int)a.g.C, N = (int)a.g.N;
     const bool bwd = a.mode == 2;
@@ -339,10 +351,10 @@ TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t
     const UnitRange ur = unit_range(a.units, a.unit_order);
     for (int u = ur.u; u < ur.end; u += ur.step) {
         int chunk, c;
-        unit_decode(u, C, a.chunks, a.unit_order, c, chunk);
+        decode_unit(a, u, c, chunk);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
-        const UnitShift us = unit_shift(a, c);
+        const UnitShift us = unit_shift(a, tbl, c);
         if (!unit_geom(a, us).fits) continue;              // consumers take the element-wise routine for this unit
         for (int nb = n0; nb < n1; nb += a.np) {
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
@@ -372,6 +384,48 @@ TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t
     }
 }
 
+// ---- fixer warp -------------------------------------------------------------------------------
+// One warp fills the halo cells of every stage (paddings other than zeros) between the copy engine and the consumers:
+// it waits for full[s], patches the tiles and arrives on ready[s]; the consumers wait for ready[s] instead of full[s].
+// It runs ahead of the consumers by the ring depth, so the arithmetic warps never meet at a barrier.
+TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* ready, int lane, const UnitShift* tbl) {
+    int s = 0;
+    unsigned phase = 0;
+    const int C = (int)a.g.C, N = (int)a.g.N;
+    const bool bwd = a.mode == 2;
+    const int steps = a.dim == 3 ? a.IA + 1 : 1;
+    const UnitRange ur = unit_range(a.units, a.unit_order);
+    for (int u = ur.u; u < ur.end; u += ur.step) {
+        int chunk, c;
+        decode_unit(a, u, c, chunk);
+        const int n0 = chunk * a.n_per_unit;
+        const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
+        const UnitShift us = unit_shift(a, tbl, c);
+        if (!unit_geom(a, us).fits) continue;
+        const int xr_lo = (bwd ? 0 : a.lbB) - us.sx[1], xc_lo = (bwd ? 0 : a.lbL) - us.sx[2];
+        const int sgr = a.active ? -us.sg[1] : us.sg[1], sgc = a.active ? -us.sg[2] : us.sg[2], ex = a.active ? 1 : 0;
+        for (int nb = n0; nb < n1; nb += a.np) {
+            const int npl = n1 - nb < a.np ? n1 - nb : a.np;
+            for (int k = 0; k < steps; ++k) {
+                unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
+                const bool has_g = bwd && (a.dim == 2 || a.active || k >= 1);
+                mbar_wait(&full[s], phase);
+                for (int pl = 0; pl < npl; ++pl) {
+                    fill_halo((float*)(st + (size_t)pl * a.tile_x), a.px, a.B, a.L, a.hr, a.hc, a.g.pad, xr_lo, xr_lo + a.IB, xc_lo,
+                              xc_lo + 4 * a.IG, lane);
+                    if (has_g)
+                        fill_halo((float*)(st + a.off_g + (size_t)pl * a.tile_g), a.pg, a.OB, a.OL, a.hr, a.hc, a.g.pad, sgr,
+                                  a.OB - 1 + sgr + ex, sgc, a.OL - 1 + sgc + ex, lane);
+                }
+                fence_proxy_async();             // the next TMA load of this stage must not overtake these generic-proxy writes
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready[s]);
+                if (++s == a.stages) { s = 0; phase ^= 1u; }
+            }
+        }
+    }
+}
+
 // ---- consumers ----------------------------------------------------------------------------------
 // pair index -> (image of the stage, first row of the pair, column group); false = padding lane
 struct Pair { int pl, r, cg; };
@@ -387,8 +441,8 @@ TS_D bool decode_pair(const HArgs& a, int p, Pair& q) {
 
 // Everything about one pair that does not change from stage to stage of a unit.
 struct PairCtx {
-    unsigned xo, go, vo;       // byte offsets (inside one image's tile) of the aligned group of the pair's FIRST row
-    unsigned out_off;          // byte offset of the first row's 16-byte output inside the (image, slab 0) output
+    unsigned xo, go, vo;       // byte offsets (from the stage base) of the aligned group of the pair's FIRST row in the x / grad / unshifted-grad tile
+    long long out_off;         // byte offset of the first row's 16-byte output from the output of (first image of the stage, slab 0)
     int rows;                  // rows of the pair that exist (1 or 2), 0: padding lane
     unsigned cmask;            // bit t of nibble j: element t of row j takes part (inside the crop)
 };
@@ -397,8 +451,8 @@ template <int MODE>
 TS_D PairCtx pair_ctx(const HArgs& a, const UnitGeom& ug, const Pair& q, bool valid) {
     PairCtx p;
     p.rows = !valid ? 0 : (q.r + 1 < a.IB ? 2 : 1);
-    p.xo = (unsigned)(((q.r + ug.xr0) * a.px + ((4 * q.cg + ug.xc0) & ~3)) * 4);
-    p.out_off = (unsigned)((q.r * a.IG + q.cg) * 16);
+    p.xo = (unsigned)(q.pl * a.tile_x + ((q.r + ug.xr0) * a.px + ((4 * q.cg + ug.xc0) & ~3)) * 4);
+    p.out_off = (long long)q.pl * (a.g.C * (MODE == 2 ? a.g.in_plane : a.g.out_plane) * 4) + (long long)((q.r * a.IG + q.cg) * 16);
     p.go = p.vo = 0;
     p.cmask = 0xffu;
     if (MODE == 2) {
@@ -418,9 +472,9 @@ TS_D PairCtx pair_ctx(const HArgs& a, const UnitGeom& ug, const Pair& q, bool va
         // the pair outside the crop (masked) may then lie one row before / after its tile -- still inside the stage
         // (tiles are preceded by other tiles or the head guard and followed by a tail of one row pitch).
         if (m) {
-            const int vp = a.dim == 3 ? a.OL : a.pg;
-            p.go = (unsigned)(((q.r + ug.gr0) * a.pg + ((4 * q.cg + ug.gc0) & ~3)) * 4);
-            p.vo = (unsigned)(((q.r + ug.vr0) * vp + ((4 * q.cg + ug.vc0) & ~3)) * 4);
+            p.go = (unsigned)(a.off_g + q.pl * a.tile_g + ((q.r + ug.gr0) * a.pg + ((4 * q.cg + ug.gc0) & ~3)) * 4);
+            if (a.dim == 3) p.vo = (unsigned)(a.off_v + q.pl * a.tile_v + ((q.r + ug.vr0) * a.OL + ((4 * q.cg + ug.vc0) & ~3)) * 4);
+            else p.vo = (unsigned)(a.off_g + q.pl * a.tile_g + ((q.r + ug.vr0) * a.pg + ((4 * q.cg + ug.vc0) & ~3)) * 4);
         }
     }
     return p;
@@ -431,19 +485,26 @@ struct Ring {
     unsigned phase;
 };
 
+// ROLE (3-D interpolating backward only): 0 = a thread does everything for ONE pair; 1 = grad_weight terms (x windows) of
+// TWO pairs; 2 = grad_input (grad windows + stores) of TWO pairs.  Splitting the two halves of the arithmetic over
+// different warps halves the window state a thread carries from slab to slab (30 instead of 60 registers).
 template <int DIM, int MODE, bool ACTIVE>
 struct Body {
     const HArgs& a;
     const int tid, nt, wid, lane;
+    uint64_t* const wait_bar;      // ready[] when a fixer warp patches the stages, else full[]
+    uint64_t* const empty;
     UnitShift us;
     UnitGeom ug;
     int wsx, wsg, wsv;
     double acc[3];
 
-    TS_D Body(const HArgs& a_, int tid_, int nt_, int wid_, int lane_) : a(a_), tid(tid_), nt(nt_), wid(wid_), lane(lane_) {}
+    const UnitShift* const tbl;
+    TS_D Body(const HArgs& a_, int tid_, int nt_, int wid_, int lane_, uint64_t* wait_, uint64_t* empty_, const UnitShift* tbl_)
+        : a(a_), tid(tid_), nt(nt_), wid(wid_), lane(lane_), wait_bar(wait_), empty(empty_), tbl(tbl_) {}
 
     TS_D void begin_unit(int c) {
-        us = unit_shift(a, c);
+        us = unit_shift(a, tbl, c);
         ug = unit_geom(a, us);
         wsx = ug.xc0 & 3; wsg = ug.gc0 & 3; wsv = ug.vc0 & 3;
         acc[0] = acc[1] = acc[2] = 0.0;
@@ -458,207 +519,224 @@ struct Body {
             if (lane == 0) a.partials[((long long)chunk * a.nw + wid) * (a.g.C * DIM) + (long long)c * DIM + k] = v;
         }
     }
-
-    // halo cells of every tile of the stage (padding != zeros), then a barrier among the consumer warps
-    TS_D void fix_stage(unsigned char* st, int npl, bool has_g) const {
-        if (!a.need_fix) return;
-        const bool bwd = MODE == 2;
-        const int xr_lo = (bwd ? 0 : a.lbB) - us.sx[1], xc_lo = (bwd ? 0 : a.lbL) - us.sx[2];
-        for (int pl = 0; pl < npl; ++pl) {
-            fill_halo((float*)(st + (size_t)pl * a.tile_x), a.px, a.B, a.L, a.hr, a.hc, a.g.pad, xr_lo, xr_lo + a.IB, xc_lo, xc_lo + 4 * a.IG,
-                      tid, nt);
-            if (bwd && has_g) {
-                const int sgr = ACTIVE ? -us.sg[1] : us.sg[1], sgc = ACTIVE ? -us.sg[2] : us.sg[2], ex = ACTIVE ? 1 : 0;
-                fill_halo((float*)(st + a.off_g + (size_t)pl * a.tile_g), a.pg, a.OB, a.OL, a.hr, a.hc, a.g.pad, sgr, a.OB - 1 + sgr + ex,
-                          sgc, a.OL - 1 + sgc + ex, tid, nt);
-            }
-        }
-        fence_proxy_async();                 // the next TMA load of this stage must not overtake these generic-proxy writes
-        named_barrier(1, nt);
+    TS_D void release(Ring& ring) const {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[ring.s]);
+        if (++ring.s == a.stages) { ring.s = 0; ring.phase ^= 1u; }
     }
 
     // ---------------------------------------------------------------------------------------------
     // 2-D: a stage = np images, every pair is independent
     template <int WSX, int WSG, int WSV>
-    TS_D void step2(const unsigned char* st, unsigned char* dst, int npl, float* ts) const {
-        const unsigned sx = shared_addr(st), sgb = sx + a.off_g;
+    TS_D void pair2(unsigned sb, unsigned char* dst, const PairCtx& pc, float* ts) const {
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
-        const int total = npl * a.img_pairs;
-        const long long img_out = a.g.C * (MODE == 2 ? a.g.in_plane : a.g.out_plane) * 4;
-        for (int p = tid; p < total; p += nt) {
-            Pair q;
-            if (!decode_pair(a, p, q)) continue;
-            const PairCtx pc = pair_ctx<MODE>(a, ug, q, true);
-            unsigned char* o = dst + (long long)q.pl * img_out + pc.out_off;
-            const unsigned xa = sx + q.pl * a.tile_x + pc.xo;
-            float X[3][5];
-            load5<WSX>(xa, wsx, X[0]);
-            load5<WSX>(xa + a.px * 4, wsx, X[1]);
-            if (pc.rows == 2) load5<WSX>(xa + 2 * a.px * 4, wsx, X[2]);
-            if (MODE == 1) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (j < pc.rows) {
-                        float R[5], y[4];
-#pragma unroll
-                        for (int t = 0; t < 5; ++t) R[t] = lerp<float>(X[j][t], X[j + 1][t], d[0]);
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) y[t] = lerp<float>(R[t], R[t + 1], d[1]);
-                        __stcs((float4*)(o + j * a.IG * 16), make_float4(y[0], y[1], y[2], y[3]));
-                    }
-                }
-                continue;
-            }
-            const unsigned ga = sgb + q.pl * a.tile_g + pc.go, va = sgb + q.pl * a.tile_g + pc.vo;
-            float G[3][5];
-            if (ACTIVE && pc.cmask) {
-                load5<WSG>(ga, wsg, G[0]);
-                load5<WSG>(ga + a.pg * 4, wsg, G[1]);
-                if (pc.rows == 2) load5<WSG>(ga + 2 * a.pg * 4, wsg, G[2]);
-            }
+        unsigned char* o = dst + pc.out_off;
+        const unsigned xa = sb + pc.xo;
+        const int orow = a.IG * 16;
+        float X[3][5];
+        load5<WSX>(xa, wsx, X[0]);
+        load5<WSX>(xa + a.px * 4, wsx, X[1]);
+        if (pc.rows == 2) load5<WSX>(xa + 2 * a.px * 4, wsx, X[2]);
+        if (MODE == 1) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                if (j >= pc.rows) continue;
-                const unsigned m = (pc.cmask >> (4 * j)) & 15u;
-                float y[4] = {0.f, 0.f, 0.f, 0.f};
-                if (m) {
-                    float gv[4];
-                    load4<WSV>(va + j * a.pg * 4, wsv, gv);
+                if (j < pc.rows) {
+                    float R[5], y[4];
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) R[t] = lerp<float>(X[j][t], X[j + 1][t], d[0]);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) y[t] = lerp<float>(R[t], R[t + 1], d[1]);
+                    __stcs((float4*)(o + j * orow), make_float4(y[0], y[1], y[2], y[3]));
+                }
+            }
+            return;
+        }
+        const unsigned ga = sb + pc.go, va = sb + pc.vo;
+        float G[3][5];
+        if (ACTIVE && pc.cmask) {
+            load5<WSG>(ga, wsg, G[0]);
+            load5<WSG>(ga + a.pg * 4, wsg, G[1]);
+            if (pc.rows == 2) load5<WSG>(ga + 2 * a.pg * 4, wsg, G[2]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (j >= pc.rows) continue;
+            const unsigned m = (pc.cmask >> (4 * j)) & 15u;
+            float y[4] = {0.f, 0.f, 0.f, 0.f};
+            if (m) {
+                float gv[4];
+                load4<WSV>(va + j * a.pg * 4, wsv, gv);
+                if (m != 15u) {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) gv[t] = (m >> t) & 1u ? gv[t] : 0.f;
-                    wp2(X[j], X[j + 1], gv, d, ts);
-                    if (ACTIVE) {
-                        float R[5];
+                }
+                wp2(X[j], X[j + 1], gv, d, ts);
+                if (ACTIVE) {
+                    float R[5];
 #pragma unroll
-                        for (int t = 0; t < 5; ++t) R[t] = lerp<float>(G[j][t], G[j + 1][t], d[0]);
+                    for (int t = 0; t < 5; ++t) R[t] = lerp<float>(G[j][t], G[j + 1][t], d[0]);
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) y[t] = lerp<float>(R[t], R[t + 1], d[1]);
-                    } else {
-                        load4<WSG>(ga + j * a.pg * 4, wsg, y);
-                    }
+                    for (int t = 0; t < 4; ++t) y[t] = lerp<float>(R[t], R[t + 1], d[1]);
+                } else {
+                    load4<WSG>(ga + j * a.pg * 4, wsg, y);
+                }
+                if (m != 15u) {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) y[t] = (m >> t) & 1u ? y[t] : 0.f;
                 }
-                __stcs((float4*)(o + j * a.IG * 16), make_float4(y[0], y[1], y[2], y[3]));
             }
+            __stcs((float4*)(o + j * orow), make_float4(y[0], y[1], y[2], y[3]));
         }
+    }
+
+    template <int WSX, int WSG, int WSV>
+    TS_D void run_images2(unsigned char* smem, Ring& ring, unsigned char* dst, int npl, const PairCtx& pc0, float* ts) const {
+        unsigned char* st = smem + (size_t)ring.s * a.stage_stride + GUARD;
+        const unsigned sb = shared_addr(st);
+        mbar_wait(&wait_bar[ring.s], ring.phase);
+        const int total = npl * a.img_pairs;
+        if (tid < total && pc0.rows) pair2<WSX, WSG, WSV>(sb, dst, pc0, ts);      // the thread's first pair: context cached per unit
+        for (int p = tid + nt; p < total; p += nt) {
+            Pair q;
+            if (!decode_pair(a, p, q)) continue;
+            const PairCtx pc = pair_ctx<MODE>(a, ug, q, true);
+            pair2<WSX, WSG, WSV>(sb, dst, pc, ts);
+        }
+        release(ring);
     }
 
     // ---------------------------------------------------------------------------------------------
-    // 3-D: one pair per thread for the whole image; windows of the previous slab stay in registers
+    // 3-D: a thread owns its pair(s) for the whole image; windows of the previous slab stay in registers
+    template <int ROLE>
     struct Carry {
-        float X[3][5], G[3][5];
+        float X[(MODE == 1 || ROLE != 2) ? 3 : 1][5];
+        float G[(MODE == 2 && ACTIVE && ROLE != 1) ? 3 : 1][5];
     };
 
-    template <int WSX, int WSG>
-    TS_D void load_slab(const unsigned char* st, const Pair& q, const PairCtx& pc, bool has_g, float (*Xn)[5], float (*Gn)[5]) const {
-        const unsigned xa = shared_addr(st) + q.pl * a.tile_x + pc.xo;
-        load5<WSX>(xa, wsx, Xn[0]);
-        load5<WSX>(xa + a.px * 4, wsx, Xn[1]);
-        if (pc.rows == 2) load5<WSX>(xa + 2 * a.px * 4, wsx, Xn[2]);
-        if (MODE == 2 && ACTIVE && has_g && pc.cmask) {
-            const unsigned ga = shared_addr(st) + a.off_g + q.pl * a.tile_g + pc.go;
-            load5<WSG>(ga, wsg, Gn[0]);
-            load5<WSG>(ga + a.pg * 4, wsg, Gn[1]);
-            if (pc.rows == 2) load5<WSG>(ga + 2 * a.pg * 4, wsg, Gn[2]);
-        }
-    }
-
-    // iteration slab `it` (= k - 1) of the image: carry = slab it, stage = slab it + 1
-    template <int WSX, int WSG, int WSV>
-    TS_D void step3(const unsigned char* st, unsigned char* dst_img, int k, const Pair& q, const PairCtx& pc, Carry& cy, float* ts) const {
+    // stage k of an image: combine the carried windows (slab k-1) with this stage's (slab k), then carry the new ones
+    template <int WSX, int WSG, int WSV, int ROLE>
+    TS_D void step3(unsigned sb, unsigned char* dst_img, int k, const PairCtx& pc, Carry<ROLE>& cy, float* ts) const {
+        constexpr bool DOX = MODE == 1 || ROLE != 2;
+        constexpr bool DOG = MODE == 2 && ROLE != 1;
         if (pc.rows == 0) return;
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        const int it = k - 1, orow = a.IG * 16;
+        unsigned char* o = dst_img + pc.out_off + (long long)it * a.IB * orow;
+        const bool slab_pass = MODE == 1 || (it - a.lbA >= 0 && it - a.lbA < a.OA);
+        const unsigned cm = (k >= 1 && slab_pass) ? pc.cmask : 0u;
+        const unsigned xa = sb + pc.xo, ga = sb + pc.go, va = sb + pc.vo;
+        const bool gwin = DOG && ACTIVE && pc.cmask != 0u;
         float Xn[3][5], Gn[3][5];
-        load_slab<WSX, WSG>(st, q, pc, true, Xn, Gn);
-        if (k >= 1) {
-            const int it = k - 1;
-            const long long img_out = a.g.C * (MODE == 2 ? a.g.in_plane : a.g.out_plane) * 4;
-            unsigned char* o = dst_img + (long long)q.pl * img_out + (long long)it * a.IB * a.IG * 16 + pc.out_off;
-            if (MODE == 1) {
+        if (DOX) { load5<WSX>(xa, wsx, Xn[0]); load5<WSX>(xa + a.px * 4, wsx, Xn[1]); }
+        if (gwin) { load5<WSG>(ga, wsg, Gn[0]); load5<WSG>(ga + a.pg * 4, wsg, Gn[1]); }
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (j < pc.rows) {
-                        float P[5], y[4];
+        for (int j = 0; j < 2; ++j) {
+            if (j >= pc.rows) continue;
+            if (j == 1) {
+                if (DOX) load5<WSX>(xa + 2 * a.px * 4, wsx, Xn[2]);
+                if (gwin) load5<WSG>(ga + 2 * a.pg * 4, wsg, Gn[2]);
+            }
+            if (k >= 1) {
+                if (MODE == 1) {
+                    float P[5], y[4];
 #pragma unroll
-                        for (int t = 0; t < 5; ++t) P[t] = col3(cy.X[j][t], Xn[j][t], cy.X[j + 1][t], Xn[j + 1][t], d[0], d[1]);
+                    for (int t = 0; t < 5; ++t) P[t] = col3(cy.X[j][t], Xn[j][t], cy.X[j + 1][t], Xn[j + 1][t], d[0], d[1]);
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
-                        __stcs((float4*)(o + j * a.IG * 16), make_float4(y[0], y[1], y[2], y[3]));
-                    }
-                }
-            } else {
-                const int oa = it - a.lbA;
-                const bool slab_pass = oa >= 0 && oa < a.OA;
-                const unsigned sb = shared_addr(st);
-                const unsigned va = sb + a.off_v + q.pl * a.tile_v + pc.vo;
-                const unsigned ga = sb + a.off_g + q.pl * a.tile_g + pc.go;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (j >= pc.rows) continue;
-                    const unsigned m = slab_pass ? (pc.cmask >> (4 * j)) & 15u : 0u;
+                    for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
+                    __stcs((float4*)(o + j * orow), make_float4(y[0], y[1], y[2], y[3]));
+                } else {
+                    const unsigned m = (cm >> (4 * j)) & 15u;
                     float y[4] = {0.f, 0.f, 0.f, 0.f};
                     if (m) {
-                        float gv[4];
-                        load4<WSV>(va + j * a.OL * 4, wsv, gv);
+                        if (DOX) {
+                            float gv[4];
+                            load4<WSV>(va + j * a.OL * 4, wsv, gv);
+                            if (m != 15u) {
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) gv[t] = (m >> t) & 1u ? gv[t] : 0.f;
-                        wp3(cy.X[j], Xn[j], cy.X[j + 1], Xn[j + 1], gv, d, ts);
-                        if (ACTIVE) {
-                            float P[5];
-#pragma unroll
-                            for (int t = 0; t < 5; ++t) P[t] = col3(cy.G[j][t], Gn[j][t], cy.G[j + 1][t], Gn[j + 1][t], d[0], d[1]);
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
-                        } else {
-                            load4<WSG>(ga + j * a.pg * 4, wsg, y);
+                                for (int t = 0; t < 4; ++t) gv[t] = (m >> t) & 1u ? gv[t] : 0.f;
+                            }
+                            wp3(cy.X[j], Xn[j], cy.X[j + 1], Xn[j + 1], gv, d, ts);
                         }
+                        if (DOG) {
+                            if (ACTIVE) {
+                                float P[5];
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) y[t] = (m >> t) & 1u ? y[t] : 0.f;
+                                for (int t = 0; t < 5; ++t) P[t] = col3(cy.G[j][t], Gn[j][t], cy.G[j + 1][t], Gn[j + 1][t], d[0], d[1]);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
+                            } else {
+                                load4<WSG>(ga + j * a.pg * 4, wsg, y);
+                            }
+                            if (m != 15u) {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) y[t] = (m >> t) & 1u ? y[t] : 0.f;
+                            }
+                        }
                     }
-                    __stcs((float4*)(o + j * a.IG * 16), make_float4(y[0], y[1], y[2], y[3]));
+                    if (DOG) __stcs((float4*)(o + j * orow), make_float4(y[0], y[1], y[2], y[3]));
                 }
             }
-        }
+            // row j of the carried slab is not needed any more
+            if (DOX) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-            for (int t = 0; t < 5; ++t) {
-                cy.X[j][t] = Xn[j][t];
-                if (MODE == 2 && ACTIVE) cy.G[j][t] = Gn[j][t];
+                for (int t = 0; t < 5; ++t) cy.X[j][t] = Xn[j][t];
             }
+            if (gwin) {
+#pragma unroll
+                for (int t = 0; t < 5; ++t) cy.G[j][t] = Gn[j][t];
+            }
+        }
+        const int last = pc.rows;            // the row below the pair
+        if (DOX) {
+#pragma unroll
+            for (int t = 0; t < 5; ++t) { if (last == 2) cy.X[2][t] = Xn[2][t]; else cy.X[1][t] = Xn[1][t]; }
+        }
+        if (gwin) {
+#pragma unroll
+            for (int t = 0; t < 5; ++t) { if (last == 2) cy.G[2][t] = Gn[2][t]; else cy.G[1][t] = Gn[1][t]; }
+        }
     }
 
-    // one image group (np images) of the unit, all its stages; WS* < 0: run-time window misalignment
-    template <int WSX, int WSG, int WSV>
-    TS_D void run_images(unsigned char* smem, uint64_t* full, uint64_t* empty, Ring& ring, unsigned char* dst_img, int npl, float* ts) {
-        if constexpr (DIM == 2) {
-            unsigned char* st = smem + (size_t)ring.s * a.stage_stride + GUARD;
-            mbar_wait(&full[ring.s], ring.phase);
-            fix_stage(st, npl, true);
-            step2<WSX, WSG, WSV>(st, dst_img, npl, ts);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[ring.s]);
-            if (++ring.s == a.stages) { ring.s = 0; ring.phase ^= 1u; }
-        } else {
+    template <int WSX, int WSG, int WSV, int ROLE>
+    TS_D void run_images3(unsigned char* smem, Ring& ring, unsigned char* dst_img, int npl, float* ts) const {
+        constexpr int NPT = ROLE == 0 ? 1 : 2;
+        const int half = nt >> 1;
+        PairCtx pc[NPT];
+        Carry<ROLE> cy[NPT];
+#pragma unroll
+        for (int i = 0; i < NPT; ++i) {
+            const int p = ROLE == 0 ? tid : (tid < half ? tid : tid - half) + i * half;
             Pair q;
-            const bool valid = tid < npl * a.img_pairs && decode_pair(a, tid, q);
+            const bool valid = p < npl * a.img_pairs && decode_pair(a, p, q);
             if (!valid) { q.pl = 0; q.r = 0; q.cg = 0; }
-            const PairCtx pc = pair_ctx<MODE>(a, ug, q, valid);
-            Carry cy;
-            for (int k = 0; k <= a.IA; ++k) {
-                unsigned char* st = smem + (size_t)ring.s * a.stage_stride + GUARD;
-                mbar_wait(&full[ring.s], ring.phase);
-                fix_stage(st, npl, MODE == 2 && (ACTIVE || k >= 1));
-                step3<WSX, WSG, WSV>(st, dst_img, k, q, pc, cy, ts);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[ring.s]);
-                if (++ring.s == a.stages) { ring.s = 0; ring.phase ^= 1u; }
-            }
+            pc[i] = pair_ctx<MODE>(a, ug, q, valid);
+        }
+        for (int k = 0; k <= a.IA; ++k) {
+            const unsigned sb = shared_addr(smem + (size_t)ring.s * a.stage_stride + GUARD);
+            mbar_wait(&wait_bar[ring.s], ring.phase);
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) step3<WSX, WSG, WSV, ROLE>(sb, dst_img, k, pc[i], cy[i], ts);
+            release(ring);
         }
     }
 
-    TS_D void run_unit(unsigned char* smem, uint64_t* full, uint64_t* empty, Ring& ring, int c, int n0, int n1) {
+    template <int WSX, int WSG, int WSV>
+    TS_D void run_images(unsigned char* smem, Ring& ring, unsigned char* dst, int npl, const PairCtx& pc0, float* ts) const {
+        if constexpr (DIM == 2) {
+            run_images2<WSX, WSG, WSV>(smem, ring, dst, npl, pc0, ts);
+        } else if constexpr (MODE == 2 && ACTIVE) {
+            if (a.split) {
+                if (tid < (nt >> 1)) run_images3<WSX, WSG, WSV, 1>(smem, ring, dst, npl, ts);
+                else run_images3<WSX, WSG, WSV, 2>(smem, ring, dst, npl, ts);
+            } else {
+                run_images3<WSX, WSG, WSV, 0>(smem, ring, dst, npl, ts);
+            }
+        } else {
+            run_images3<WSX, WSG, WSV, 0>(smem, ring, dst, npl, ts);
+        }
+    }
+
+    TS_D void run_unit(unsigned char* smem, Ring& ring, int c, int n0, int n1) {
         if (!ug.fits) {
             if (MODE == 1) slow_forward<DIM>(a, c, n0, n1, us, tid, nt);
             else slow_backward<DIM, ACTIVE>(a, c, n0, n1, us, tid, nt, acc);
@@ -667,19 +745,27 @@ struct Body {
         const long long plane_bytes = (MODE == 2 ? a.g.in_plane : a.g.out_plane) * 4;
         // fast instantiations: every window misalignment known at compile time from the x window's
         const bool derived = MODE == 1 || (wsv == 0 && wsg == (ACTIVE ? wsx : ((4 - wsx) & 3)));
+        PairCtx pc0;
+        pc0.rows = 0;
+        if (DIM == 2) {
+            Pair q;
+            const bool valid = tid < a.pairs && decode_pair(a, tid, q);
+            if (!valid) { q.pl = 0; q.r = 0; q.cg = 0; }
+            pc0 = pair_ctx<MODE>(a, ug, q, valid);
+        }
         for (int nb = n0; nb < n1; nb += a.np) {
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
             unsigned char* dst = (unsigned char*)a.out + ((long long)nb * a.g.C + c) * plane_bytes;
             float ts[3] = {0.f, 0.f, 0.f};
             if (derived) {
                 switch (wsx) {
-                case 0: run_images<0, 0, 0>(smem, full, empty, ring, dst, npl, ts); break;
-                case 1: run_images<1, ACTIVE ? 1 : 3, 0>(smem, full, empty, ring, dst, npl, ts); break;
-                case 2: run_images<2, 2, 0>(smem, full, empty, ring, dst, npl, ts); break;
-                default: run_images<3, ACTIVE ? 3 : 1, 0>(smem, full, empty, ring, dst, npl, ts); break;
+                case 0: run_images<0, 0, 0>(smem, ring, dst, npl, pc0, ts); break;
+                case 1: run_images<1, ACTIVE ? 1 : 3, 0>(smem, ring, dst, npl, pc0, ts); break;
+                case 2: run_images<2, 2, 0>(smem, ring, dst, npl, pc0, ts); break;
+                default: run_images<3, ACTIVE ? 3 : 1, 0>(smem, ring, dst, npl, pc0, ts); break;
                 }
             } else {
-                run_images<-1, -1, -1>(smem, full, empty, ring, dst, npl, ts);
+                run_images<-1, -1, -1>(smem, ring, dst, npl, pc0, ts);
             }
 #pragma unroll
             for (int k = 0; k < DIM; ++k) acc[k] += (double)ts[k];     // fp32 inside an image group, fp64 across
@@ -692,24 +778,29 @@ __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs 
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
     uint64_t* empty = full + a.stages;
+    uint64_t* ready = empty + a.stages;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)a.nw); }
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)a.nw); mbar_init(&ready[s], 1); }
         fence_barrier_init();
     }
+    UnitShift* tbl = (UnitShift*)(ready + a.stages);
+    if (a.table)
+        for (int c = threadIdx.x; c < (int)a.g.C; c += blockDim.x) tbl[c] = compute_unit_shift(a, c);
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
-    Body<DIM, MODE, ACTIVE> body(a, threadIdx.x, a.nt, wid, lane);
+    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty, tbl); return; }
+    if (wid > a.nw) { fixer(a, smem, full, ready, lane, tbl); return; }      // launched only when the padding needs it
+    Body<DIM, MODE, ACTIVE> body(a, threadIdx.x, a.nt, wid, lane, a.need_fix ? ready : full, empty, tbl);
     Ring ring = {0, 0u};
     const int C = (int)a.g.C, N = (int)a.g.N;
     const UnitRange ur = unit_range(a.units, a.unit_order);
     for (int u = ur.u; u < ur.end; u += ur.step) {
         int chunk, c;
-        unit_decode(u, C, a.chunks, a.unit_order, c, chunk);
+        decode_unit(a, u, c, chunk);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         body.begin_unit(c);
-        body.run_unit(smem, full, empty, ring, c, n0, n1);
+        body.run_unit(smem, ring, c, n0, n1);
         body.end_unit(c, chunk);
     }
 }
@@ -719,7 +810,7 @@ long long round_up(long long v, long long q) { return (v + q - 1) / q * q; }
 template <class K>
 int launch(K kernel, const HArgs& a, const HaloPlan& p, cudaStream_t s) {
     if (!ensure_dynamic_smem((const void*)kernel, p.smem_bytes)) return check_launch();
-    kernel<<<p.grid, (p.warps + 1) * 32, p.smem_bytes, s>>>(a);
+    kernel<<<p.grid, (p.warps + 1 + (a.need_fix ? 1 : 0)) * 32, p.smem_bytes, s>>>(a);
     note_launch();
     return check_launch();
 }
@@ -753,7 +844,11 @@ bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, const void
     a.n_per_unit = p.n_per_unit; a.units = p.units;
     a.chunks = (int)(p.units / (g.C > 0 ? g.C : 1));
     a.unit_order = tuning().unit_order;
+    a.d_C = make_fastdivu((unsigned)g.C);
+    a.d_chunks = make_fastdivu((unsigned)a.chunks);
+    a.table = g.C <= TABLE_MAX_C ? 1 : 0;
     a.need_fix = g.pad != TS_PAD_ZEROS;
+    a.split = (d == 3 && mode == 2 && active && p.warps % 2 == 0 && a.pairs <= a.nt) ? 1 : 0;
     a.d_GP = make_fastdivu((unsigned)a.GP);
     a.d_img = make_fastdivu((unsigned)a.img_pairs);
     if (!make_tensor_map5(&a.map_x, x, 4, g.N, g.C, a.A, a.B, a.L, a.px, a.bpx, 1, 1)) return false;
@@ -788,8 +883,11 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     const int halo = t.halo > 0 ? t.halo : 4;
     p.hr = halo;
     p.hc = (halo + 3) / 4 * 4;
+    // row pitch = 4 (mod 8) words: the fixer warp walks DOWN the rows of a halo column (4-way bank conflicts instead of 32-way)
     p.px = L + 2 * p.hc;   p.bpx = B + 2 * p.hr;
     p.pg = OL + 2 * p.hc;  p.bpg = OB + 2 * p.hr;
+    if (p.px % 8 == 0) p.px += 4;
+    if (p.pg % 8 == 0) p.pg += 4;
     if (p.px > 256 || p.bpx > 256 || p.pg > 256 || p.bpg > 256) return p;           // TMA box extents
     p.tile_x = (int)round_up((long long)p.px * p.bpx * 4, 128);
     p.tile_g = mode == 2 ? (int)round_up((long long)p.pg * p.bpg * 4, 128) : 0;
@@ -799,8 +897,9 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     int GP = IG;
     if (IG % 8 != 0 && (double)IG / (double)((IG + 7) / 8 * 8) >= 0.85) GP = (IG + 7) / 8 * 8;
     const int img_pairs = (IB + 1) / 2 * GP;
-    const int max_nt = MAXT - 32;
-    const long long budget = SMEM_LIMIT - 1024;
+    const int max_nt = MAXT - 64;                          // producer warp + fixer warp
+    const long long table_bytes = g.C <= TABLE_MAX_C ? g.C * 36 : 0;
+    const long long budget = SMEM_LIMIT - 1024 - table_bytes;
     long long np;
     if (d == 3) {
         if (img_pairs > max_nt) return p;                  // one (row pair, group) per thread for the whole image
@@ -813,8 +912,8 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     const long long tail = 4ll * (p.px > p.pg ? p.px : p.pg) + 256;       // a masked row may be read one row past the last tile
     auto stride_of = [&](long long n) { return round_up(n * per_image + GUARD + tail, 1024); };
     const int min_stages = d == 3 ? 3 : 2;
-    while (np > 1 && budget / (stride_of(np) + 16) < min_stages + 1) --np;
-    long long stages = budget / (stride_of(np) + 16);
+    while (np > 1 && budget / (stride_of(np) + 24) < min_stages + 1) --np;
+    long long stages = budget / (stride_of(np) + 24);
     if (stages < min_stages) return p;
     const int want = t.halo_stages > 0 ? t.halo_stages : (d == 3 ? 6 : 5);
     if (stages > want) stages = want;
@@ -826,6 +925,7 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     int warps;
     if (d == 3) {
         warps = (int)((pairs + 31) / 32);
+        if (mode == 2 && active && warps % 2 && warps < max_nt / 32) ++warps;      // x-window warps and grad-window warps
     } else {
         auto eff = [&](int w) {
             const long long nt = 32ll * w, passes = (pairs + nt - 1) / nt;
@@ -851,7 +951,7 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     p.n_per_unit = (int)npu; p.units = (int)units;
     p.grid = (int)(units < sm_count ? units : sm_count);
     p.slots = (int)(chunks * warps);
-    p.smem_bytes = (size_t)(stages * stride_of(np) + 16 * stages + 64);
+    p.smem_bytes = (size_t)(stages * stride_of(np) + 24 * stages + 64 + table_bytes);
     return p;
 }
 

@@ -37,6 +37,7 @@ namespace {
 
 constexpr int SMEM_LIMIT = 232448;
 constexpr int MAXT_TMA_GATHER = 1024, MAXT_TMA_ARITH = 512;
+constexpr int TABLE_MAX_C = 512;      // channels whose shift parameters are tabulated in shared memory (24 bytes each)
 
 // ---- exact division by a launch-invariant (n < 2^31) ------------------------------------------
 struct FastDiv { unsigned m, l, d; };
@@ -177,18 +178,19 @@ struct alignas(64) TArgs {
     int GP, img_items;       // padded groups per row of the item index space; items per image = TA*TB*GP
     int img_stride16;        // output distance between consecutive images of one channel, in 16-byte units
     int R, nchunk;           // strip-mined arithmetic kernels: rows per strip, strips per tile column
-    FastDiv d_img, d_GP, d_TB, d_tg, d_tb, d_TG, d_nchunk, d_TA;
+    FastDiv d_img, d_GP, d_TB, d_tg, d_tb, d_TG, d_nchunk, d_TA, d_C, d_chunks;
+    int table;               // per-channel shift table in shared memory (C <= TABLE_MAX_C): built once per CTA
 };
 
 TS_D int level_axis(int level, int dim) { return level - (3 - dim); }
-TS_D int floor_to(int v, int q) { return v - pmod(v, q); }
+TS_D int floor_to(int v, int q) { return v & ~(q - 1); }      // q is a power of two (elements per 16 bytes)
 
 struct UnitShift {
     int sh[3];     // integer shift per level (0 slab, 1 row, 2 column); absent levels 0
     float d[3];    // fractional part per TENSOR AXIS (reference order), 0 for the sparse forward
 };
 
-TS_D UnitShift unit_shift(const TArgs& a, long long c) {
+TS_D UnitShift compute_unit_shift(const TArgs& a, long long c) {
     UnitShift u;
     const int dim = a.g.dim;
     u.d[0] = u.d[1] = u.d[2] = 0.f;
@@ -223,6 +225,17 @@ TS_D UnitShift unit_shift(const TArgs& a, long long c) {
     return u;
 }
 
+// The per-channel parameters cost a few hundred dependent instructions (64-bit conversions, saturation, the reduced
+// shift): computed per work unit by the single producer thread they bounded small batches (one stage per unit).
+// Every CTA tabulates them once in shared memory instead; a unit then costs one 24-byte read.
+TS_D UnitShift unit_shift(const TArgs& a, const UnitShift* tbl, long long c) { return a.table ? tbl[c] : compute_unit_shift(a, c); }
+
+// u -> (channel, chunk) without an integer division
+TS_D void decode_unit(const TArgs& a, int u, int& c, int& chunk) {
+    if (a.unit_order) { chunk = (int)fdiv((unsigned)u, a.d_C); c = u - chunk * (int)a.g.C; }
+    else { c = (int)fdiv((unsigned)u, a.d_chunks); chunk = u - c * a.chunks; }
+}
+
 struct Tile { int a0, b0, g0; };
 TS_D Tile tile_of(const TArgs& a, int t) {
     Tile tl;
@@ -235,18 +248,18 @@ TS_D Tile tile_of(const TArgs& a, int t) {
 }
 
 // ---- producer ---------------------------------------------------------------------------------
-TS_D void producer(const TArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty) {
+TS_D void producer(const TArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, const UnitShift* tbl) {
     int s = 0, k = 0;
     const long long C = a.g.C, N = a.g.N;
     const int dim = a.g.dim;
     const UnitRange ur = unit_range(a.units, a.unit_order);
     for (int u = ur.u; u < ur.end; u += ur.step) {
         int ci, chunki;
-        unit_decode(u, (int)C, a.chunks, a.unit_order, ci, chunki);
+        decode_unit(a, u, ci, chunki);
         const long long c = ci, chunk = chunki;
         const long long n0 = chunk * a.n_per_unit;
         const long long n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
-        const UnitShift us = unit_shift(a, c);
+        const UnitShift us = unit_shift(a, tbl, c);
         for (long long nb = n0; nb < n1; nb += a.np) {
             for (int t = 0; t < a.tiles; ++t) {
                 if (k > 0) mbar_wait(&empty[s], (unsigned)((k - 1) & 1));
@@ -293,7 +306,7 @@ TS_D void consumer_loop(const TArgs& a, unsigned char* smem, uint64_t* full, uin
     const UnitRange ur = unit_range(a.units, a.unit_order);
     for (int u = ur.u; u < ur.end; u += ur.step) {
         int chunk, c;
-        unit_decode(u, C, a.chunks, a.unit_order, c, chunk);
+        decode_unit(a, u, c, chunk);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         body.begin_unit(c);
@@ -355,9 +368,10 @@ struct GatherBody {
     const int tid, nt;
     int ws, bs8;
 
-    TS_D GatherBody(const TArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), ws(0), bs8(0) {}
+    const UnitShift* tbl;
+    TS_D GatherBody(const TArgs& a_, int tid_, int nt_, const UnitShift* tbl_) : a(a_), tid(tid_), nt(nt_), ws(0), bs8(0), tbl(tbl_) {}
     TS_D void begin_unit(int c) {
-        const UnitShift us = unit_shift(a, c);
+        const UnitShift us = unit_shift(a, tbl, c);
         const int mb = pmod((a.lbL - us.sh[2]) * a.es, 16);    // tiles start at multiples of 16 bytes
         ws = mb >> 2;
         bs8 = (mb & 3) * 8;
@@ -459,9 +473,10 @@ struct ActiveFwdBody {
     UnitShift us;
     int m;
 
-    TS_D ActiveFwdBody(const TArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), m(0) {}
+    const UnitShift* tbl;
+    TS_D ActiveFwdBody(const TArgs& a_, int tid_, int nt_, const UnitShift* tbl_) : a(a_), tid(tid_), nt(nt_), m(0), tbl(tbl_) {}
     TS_D void begin_unit(int c) {
-        us = unit_shift(a, c);
+        us = unit_shift(a, tbl, c);
         m = pmod(a.lbL - us.sh[2], 4);
     }
     TS_D void end_unit(int, int) {}
@@ -563,9 +578,11 @@ struct BackwardBody {
     int m;
     double acc[DIM];
 
-    TS_D BackwardBody(const TArgs& a_, int tid_, int nt_, int wid_, int lane_) : a(a_), tid(tid_), nt(nt_), wid(wid_), lane(lane_), m(0) {}
+    const UnitShift* tbl;
+    TS_D BackwardBody(const TArgs& a_, int tid_, int nt_, int wid_, int lane_, const UnitShift* tbl_)
+        : a(a_), tid(tid_), nt(nt_), wid(wid_), lane(lane_), m(0), tbl(tbl_) {}
     TS_D void begin_unit(int c) {
-        us = unit_shift(a, c);
+        us = unit_shift(a, tbl, c);
         m = pmod(-us.sh[2], 4);
 #pragma unroll
         for (int d = 0; d < DIM; ++d) acc[d] = 0.0;
@@ -738,24 +755,28 @@ struct BackwardBody {
 };
 
 // ---- kernels -----------------------------------------------------------------------------------
-TS_D void setup_barriers(const TArgs& a, unsigned char* smem, uint64_t*& full, uint64_t*& empty) {
+TS_D const UnitShift* setup_barriers(const TArgs& a, unsigned char* smem, uint64_t*& full, uint64_t*& empty) {
     full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
     empty = full + a.stages;
+    UnitShift* tbl = (UnitShift*)(empty + a.stages);
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)a.nw); }
         fence_barrier_init();
     }
+    if (a.table)
+        for (int c = threadIdx.x; c < (int)a.g.C; c += blockDim.x) tbl[c] = compute_unit_shift(a, c);
     __syncthreads();
+    return tbl;
 }
 
 template <bool SLABS>
 __global__ void __launch_bounds__(MAXT_TMA_GATHER, 1) k_tma_gather(const __grid_constant__ TArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    setup_barriers(a, smem, full, empty);
+    const UnitShift* tbl = setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
-    GatherBody<SLABS> body(a, threadIdx.x, a.nw * 32);
+    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty, tbl); return; }
+    GatherBody<SLABS> body(a, threadIdx.x, a.nw * 32, tbl);
     consumer_loop(a, smem, full, empty, lane, body);
 }
 
@@ -763,10 +784,10 @@ template <int DIM>
 __global__ void __launch_bounds__(MAXT_TMA_ARITH, 1) k_tma_active_forward(const __grid_constant__ TArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    setup_barriers(a, smem, full, empty);
+    const UnitShift* tbl = setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
-    ActiveFwdBody<DIM> body(a, threadIdx.x, a.nw * 32);
+    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty, tbl); return; }
+    ActiveFwdBody<DIM> body(a, threadIdx.x, a.nw * 32, tbl);
     consumer_loop(a, smem, full, empty, lane, body);
 }
 
@@ -774,10 +795,10 @@ template <int DIM, bool ACTIVE>
 __global__ void __launch_bounds__(MAXT_TMA_ARITH, 1) k_tma_backward(const __grid_constant__ TArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    setup_barriers(a, smem, full, empty);
+    const UnitShift* tbl = setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
-    BackwardBody<DIM, ACTIVE> body(a, threadIdx.x, a.nw * 32, wid, lane);
+    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty, tbl); return; }
+    BackwardBody<DIM, ACTIVE> body(a, threadIdx.x, a.nw * 32, wid, lane, tbl);
     consumer_loop(a, smem, full, empty, lane, body);
 }
 
@@ -822,6 +843,9 @@ bool make_args(const Geo& g, const TmaPlan& p, int mode, int active, int es, TAr
     a.units = p.units;
     a.chunks = (int)(p.units / (g.C > 0 ? g.C : 1));
     a.unit_order = tuning().unit_order;
+    a.d_C = make_fastdiv((unsigned)g.C);
+    a.d_chunks = make_fastdiv((unsigned)a.chunks);
+    a.table = g.C <= TABLE_MAX_C ? 1 : 0;
     a.GP = p.gp;
     a.img_items = a.TA * a.TB * a.GP;
     a.img_stride16 = (int)(g.C * (mode == 2 ? g.in_plane : g.out_plane) * es / 16);
@@ -895,7 +919,8 @@ TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool 
         if (mode != 2) return xbytes;
         return xbytes + gsbytes + (active ? xbytes : gsbytes);
     };
-    const long long budget = SMEM_LIMIT - 1024;
+    const long long table_bytes = g.C <= TABLE_MAX_C ? g.C * 24 : 0;
+    const long long budget = SMEM_LIMIT - 1024 - table_bytes;
     // defaults from the cfg3 sweep on B200 (tools/tune.py --tma): forward 6 x 28 KB, backward 5 x 42 KB
     // 3-D volumes: few large stages (deep slab tiles re-read fewer +1 neighbour slabs)
     const int want_stages = t.tma_stages > 0 ? t.tma_stages : d == 3 ? (mode == 2 ? 2 : 3) : (mode == 2 ? 5 : 6);
@@ -987,7 +1012,7 @@ TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool 
     p.grid = (int)(units < grid_max ? units : grid_max);
     p.warps = warps;
     p.slots = (int)(chunks * warps);
-    p.smem_bytes = (size_t)(stages * stride + 16 * stages + 64);
+    p.smem_bytes = (size_t)(stages * stride + 16 * stages + 64 + table_bytes);
     return p;
 }
 
