@@ -172,27 +172,56 @@ TS_D void load4(unsigned addr, int ws, float* out) {
 // ---- halo fill --------------------------------------------------------------------------------
 // Cells of the needed extended range [rn_lo, rn_hi] x [cn_lo, cn_hi] that lie outside [0, rows) x [0, cols) take
 // tile[P(r)][P(c)].  Writers touch halo cells only, readers interior cells only: one pass, no ordering inside.
-// Run by ONE warp (the fixer): halo rows with the lanes along the columns (consecutive words), then the halo columns
-// of the interior rows with the lanes down the rows (the pitch is 4 mod 8 words: 4-way bank conflicts at worst).
+// The (destination, source) word offsets are the same for every stage of a work unit, so the fixer warp lists them
+// ONCE per unit in shared memory (16 + 16 bits per cell) and a stage costs one list read, one LDS and one STS per cell.
 TS_D int remap_any(int idx, int len, int pad, bool bounded) { return bounded ? axis_index(idx, len, pad) : axis_index_literal(idx, len, pad); }
 
-TS_D void fill_halo(float* tile, int pitch, int rows, int cols, int hr, int hc, int pad, int rn_lo, int rn_hi, int cn_lo, int cn_hi,
-                    int lane) {
-    const int nrt = rn_lo < 0 ? -rn_lo : 0, nrb = rn_hi > rows - 1 ? rn_hi - (rows - 1) : 0;
-    const int nct = cn_lo < 0 ? -cn_lo : 0, ncb = cn_hi > cols - 1 ? cn_hi - (cols - 1) : 0;
+constexpr int FIXCAP = 1536;       // cells per tile list; a unit that needs more is patched without a list
+
+struct HaloRange { int rn_lo, rn_hi, cn_lo, cn_hi; };
+
+TS_D int halo_cells(const HaloRange& h, int rows, int cols) {
+    const int nr = (h.rn_lo < 0 ? -h.rn_lo : 0) + (h.rn_hi > rows - 1 ? h.rn_hi - (rows - 1) : 0);
+    const int nc = (h.cn_lo < 0 ? -h.cn_lo : 0) + (h.cn_hi > cols - 1 ? h.cn_hi - (cols - 1) : 0);
+    return nr * (h.cn_hi - h.cn_lo + 1) + rows * nc;
+}
+
+// list != nullptr: write the cell list (entry = dst | src << 16, word offsets inside the tile); else copy in `tile`
+TS_D void halo_walk(unsigned* list, float* tile, int pitch, int rows, int cols, int hr, int hc, int pad, const HaloRange& h, int lane) {
+    const int nrt = h.rn_lo < 0 ? -h.rn_lo : 0, nrb = h.rn_hi > rows - 1 ? h.rn_hi - (rows - 1) : 0;
+    const int nct = h.cn_lo < 0 ? -h.cn_lo : 0, ncb = h.cn_hi > cols - 1 ? h.cn_hi - (cols - 1) : 0;
+    const int wc = h.cn_hi - h.cn_lo + 1;
     // the division-free remap is valid for indices within one period of the axis: halo <= hr (hc) < len
     const bool rb = rows > hr + 1, cb = cols > hc + 1;
     for (int ri = 0; ri < nrt + nrb; ++ri) {
-        const int r = ri < nrt ? rn_lo + ri : rows + (ri - nrt);
+        const int r = ri < nrt ? h.rn_lo + ri : rows + (ri - nrt);
         const int sr = remap_any(r, rows, pad, rb);
-        float* dst = tile + (r + hr) * pitch + hc;
-        const float* src = tile + (sr + hr) * pitch + hc;
-        for (int c = cn_lo + lane; c <= cn_hi; c += 32) dst[c] = src[remap_any(c, cols, pad, cb)];
+        for (int c = h.cn_lo + lane; c <= h.cn_hi; c += 32) {
+            const unsigned dst = (unsigned)((r + hr) * pitch + c + hc), src = (unsigned)((sr + hr) * pitch + remap_any(c, cols, pad, cb) + hc);
+            if (list) list[ri * wc + (c - h.cn_lo)] = dst | (src << 16); else tile[dst] = tile[src];
+        }
     }
+    const int nA = (nrt + nrb) * wc;
     for (int k = 0; k < nct + ncb; ++k) {
-        const int c = k < nct ? cn_lo + k : cols + (k - nct);
+        const int c = k < nct ? h.cn_lo + k : cols + (k - nct);
         const int sc = remap_any(c, cols, pad, cb);
-        for (int r = lane; r < rows; r += 32) tile[(r + hr) * pitch + c + hc] = tile[(r + hr) * pitch + sc + hc];
+        for (int r = lane; r < rows; r += 32) {
+            const unsigned dst = (unsigned)((r + hr) * pitch + c + hc), src = (unsigned)((r + hr) * pitch + sc + hc);
+            if (list) list[nA + k * rows + r] = dst | (src << 16); else tile[dst] = tile[src];
+        }
+    }
+}
+
+TS_D void halo_apply(const unsigned* list, int n, float* tile, int lane) {
+    int e = lane;
+    for (; e + 96 < n; e += 128) {          // four independent cells in flight per lane
+        const unsigned e0 = list[e], e1 = list[e + 32], e2 = list[e + 64], e3 = list[e + 96];
+        const float v0 = tile[e0 >> 16], v1 = tile[e1 >> 16], v2 = tile[e2 >> 16], v3 = tile[e3 >> 16];
+        tile[e0 & 0xffffu] = v0; tile[e1 & 0xffffu] = v1; tile[e2 & 0xffffu] = v2; tile[e3 & 0xffffu] = v3;
+    }
+    for (; e < n; e += 32) {
+        const unsigned e0 = list[e];
+        tile[e0 & 0xffffu] = tile[e0 >> 16];
     }
 }
 
@@ -388,12 +417,15 @@ TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t
 // One warp fills the halo cells of every stage (paddings other than zeros) between the copy engine and the consumers:
 // it waits for full[s], patches the tiles and arrives on ready[s]; the consumers wait for ready[s] instead of full[s].
 // It runs ahead of the consumers by the ring depth, so the arithmetic warps never meet at a barrier.
-TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* ready, int lane, const UnitShift* tbl) {
+TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* ready, int lane, const UnitShift* tbl, unsigned* lists) {
     int s = 0;
     unsigned phase = 0;
     const int C = (int)a.g.C, N = (int)a.g.N;
     const bool bwd = a.mode == 2;
     const int steps = a.dim == 3 ? a.IA + 1 : 1;
+    unsigned* list_x = lists;
+    unsigned* list_g = lists + FIXCAP;
+    const bool listable = a.px * a.bpx < 65536 && a.pg * a.bpg < 65536;
     const UnitRange ur = unit_range(a.units, a.unit_order);
     for (int u = ur.u; u < ur.end; u += ur.step) {
         int chunk, c;
@@ -404,6 +436,16 @@ TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* r
         if (!unit_geom(a, us).fits) continue;
         const int xr_lo = (bwd ? 0 : a.lbB) - us.sx[1], xc_lo = (bwd ? 0 : a.lbL) - us.sx[2];
         const int sgr = a.active ? -us.sg[1] : us.sg[1], sgc = a.active ? -us.sg[2] : us.sg[2], ex = a.active ? 1 : 0;
+        const HaloRange hx = {xr_lo, xr_lo + a.IB, xc_lo, xc_lo + 4 * a.IG};
+        const HaloRange hg = {sgr, a.OB - 1 + sgr + ex, sgc, a.OL - 1 + sgc + ex};
+        const int nx = halo_cells(hx, a.B, a.L), ng = bwd ? halo_cells(hg, a.OB, a.OL) : 0;
+        const bool use_list = listable && nx <= FIXCAP && ng <= FIXCAP;
+        if (use_list) {
+            __syncwarp();                       // every lane is done with the previous unit's lists
+            halo_walk(list_x, nullptr, a.px, a.B, a.L, a.hr, a.hc, a.g.pad, hx, lane);
+            if (bwd) halo_walk(list_g, nullptr, a.pg, a.OB, a.OL, a.hr, a.hc, a.g.pad, hg, lane);
+            __syncwarp();
+        }
         for (int nb = n0; nb < n1; nb += a.np) {
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
             for (int k = 0; k < steps; ++k) {
@@ -411,11 +453,15 @@ TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* r
                 const bool has_g = bwd && (a.dim == 2 || a.active || k >= 1);
                 mbar_wait(&full[s], phase);
                 for (int pl = 0; pl < npl; ++pl) {
-                    fill_halo((float*)(st + (size_t)pl * a.tile_x), a.px, a.B, a.L, a.hr, a.hc, a.g.pad, xr_lo, xr_lo + a.IB, xc_lo,
-                              xc_lo + 4 * a.IG, lane);
-                    if (has_g)
-                        fill_halo((float*)(st + a.off_g + (size_t)pl * a.tile_g), a.pg, a.OB, a.OL, a.hr, a.hc, a.g.pad, sgr,
-                                  a.OB - 1 + sgr + ex, sgc, a.OL - 1 + sgc + ex, lane);
+                    float* tx = (float*)(st + (size_t)pl * a.tile_x);
+                    float* tg = (float*)(st + a.off_g + (size_t)pl * a.tile_g);
+                    if (use_list) {
+                        halo_apply(list_x, nx, tx, lane);
+                        if (has_g) halo_apply(list_g, ng, tg, lane);
+                    } else {
+                        halo_walk(nullptr, tx, a.px, a.B, a.L, a.hr, a.hc, a.g.pad, hx, lane);
+                        if (has_g) halo_walk(nullptr, tg, a.pg, a.OB, a.OL, a.hr, a.hc, a.g.pad, hg, lane);
+                    }
                 }
                 fence_proxy_async();             // the next TMA load of this stage must not overtake these generic-proxy writes
                 __syncwarp();
@@ -789,7 +835,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs 
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty, tbl); return; }
-    if (wid > a.nw) { fixer(a, smem, full, ready, lane, tbl); return; }      // launched only when the padding needs it
+    if (wid > a.nw) {                                                         // launched only when the padding needs it
+        fixer(a, smem, full, ready, lane, tbl, (unsigned*)(tbl + (a.table ? (int)a.g.C : 0)));
+        return;
+    }
     Body<DIM, MODE, ACTIVE> body(a, threadIdx.x, a.nt, wid, lane, a.need_fix ? ready : full, empty, tbl);
     Ring ring = {0, 0u};
     const int C = (int)a.g.C, N = (int)a.g.N;
@@ -898,7 +947,7 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     if (IG % 8 != 0 && (double)IG / (double)((IG + 7) / 8 * 8) >= 0.85) GP = (IG + 7) / 8 * 8;
     const int img_pairs = (IB + 1) / 2 * GP;
     const int max_nt = MAXT - 64;                          // producer warp + fixer warp
-    const long long table_bytes = g.C <= TABLE_MAX_C ? g.C * 36 : 0;
+    const long long table_bytes = (g.C <= TABLE_MAX_C ? g.C * 36 : 0) + (g.pad != TS_PAD_ZEROS ? 2 * FIXCAP * 4 : 0);   // + the fixer's cell lists
     const long long budget = SMEM_LIMIT - 1024 - table_bytes;
     long long np;
     if (d == 3) {
@@ -938,7 +987,8 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     if (t.halo_warps > 0 && d != 3) warps = t.halo_warps < max_nt / 32 ? t.halo_warps : max_nt / 32;
     if (warps < 1) warps = 1;
     const long long planes = g.N * g.C;
-    long long npu = t.chunk_planes > 0 ? t.chunk_planes : planes / ((long long)sm_count * 32);
+    long long npu = t.chunk_planes > 0 ? t.chunk_planes : pick_unit_images(g.N, g.C, np, sm_count, mode == 2 ? 0.4 : 0.1);
+    (void)planes;
     npu = (npu / np) * np;
     if (npu < np) npu = np;
     if (npu > g.N) npu = g.N;

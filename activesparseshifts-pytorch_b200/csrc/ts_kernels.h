@@ -25,6 +25,24 @@ TS_D void load_int_shifts(const void* __restrict__ w, int qkind, long long wzp, 
     }
 }
 
+// Images per work unit (a multiple of `np`, the images of one stage).  A unit has a fixed cost (parameter fetch, the
+// pipeline restart of its first stage, for the backward the shuffle tree and the partial store: measured ~0.4 plane
+// times in the 2-D backward, ~0.1 in the forward), the last round of units leaves CTAs idle: pick the size that
+// minimises  rounds * (images + unit_cost)  -- large units for small per-GPU batches, where one-image units made the
+// 32-image shard of the 8-GPU strong-scaling run 60 % slower than its HBM floor.
+inline long long pick_unit_images(long long N, long long C, long long np, long long grid, double unit_cost) {
+    long long best = np < N ? np : N;
+    double best_cost = 1e300;
+    const long long kmax = (N + np - 1) / np < 4096 ? (N + np - 1) / np : 4096;
+    for (long long k = 1; k <= kmax; ++k) {
+        const long long npu = k * np < N ? k * np : N;
+        const long long chunks = (N + npu - 1) / npu, units = chunks * C, rounds = (units + grid - 1) / grid;
+        const double cost = (double)rounds * ((double)npu + unit_cost);
+        if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = npu; }
+    }
+    return best;
+}
+
 // ---- generic family (ts_generic.cu) ----------------------------------------------------------
 struct GenericBwdPlan { int threads, tiles, n_per_chunk, units; };
 GenericBwdPlan plan_generic_backward(const Geo& g);

@@ -962,13 +962,14 @@ TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool 
 
     const long long planes = g.N * g.C;
     const long long grid_max = (long long)sm_count;
-    long long npu = t.chunk_planes > 0 ? t.chunk_planes : planes / (grid_max * 32);
+    long long npu = t.chunk_planes > 0 ? t.chunk_planes : pick_unit_images(g.N, g.C, np, grid_max, mode == 2 ? 0.4 : 0.1);
     npu = (npu / np) * np;
     if (npu < np) npu = np;
     if (npu > g.N) npu = g.N;
     const long long chunks = (g.N + npu - 1) / npu;
     const long long units = chunks * g.C;
     if (units > 0x7fffffffLL) return p;
+    (void)planes;
 
     // padded row length of the item index space: a multiple of 8 groups keeps every quarter-warp inside
     // one box row (conflict-free 128-bit shared loads) -- used when it idles <= 15 % of the lanes
