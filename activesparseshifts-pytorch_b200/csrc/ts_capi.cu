@@ -169,8 +169,10 @@ int ts_set_tuning(const char* spec) {
         else if (!strcmp(key, "halo")) t.halo = val;
         else if (!strcmp(key, "halo_stages")) t.halo_stages = val;
         else if (!strcmp(key, "halo_warps")) t.halo_warps = val;
+        else if (!strcmp(key, "halo_split")) t.halo_split = val != 0;
         else if (!strcmp(key, "unit_order")) t.unit_order = val != 0;
         else if (!strcmp(key, "use_flat")) t.use_flat = val != 0;
+        else if (!strcmp(key, "flat_variant")) t.flat_variant = val;
         else if (!strcmp(key, "flat_ctas")) t.flat_ctas = val;
         else if (!strcmp(key, "flat_stage_kb")) t.flat_stage_kb = val;
         else if (!strcmp(key, "flat_stages")) t.flat_stages = val;

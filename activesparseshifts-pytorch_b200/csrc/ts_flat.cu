@@ -53,7 +53,8 @@ struct FArgs {
     int plane_bytes, ipp;      // bytes / 16-byte items of one plane
     int K, stages, stage_stride, nw;
     int nstages;               // ceil(planes / K)
-    FastDivU d_ipp, d_Lb;
+    int table;                 // per-channel (row shift, column shift in bytes) table in shared memory
+    FastDivU d_ipp, d_Lb, d_C;
 };
 
 // (row shift, column shift in bytes) of channel c; a size-1 axis ignores its shift (reduce_shift)
@@ -178,6 +179,101 @@ __global__ void __launch_bounds__(512, 1) k_flat_gather(const __grid_constant__ 
     }
 }
 
+// ---- variant 2: a WARP owns whole planes ----------------------------------------------------------
+// The plane's shift is warp-uniform, so the window misalignment is a compile-time constant of the inner loop (no
+// select network, no shuffles) and everything that depends on the shift only is hoisted out of it; the per-channel
+// shifts come from a table every CTA builds once in shared memory.
+template <int WS>
+TS_D void plane_items(const FArgs& a, unsigned src_plane, unsigned char* dst, int sr, int scb, int lane) {
+    const int Lb = a.Lb, B = a.B;
+    const unsigned fillw = a.fillw;
+    const int delta = sr * Lb + scb;
+    const int bs8 = ((-delta) & 3) * 8;
+    const int lo = scb > 0 ? scb : 0, hi = scb < 0 ? Lb + scb : Lb;          // valid byte columns of a row
+    const int base = (-delta) & ~15;                                            // so & ~15 = 16 m + base  (16 m is a multiple of 16)
+    for (int m = lane; m < a.ipp; m += 32) {
+        const int o = 16 * m;
+        const int r0 = (int)fdivu((unsigned)o, a.d_Lb), c0 = o - r0 * Lb;
+        const int n0b = Lb - c0 < 16 ? Lb - c0 : 16;
+        unsigned mask = 0u;
+        if ((unsigned)(r0 - sr) < (unsigned)B) {
+            const int l = lo - c0 > 0 ? lo - c0 : 0, h = hi - c0 < n0b ? hi - c0 : n0b;
+            mask |= bits_range(l, h);
+        }
+        if (n0b < 16 && (unsigned)(r0 + 1 - sr) < (unsigned)B) {
+            const int h = n0b + hi < 16 ? n0b + hi : 16;
+            mask |= bits_range(n0b + lo, h);
+        }
+        uint4 out = make_uint4(fillw, fillw, fillw, fillw);
+        if (mask) {
+            const unsigned addr = src_plane + (unsigned)(o + base);
+            const uint4 A = lds128(addr), Bv = lds128(addr + 16);
+            const unsigned W[9] = {A.x, A.y, A.z, A.w, Bv.x, Bv.y, Bv.z, Bv.w, 0u};
+            unsigned v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = __funnelshift_r(W[k + WS], W[k + WS + 1], bs8);
+            if (mask != 0xffffu) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned wm = spread_nibble((mask >> (4 * k)) & 15u);
+                    v[k] = (v[k] & wm) | (fillw & ~wm);
+                }
+            }
+            out = make_uint4(v[0], v[1], v[2], v[3]);
+        }
+        __stcs((uint4*)(dst + o), out);
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) k_flat_gather_wp(const __grid_constant__ FArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
+    uint64_t* empty = full + a.stages;
+    int2* tbl = (int2*)(empty + a.stages);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)a.nw); }
+        fence_barrier_init();
+    }
+    const int C = (int)a.g.C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        int sr, scb;
+        flat_shift(a, c, sr, scb);
+        tbl[c] = make_int2(sr, scb);
+    }
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
+    int s = 0;
+    unsigned phase = 0;
+    for (int t = blockIdx.x; t < a.nstages; t += gridDim.x) {
+        const long long p0 = (long long)t * a.K;
+        const int np = a.planes - p0 < a.K ? (int)(a.planes - p0) : a.K;
+        const unsigned sbase = shared_addr(smem + (size_t)s * a.stage_stride + GUARD);
+        unsigned char* dst0 = a.y + p0 * a.plane_bytes;
+        int c0;                                  // channel of the stage's first plane
+        if (a.planes < 0x7fffffffLL) { const unsigned pu = (unsigned)p0; c0 = (int)(pu - fdivu(pu, a.d_C) * (unsigned)C); }
+        else c0 = (int)(p0 % C);
+        mbar_wait(&full[s], phase);
+        for (int q = wid; q < np; q += a.nw) {
+            int c = c0 + q;
+            while (c >= C) c -= C;
+            const int2 sh = tbl[c];
+            const int ws = ((-(sh.x * a.Lb + sh.y)) & 15) >> 2;
+            const unsigned src = sbase + (unsigned)(q * a.plane_bytes);
+            unsigned char* dst = dst0 + (size_t)q * a.plane_bytes;
+            switch (ws) {
+            case 0: plane_items<0>(a, src, dst, sh.x, sh.y, lane); break;
+            case 1: plane_items<1>(a, src, dst, sh.x, sh.y, lane); break;
+            case 2: plane_items<2>(a, src, dst, sh.x, sh.y, lane); break;
+            default: plane_items<3>(a, src, dst, sh.x, sh.y, lane); break;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == a.stages) { s = 0; phase ^= 1u; }
+    }
+}
+
 long long round_up(long long v, long long q) { return (v + q - 1) / q * q; }
 
 }  // namespace
@@ -201,7 +297,9 @@ FlatPlan plan_flat(const Geo& g, int esize, bool dense_x, const void* x, const v
     if (g.N * g.C >= (1ll << 40)) return p;
     const Tuning& t = tuning();
     const int ctas = t.flat_ctas > 0 ? t.flat_ctas : 2;
-    const long long budget = SMEM_LIMIT / ctas - 1024;
+    const bool wp = t.flat_variant != 1 && g.C <= 512;                 // warp-per-plane variant with the shift table
+    const long long table_bytes = wp ? g.C * 8 : 0;
+    const long long budget = SMEM_LIMIT / ctas - 1024 - table_bytes;
     const long long target = (long long)(t.flat_stage_kb > 0 ? t.flat_stage_kb : 24) * 1024;
     long long K = target / plane;
     if (K < 1) K = 1;
@@ -219,13 +317,13 @@ FlatPlan plan_flat(const Geo& g, int esize, bool dense_x, const void* x, const v
     const long long nstages = (g.N * g.C + K - 1) / K;
     if (nstages > 0x7fffffffLL) return p;
     const long long grid_max = (long long)sm_count * ctas;
-    int warps = t.flat_warps > 0 ? t.flat_warps : (ctas >= 2 ? 7 : 15);
+    int warps = t.flat_warps > 0 ? t.flat_warps : (ctas >= 2 ? (wp ? 8 : 7) : 15);
     if (warps > 15) warps = 15;
     p.ok = true;
     p.np = (int)K; p.stages = stages; p.stage_stride = (int)stride_of(K); p.warps = warps;
-    p.n_per_unit = 0; p.units = (int)nstages;
+    p.n_per_unit = wp ? 1 : 0; p.units = (int)nstages;      // n_per_unit doubles as the variant flag
     p.grid = (int)(nstages < grid_max ? nstages : grid_max);
-    p.smem_bytes = (size_t)(stages * stride_of(K) + 16 * stages + 64);
+    p.smem_bytes = (size_t)(stages * stride_of(K) + 16 * stages + 64 + table_bytes);
     return p;
 }
 
@@ -247,8 +345,15 @@ int flat_gather(const Geo& g, const FlatPlan& p, int wk, const void* x, void* y,
     a.nstages = p.units;
     a.d_ipp = make_fastdivu((unsigned)a.ipp);
     a.d_Lb = make_fastdivu((unsigned)a.Lb);
-    if (!ensure_dynamic_smem((const void*)k_flat_gather, p.smem_bytes)) return check_launch();
-    k_flat_gather<<<p.grid, (p.warps + 1) * 32, p.smem_bytes, s>>>(a);
+    a.table = p.n_per_unit;
+    a.d_C = make_fastdivu((unsigned)g.C);
+    if (a.table) {
+        if (!ensure_dynamic_smem((const void*)k_flat_gather_wp, p.smem_bytes)) return check_launch();
+        k_flat_gather_wp<<<p.grid, (p.warps + 1) * 32, p.smem_bytes, s>>>(a);
+    } else {
+        if (!ensure_dynamic_smem((const void*)k_flat_gather, p.smem_bytes)) return check_launch();
+        k_flat_gather<<<p.grid, (p.warps + 1) * 32, p.smem_bytes, s>>>(a);
+    }
     note_launch();
     return check_launch();
 }

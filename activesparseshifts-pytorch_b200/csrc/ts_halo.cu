@@ -636,7 +636,7 @@ struct Body {
     }
 
     template <int WSX, int WSG, int WSV>
-    TS_D void run_images2(unsigned char* smem, Ring& ring, unsigned char* dst, int npl, const PairCtx& pc0, float* ts) const {
+    __device__ __noinline__ void run_images2(unsigned char* smem, Ring& ring, unsigned char* dst, int npl, const PairCtx& pc0, float* ts) const {
         unsigned char* st = smem + (size_t)ring.s * a.stage_stride + GUARD;
         const unsigned sb = shared_addr(st);
         mbar_wait(&wait_bar[ring.s], ring.phase);
@@ -744,7 +744,7 @@ struct Body {
     }
 
     template <int WSX, int WSG, int WSV, int ROLE>
-    TS_D void run_images3(unsigned char* smem, Ring& ring, unsigned char* dst_img, int npl, float* ts) const {
+    __device__ __noinline__ void run_images3(unsigned char* smem, Ring& ring, unsigned char* dst_img, int npl, float* ts) const {
         constexpr int NPT = ROLE == 0 ? 1 : 2;
         const int half = nt >> 1;
         PairCtx pc[NPT];
@@ -766,17 +766,24 @@ struct Body {
         }
     }
 
+    // run_images2 / run_images3 are NOT inlined: one body per window misalignment (and role), each with its own register allocation.  Inlined into one switch
+    // the five variants shared a single allocation and spilled ~70 words each (local memory goes to L2 here: with the
+    // shared-memory carve-out at its maximum the L1 is ~28 KB); compiled alone a variant spills nothing.
     template <int WSX, int WSG, int WSV>
     TS_D void run_images(unsigned char* smem, Ring& ring, unsigned char* dst, int npl, const PairCtx& pc0, float* ts) const {
         if constexpr (DIM == 2) {
             run_images2<WSX, WSG, WSV>(smem, ring, dst, npl, pc0, ts);
         } else if constexpr (MODE == 2 && ACTIVE) {
+#if defined(TS_EXP_ROLE)
+            run_images3<WSX, WSG, WSV, TS_EXP_ROLE>(smem, ring, dst, npl, ts);
+#else
             if (a.split) {
                 if (tid < (nt >> 1)) run_images3<WSX, WSG, WSV, 1>(smem, ring, dst, npl, ts);
                 else run_images3<WSX, WSG, WSV, 2>(smem, ring, dst, npl, ts);
             } else {
                 run_images3<WSX, WSG, WSV, 0>(smem, ring, dst, npl, ts);
             }
+#endif
         } else {
             run_images3<WSX, WSG, WSV, 0>(smem, ring, dst, npl, ts);
         }
@@ -803,6 +810,9 @@ struct Body {
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
             unsigned char* dst = (unsigned char*)a.out + ((long long)nb * a.g.C + c) * plane_bytes;
             float ts[3] = {0.f, 0.f, 0.f};
+#if defined(TS_EXP_ONEWS)
+            run_images<1, ACTIVE ? 1 : 3, 0>(smem, ring, dst, npl, pc0, ts);
+#else
             if (derived) {
                 switch (wsx) {
                 case 0: run_images<0, 0, 0>(smem, ring, dst, npl, pc0, ts); break;
@@ -813,6 +823,7 @@ struct Body {
             } else {
                 run_images<-1, -1, -1>(smem, ring, dst, npl, pc0, ts);
             }
+#endif
 #pragma unroll
             for (int k = 0; k < DIM; ++k) acc[k] += (double)ts[k];     // fp32 inside an image group, fp64 across
         }
@@ -897,7 +908,7 @@ bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, const void
     a.d_chunks = make_fastdivu((unsigned)a.chunks);
     a.table = g.C <= TABLE_MAX_C ? 1 : 0;
     a.need_fix = g.pad != TS_PAD_ZEROS;
-    a.split = (d == 3 && mode == 2 && active && p.warps % 2 == 0 && a.pairs <= a.nt) ? 1 : 0;
+    a.split = (tuning().halo_split && d == 3 && mode == 2 && active && p.warps % 2 == 0 && a.pairs <= a.nt) ? 1 : 0;
     a.d_GP = make_fastdivu((unsigned)a.GP);
     a.d_img = make_fastdivu((unsigned)a.img_pairs);
     if (!make_tensor_map5(&a.map_x, x, 4, g.N, g.C, a.A, a.B, a.L, a.px, a.bpx, 1, 1)) return false;

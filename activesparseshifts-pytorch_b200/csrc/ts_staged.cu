@@ -26,12 +26,23 @@
 // ones of ts_common.cuh (unfused lerp nest), so forward and grad_input are bit-identical to the
 // generic family and to the CPU reference; grad_weight terms are summed in fp32 per stage, fp64
 // across stages.
+#include <cstring>
+
 #include "ts_kernels.h"
 
 namespace ts {
 
 Tuning& tuning() {
-    static Tuning t = {0, 0, 15, 1, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0};   // 0 = automatic (per-mode defaults in the planners)
+    static Tuning t = [] {
+        Tuning d;
+        memset(&d, 0, sizeof(d));          // 0 = automatic (per-mode defaults in the planners)
+        d.warps = 15;
+        d.ctas_per_sm = 1;
+        d.use_tma = d.use_halo = d.use_flat = 1;
+        d.halo_split = 1;
+        d.unit_order = 1;
+        return d;
+    }();
     return t;
 }
 
