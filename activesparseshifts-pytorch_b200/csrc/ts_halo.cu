@@ -534,7 +534,7 @@ struct Ring {
 // ROLE (3-D interpolating backward only): 0 = a thread does everything for ONE pair; 1 = grad_weight terms (x windows) of
 // TWO pairs; 2 = grad_input (grad windows + stores) of TWO pairs.  Splitting the two halves of the arithmetic over
 // different warps halves the window state a thread carries from slab to slab (30 instead of 60 registers).
-template <int DIM, int MODE, bool ACTIVE>
+template <int DIM, int MODE, bool ACTIVE, bool SPLIT>
 struct Body {
     const HArgs& a;
     const int tid, nt, wid, lane;
@@ -636,7 +636,7 @@ struct Body {
     }
 
     template <int WSX, int WSG, int WSV>
-    __device__ __noinline__ void run_images2(unsigned char* smem, Ring& ring, unsigned char* dst, int npl, const PairCtx& pc0, float* ts) const {
+    TS_D void run_images2(unsigned char* smem, Ring& ring, unsigned char* dst, int npl, const PairCtx& pc0, float* ts) const {
         unsigned char* st = smem + (size_t)ring.s * a.stage_stride + GUARD;
         const unsigned sb = shared_addr(st);
         mbar_wait(&wait_bar[ring.s], ring.phase);
@@ -744,7 +744,7 @@ struct Body {
     }
 
     template <int WSX, int WSG, int WSV, int ROLE>
-    __device__ __noinline__ void run_images3(unsigned char* smem, Ring& ring, unsigned char* dst_img, int npl, float* ts) const {
+    TS_D void run_images3(unsigned char* smem, Ring& ring, unsigned char* dst_img, int npl, float* ts) const {
         constexpr int NPT = ROLE == 0 ? 1 : 2;
         const int half = nt >> 1;
         PairCtx pc[NPT];
@@ -766,7 +766,8 @@ struct Body {
         }
     }
 
-    // run_images2 / run_images3 are NOT inlined: one body per window misalignment (and role), each with its own register allocation.  Inlined into one switch
+    // (Tried: NOT inlining one body per window misalignment so each gets its own register allocation -- the accumulators
+    // and the ring state then live in local memory behind pointers and everything got 2-4x slower.)  Inlined into one switch
     // the five variants shared a single allocation and spilled ~70 words each (local memory goes to L2 here: with the
     // shared-memory carve-out at its maximum the L1 is ~28 KB); compiled alone a variant spills nothing.
     template <int WSX, int WSG, int WSV>
@@ -774,16 +775,12 @@ struct Body {
         if constexpr (DIM == 2) {
             run_images2<WSX, WSG, WSV>(smem, ring, dst, npl, pc0, ts);
         } else if constexpr (MODE == 2 && ACTIVE) {
-#if defined(TS_EXP_ROLE)
-            run_images3<WSX, WSG, WSV, TS_EXP_ROLE>(smem, ring, dst, npl, ts);
-#else
-            if (a.split) {
+if constexpr (SPLIT) {         // chosen at LAUNCH: both role layouts in one kernel cost 600 bytes of spills
                 if (tid < (nt >> 1)) run_images3<WSX, WSG, WSV, 1>(smem, ring, dst, npl, ts);
                 else run_images3<WSX, WSG, WSV, 2>(smem, ring, dst, npl, ts);
             } else {
                 run_images3<WSX, WSG, WSV, 0>(smem, ring, dst, npl, ts);
             }
-#endif
         } else {
             run_images3<WSX, WSG, WSV, 0>(smem, ring, dst, npl, ts);
         }
@@ -813,7 +810,14 @@ struct Body {
 #if defined(TS_EXP_ONEWS)
             run_images<1, ACTIVE ? 1 : 3, 0>(smem, ring, dst, npl, pc0, ts);
 #else
-            if (derived) {
+            // One body per compile-time misalignment is free of select instructions, but ptxas allocates the four (or
+            // twelve, with the roles) inlined bodies of the heavy kernels together and spills ~75 registers in each
+            // (measured: 16 GB of local-memory traffic through L2 for cfg4's backward).  The interpolating and the 3-D
+            // backward therefore use the ONE body with run-time misalignment (a 12-select network per 5-wide window).
+            constexpr bool RTWS = MODE == 2 && (ACTIVE || DIM == 3);
+            if constexpr (RTWS) {
+                run_images<-1, -1, -1>(smem, ring, dst, npl, pc0, ts);
+            } else if (derived) {
                 switch (wsx) {
                 case 0: run_images<0, 0, 0>(smem, ring, dst, npl, pc0, ts); break;
                 case 1: run_images<1, ACTIVE ? 1 : 3, 0>(smem, ring, dst, npl, pc0, ts); break;
@@ -830,7 +834,7 @@ struct Body {
     }
 };
 
-template <int DIM, int MODE, bool ACTIVE>
+template <int DIM, int MODE, bool ACTIVE, bool SPLIT>
 __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
@@ -850,7 +854,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs 
         fixer(a, smem, full, ready, lane, tbl, (unsigned*)(tbl + (a.table ? (int)a.g.C : 0)));
         return;
     }
-    Body<DIM, MODE, ACTIVE> body(a, threadIdx.x, a.nt, wid, lane, a.need_fix ? ready : full, empty, tbl);
+    Body<DIM, MODE, ACTIVE, SPLIT> body(a, threadIdx.x, a.nt, wid, lane, a.need_fix ? ready : full, empty, tbl);
     Ring ring = {0, 0u};
     const int C = (int)a.g.C, N = (int)a.g.N;
     const UnitRange ur = unit_range(a.units, a.unit_order);
@@ -1019,7 +1023,7 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
 int halo_active_forward(const Geo& g, const HaloPlan& p, const void* x, const void* w, void* y, cudaStream_t s) {
     HArgs a;
     if (!make_args(g, p, 1, 1, x, nullptr, y, w, nullptr, &a)) return TS_ERR_UNSUPPORTED;
-    return g.dim == 3 ? launch(k_halo<3, 1, true>, a, p, s) : launch(k_halo<2, 1, true>, a, p, s);
+    return g.dim == 3 ? launch(k_halo<3, 1, true, false>, a, p, s) : launch(k_halo<2, 1, true, false>, a, p, s);
 }
 
 int halo_backward(const Geo& g, const HaloPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
@@ -1028,10 +1032,10 @@ int halo_backward(const Geo& g, const HaloPlan& p, int active, const void* grad,
     if (!make_args(g, p, 2, active ? 1 : 0, x, grad, gi, w, partials, &a)) return TS_ERR_UNSUPPORTED;
     int rc;
     switch (g.dim * 2 + (active ? 1 : 0)) {
-    case 4: rc = launch(k_halo<2, 2, false>, a, p, s); break;
-    case 5: rc = launch(k_halo<2, 2, true>, a, p, s); break;
-    case 6: rc = launch(k_halo<3, 2, false>, a, p, s); break;
-    default: rc = launch(k_halo<3, 2, true>, a, p, s); break;
+    case 4: rc = launch(k_halo<2, 2, false, false>, a, p, s); break;
+    case 5: rc = launch(k_halo<2, 2, true, false>, a, p, s); break;
+    case 6: rc = launch(k_halo<3, 2, false, false>, a, p, s); break;
+    default: rc = a.split ? launch(k_halo<3, 2, true, true>, a, p, s) : launch(k_halo<3, 2, true, false>, a, p, s); break;
     }
     if (rc != TS_OK) return rc;
     return launch_reduce_partials<float>(partials, p.slots, (int)(g.C * g.dim), gw, peers, s);

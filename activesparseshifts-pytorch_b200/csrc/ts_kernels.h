@@ -82,7 +82,7 @@ struct Tuning {
     int halo;          // halo rows / columns of the halo family (0 = 4)
     int halo_stages;   // ring depth of the halo family (0 = auto)
     int halo_warps;    // consumer warps of the 2-D halo kernels (0 = auto)
-    int halo_split;    // 3-D interpolating backward: 1 = x-window warps + grad-window warps (two pairs per thread), 0 = one pair per thread
+    int halo_split;    // 3-D interpolating backward: 0 (default) = one pair per thread, 1 = x-window warps + grad-window warps (two pairs per thread)
     int unit_order;    // 1 (default): units dealt round-robin over (chunk, channel); 0: contiguous channel-major ranges per CTA
                        // (measured on B200: 4 % faster for 32-image shards, 5 % slower for cfg3 at N=256)
     int use_flat;      // 0: the automatic path choice never picks the flat zero-padding gather

@@ -39,7 +39,6 @@ Tuning& tuning() {
         d.warps = 15;
         d.ctas_per_sm = 1;
         d.use_tma = d.use_halo = d.use_flat = 1;
-        d.halo_split = 1;
         d.unit_order = 1;
         return d;
     }();
