@@ -284,6 +284,22 @@ int ts_shift_forward(const ts_geometry* gin, int dtype, int padding, int active,
                   : generic_gather(g, dtype, x, y, 0ull, es, weights, 0, 0, s);
 }
 
+int ts_shift2d_avgpool2_forward(const ts_geometry* gin, int dtype, int padding, int active, const void* x, const void* weights,
+                                void* y_pooled, void* stream) {
+    Geo g;
+    int rc = make_geo(gin, padding, &g);
+    if (rc != TS_OK) return rc;
+    if (g.dim != 2 || dtype != TS_F32) return TS_ERR_UNSUPPORTED;
+    if (g.N * g.C == 0 || g.out_plane == 0) return TS_OK;
+    if (!x || !weights || !y_pooled) return TS_ERR_INVALID_ARGUMENT;
+    int sms = 0;
+    if ((rc = sm_count(&sms)) != TS_OK) return rc;
+    const HaloPlan hp = plan_halo(g, active ? 1 : 0, active, dtype, x_is_dense(g), x, y_pooled, nullptr, sms, true);
+    if (!hp.ok) return TS_ERR_UNSUPPORTED;
+    t_last_path = TS_PATH_HALO;
+    return halo_forward2d(g, hp, active, 1, x, weights, y_pooled, (cudaStream_t)stream);
+}
+
 size_t ts_shift_backward_workspace_bytes(const ts_geometry* gin, int dtype) {
     if (!gin) return 0;
     // memo of the last query of this thread: ts_shift_backward validates its workspace on every call

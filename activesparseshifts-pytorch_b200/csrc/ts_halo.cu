@@ -66,6 +66,8 @@ struct alignas(64) HArgs {
     int stage_stride, stages, nw, nt, np;
     int img_pairs, pairs;                     // RP * GP, np * RP * GP
     int n_per_unit, units, chunks, unit_order;
+    long long out_plane_bytes;                // bytes of one (n, c) plane of the OUTPUT (pooled plane for the fused avg-pool epilogue)
+    int pool;                                 // forward only: 2x2 / stride 2 / ceil_mode average pooling fused into the store
     int need_fix;                             // padding != zeros: a fixer warp patches the halo of every stage
     int split;                                // 3-D interpolating backward: x-window warps and grad-window warps (two pairs per thread)
     FastDivU d_GP, d_img, d_C, d_chunks;
@@ -90,7 +92,7 @@ TS_D UnitShift compute_unit_shift(const HArgs& a, long long c) {
         long long iw;
         float d;
         const float wv = a.w[c * a.dim + ax];
-        if (a.mode == 1) split_forward<float>(wv, true, iw, d);
+        if (a.mode != 2) split_forward<float>(wv, a.mode == 1, iw, d);
         else split_backward<float>(wv, a.active != 0, iw, d);
         u.d[ax] = d;
         u.sx[lev] = reduce_shift(iw, a.g.S[ax], a.g.pad);
@@ -158,7 +160,7 @@ TS_D void load5(unsigned addr, int ws, float* out) {
 }
 template <int WS>
 TS_D void load4(unsigned addr, int ws, float* out) {
-    if constexpr (WS == 0) {
+    if (WS == 0 || (WS < 0 && ws == 0)) {         // (run-time: the unshifted grad window is aligned unless the crop is not)
         const uint4 A = lds128(addr);
         out[0] = __uint_as_float(A.x); out[1] = __uint_as_float(A.y); out[2] = __uint_as_float(A.z); out[3] = __uint_as_float(A.w);
     } else {
@@ -285,26 +287,62 @@ TS_D void fetch8(const float* __restrict__ vol, const int* idx, const int* sizes
     }
 }
 
-template <int DIM>
+template <int DIM, bool ACTIVE>
+TS_D float slow_forward_value(const Geo& g, const float* xp, const int* o, const int* sx, const float* d) {
+    int idx[DIM];
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) idx[ax] = o[ax] + g.lb[ax] - sx[ax];
+    if (ACTIVE) {
+        float v[8];
+        fetch8<DIM>(xp, idx, g.S, g.pad, v);
+        return interpolate<float, DIM>(v, d);
+    }
+    bool ok = true;
+    long long off = 0;
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) {
+        const int t = axis_index_literal(idx[ax], g.S[ax], g.pad);
+        ok = ok && t >= 0;
+        off = off * g.S[ax] + t;
+    }
+    return ok ? xp[off] : 0.f;
+}
+
+template <int DIM, bool ACTIVE, bool POOL>
 TS_D void slow_forward(const HArgs& a, int c, int n0, int n1, const UnitShift& us, int tid, int nt) {
     const Geo& g = a.g;
-    const int plane = (int)g.out_plane;
     int sx[DIM];
     float d[3] = {us.d[0], us.d[1], us.d[2]};
 #pragma unroll
     for (int ax = 0; ax < DIM; ++ax) sx[ax] = us.sx[ax + 3 - DIM];
     for (int n = n0; n < n1; ++n) {
         const float* xp = a.x + ((long long)n * g.C + c) * g.in_plane;
-        float* yp = a.out + ((long long)n * g.C + c) * g.out_plane;
-        for (int e = tid; e < plane; e += nt) {
-            int o[DIM], rem = e, idx[DIM];
+        float* yp = (float*)((unsigned char*)a.out + ((long long)n * g.C + c) * a.out_plane_bytes);
+        if (POOL && DIM == 2) {
+            const int PH = (g.OS[0] + 1) / 2, PW = g.OS[1] / 2;
+            for (int e = tid; e < PH * PW; e += nt) {
+                const int ph = e / PW, pw = e - ph * PW;
+                float sum = 0.f;
+                int cnt = 0;
+                for (int i = 0; i < 2; ++i)
+                    for (int j = 0; j < 2; ++j) {
+                        int o[DIM];
+                        o[0] = 2 * ph + i; o[DIM - 1] = 2 * pw + j;
+                        if (o[0] >= g.OS[0]) continue;
+                        const float v = slow_forward_value<DIM, ACTIVE>(g, xp, o, sx, d);
+                        sum = cnt ? __fadd_rn(sum, v) : v;
+                        ++cnt;
+                    }
+                yp[e] = __fdiv_rn(sum, (float)cnt);
+            }
+        } else {
+            const int plane = (int)g.out_plane;
+            for (int e = tid; e < plane; e += nt) {
+                int o[DIM], rem = e;
 #pragma unroll
-            for (int ax = DIM - 1; ax >= 0; --ax) { o[ax] = rem % g.OS[ax]; rem /= g.OS[ax]; }
-#pragma unroll
-            for (int ax = 0; ax < DIM; ++ax) idx[ax] = o[ax] + g.lb[ax] - sx[ax];
-            float v[8];
-            fetch8<DIM>(xp, idx, g.S, g.pad, v);
-            yp[e] = interpolate<float, DIM>(v, d);
+                for (int ax = DIM - 1; ax >= 0; --ax) { o[ax] = rem % g.OS[ax]; rem /= g.OS[ax]; }
+                yp[e] = slow_forward_value<DIM, ACTIVE>(g, xp, o, sx, d);
+            }
         }
     }
 }
@@ -388,7 +426,7 @@ TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t
         for (int nb = n0; nb < n1; nb += a.np) {
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
             for (int k = 0; k < steps; ++k) {
-                if (kk > 0) mbar_wait(&empty[s], (unsigned)((kk - 1) & 1));
+                if (kk > 0) mbar_wait_relaxed(&empty[s], (unsigned)((kk - 1) & 1), 100);
                 unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
                 const bool has_g = bwd && (a.dim == 2 || a.active || k >= 1);
                 const bool has_v = bwd && a.dim == 3 && k >= 1;
@@ -451,7 +489,7 @@ TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* r
             for (int k = 0; k < steps; ++k) {
                 unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
                 const bool has_g = bwd && (a.dim == 2 || a.active || k >= 1);
-                mbar_wait(&full[s], phase);
+                mbar_wait_relaxed(&full[s], phase, 40);
                 for (int pl = 0; pl < npl; ++pl) {
                     float* tx = (float*)(st + (size_t)pl * a.tile_x);
                     float* tg = (float*)(st + a.off_g + (size_t)pl * a.tile_g);
@@ -498,7 +536,7 @@ TS_D PairCtx pair_ctx(const HArgs& a, const UnitGeom& ug, const Pair& q, bool va
     PairCtx p;
     p.rows = !valid ? 0 : (q.r + 1 < a.IB ? 2 : 1);
     p.xo = (unsigned)(q.pl * a.tile_x + ((q.r + ug.xr0) * a.px + ((4 * q.cg + ug.xc0) & ~3)) * 4);
-    p.out_off = (long long)q.pl * (a.g.C * (MODE == 2 ? a.g.in_plane : a.g.out_plane) * 4) + (long long)((q.r * a.IG + q.cg) * 16);
+    p.out_off = (long long)q.pl * (a.g.C * a.out_plane_bytes) + (a.pool ? (long long)(((q.r >> 1) * a.IG + q.cg) * 8) : (long long)((q.r * a.IG + q.cg) * 16));
     p.go = p.vo = 0;
     p.cmask = 0xffu;
     if (MODE == 2) {
@@ -534,7 +572,7 @@ struct Ring {
 // ROLE (3-D interpolating backward only): 0 = a thread does everything for ONE pair; 1 = grad_weight terms (x windows) of
 // TWO pairs; 2 = grad_input (grad windows + stores) of TWO pairs.  Splitting the two halves of the arithmetic over
 // different warps halves the window state a thread carries from slab to slab (30 instead of 60 registers).
-template <int DIM, int MODE, bool ACTIVE, bool SPLIT>
+template <int DIM, int MODE, bool ACTIVE, bool SPLIT, bool POOL>
 struct Body {
     const HArgs& a;
     const int tid, nt, wid, lane;
@@ -582,18 +620,37 @@ struct Body {
         float X[3][5];
         load5<WSX>(xa, wsx, X[0]);
         load5<WSX>(xa + a.px * 4, wsx, X[1]);
-        if (pc.rows == 2) load5<WSX>(xa + 2 * a.px * 4, wsx, X[2]);
-        if (MODE == 1) {
+        if (pc.rows == 2 && MODE != 0) load5<WSX>(xa + 2 * a.px * 4, wsx, X[2]);
+        if (MODE != 2) {
+            float y[2][4];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (j < pc.rows) {
-                    float R[5], y[4];
+                    if (MODE == 1) {
+                        float R[5];
 #pragma unroll
-                    for (int t = 0; t < 5; ++t) R[t] = lerp<float>(X[j][t], X[j + 1][t], d[0]);
+                        for (int t = 0; t < 5; ++t) R[t] = lerp<float>(X[j][t], X[j + 1][t], d[0]);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) y[t] = lerp<float>(R[t], R[t + 1], d[1]);
-                    __stcs((float4*)(o + j * orow), make_float4(y[0], y[1], y[2], y[3]));
+                        for (int t = 0; t < 4; ++t) y[j][t] = lerp<float>(R[t], R[t + 1], d[1]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) y[j][t] = X[j][t];
+                    }
+                    if (!POOL) __stcs((float4*)(o + j * orow), make_float4(y[j][0], y[j][1], y[j][2], y[j][3]));
                 }
+            }
+            if (POOL) {
+                // avg_pool2d(kernel 2, stride 2, ceil_mode) of the row pair: the window's elements are added in
+                // row-major order and divided by their count, like ATen's kernel (modules/shifts.py:85-89)
+                float q0, q1;
+                if (pc.rows == 2) {
+                    q0 = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(y[0][0], y[0][1]), y[1][0]), y[1][1]), 4.f);
+                    q1 = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(y[0][2], y[0][3]), y[1][2]), y[1][3]), 4.f);
+                } else {
+                    q0 = __fdiv_rn(__fadd_rn(y[0][0], y[0][1]), 2.f);
+                    q1 = __fdiv_rn(__fadd_rn(y[0][2], y[0][3]), 2.f);
+                }
+                __stcs((float2*)o, make_float2(q0, q1));
             }
             return;
         }
@@ -655,20 +712,20 @@ struct Body {
     // 3-D: a thread owns its pair(s) for the whole image; windows of the previous slab stay in registers
     template <int ROLE>
     struct Carry {
-        float X[(MODE == 1 || ROLE != 2) ? 3 : 1][5];
+        float X[(MODE != 2 || ROLE != 2) ? 3 : 1][5];
         float G[(MODE == 2 && ACTIVE && ROLE != 1) ? 3 : 1][5];
     };
 
     // stage k of an image: combine the carried windows (slab k-1) with this stage's (slab k), then carry the new ones
     template <int WSX, int WSG, int WSV, int ROLE>
     TS_D void step3(unsigned sb, unsigned char* dst_img, int k, const PairCtx& pc, Carry<ROLE>& cy, float* ts) const {
-        constexpr bool DOX = MODE == 1 || ROLE != 2;
+        constexpr bool DOX = MODE != 2 || ROLE != 2;
         constexpr bool DOG = MODE == 2 && ROLE != 1;
         if (pc.rows == 0) return;
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
         const int it = k - 1, orow = a.IG * 16;
         unsigned char* o = dst_img + pc.out_off + (long long)it * a.IB * orow;
-        const bool slab_pass = MODE == 1 || (it - a.lbA >= 0 && it - a.lbA < a.OA);
+        const bool slab_pass = MODE != 2 || (it - a.lbA >= 0 && it - a.lbA < a.OA);
         const unsigned cm = (k >= 1 && slab_pass) ? pc.cmask : 0u;
         const unsigned xa = sb + pc.xo, ga = sb + pc.go, va = sb + pc.vo;
         const bool gwin = DOG && ACTIVE && pc.cmask != 0u;
@@ -683,7 +740,7 @@ struct Body {
                 if (gwin) load5<WSG>(ga + 2 * a.pg * 4, wsg, Gn[2]);
             }
             if (k >= 1) {
-                if (MODE == 1) {
+                if (MODE != 2) {
                     float P[5], y[4];
 #pragma unroll
                     for (int t = 0; t < 5; ++t) P[t] = col3(cy.X[j][t], Xn[j][t], cy.X[j + 1][t], Xn[j + 1][t], d[0], d[1]);
@@ -788,13 +845,13 @@ if constexpr (SPLIT) {         // chosen at LAUNCH: both role layouts in one ker
 
     TS_D void run_unit(unsigned char* smem, Ring& ring, int c, int n0, int n1) {
         if (!ug.fits) {
-            if (MODE == 1) slow_forward<DIM>(a, c, n0, n1, us, tid, nt);
+            if (MODE != 2) slow_forward<DIM, MODE == 1, POOL>(a, c, n0, n1, us, tid, nt);
             else slow_backward<DIM, ACTIVE>(a, c, n0, n1, us, tid, nt, acc);
             return;
         }
-        const long long plane_bytes = (MODE == 2 ? a.g.in_plane : a.g.out_plane) * 4;
+        const long long plane_bytes = a.out_plane_bytes;
         // fast instantiations: every window misalignment known at compile time from the x window's
-        const bool derived = MODE == 1 || (wsv == 0 && wsg == (ACTIVE ? wsx : ((4 - wsx) & 3)));
+        const bool derived = MODE != 2 || (wsv == 0 && wsg == (ACTIVE ? wsx : ((4 - wsx) & 3)));
         PairCtx pc0;
         pc0.rows = 0;
         if (DIM == 2) {
@@ -834,7 +891,7 @@ if constexpr (SPLIT) {         // chosen at LAUNCH: both role layouts in one ker
     }
 };
 
-template <int DIM, int MODE, bool ACTIVE, bool SPLIT>
+template <int DIM, int MODE, bool ACTIVE, bool SPLIT, bool POOL>
 __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
@@ -854,7 +911,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs 
         fixer(a, smem, full, ready, lane, tbl, (unsigned*)(tbl + (a.table ? (int)a.g.C : 0)));
         return;
     }
-    Body<DIM, MODE, ACTIVE, SPLIT> body(a, threadIdx.x, a.nt, wid, lane, a.need_fix ? ready : full, empty, tbl);
+    Body<DIM, MODE, ACTIVE, SPLIT, POOL> body(a, threadIdx.x, a.nt, wid, lane, a.need_fix ? ready : full, empty, tbl);
     Ring ring = {0, 0u};
     const int C = (int)a.g.C, N = (int)a.g.N;
     const UnitRange ur = unit_range(a.units, a.unit_order);
@@ -879,7 +936,7 @@ int launch(K kernel, const HArgs& a, const HaloPlan& p, cudaStream_t s) {
     return check_launch();
 }
 
-bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, const void* x, const void* grad, void* out, const void* w,
+bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, int pool, const void* x, const void* grad, void* out, const void* w,
                double* partials, HArgs* o) {
     HArgs& a = *o;
     memset(&a, 0, sizeof(a));
@@ -911,6 +968,8 @@ bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, const void
     a.d_C = make_fastdivu((unsigned)g.C);
     a.d_chunks = make_fastdivu((unsigned)a.chunks);
     a.table = g.C <= TABLE_MAX_C ? 1 : 0;
+    a.pool = pool;
+    a.out_plane_bytes = pool ? (long long)((a.OB + 1) / 2) * (a.OL / 2) * 4 : (mode == 2 ? g.in_plane : g.out_plane) * 4;
     a.need_fix = g.pad != TS_PAD_ZEROS;
     a.split = (tuning().halo_split && d == 3 && mode == 2 && active && p.warps % 2 == 0 && a.pairs <= a.nt) ? 1 : 0;
     a.d_GP = make_fastdivu((unsigned)a.GP);
@@ -931,9 +990,10 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     HaloPlan p;
     memset(&p, 0, sizeof(p));
     p.ok = false;
-    if (!tma_available() || !dense_x || dtype != TS_F32 || (mode != 1 && mode != 2)) return p;
+    if (!tma_available() || !dense_x || dtype != TS_F32 || mode < 0 || mode > 2) return p;
     const int d = g.dim;
     if (d != 2 && d != 3) return p;
+    if (mode == 0 && d != 2) return p;                     // sparse forward: 2-D only (the pooled epilogue); 3-D gathers stay on ts_staged.cu
     if (g.N * g.C == 0 || g.in_plane == 0 || g.out_plane == 0) return p;
     for (int ax = 0; ax < d; ++ax)
         if (g.S[ax] < 2 || g.OS[ax] < 2) return p;        // a size-1 axis ignores its shift (shifts_kernels.h:40-50): other families
@@ -1022,20 +1082,30 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
 
 int halo_active_forward(const Geo& g, const HaloPlan& p, const void* x, const void* w, void* y, cudaStream_t s) {
     HArgs a;
-    if (!make_args(g, p, 1, 1, x, nullptr, y, w, nullptr, &a)) return TS_ERR_UNSUPPORTED;
-    return g.dim == 3 ? launch(k_halo<3, 1, true, false>, a, p, s) : launch(k_halo<2, 1, true, false>, a, p, s);
+    if (!make_args(g, p, 1, 1, 0, x, nullptr, y, w, nullptr, &a)) return TS_ERR_UNSUPPORTED;
+    return g.dim == 3 ? launch(k_halo<3, 1, true, false, false>, a, p, s) : launch(k_halo<2, 1, true, false, false>, a, p, s);
+}
+
+// 2-D forward (sparse or active) with the 2x2 / stride-2 / ceil_mode average pooling of modules/shifts.py:85-89 fused
+// into the store: one read of x, one QUARTER-size write (pool == 0: the plain 2-D forward through the same kernels).
+int halo_forward2d(const Geo& g, const HaloPlan& p, int active, int pool, const void* x, const void* w, void* y, cudaStream_t s) {
+    HArgs a;
+    if (g.dim != 2) return TS_ERR_UNSUPPORTED;
+    if (!make_args(g, p, active ? 1 : 0, active ? 1 : 0, pool, x, nullptr, y, w, nullptr, &a)) return TS_ERR_UNSUPPORTED;
+    if (active) return pool ? launch(k_halo<2, 1, true, false, true>, a, p, s) : launch(k_halo<2, 1, true, false, false>, a, p, s);
+    return pool ? launch(k_halo<2, 0, false, false, true>, a, p, s) : launch(k_halo<2, 0, false, false, false>, a, p, s);
 }
 
 int halo_backward(const Geo& g, const HaloPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
                   double* partials, const ts_peer_group* peers, cudaStream_t s) {
     HArgs a;
-    if (!make_args(g, p, 2, active ? 1 : 0, x, grad, gi, w, partials, &a)) return TS_ERR_UNSUPPORTED;
+    if (!make_args(g, p, 2, active ? 1 : 0, 0, x, grad, gi, w, partials, &a)) return TS_ERR_UNSUPPORTED;
     int rc;
     switch (g.dim * 2 + (active ? 1 : 0)) {
-    case 4: rc = launch(k_halo<2, 2, false, false>, a, p, s); break;
-    case 5: rc = launch(k_halo<2, 2, true, false>, a, p, s); break;
-    case 6: rc = launch(k_halo<3, 2, false, false>, a, p, s); break;
-    default: rc = a.split ? launch(k_halo<3, 2, true, true>, a, p, s) : launch(k_halo<3, 2, true, false>, a, p, s); break;
+    case 4: rc = launch(k_halo<2, 2, false, false, false>, a, p, s); break;
+    case 5: rc = launch(k_halo<2, 2, true, false, false>, a, p, s); break;
+    case 6: rc = launch(k_halo<3, 2, false, false, false>, a, p, s); break;
+    default: rc = a.split ? launch(k_halo<3, 2, true, true, false>, a, p, s) : launch(k_halo<3, 2, true, false, false>, a, p, s); break;
     }
     if (rc != TS_OK) return rc;
     return launch_reduce_partials<float>(partials, p.slots, (int)(g.C * g.dim), gw, peers, s);

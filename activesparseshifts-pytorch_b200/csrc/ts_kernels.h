@@ -155,10 +155,12 @@ struct HaloPlan {
     int stages, stage_stride, warps, n_per_unit, units, grid, slots;
     size_t smem_bytes;
 };
-// mode: 1 active forward, 2 backward (active = interpolating backward).  fp32, dims 2 and 3, every padding, border crops.
+// mode: 0 sparse forward (2-D only), 1 active forward, 2 backward (active = interpolating backward).  fp32, dims 2 and 3,
+// every padding, border crops.
 HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, const void* x, const void* out, const void* grad,
                    int sm_count, bool forced);
 int halo_active_forward(const Geo& g, const HaloPlan& p, const void* x, const void* w, void* y, cudaStream_t s);
+int halo_forward2d(const Geo& g, const HaloPlan& p, int active, int pool, const void* x, const void* w, void* y, cudaStream_t s);
 int halo_backward(const Geo& g, const HaloPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
                   double* partials, const ts_peer_group* peers, cudaStream_t s);
 

@@ -13,7 +13,7 @@ TS_OK = 0
 ABI_VERSION = 2
 STATUS_NAMES = {0: 'TS_OK', 1: 'TS_ERR_INVALID_ARGUMENT', 2: 'TS_ERR_UNSUPPORTED', 3: 'TS_ERR_WORKSPACE',
                 4: 'TS_ERR_TOO_LARGE', 5: 'TS_ERR_BORDERS', 6: 'TS_ERR_CUDA', 7: 'TS_ERR_NO_DEVICE'}
-PATH_NONE, PATH_GENERIC, PATH_STAGED, PATH_TMA = 0, 1, 2, 3
+PATH_NONE, PATH_GENERIC, PATH_STAGED, PATH_TMA, PATH_NHWC, PATH_HALO, PATH_FLAT = 0, 1, 2, 3, 4, 5, 6
 QW_U8, QW_I8, QW_I32 = 0, 1, 2
 
 # every symbol include/torchshifts_b200.h declares (tests check the library exports all of them)
@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     'ts_set_kernel_path', 'ts_launch_count', 'ts_set_tuning', 'ts_check_borders', 'ts_debug_remap',
     'ts_debug_remap_reduced', 'ts_debug_split_f32', 'ts_debug_split_f64', 'ts_shift_forward',
     'ts_shift_backward_workspace_bytes', 'ts_shift_backward', 'ts_qshift_forward', 'ts_shift_backward_allreduce',
-    'ts_qshift_forward_nhwc', 'ts_debug_nhwc_emulate', 'ts_nhwc_to_nchw',
+    'ts_qshift_forward_nhwc', 'ts_debug_nhwc_emulate', 'ts_nhwc_to_nchw', 'ts_shift2d_avgpool2_forward',
 )
 
 
@@ -72,6 +72,7 @@ class NativeLibrary:
             'ts_debug_split_f32': (None, [i, i, ct.c_float, i64p, ct.POINTER(ct.c_float)]),
             'ts_debug_split_f64': (None, [i, i, ct.c_double, i64p, ct.POINTER(ct.c_double)]),
             'ts_shift_forward': (i, [gp, i, i, i, vp, vp, vp, vp]),
+            'ts_shift2d_avgpool2_forward': (i, [gp, i, i, i, vp, vp, vp, vp]),
             'ts_shift_backward_workspace_bytes': (sz, [gp, i]),
             'ts_shift_backward': (i, [gp, i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]),
             'ts_qshift_forward': (i, [gp, i, i, i64, vp, vp, i, i64, vp, vp]),

@@ -153,6 +153,49 @@ def _forward_cuda(dim, input, weights, borders, new_size, padding_mode, active_f
     return out
 
 
+def _pool_forward_cuda(input, weights, borders, new_size, padding_mode, active_flag):
+    """Shift2d forward + avg_pool2d(kernel 2, stride 2, ceil_mode=True) in ONE kernel (ts_shift2d_avgpool2_forward): one
+    read of x, one quarter-size write.  Shapes the fused kernel does not serve (non-fp32, odd row lengths, strided
+    inputs, planes too large to stage) run the two steps separately -- same values."""
+    fn = 'shift2d_avgpool2_forward'
+    _check_mode(padding_mode)
+    _same_device_and_type(fn, input, weights)
+    lb, rb = _borders_lists(borders, 2)
+    oh, ow = rb[0] - lb[0], rb[1] - lb[1]
+    if input.dtype == torch.float32 and input.is_contiguous() and ow % 4 == 0 and input.dim() == 4:
+        out = torch.empty((input.shape[0], input.shape[1], (oh + 1) // 2, ow // 2), dtype=input.dtype, device=input.device)
+        w = weights.contiguous()
+        geo, _ = _geometry(2, input, lb, rb)
+        with _guard(input.device):
+            st = _NATIVE.lib.ts_shift2d_avgpool2_forward(ct.byref(geo), 0, int(padding_mode), int(bool(active_flag)), input.data_ptr(),
+                                                         w.data_ptr(), out.data_ptr(), _stream(input.device))
+        if st == 0:
+            return out
+        if st != 2:        # TS_ERR_UNSUPPORTED: fall through to the two-step path
+            _NATIVE.check(st, 'ts_shift2d_avgpool2_forward')
+    y = _forward_cuda(2, input, weights, borders, new_size, padding_mode, active_flag)
+    return torch.nn.functional.avg_pool2d(y, kernel_size=2, stride=2, ceil_mode=True)
+
+
+def _pool_forward_meta(input, weights, borders, new_size, padding_mode, active_flag):
+    return input.new_empty([new_size[0], new_size[1], (new_size[2] + 1) // 2, (new_size[3] + 1) // 2])
+
+
+def _pool_setup_context(ctx, inputs, output):
+    input, weights, borders, new_size, padding_mode, active_flag = inputs
+    ctx.save_for_backward(input, weights, borders)
+    ctx.padding_mode, ctx.active_flag, ctx.new_size = padding_mode, active_flag, list(new_size)
+
+
+def _pool_backward(ctx, grad_pooled):
+    # adjoint of the pooling (every window element receives grad / count), then the shift backward
+    input, weights, borders = ctx.saved_tensors
+    like = torch.empty(ctx.new_size, dtype=grad_pooled.dtype, device=grad_pooled.device)
+    grad_y = torch.ops.aten.avg_pool2d_backward(grad_pooled.contiguous(), like, [2, 2], [2, 2], [0, 0], True, True, None)
+    grad_input, grad_weight = torch.ops.torchshifts._shift2d_backward(grad_y, weights, input, borders, ctx.padding_mode, ctx.active_flag)
+    return grad_input, grad_weight, None, None, None, None
+
+
 def _backward_cuda(dim, grad, weights, input, borders, padding_mode, active_flag):
     fn = f'shift{dim}d_backward'
     _check_mode(padding_mode)
@@ -360,4 +403,11 @@ def register(native):
         for key in ('CPU', 'QuantizedCPU'):
             lib.impl(fwd, _no_cpu, key)
             lib.impl(bwd, _no_cpu, key)
+    # fused epilogue of the strided depth-wise-conv emulation (modules/shifts.py:85-89): shift + crop + avg_pool2d(2, 2, ceil)
+    pool = '_shift2d_avgpool2_forward'
+    lib.define(f'{pool}(Tensor input, Tensor weights, Tensor borders, int[] new_size, int padding_mode, bool active_flag) -> Tensor')
+    lib.impl(pool, _pool_forward_cuda, 'CUDA')
+    lib.impl(pool, _no_cpu, 'CPU')
+    torch.library.register_fake(f'torchshifts::{pool}', _pool_forward_meta, lib=lib)
+    torch.library.register_autograd(f'torchshifts::{pool}', _pool_backward, setup_context=_pool_setup_context, lib=lib)
     _LIB = lib

@@ -97,5 +97,28 @@ def shift3d_func(input: Tensor, weights: Tensor, padding_mode: int, active_flag:
     return _shift_func(3, input, weights, padding_mode, active_flag, borders, _border_ints)
 
 
+def shift2d_avgpool2_func(input: Tensor, weights: Tensor, padding_mode: int, active_flag: bool,
+                          borders: Optional[Tensor] = None, _border_ints=None) -> Tensor:
+    """``avg_pool2d(shift2d_func(...), kernel_size=2, stride=2, ceil_mode=True)`` in one kernel: what a ``Shift2d`` built
+    with ``emulate_dw={..., 'stride': 2}`` computes (reference ``modules/shifts.py:85-89, 153``), with one read of the
+    input and one quarter-size write.  Same argument checks as :func:`shift2d_func`."""
+    name = 'shift2d_avgpool2_func'
+    _assert_has_ops()
+    assert padding_mode in [0, 1, 2, 3, 4], f'{name}() expected padding_mode can be {_MODES}'
+    assert len(input.shape) == 4, f'{name}(): expected 4D tensor as input, but it is shape is {input.shape}'
+    assert weights.shape[-1] == 2, f'{name}(): expected [n_channels,2] tensor as weight, but it is shape is {weights.shape}'
+    assert input.shape[1] == weights.shape[0], f'{name}(): expected that input and weight have equal number of channels'
+    assert input.device == weights.device, f'{name}(): expected input and weights to be on same device'
+    if borders is None:
+        cuts = [[0, 0], [0, 0]]
+    else:
+        assert tuple(borders.shape) == (2, 2), 'borders must have shape [2, 2]'
+        cuts = _border_ints if _border_ints is not None else [[int(v) for v in row] for row in borders.tolist()]
+    lb, rb = _resolve_borders(2, input.shape[2:], cuts)
+    std = _std_borders((lb[0], rb[0], lb[1], rb[1], lb[2], rb[2]))
+    new_size = [input.shape[0], input.shape[1], rb[0] - lb[0], rb[1] - lb[1]]
+    return torch.ops.torchshifts._shift2d_avgpool2_forward(input, weights, std, new_size, padding_mode, active_flag)
+
+
 # BASELINE.json names these "functional.shift1d/2d/3d"; keep the real names and add the aliases.
 shift1d, shift2d, shift3d = shift1d_func, shift2d_func, shift3d_func

@@ -18,7 +18,7 @@ from functools import partial
 import torch
 from torch import nn
 
-from torchshifts.functional import shift1d_func, shift2d_func, shift3d_func
+from torchshifts.functional import shift1d_func, shift2d_avgpool2_func, shift2d_func, shift3d_func
 
 paddings_dict = {'zeros': 0, 'border': 1, 'periodic': 2, 'reflect': 3, 'symmetric': 4}
 _SHIFT_FUNCS = {1: shift1d_func, 2: shift2d_func, 3: shift3d_func}
@@ -126,6 +126,7 @@ class _Shiftnd(nn.Module):
                 self._reduction_fn = self._pooling(self._w_post_init_scale, self.dim)
         self._cut_cache = None
         self._border_ints()
+        self._stride_ints = [int(v) for v in self._w_post_init_scale.reshape(-1).tolist()]
         self._init_weights()
 
     def _init_shift_fn(self):
@@ -156,8 +157,18 @@ class _Shiftnd(nn.Module):
             cached = self._cut_cache = (cb, [[int(v) for v in row] for row in cb.tolist()])
         return cached[1]
 
+    def _pool_is_fused(self, input):
+        """The stride-2 average pooling of a 2-D depth-wise-conv emulation runs inside the shift kernel (one read, one
+        quarter-size write) for float32 CUDA tensors; everything else takes the shift followed by ``_reduction_fn``."""
+        return (self.dim == 2 and self._reduction_fn is not self._identity and input.is_cuda and input.dtype == torch.float32
+                and not input.is_quantized and self._stride_ints == [2, 2])
+
     def forward(self, input):
         loss = self._compute_weight_loss() if bool(self.sparsity_term) else None
+        if self._pool_is_fused(input):
+            out = shift2d_avgpool2_func(input, self.weight, self.padding, self._active_flag, self.cut_borders,
+                                        _border_ints=self._border_ints())
+            return out, loss
         if self.cut_borders is None:
             out = self._shift_func(input, self.weight, self.padding, self._active_flag, None)
         else:

@@ -116,6 +116,15 @@ void    ts_debug_split_f64(int backward, int active, double w, int64_t* iw, doub
 int ts_shift_forward(const ts_geometry* g, int dtype, int padding, int active,
                      const void* x, const void* weights, void* y, void* stream);
 
+/* Shift2d forward fused with the average pooling the reference module applies to a strided depth-wise-conv emulation
+ * (modules/shifts.py:85-89, :153: avg_pool2d(kernel_size=stride, stride=stride, ceil_mode=True) after the shift and the
+ * border crop), for stride 2: y_pooled is dense [N, C, ceil(O0/2), O1/2]; every window's elements are added in row-major
+ * order and divided by their count (2 for the last row of an odd O0), like ATen's kernel.  One read of x, one
+ * quarter-size write.  fp32, dim 2, dense x, O1 a multiple of 4: otherwise TS_ERR_UNSUPPORTED (callers then run
+ * ts_shift_forward and pool separately).  Replaces the pair shiftnd_forward + at::avg_pool2d on that path. */
+int ts_shift2d_avgpool2_forward(const ts_geometry* g, int dtype, int padding, int active,
+                                const void* x, const void* weights, void* y_pooled, void* stream);
+
 size_t ts_shift_backward_workspace_bytes(const ts_geometry* g, int dtype);
 
 /* grad: dense [N,C,rb-lb]; grad_input: dense like x's logical shape; grad_weight: dense [C,dim]

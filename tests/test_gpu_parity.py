@@ -594,6 +594,54 @@ def test_torch_compile_cropping_layer_and_inductor(dev, auto_path):
         assert torch.allclose(sh.weight.grad, gw, rtol=1e-4, atol=1e-5), backend
 
 
+def test_fused_avgpool_epilogue(dev, lib, oracle_port, auto_path):
+    """a Shift2d that emulates a stride-2 depth-wise convolution (modules/shifts.py:85-89) shifts, crops and
+    average-pools in ONE kernel.  Forward: bit-exact against the oracle's shift followed by a sequential-sum pooling in
+    numpy, and against the two-step path (shift op + torch's avg_pool2d); backward: the pooling adjoint + shift backward
+    against autograd through the two-step path."""
+    import torchshifts
+    from torchshifts.functional import shift2d_func
+    rng = np.random.default_rng(61)
+    for shape, pad_name, active, conv_pad in [((2, 8, 16, 16), 'zeros', False, 1), ((2, 8, 15, 20), 'reflect', True, 1),
+                                              ((3, 4, 18, 24), 'periodic', False, 0), ((2, 4, 17, 12), 'symmetric', True, 0),
+                                              ((2, 6, 16, 24), 'border', True, 1)]:
+        torch.manual_seed(3)
+        m = torchshifts.Shift2d(shape[1], padding=pad_name, active_flag=active, sparsity_term=0,
+                                emulate_dw={'kernel_size': 3, 'stride': 2, 'padding': conv_pad}).to(dev)
+        assert (m.cut_borders is not None) == (conv_pad == 0)
+        x = rng.standard_normal(shape).astype(np.float32)
+        w = m.weight.detach().cpu().numpy()
+        pad = torchshifts.modules.shifts.paddings_dict[pad_name]
+        borders = m.cut_borders.tolist() if m.cut_borders is not None else None
+        xd = torch.from_numpy(x).to(dev).requires_grad_(True)
+        out, loss = m(xd)
+        assert loss is None and lib.ts_last_kernel_path() == 5
+        y = oracle_port.forward(x, w, pad, active, borders)
+        oh, ow = y.shape[2:]
+        want = np.zeros(y.shape[:2] + ((oh + 1) // 2, (ow + 1) // 2), np.float32)
+        for i in range(want.shape[2]):
+            for j in range(want.shape[3]):
+                acc, cnt = None, 0
+                for di in range(2):
+                    for dj in range(2):
+                        if 2 * i + di < oh and 2 * j + dj < ow:
+                            v = y[:, :, 2 * i + di, 2 * j + dj]
+                            acc = v.copy() if acc is None else (acc + v).astype(np.float32)
+                            cnt += 1
+                want[:, :, i, j] = (acc / np.float32(cnt)).astype(np.float32)
+        assert np.array_equal(out.detach().cpu().numpy(), want), (shape, pad_name, active)
+        # the two-step path: same values, and its autograd gives the reference gradients
+        x2 = torch.from_numpy(x).to(dev).requires_grad_(True)
+        w2 = m.weight.detach().clone().requires_grad_(True)
+        two = torch.nn.functional.avg_pool2d(shift2d_func(x2, w2, pad, active, m.cut_borders), 2, 2, ceil_mode=True)
+        assert torch.equal(two, out)
+        g = torch.from_numpy(rng.standard_normal(want.shape).astype(np.float32)).to(dev)
+        out.backward(g)
+        two.backward(g)
+        assert torch.equal(xd.grad, x2.grad)
+        assert torch.allclose(m.weight.grad, w2.grad, rtol=1e-5, atol=1e-6)
+
+
 def test_cuda_graph_capture_and_replay(dev, lib, oracle_port, auto_path):
     """The C ABI only enqueues work on the caller's stream (no sync, no allocation, tensor maps are
     encoded on the host and passed by value), so forward + backward capture into a CUDA graph; the
