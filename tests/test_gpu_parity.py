@@ -22,7 +22,8 @@ ROOT = Path(__file__).resolve().parents[1]
 pytestmark = pytest.mark.gpu
 
 BORDERS = {1: [[1, 2]], 2: [[1, 1], [2, 1]], 3: [[1, 0], [0, 2], [1, 1]]}
-GENERIC, STAGED, TMA = 1, 2, 3
+GENERIC, STAGED, TMA, HALO, FLAT = 1, 2, 3, 5, 6
+BANDWIDTH = (STAGED, TMA, HALO, FLAT)        # the shared-memory staged families (anything but the generic kernels)
 
 
 @pytest.fixture(scope="module")
@@ -40,21 +41,23 @@ def lib():
 @pytest.fixture()
 def auto_path(lib):
     lib.ts_set_kernel_path(0)
-    lib.ts_set_tuning(b"use_tma=1,nhwc_variant=0,nhwc_ring_rows=0")
+    lib.ts_set_tuning(b"use_tma=1,use_halo=1,use_flat=1,nhwc_variant=0,nhwc_ring_rows=0")
     yield
     lib.ts_set_kernel_path(0)
-    lib.ts_set_tuning(b"use_tma=1,nhwc_variant=0,nhwc_ring_rows=0")
+    lib.ts_set_tuning(b"use_tma=1,use_halo=1,use_flat=1,nhwc_variant=0,nhwc_ring_rows=0")
 
 
 # kernel-family selection modes exercised by the sweeps: the automatic choice (TMA-tensor family for
 # zeros padding, bulk-staged otherwise, generic for odd shapes), the automatic choice without the
 # TMA-tensor family (so the bulk-staged kernels also see zeros padding), and the generic family only.
-MODES = ["auto", "no_tma", "generic"]
+# "staged" switches the round-2 families (halo, flat) off as well, so the bulk-staged kernels keep their full coverage.
+MODES = ["auto", "no_tma", "staged", "generic"]
 
 
 def _set_mode(lib, mode):
     lib.ts_set_kernel_path(GENERIC if mode == "generic" else 0)
-    lib.ts_set_tuning(b"use_tma=0" if mode == "no_tma" else b"use_tma=1")
+    lib.ts_set_tuning({"no_tma": b"use_tma=0,use_halo=1,use_flat=1", "staged": b"use_tma=0,use_halo=0,use_flat=0"}.get(
+        mode, b"use_tma=1,use_halo=1,use_flat=1"))
 
 
 def _func(dim):
@@ -171,7 +174,7 @@ def test_randomised_sweep_vs_oracle(dev, lib, oracle_port, mode, dtype):
                         y_ref = oracle_port.forward(x, w, pad, active, borders)
                         grad = rng.standard_normal(y_ref.shape).astype(dtype)
                         y, gi, gw = _run_cuda(dev, dim, x, w, grad, pad, active, borders)
-                        staged_hits += lib.ts_last_kernel_path() in (STAGED, TMA)
+                        staged_hits += lib.ts_last_kernel_path() in BANDWIDTH
                         tma_hits += lib.ts_last_kernel_path() == TMA
                         tag = (shape, pad, active, borders, dtype.__name__)
                         assert np.array_equal(y, y_ref), ("forward",) + tag
@@ -183,7 +186,7 @@ def test_randomised_sweep_vs_oracle(dev, lib, oracle_port, mode, dtype):
         _set_mode(lib, "auto")
     if mode == "generic":
         assert staged_hits == 0
-    if mode == "no_tma":
+    if mode in ("no_tma", "staged"):
         assert tma_hits == 0
     if mode == "auto" and dtype is np.float32:
         assert tma_hits > 0 and staged_hits > tma_hits
@@ -248,9 +251,9 @@ def test_large_channels_last_input_takes_the_bandwidth_path(dev, lib, oracle_por
         xd = torch.from_numpy(x).to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
         wd = torch.from_numpy(w).to(dev).requires_grad_(True)
         y = shift2d_func(xd, wd, pad, active)
-        assert lib.ts_last_kernel_path() in (STAGED, TMA)
+        assert lib.ts_last_kernel_path() in BANDWIDTH
         y.backward(torch.from_numpy(g).to(dev))
-        assert lib.ts_last_kernel_path() in (STAGED, TMA)
+        assert lib.ts_last_kernel_path() in BANDWIDTH
         assert np.array_equal(y.detach().cpu().numpy(), oracle_port.forward(x, w, pad, active))
         gi_ref, _ = oracle_port.backward(g, x, w, pad, active)
         assert np.array_equal(xd.grad.cpu().numpy(), gi_ref)
@@ -358,9 +361,9 @@ def test_full_size_cfg3_shift2d(dev, lib, oracle_port, auto_path):
     w = ((torch.rand(C, 2, device=dev) * 2 - 1) * 3).requires_grad_(True)
     xr = x.clone().requires_grad_(True)
     y = shift2d_func(xr, w, 0, False)
-    assert lib.ts_last_kernel_path() in (STAGED, TMA), "cfg3 must run on a staged (bulk-async / TMA) path"
+    assert lib.ts_last_kernel_path() in BANDWIDTH, "cfg3 must run on a staged (bulk-async / TMA) path"
     y.backward(g)
-    assert lib.ts_last_kernel_path() in (STAGED, TMA)
+    assert lib.ts_last_kernel_path() in BANDWIDTH
     gi, gw = xr.grad, w.grad.clone()
     idx = [0, 17, 255]
     _sample_check(dev, oracle_port, 2, x, w, g, 0, False, y, gi, idx)
@@ -463,7 +466,7 @@ def test_full_size_cfg5_quantized_shift2d(dev, lib, oracle_port, auto_path):
         qw = quantize_shift_weights(w)
         assert np.array_equal(qw.int_repr().cpu().numpy().astype(np.int64), raw)
         yq = shift2d_quantized(xq, qw, 0)
-        assert lib.ts_last_kernel_path() in (STAGED, TMA)
+        assert lib.ts_last_kernel_path() in BANDWIDTH
         idx = [0, 100, 255]
         want = oracle_port.qforward(xq.int_repr()[idx].cpu().numpy(), raw, wzp, zp, 0)
         assert np.array_equal(yq.int_repr()[idx].cpu().numpy(), want)
@@ -876,6 +879,6 @@ def test_channels_last_to_planar_adapter(dev, lib, oracle_port, auto_path):
     w = (torch.rand(96, 2, device=dev) * 2 - 1) * 2
     before = lib.ts_launch_count()
     y = shift2d_func(x.contiguous(memory_format=torch.channels_last), w, 3, True)
-    assert lib.ts_launch_count() - before == 2 and lib.ts_last_kernel_path() in (STAGED, TMA)
+    assert lib.ts_launch_count() - before == 2 and lib.ts_last_kernel_path() in BANDWIDTH
     assert y.is_contiguous()
     assert np.array_equal(y.cpu().numpy(), oracle_port.forward(x.cpu().numpy(), w.cpu().numpy(), 3, True))

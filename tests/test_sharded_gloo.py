@@ -93,3 +93,54 @@ def test_shard_range_tiles_the_batch():
             assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in ranges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _ddp_worker(rank, world, port, out_dir):
+    for p in (str(ROOT), str(ROOT / "activesparseshifts-pytorch_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from torchshifts import Shift2d
+        from torchshifts.sharded import FusedGradWeightAllReduce, ddp_sum_to_mean_hook
+
+        class Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.lin = torch.nn.Linear(4, 4)
+                self.shift = Shift2d(3, init_shift=2)          # never run here: there is no CPU compute path
+                self.block = torch.nn.Sequential(Shift2d(2))
+
+            def forward(self, x):
+                return self.lin(x)
+
+        torch.manual_seed(0)
+        net = Net()
+        names = FusedGradWeightAllReduce.exclude_from_ddp(net)
+        assert sorted(names) == ["block.0.weight", "shift.weight"]
+        ddp = torch.nn.parallel.DistributedDataParallel(net)
+        # DDP keeps only the Linear's parameters in its buckets: the shift weights are reduced by the in-kernel exchange
+        managed = {n for n, p in ddp.module.named_parameters() if n not in ddp.parameters_to_ignore}
+        assert managed == {"lin.weight", "lin.bias"}, managed
+        x = torch.full((2, 4), float(rank + 1))
+        ddp(x).sum().backward()
+        mean_x = sum(range(1, world + 1)) / world                 # DDP averaged the Linear's gradient over the ranks
+        assert torch.allclose(net.lin.weight.grad, torch.full((4, 4), 2 * mean_x))
+        # the fused exchange SUMS; the hook turns that into DDP's mean for the excluded weights
+        handles = ddp_sum_to_mean_hook(net)
+        assert len(handles) == 2
+        (net.shift.weight * 3.0).sum().backward()                 # stands for "grad already summed over the ranks"
+        assert torch.allclose(net.shift.weight.grad, torch.full_like(net.shift.weight, 3.0 / world))
+        Path(out_dir, f"ddp{rank}").write_text("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_leaves_the_shift_weights_to_the_fused_exchange(tmp_path):
+    """with the in-kernel exchange the shift weights must NOT sit in DDP's gradient buckets as well
+    (they would be reduced twice): exclude_from_ddp + the sum->mean hook, world size 2 on gloo."""
+    world, port = 2, _free_port()
+    mp.spawn(_ddp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ddp{r}").exists() for r in range(world))
