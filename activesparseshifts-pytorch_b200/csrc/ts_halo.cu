@@ -716,9 +716,10 @@ struct Body {
         float G[(MODE == 2 && ACTIVE && ROLE != 1) ? 3 : 1][5];
     };
 
-    // stage k of an image: combine the carried windows (slab k-1) with this stage's (slab k), then carry the new ones
+    // stage k of an image: combine the windows of slab k-1 (`prev`, registers) with this stage's (slab k), which are
+    // loaded straight into `next`: the caller alternates two register sets, so nothing is copied from step to step
     template <int WSX, int WSG, int WSV, int ROLE>
-    TS_D void step3(unsigned sb, unsigned char* dst_img, int k, const PairCtx& pc, Carry<ROLE>& cy, float* ts) const {
+    TS_D void step3(unsigned sb, unsigned char* dst_img, int k, const PairCtx& pc, const Carry<ROLE>& cy, Carry<ROLE>& nx, float* ts) const {
         constexpr bool DOX = MODE != 2 || ROLE != 2;
         constexpr bool DOG = MODE == 2 && ROLE != 1;
         if (pc.rows == 0) return;
@@ -728,75 +729,56 @@ struct Body {
         const bool slab_pass = MODE != 2 || (it - a.lbA >= 0 && it - a.lbA < a.OA);
         const unsigned cm = (k >= 1 && slab_pass) ? pc.cmask : 0u;
         const unsigned xa = sb + pc.xo, ga = sb + pc.go, va = sb + pc.vo;
+        const int pxb = a.px * 4, pgb = a.pg * 4;
         const bool gwin = DOG && ACTIVE && pc.cmask != 0u;
-        float Xn[3][5], Gn[3][5];
-        if (DOX) { load5<WSX>(xa, wsx, Xn[0]); load5<WSX>(xa + a.px * 4, wsx, Xn[1]); }
-        if (gwin) { load5<WSG>(ga, wsg, Gn[0]); load5<WSG>(ga + a.pg * 4, wsg, Gn[1]); }
+        if (DOX) { load5<WSX>(xa, wsx, nx.X[0]); load5<WSX>(xa + pxb, wsx, nx.X[1]); }
+        if (gwin) { load5<WSG>(ga, wsg, nx.G[0]); load5<WSG>(ga + pgb, wsg, nx.G[1]); }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             if (j >= pc.rows) continue;
             if (j == 1) {
-                if (DOX) load5<WSX>(xa + 2 * a.px * 4, wsx, Xn[2]);
-                if (gwin) load5<WSG>(ga + 2 * a.pg * 4, wsg, Gn[2]);
+                if (DOX) load5<WSX>(xa + 2 * pxb, wsx, nx.X[2]);
+                if (gwin) load5<WSG>(ga + 2 * pgb, wsg, nx.G[2]);
             }
-            if (k >= 1) {
-                if (MODE != 2) {
-                    float P[5], y[4];
+            if (k < 1) continue;
+            if (MODE != 2) {
+                float P[5], y[4];
 #pragma unroll
-                    for (int t = 0; t < 5; ++t) P[t] = col3(cy.X[j][t], Xn[j][t], cy.X[j + 1][t], Xn[j + 1][t], d[0], d[1]);
+                for (int t = 0; t < 5; ++t) P[t] = col3(cy.X[j][t], nx.X[j][t], cy.X[j + 1][t], nx.X[j + 1][t], d[0], d[1]);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
-                    __stcs((float4*)(o + j * orow), make_float4(y[0], y[1], y[2], y[3]));
-                } else {
-                    const unsigned m = (cm >> (4 * j)) & 15u;
-                    float y[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (m) {
-                        if (DOX) {
-                            float gv[4];
-                            load4<WSV>(va + j * a.OL * 4, wsv, gv);
-                            if (m != 15u) {
+                for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
+                __stcs((float4*)(o + j * orow), make_float4(y[0], y[1], y[2], y[3]));
+            } else {
+                const unsigned m = (cm >> (4 * j)) & 15u;
+                float y[4] = {0.f, 0.f, 0.f, 0.f};
+                if (m) {
+                    if (DOX) {
+                        float gv[4];
+                        load4<WSV>(va + j * a.OL * 4, wsv, gv);
+                        if (m != 15u) {
 #pragma unroll
-                                for (int t = 0; t < 4; ++t) gv[t] = (m >> t) & 1u ? gv[t] : 0.f;
-                            }
-                            wp3(cy.X[j], Xn[j], cy.X[j + 1], Xn[j + 1], gv, d, ts);
+                            for (int t = 0; t < 4; ++t) gv[t] = (m >> t) & 1u ? gv[t] : 0.f;
                         }
-                        if (DOG) {
-                            if (ACTIVE) {
-                                float P[5];
+                        wp3(cy.X[j], nx.X[j], cy.X[j + 1], nx.X[j + 1], gv, d, ts);
+                    }
+                    if (DOG) {
+                        if (ACTIVE) {
+                            float P[5];
 #pragma unroll
-                                for (int t = 0; t < 5; ++t) P[t] = col3(cy.G[j][t], Gn[j][t], cy.G[j + 1][t], Gn[j + 1][t], d[0], d[1]);
+                            for (int t = 0; t < 5; ++t) P[t] = col3(cy.G[j][t], nx.G[j][t], cy.G[j + 1][t], nx.G[j + 1][t], d[0], d[1]);
 #pragma unroll
-                                for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
-                            } else {
-                                load4<WSG>(ga + j * a.pg * 4, wsg, y);
-                            }
-                            if (m != 15u) {
+                            for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
+                        } else {
+                            load4<WSG>(ga + j * pgb, wsg, y);
+                        }
+                        if (m != 15u) {
 #pragma unroll
-                                for (int t = 0; t < 4; ++t) y[t] = (m >> t) & 1u ? y[t] : 0.f;
-                            }
+                            for (int t = 0; t < 4; ++t) y[t] = (m >> t) & 1u ? y[t] : 0.f;
                         }
                     }
-                    if (DOG) __stcs((float4*)(o + j * orow), make_float4(y[0], y[1], y[2], y[3]));
                 }
+                if (DOG) __stcs((float4*)(o + j * orow), make_float4(y[0], y[1], y[2], y[3]));
             }
-            // row j of the carried slab is not needed any more
-            if (DOX) {
-#pragma unroll
-                for (int t = 0; t < 5; ++t) cy.X[j][t] = Xn[j][t];
-            }
-            if (gwin) {
-#pragma unroll
-                for (int t = 0; t < 5; ++t) cy.G[j][t] = Gn[j][t];
-            }
-        }
-        const int last = pc.rows;            // the row below the pair
-        if (DOX) {
-#pragma unroll
-            for (int t = 0; t < 5; ++t) { if (last == 2) cy.X[2][t] = Xn[2][t]; else cy.X[1][t] = Xn[1][t]; }
-        }
-        if (gwin) {
-#pragma unroll
-            for (int t = 0; t < 5; ++t) { if (last == 2) cy.G[2][t] = Gn[2][t]; else cy.G[1][t] = Gn[1][t]; }
         }
     }
 
@@ -805,7 +787,7 @@ struct Body {
         constexpr int NPT = ROLE == 0 ? 1 : 2;
         const int half = nt >> 1;
         PairCtx pc[NPT];
-        Carry<ROLE> cy[NPT];
+        Carry<ROLE> ca[NPT], cb[NPT];          // the windows of two consecutive slabs, roles alternating from step to step
 #pragma unroll
         for (int i = 0; i < NPT; ++i) {
             const int p = ROLE == 0 ? tid : (tid < half ? tid : tid - half) + i * half;
@@ -814,19 +796,39 @@ struct Body {
             if (!valid) { q.pl = 0; q.r = 0; q.cg = 0; }
             pc[i] = pair_ctx<MODE>(a, ug, q, valid);
         }
-        for (int k = 0; k <= a.IA; ++k) {
-            const unsigned sb = shared_addr(smem + (size_t)ring.s * a.stage_stride + GUARD);
-            mbar_wait(&wait_bar[ring.s], ring.phase);
+        if constexpr (MODE != 2) {
+            // forward: four compile-time misalignment bodies; unrolling the slab loop by two on top of that spills, so the
+            // new windows are copied into the carried set instead (15 moves per step)
+            for (int k = 0; k <= a.IA; ++k) {
+                const unsigned sb = shared_addr(smem + (size_t)ring.s * a.stage_stride + GUARD);
+                mbar_wait(&wait_bar[ring.s], ring.phase);
+                step3<WSX, WSG, WSV, ROLE>(sb, dst_img, k, pc[0], ca[0], cb[0], ts);
 #pragma unroll
-            for (int i = 0; i < NPT; ++i) step3<WSX, WSG, WSV, ROLE>(sb, dst_img, k, pc[i], cy[i], ts);
-            release(ring);
+                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) ca[0].X[j][t] = cb[0].X[j][t];
+                release(ring);
+            }
+            return;
+        }
+        for (int k = 0; k <= a.IA; k += 2) {
+            {
+                const unsigned sb = shared_addr(smem + (size_t)ring.s * a.stage_stride + GUARD);
+                mbar_wait(&wait_bar[ring.s], ring.phase);
+#pragma unroll
+                for (int i = 0; i < NPT; ++i) step3<WSX, WSG, WSV, ROLE>(sb, dst_img, k, pc[i], cb[i], ca[i], ts);
+                release(ring);
+            }
+            if (k + 1 <= a.IA) {
+                const unsigned sb = shared_addr(smem + (size_t)ring.s * a.stage_stride + GUARD);
+                mbar_wait(&wait_bar[ring.s], ring.phase);
+#pragma unroll
+                for (int i = 0; i < NPT; ++i) step3<WSX, WSG, WSV, ROLE>(sb, dst_img, k + 1, pc[i], ca[i], cb[i], ts);
+                release(ring);
+            }
         }
     }
 
-    // (Tried: NOT inlining one body per window misalignment so each gets its own register allocation -- the accumulators
-    // and the ring state then live in local memory behind pointers and everything got 2-4x slower.)  Inlined into one switch
-    // the five variants shared a single allocation and spilled ~70 words each (local memory goes to L2 here: with the
-    // shared-memory carve-out at its maximum the L1 is ~28 KB); compiled alone a variant spills nothing.
     template <int WSX, int WSG, int WSV>
     TS_D void run_images(unsigned char* smem, Ring& ring, unsigned char* dst, int npl, const PairCtx& pc0, float* ts) const {
         if constexpr (DIM == 2) {

@@ -845,7 +845,7 @@ bool make_args(const Geo& g, const TmaPlan& p, int mode, int active, int es, TAr
     a.unit_order = tuning().unit_order;
     a.d_C = make_fastdiv((unsigned)g.C);
     a.d_chunks = make_fastdiv((unsigned)a.chunks);
-    a.table = g.C <= TABLE_MAX_C ? 1 : 0;
+    a.table = (g.C <= TABLE_MAX_C && !tuning().no_table) ? 1 : 0;
     a.GP = p.gp;
     a.img_items = a.TA * a.TB * a.GP;
     a.img_stride16 = (int)(g.C * (mode == 2 ? g.in_plane : g.out_plane) * es / 16);
@@ -923,7 +923,10 @@ TmaPlan plan_tma(const Geo& g, int mode, int active, int esize, int dtype, bool 
     const long long budget = SMEM_LIMIT - 1024 - table_bytes;
     // defaults from the cfg3 sweep on B200 (tools/tune.py --tma): forward 6 x 28 KB, backward 5 x 42 KB
     // 3-D volumes: few large stages (deep slab tiles re-read fewer +1 neighbour slabs)
-    const int want_stages = t.tma_stages > 0 ? t.tma_stages : d == 3 ? (mode == 2 ? 2 : 3) : (mode == 2 ? 5 : 6);
+    // Ring depth, 1-D / 2-D: re-tuned in round 2 (tools/tma_sweep.py, cfg3, CUDA-graph replays).  Once the producer stopped
+    // computing the shift parameters per unit it ran a full ring ahead, and MORE stages in flight made the kernels slower
+    // (HBM page locality: forward 293 us with 6 stages, 256 us with 3; sparse backward 409 us with 5, 372 us with 4).
+    const int want_stages = t.tma_stages > 0 ? t.tma_stages : d == 3 ? (mode == 2 ? 2 : 3) : (mode == 0 ? 3 : mode == 1 ? 4 : (active ? 5 : 4));
     const long long auto_target = d == 3 ? (mode == 2 ? 108 * 1024 : 72 * 1024) : (mode == 2 ? 42 * 1024 : 28 * 1024);
     const long long target = t.tma_stage_kb > 0 ? (long long)t.tma_stage_kb * 1024
                                                 : (auto_target < budget / want_stages - 64 ? auto_target : budget / want_stages - 64);

@@ -53,6 +53,8 @@ def make_geometry(dim, shape, strides, lb, rb):
 
 class NativeLibrary:
     def __init__(self, path=None):
+        # TORCHSHIFTS_B200_LIB: another build of the same ABI (A/B measurements of kernel changes)
+        path = path or os.environ.get('TORCHSHIFTS_B200_LIB')
         self.path = Path(path) if path else Path(__file__).resolve().parent / LIB_NAME
         if not self.path.exists():
             raise ImportError(f'{self.path} not found: build it with `python __graft_entry__.py` '
@@ -82,6 +84,8 @@ class NativeLibrary:
             'ts_shift_backward_allreduce': (i, [gp, i, i, i, vp, vp, vp, vp, vp, vp, sz, ct.POINTER(PeerGroup), vp]),
         }
         for name, (res, args) in sig.items():
+            if not hasattr(lib, name) and os.environ.get('TORCHSHIFTS_B200_LIB'):
+                continue              # an older build under A/B measurement may lack the newest entry points
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
         if lib.ts_abi_version() != ABI_VERSION:

@@ -605,12 +605,16 @@ def test_fused_avgpool_epilogue(dev, lib, oracle_port, auto_path):
     import torchshifts
     from torchshifts.functional import shift2d_func
     rng = np.random.default_rng(61)
-    for shape, pad_name, active, conv_pad in [((2, 8, 16, 16), 'zeros', False, 1), ((2, 8, 15, 20), 'reflect', True, 1),
-                                              ((3, 4, 18, 24), 'periodic', False, 0), ((2, 4, 17, 12), 'symmetric', True, 0),
-                                              ((2, 6, 16, 24), 'border', True, 1)]:
+    # (shape, padding, active, conv kernel, conv padding, fused?)  -- the fused kernel needs input AND output rows of a multiple
+    # of 4 elements (a 3x3 "valid" conv crops 1 + 1 columns: never both); such layers take the two-step path inside the
+    # same operator and must give the same values (last two cases)
+    for shape, pad_name, active, ks, conv_pad, fused in [((2, 8, 16, 16), 'zeros', False, 3, 1, True), ((2, 8, 15, 20), 'reflect', True, 3, 1, True),
+                                                         ((3, 4, 18, 28), 'periodic', False, 5, 0, True), ((2, 4, 17, 16), 'symmetric', True, 5, 0, True),
+                                                         ((2, 6, 16, 24), 'border', True, 3, 1, True), ((2, 4, 9, 22), 'zeros', True, 3, 1, False),
+                                                         ((2, 4, 18, 26), 'reflect', False, 3, 0, False)]:
         torch.manual_seed(3)
         m = torchshifts.Shift2d(shape[1], padding=pad_name, active_flag=active, sparsity_term=0,
-                                emulate_dw={'kernel_size': 3, 'stride': 2, 'padding': conv_pad}).to(dev)
+                                emulate_dw={'kernel_size': ks, 'stride': 2, 'padding': conv_pad}).to(dev)
         assert (m.cut_borders is not None) == (conv_pad == 0)
         x = rng.standard_normal(shape).astype(np.float32)
         w = m.weight.detach().cpu().numpy()
@@ -618,7 +622,7 @@ def test_fused_avgpool_epilogue(dev, lib, oracle_port, auto_path):
         borders = m.cut_borders.tolist() if m.cut_borders is not None else None
         xd = torch.from_numpy(x).to(dev).requires_grad_(True)
         out, loss = m(xd)
-        assert loss is None and lib.ts_last_kernel_path() == 5
+        assert loss is None and (lib.ts_last_kernel_path() == HALO) == fused, (shape, lib.ts_last_kernel_path())
         y = oracle_port.forward(x, w, pad, active, borders)
         oh, ow = y.shape[2:]
         want = np.zeros(y.shape[:2] + ((oh + 1) // 2, (ow + 1) // 2), np.float32)
