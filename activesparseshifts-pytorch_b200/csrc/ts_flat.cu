@@ -18,7 +18,8 @@
 //    quantized/shifts_quantized.cpp:113) is blended in with byte masks derived from the item's offset; items
 //    without an invalid byte skip that.
 //
-// CTA = nw consumer warps + 1 producer warp, several small CTAs per SM (default 2); stages are dealt round-robin.
+// CTA = nw consumer warps + 1 producer warp (one CTA of 15 warps per SM by default, `flat_ctas` for several smaller
+// ones); stages are dealt round-robin.
 #include <cstring>
 
 #include "ts_kernels.h"
@@ -296,11 +297,13 @@ FlatPlan plan_flat(const Geo& g, int esize, bool dense_x, const void* x, const v
     if (((uintptr_t)x & 15) || ((uintptr_t)y & 15)) return p;
     if (g.N * g.C >= (1ll << 40)) return p;
     const Tuning& t = tuning();
-    const int ctas = t.flat_ctas > 0 ? t.flat_ctas : 2;
+    // defaults from tools/knob_sweep.py cfg5 on B200: one CTA of 15 warps per SM, 4 stages of 48 KB (74 us; two CTAs of 8 warps
+    // with 24 KB stages: 80 us; three with 16 KB: 77 us)
+    const int ctas = t.flat_ctas > 0 ? t.flat_ctas : 1;
     const bool wp = t.flat_variant != 1 && g.C <= 512;                 // warp-per-plane variant with the shift table
     const long long table_bytes = wp ? g.C * 8 : 0;
     const long long budget = SMEM_LIMIT / ctas - 1024 - table_bytes;
-    const long long target = (long long)(t.flat_stage_kb > 0 ? t.flat_stage_kb : 24) * 1024;
+    const long long target = (long long)(t.flat_stage_kb > 0 ? t.flat_stage_kb : (ctas == 1 ? 48 : 24)) * 1024;
     long long K = target / plane;
     if (K < 1) K = 1;
     if (K > MAX_K) K = MAX_K;

@@ -1041,7 +1041,7 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     while (np > 1 && budget / (stride_of(np) + 24) < min_stages + 1) --np;
     long long stages = budget / (stride_of(np) + 24);
     if (stages < min_stages) return p;
-    const int want = t.halo_stages > 0 ? t.halo_stages : (d == 3 ? 6 : 5);
+    const int want = t.halo_stages > 0 ? t.halo_stages : (d == 3 ? 6 : 4);     // tools/knob_sweep.py cfg3ra / cfg4r
     if (stages > want) stages = want;
     if (np * per_image >= (1 << 20)) return p;             // mbarrier tx-count range
     const long long pairs = np * img_pairs;

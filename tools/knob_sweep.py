@@ -15,7 +15,7 @@ from torchshifts.quantized.modules.shifts import quantize_shift_weights  # noqa:
 
 lib = native().lib
 dev = torch.device("cuda:0")
-CASES = {"cfg3": ((256, 256, 56, 56), 0, False, torch.float32), "cfg3a": ((256, 256, 56, 56), 0, True, torch.float32),
+CASES = {"cfg1": ((8, 64, 32, 32), 0, False, torch.float32), "cfg3": ((256, 256, 56, 56), 0, False, torch.float32), "cfg3a": ((256, 256, 56, 56), 0, True, torch.float32),
          "cfg3r": ((256, 256, 56, 56), 3, False, torch.float32), "cfg3ra": ((256, 256, 56, 56), 3, True, torch.float32),
          "cfg4": ((32, 128, 16, 56, 56), 0, True, torch.float32), "cfg4r": ((32, 128, 16, 56, 56), 3, True, torch.float32),
          "cfg4rs": ((32, 128, 16, 56, 56), 3, False, torch.float32), "cfg5": ((256, 256, 56, 56), 0, False, torch.qint8),
