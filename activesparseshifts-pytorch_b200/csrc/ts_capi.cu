@@ -172,6 +172,7 @@ int ts_set_tuning(const char* spec) {
         else if (!strcmp(key, "halo_split")) t.halo_split = val != 0;
         else if (!strcmp(key, "unit_order")) t.unit_order = val != 0;
         else if (!strcmp(key, "no_table")) t.no_table = val != 0;
+        else if (!strcmp(key, "no_pdl")) t.no_pdl = val != 0;
         else if (!strcmp(key, "use_flat")) t.use_flat = val != 0;
         else if (!strcmp(key, "flat_variant")) t.flat_variant = val;
         else if (!strcmp(key, "flat_ctas")) t.flat_ctas = val;

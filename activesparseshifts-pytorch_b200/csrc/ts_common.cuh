@@ -307,6 +307,32 @@ TS_D void unit_decode(int u, int C, int chunks, int order, int& c, int& chunk) {
 #endif
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A kernel launched with launch_pdl() may start while its predecessor in the stream is
+// still draining: its CTAs are scheduled, set up their barriers and then block in pdl_wait() until the predecessor
+// has completed and flushed -- so NOTHING that touches global memory may precede pdl_wait().  pdl_trigger() at the
+// top of a kernel lets its successor do the same.  Hides ~2 us of launch latency and ramp per kernel boundary, which is
+// 5 % of the three-kernel step of a 32-image shard (8-GPU strong scaling); also inside captured CUDA graphs.
+#ifdef __CUDACC__
+TS_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+TS_D void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#endif
+
+// ------------------------------------------------------------------------------------------
 // Launch bookkeeping shared by the translation units.
 struct LaunchCtx {
     cudaStream_t stream;

@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(256) k_backward_generic(Geo g, const ST* __res
 template <typename ST>
 __global__ void k_reduce_partials(const double* __restrict__ partials, int slots, int outputs, ST* __restrict__ gw) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();             // the partials are the previous kernel's output
     if (warp >= outputs) return;
     double s = 0.0;
     for (int k = lane; k < slots; k += 32) s += partials[(long long)k * outputs + warp];
@@ -236,6 +238,8 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_partials_allreduce(const dou
     __shared__ unsigned s_epoch;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int o = blockIdx.x * 32 + wid;
+    pdl_trigger();
+    pdl_wait();             // the partials are the previous kernel's output
     if (threadIdx.x == 0) { const unsigned e = pa.state[blockIdx.x] + 1u; pa.state[blockIdx.x] = e; s_epoch = e; }
     __syncthreads();
     const unsigned epoch = s_epoch;
@@ -282,14 +286,22 @@ int launch_reduce_partials(const double* partials, int slots, int outputs, void*
             for (int p = 0; p < 8; ++p) pa.bufs[p] = (unsigned long long*)pg->bufs[p];
             pa.state = (unsigned*)pg->state;
             if (outputs > 32 * PEER_MAX_CTAS || outputs > pg->capacity) return TS_ERR_INVALID_ARGUMENT;
-            k_reduce_partials_allreduce<ST><<<(outputs + 31) / 32, 1024, 0, stream>>>(partials, slots, outputs, (ST*)gw, pa);
+            if (tuning().no_pdl || launch_pdl(k_reduce_partials_allreduce<ST>, dim3((outputs + 31) / 32), dim3(1024), 0, stream, partials, slots,
+                                              outputs, (ST*)gw, pa) != cudaSuccess) {
+                (void)cudaGetLastError();
+                k_reduce_partials_allreduce<ST><<<(outputs + 31) / 32, 1024, 0, stream>>>(partials, slots, outputs, (ST*)gw, pa);
+            }
             note_launch();
             return check_launch();
         }
     }
     const int threads = 128;
     const int blocks = (outputs * 32 + threads - 1) / threads;
-    k_reduce_partials<ST><<<blocks, threads, 0, stream>>>(partials, slots, outputs, (ST*)gw);
+    if (tuning().no_pdl || launch_pdl(k_reduce_partials<ST>, dim3(blocks), dim3(threads), 0, stream, partials, slots, outputs, (ST*)gw) !=
+                               cudaSuccess) {
+        (void)cudaGetLastError();
+        k_reduce_partials<ST><<<blocks, threads, 0, stream>>>(partials, slots, outputs, (ST*)gw);
+    }
     note_launch();
     return check_launch();
 }

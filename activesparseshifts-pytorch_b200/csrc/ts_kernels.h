@@ -85,6 +85,7 @@ struct Tuning {
     int halo_split;    // 3-D interpolating backward: 0 (default) = one pair per thread, 1 = x-window warps + grad-window warps (two pairs per thread)
     int unit_order;    // 1 (default): units dealt round-robin over (chunk, channel); 0: contiguous channel-major ranges per CTA
                        // (measured on B200: 4 % faster for 32-image shards, 5 % slower for cfg3 at N=256)
+    int no_pdl;        // 1: plain launches instead of programmatic dependent launches (TMA family, pass 2)
     int no_table;      // 1: do not tabulate the per-channel shift parameters in shared memory (A/B measurements)
     int use_flat;      // 0: the automatic path choice never picks the flat zero-padding gather
     int flat_variant;  // 0 auto (a warp owns whole planes when C <= 512), 1 item-per-thread with shuffled shifts

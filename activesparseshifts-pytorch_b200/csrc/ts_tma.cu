@@ -763,6 +763,8 @@ TS_D const UnitShift* setup_barriers(const TArgs& a, unsigned char* smem, uint64
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)a.nw); }
         fence_barrier_init();
     }
+    pdl_trigger();          // the next kernel of the stream may be scheduled as soon as SMs free up
+    pdl_wait();             // nothing above touches global memory; everything below may depend on the previous kernel
     if (a.table)
         for (int c = threadIdx.x; c < (int)a.g.C; c += blockDim.x) tbl[c] = compute_unit_shift(a, c);
     __syncthreads();
@@ -805,7 +807,14 @@ __global__ void __launch_bounds__(MAXT_TMA_ARITH, 1) k_tma_backward(const __grid
 template <class K>
 int launch(K kernel, const TArgs& a, const TmaPlan& p, cudaStream_t s) {
     if (!ensure_dynamic_smem((const void*)kernel, p.smem_bytes)) return check_launch();
-    kernel<<<p.grid, (p.warps + 1) * 32, p.smem_bytes, s>>>(a);
+    if (!tuning().no_pdl) {
+        if (launch_pdl(kernel, dim3(p.grid), dim3((p.warps + 1) * 32), p.smem_bytes, s, a) != cudaSuccess) {
+            (void)cudaGetLastError();
+            kernel<<<p.grid, (p.warps + 1) * 32, p.smem_bytes, s>>>(a);
+        }
+    } else {
+        kernel<<<p.grid, (p.warps + 1) * 32, p.smem_bytes, s>>>(a);
+    }
     note_launch();
     return check_launch();
 }
