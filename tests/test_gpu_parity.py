@@ -252,8 +252,10 @@ def test_large_channels_last_input_takes_the_bandwidth_path(dev, lib, oracle_por
         wd = torch.from_numpy(w).to(dev).requires_grad_(True)
         y = shift2d_func(xd, wd, pad, active)
         assert lib.ts_last_kernel_path() in BANDWIDTH
+        before = lib.ts_launch_count()
         y.backward(torch.from_numpy(g).to(dev))
         assert lib.ts_last_kernel_path() in BANDWIDTH
+        assert lib.ts_launch_count() - before == 2, "the backward must reuse the forward's planar copy (no second layout pass)"
         assert np.array_equal(y.detach().cpu().numpy(), oracle_port.forward(x, w, pad, active))
         gi_ref, _ = oracle_port.backward(g, x, w, pad, active)
         assert np.array_equal(xd.grad.cpu().numpy(), gi_ref)
