@@ -188,9 +188,13 @@ TS_D int gi_slot_slab(const SArgs& a, const UnitShift& us, int a0, int k) {
     return axis_index(oa + us.sg[0], a.OA, a.g.pad);
 }
 
-TS_D void producer(const SArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty) {
+// The whole producer WARP runs this: lane 0 waits for the slot and posts the byte count, then the copies of a stage are
+// dealt to the lanes (one elected thread spent ~40 instructions per copy on addresses at single-thread issue rates:
+// with many small slabs per stage -- 16-bit rows, 12 copies of 8 KB -- the consumers waited for the producer, not for HBM).
+TS_D void producer(const SArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int lane) {
     int s = 0, k = 0;
     const int C = (int)a.g.C, N = (int)a.g.N;
+    const int per_img = a.xs + (a.mode == 2 ? a.gvs + a.gis : 0);
     const UnitRange ur = unit_range(a.units, a.unit_order);
     for (int u = ur.u; u < ur.end; u += ur.step) {
         int chunk, c;
@@ -201,38 +205,39 @@ TS_D void producer(const SArgs& a, unsigned char* smem, uint64_t* full, uint64_t
         for (int nb = n0; nb < n1; nb += a.np) {
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
             for (int t = 0; t < a.tiles; ++t) {
-                if (k > 0) mbar_wait(&empty[s], (unsigned)((k - 1) & 1));
                 const int a0 = t * a.TA;
                 unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
-                // bytes first (slots outside the tensor under zeros padding are not copied)
-                int vx = 0, vgv = 0, vgi = 0;
-                for (int q = 0; q < a.xs; ++q) vx += x_slot_slab(a, us, a0, q) >= 0;
-                if (a.mode == 2) {
-                    for (int q = 0; q < a.gvs; ++q) vgv += gv_slot_slab(a, a0, q) >= 0;
-                    for (int q = 0; q < a.gis; ++q) vgi += gi_slot_slab(a, us, a0, q) >= 0;
+                if (lane == 0) {
+                    if (k > 0) mbar_wait(&empty[s], (unsigned)((k - 1) & 1));
+                    // bytes first (slots outside the tensor under zeros padding are not copied)
+                    int vx = 0, vgv = 0, vgi = 0;
+                    for (int q = 0; q < a.xs; ++q) vx += x_slot_slab(a, us, a0, q) >= 0;
+                    if (a.mode == 2) {
+                        for (int q = 0; q < a.gvs; ++q) vgv += gv_slot_slab(a, a0, q) >= 0;
+                        for (int q = 0; q < a.gis; ++q) vgi += gi_slot_slab(a, us, a0, q) >= 0;
+                    }
+                    mbar_expect_tx(&full[s], (unsigned)npl * ((unsigned)vx * a.slab_x + (unsigned)(vgv + vgi) * a.slab_g));
                 }
-                const unsigned tx = (unsigned)npl * ((unsigned)vx * a.slab_x + (unsigned)(vgv + vgi) * a.slab_g);
-                mbar_expect_tx(&full[s], tx);
-                for (int pl = 0; pl < npl; ++pl) {
+                __syncwarp();        // the slot is free (lane 0 saw empty[s]) before any lane writes into it
+                for (int job = lane; job < npl * per_img; job += 32) {
+                    const int pl = job / per_img;
+                    int q = job - pl * per_img;
                     const long long plane = (long long)(nb + pl) * C + c;
-                    for (int q = 0; q < a.xs; ++q) {
+                    if (q < a.xs) {
                         const int slab = x_slot_slab(a, us, a0, q);
                         if (slab >= 0)
                             bulk_g2s(st + (size_t)(pl * a.xs + q) * a.slab_x, a.x + (plane * a.A + slab) * a.slab_x, (unsigned)a.slab_x, &full[s]);
-                    }
-                    if (a.mode == 2) {
-                        for (int q = 0; q < a.gvs; ++q) {
-                            const int slab = gv_slot_slab(a, a0, q);
-                            if (slab >= 0)
-                                bulk_g2s(st + a.off_gv + (size_t)(pl * a.gvs + q) * a.slab_g, a.grad + (plane * a.OA + slab) * a.slab_g,
-                                         (unsigned)a.slab_g, &full[s]);
-                        }
-                        for (int q = 0; q < a.gis; ++q) {
-                            const int slab = gi_slot_slab(a, us, a0, q);
-                            if (slab >= 0)
-                                bulk_g2s(st + a.off_gi + (size_t)(pl * a.gis + q) * a.slab_g, a.grad + (plane * a.OA + slab) * a.slab_g,
-                                         (unsigned)a.slab_g, &full[s]);
-                        }
+                    } else if ((q -= a.xs) < a.gvs) {
+                        const int slab = gv_slot_slab(a, a0, q);
+                        if (slab >= 0)
+                            bulk_g2s(st + a.off_gv + (size_t)(pl * a.gvs + q) * a.slab_g, a.grad + (plane * a.OA + slab) * a.slab_g,
+                                     (unsigned)a.slab_g, &full[s]);
+                    } else {
+                        q -= a.gvs;
+                        const int slab = gi_slot_slab(a, us, a0, q);
+                        if (slab >= 0)
+                            bulk_g2s(st + a.off_gi + (size_t)(pl * a.gis + q) * a.slab_g, a.grad + (plane * a.OA + slab) * a.slab_g,
+                                     (unsigned)a.slab_g, &full[s]);
                     }
                 }
                 if (++s == a.stages) { s = 0; ++k; }
@@ -441,6 +446,10 @@ template <> struct Pack<float> {
 #pragma unroll
         for (int t = 0; t < NV; ++t) out[t] = __uint_as_float(w[t]);
     }
+    template <int NV, int HS> static TS_D void unpack_c(const unsigned* w, float* out) {
+#pragma unroll
+        for (int t = 0; t < NV; ++t) out[t] = __uint_as_float(w[t]);
+    }
     static TS_D uint4 pack(const float* o) {
         return make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
     }
@@ -454,6 +463,14 @@ template <> struct Pack<__nv_bfloat16> {
             const unsigned v = __funnelshift_r(w[k], w[k + 1], hs);
             out[2 * k] = __uint_as_float(v << 16);
             if (2 * k + 1 < NV) out[2 * k + 1] = __uint_as_float(v & 0xffff0000u);
+        }
+    }
+    // compile-time half-word phase HS (0 / 16 bits): no funnel shift, one conversion per element
+    template <int NV, int HS> static TS_D void unpack_c(const unsigned* w, float* out) {
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+            const int h = t + (HS ? 1 : 0);
+            out[t] = __uint_as_float((h & 1) ? (w[h >> 1] & 0xffff0000u) : (w[h >> 1] << 16));
         }
     }
     static TS_D uint4 pack(const float* o) {
@@ -476,6 +493,14 @@ template <> struct Pack<__half> {
             const float2 f = __half22float2(*(const __half2*)&v);
             out[2 * k] = f.x;
             if (2 * k + 1 < NV) out[2 * k + 1] = f.y;
+        }
+    }
+    template <int NV, int HS> static TS_D void unpack_c(const unsigned* w, float* out) {
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+            const int h = t + (HS ? 1 : 0);
+            const __half2 v = *(const __half2*)&w[h >> 1];
+            out[t] = (h & 1) ? __high2float(v) : __low2float(v);
         }
     }
     static TS_D uint4 pack(const float* o) {
@@ -509,6 +534,31 @@ TS_D void load_window_rt(unsigned region, int e0, float* out) {
     w[NW] = 0u;
     Pack<ST>::template unpack<NV>(w, (byte & 2) * 8, out);
 }
+
+// window of NV elements whose first element sits PH bytes (compile-time, a multiple of sizeof(ST)) into the
+// 16-byte group at shared address `group`: exactly the words the window touches are loaded, no run-time realignment
+template <typename ST, int PH, int NV>
+TS_D void load_window_c(unsigned group, float* out) {
+    constexpr int WS = PH >> 2, HS = (PH & 2) * 8;
+    constexpr int NW = sizeof(ST) == 4 ? NV : (NV + (HS ? 1 : 0) + 1) / 2;
+    unsigned w[NW];
+    load_words<WS, NW>(group, 0, w);
+    Pack<ST>::template unpack_c<NV, HS>(w, out);
+}
+
+// 1-D tensors (an image is ONE row): per-unit stepping of the flat (image, interior group) loop of a thread
+struct LineWalk {
+    int ci, pl0, j0, dpl, dj;
+    TS_D void init(int ci_, int tid, int nt) {
+        ci = ci_;
+        pl0 = j0 = dpl = dj = 0;
+        if (ci > 0) { pl0 = tid / ci; j0 = tid - pl0 * ci; dpl = nt / ci; dj = nt - dpl * ci; }
+    }
+    TS_D void next(int& pl, int& j) const {
+        pl += dpl; j += dj;
+        if (j >= ci) { j -= ci; ++pl; }
+    }
+};
 
 // Column part of an edge item's window, shared by all its rows: either fully inside the row (vector
 // loads with a run-time misalignment) or remapped element by element (hoisted out of the row loop).
@@ -797,6 +847,7 @@ struct ActiveFwdBody {
     bool any_interior;
     int R, nchunk;        // rows per strip / strips per column of the interior box (per unit)
     UDiv d_nchunk;
+    LineWalk lw;          // DIM == 1 only
 
     TS_D ActiveFwdBody(const SArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), any_interior(false), R(1), nchunk(1) {}
     TS_D void begin_unit(int c) {
@@ -814,8 +865,32 @@ struct ActiveFwdBody {
         if (!any_interior) in.b_hi = in.b_lo = in.c_hi = in.c_lo = 0;
         es.init_unit(in, a.OB, a.gpr);
         strip_plan(in, a.np * a.TA, nt, R, nchunk, d_nchunk);
+        if constexpr (DIM == 1) lw.init(in.c_hi - in.c_lo, tid, nt);
     }
     TS_D void end_unit(int, int) {}
+
+    // 1-D tensors: an image is ONE row, so there is nothing to decode and nothing to carry between rows -- a flat
+    // loop over (image, interior group) with every address term hoisted out; PH = byte phase of the x window inside
+    // its 16-byte group (unit-uniform), compile-time here: a window costs its loads + one conversion per element.
+    template <int PH>
+    TS_D void interior_line(const Stage& sg) const {
+        if (lw.ci <= 0) return;
+        const int xb = (a.lbL - us.sx[2] + in.c_lo * V) * ES;            // >= 0 (interior); xb & 15 == PH
+        const unsigned x0 = shared_addr(sg.st) + (unsigned)(xb & ~15);
+        const int ximg = a.xs * a.slab_x;
+        unsigned char* dst0 = sg.dst + in.c_lo * 16;
+        const unsigned istr = (unsigned)a.img_stride;
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        int pl = lw.pl0, j = lw.j0;
+        while (pl < sg.npl) {
+            float X[NVW], o[V];
+            load_window_c<ST, PH, NVW>(x0 + (unsigned)(pl * ximg + j * 16), X);
+#pragma unroll
+            for (int t = 0; t < V; ++t) o[t] = interpolate<float, 1>(X + t, d);
+            __stcs((uint4*)(dst0 + ((unsigned)pl * istr + (unsigned)(j * 16))), Pack<ST>::pack(o));
+            lw.next(pl, j);
+        }
+    }
 
     TS_D void slab_range(const Stage& sg, int& a_lo, int& a_hi) const {
         a_lo = 0;
@@ -948,6 +1023,25 @@ struct ActiveFwdBody {
     TS_D void step(const Stage& sg) {
         int a_lo, a_hi;
         slab_range(sg, a_lo, a_hi);
+        if constexpr (DIM == 1) {
+            switch (pmod((a.lbL - us.sx[2]) * ES, 16)) {
+            case 0: interior_line<0>(sg); break;
+            case 4: interior_line<4>(sg); break;
+            case 8: interior_line<8>(sg); break;
+            case 12: interior_line<12>(sg); break;
+            default:
+                if constexpr (ES == 2) {
+                    switch (pmod((a.lbL - us.sx[2]) * ES, 16)) {
+                    case 2: interior_line<2>(sg); break;
+                    case 6: interior_line<6>(sg); break;
+                    case 10: interior_line<10>(sg); break;
+                    default: interior_line<14>(sg); break;
+                    }
+                }
+            }
+            edges(sg, a_lo, a_hi);
+            return;
+        }
         const int ws = (pmod((a.lbL - us.sx[2]) * ES, 16)) >> 2;
         switch (ws) {
         case 0: interior<0>(sg, a_lo, a_hi); break;
@@ -973,6 +1067,7 @@ struct BackwardBody {
     bool any_interior;
     int R, nchunk;        // rows per strip / strips per column of the interior box (per unit)
     UDiv d_nchunk;
+    LineWalk lw;          // DIM == 1 only
     double acc[DIM];
 
     TS_D BackwardBody(const SArgs& a_, int tid_, int nt_, int wid_, int lane_)
@@ -1011,6 +1106,51 @@ struct BackwardBody {
         if (!any_interior) in.b_hi = in.b_lo = in.c_hi = in.c_lo = 0;
         es.init_unit(in, a.B, a.gpr);
         strip_plan(in, a.np * a.TA, nt, R, nchunk, d_nchunk);
+        if constexpr (DIM == 1) lw.init(in.c_hi - in.c_lo, tid, nt);
+    }
+
+    // 1-D tensors (see ActiveFwdBody::interior_line).  PH / GPH: byte phases of the x window and of the grad_input
+    // window inside their 16-byte groups; GPH = -1 when it does not follow from PH (crops): run-time realignment.
+    template <int PH, int GPH>
+    TS_D void interior_line(const Stage& sg, float* ts) const {
+        if (lw.ci <= 0) return;
+        constexpr int NG = ACTIVE ? NVW : V;
+        const unsigned sst = shared_addr(sg.st);
+        const int ximg = a.xs * a.slab_x, gvimg = a.gvs * a.slab_g, giimg = (a.gis ? a.gis : a.gvs) * a.slab_g;
+        const int xb = (in.c_lo * V - us.sx[2]) * ES;                                // >= 0 (interior); xb & 15 == PH
+        const int gvb = (in.c_lo * V - a.lbL) * ES;                                  // a multiple of 16 (any_interior)
+        const int gie = in.c_lo * V - a.lbL + (ACTIVE ? -us.sg[2] : us.sg[2]);       // >= 0 (interior)
+        const unsigned x0 = sst + (unsigned)(xb & ~15), gv0 = sst + (unsigned)(a.off_gv + gvb);
+        const unsigned gireg = sst + (unsigned)(a.gis ? a.off_gi : a.off_gv), gi0 = gireg + (unsigned)((gie * ES) & ~15);
+        unsigned char* dst0 = sg.dst + in.c_lo * 16;
+        const unsigned istr = (unsigned)a.img_stride;
+        const float d[3] = {us.d[0], us.d[1], us.d[2]};
+        float t0 = ts[0];
+        int pl = lw.pl0, j = lw.j0;
+        while (pl < sg.npl) {
+            const int o16 = j * 16;
+            float gv[V], X[NVW], G[NG], o[V];
+            load_window_c<ST, 0, V>(gv0 + (unsigned)(pl * gvimg + o16), gv);
+            load_window_c<ST, PH, NVW>(x0 + (unsigned)(pl * ximg + o16), X);
+            if constexpr (GPH >= 0) load_window_c<ST, GPH, NG>(gi0 + (unsigned)(pl * giimg + o16), G);
+            else load_window_rt<ST, NG>(gireg + (unsigned)(pl * giimg), gie + j * V, G);
+#pragma unroll
+            for (int t = 0; t < V; ++t) t0 = fmaf(gv[t], X[t + 1] - X[t], t0);
+#pragma unroll
+            for (int t = 0; t < V; ++t) {
+                if constexpr (ACTIVE) o[t] = interpolate<float, 1>(G + t, d);
+                else o[t] = G[t];
+            }
+            __stcs((uint4*)(dst0 + ((unsigned)pl * istr + (unsigned)o16)), Pack<ST>::pack(o));
+            lw.next(pl, j);
+        }
+        ts[0] = t0;
+    }
+    template <int PH>
+    TS_D void interior_line_x(const Stage& sg, float* ts) const {
+        // the grad_input window's phase follows from the x window's when both shifts agree and nothing is cropped
+        if (a.lbL == 0 && us.sg[2] == us.sx[2]) interior_line<PH, ACTIVE ? PH : ((16 - PH) & 15)>(sg, ts);
+        else interior_line<PH, -1>(sg, ts);
     }
     // one partial per (unit, consumer warp): fixed shuffle tree, no atomics
     TS_D void end_unit(int c, int chunk) {
@@ -1381,12 +1521,30 @@ struct BackwardBody {
         float ts[DIM];
 #pragma unroll
         for (int k = 0; k < DIM; ++k) ts[k] = 0.f;
-        const int ws = (pmod(-us.sx[2] * ES, 16)) >> 2;
-        switch (ws) {
-        case 0: interior<0>(sg, a_lo, a_hi, ts); break;
-        case 1: interior<1>(sg, a_lo, a_hi, ts); break;
-        case 2: interior<2>(sg, a_lo, a_hi, ts); break;
-        default: interior<3>(sg, a_lo, a_hi, ts); break;
+        if constexpr (DIM == 1) {
+            switch (pmod(-us.sx[2] * ES, 16)) {
+            case 0: interior_line_x<0>(sg, ts); break;
+            case 4: interior_line_x<4>(sg, ts); break;
+            case 8: interior_line_x<8>(sg, ts); break;
+            case 12: interior_line_x<12>(sg, ts); break;
+            default:
+                if constexpr (ES == 2) {
+                    switch (pmod(-us.sx[2] * ES, 16)) {
+                    case 2: interior_line_x<2>(sg, ts); break;
+                    case 6: interior_line_x<6>(sg, ts); break;
+                    case 10: interior_line_x<10>(sg, ts); break;
+                    default: interior_line_x<14>(sg, ts); break;
+                    }
+                }
+            }
+        } else {
+            const int ws = (pmod(-us.sx[2] * ES, 16)) >> 2;
+            switch (ws) {
+            case 0: interior<0>(sg, a_lo, a_hi, ts); break;
+            case 1: interior<1>(sg, a_lo, a_hi, ts); break;
+            case 2: interior<2>(sg, a_lo, a_hi, ts); break;
+            default: interior<3>(sg, a_lo, a_hi, ts); break;
+            }
         }
         edges(sg, a_lo, a_hi, ts);
 #pragma unroll
@@ -1411,7 +1569,7 @@ __global__ void __launch_bounds__(MAXT_GATHER, 1) k_staged_gather(const __grid_c
     uint64_t *full, *empty;
     setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
+    if (wid == a.nw) { producer(a, smem, full, empty, lane); return; }
     GatherBody<G, ES> body(a, threadIdx.x, a.nw * 32);
     consumer_loop(a, smem, full, empty, lane, body);
 }
@@ -1422,7 +1580,7 @@ __global__ void __launch_bounds__(MAXT_ARITH, 1) k_staged_active_forward(const _
     uint64_t *full, *empty;
     setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
+    if (wid == a.nw) { producer(a, smem, full, empty, lane); return; }
     ActiveFwdBody<ST, DIM> body(a, threadIdx.x, a.nw * 32);
     consumer_loop(a, smem, full, empty, lane, body);
 }
@@ -1433,7 +1591,7 @@ __global__ void __launch_bounds__(MAXT_ARITH, 1) k_staged_backward(const __grid_
     uint64_t *full, *empty;
     setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty); return; }
+    if (wid == a.nw) { producer(a, smem, full, empty, lane); return; }
     BackwardBody<ST, DIM, ACTIVE> body(a, threadIdx.x, a.nw * 32, wid, lane);
     consumer_loop(a, smem, full, empty, lane, body);
 }

@@ -217,6 +217,37 @@ def test_half_precision_vs_fp32_oracle(dev, oracle_port, auto_path):
                     assert np.allclose(wd.grad.float().cpu().numpy(), gw_ref, rtol=1e-2, atol=1e-2 * np.abs(gw_ref).max())
 
 
+def test_rows_every_window_phase(dev, oracle_port, auto_path):
+    """1-D tensors (cfg2's layout) through the flat row loop of the staged family: shifts in +-9 put the x and grad
+    windows on every byte phase of a 16-byte group (8 phases for 16-bit elements), crops untie the grad_input window's
+    phase from the x window's (run-time realignment) or leave no aligned interior at all.  16-bit results must equal the
+    fp32 oracle rounded ONCE to the storage type (fp32 arithmetic, one rounding at the store)."""
+    rng = np.random.default_rng(17)
+    from torchshifts.functional import shift1d_func
+    for tdtype in (torch.bfloat16, torch.float16, torch.float32):
+        for shape in ((3, 20, 256), (2, 9, 1040)):
+            x = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).to(tdtype)
+            w = torch.from_numpy(((rng.random((shape[1], 1)) * 2 - 1) * 9).astype(np.float32)).to(tdtype)
+            x32, w32 = x.float().numpy(), w.float().numpy()
+            for borders in (None, [[8, 0]], [[16, 24]], [[3, 2]]):
+                b = torch.tensor(borders, dtype=torch.long) if borders else None
+                for pad in range(5):
+                    for active in (False, True):
+                        y_ref = oracle_port.forward(x32, w32, pad, active, borders)
+                        g = torch.from_numpy(rng.standard_normal(y_ref.shape).astype(np.float32)).to(tdtype)
+                        g32 = g.float().numpy()
+                        xd, wd = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+                        y = shift1d_func(xd, wd, pad, active, b)
+                        y.backward(g.to(dev))
+                        gi_ref, _ = oracle_port.backward(g32, x32, w32, pad, active, borders)
+                        _, gw64 = oracle_port.backward(g32.astype(np.float64), x32.astype(np.float64), w32.astype(np.float64), pad, active, borders)
+                        tag = (str(tdtype), shape, borders, pad, active)
+                        assert torch.equal(y.detach().cpu(), torch.from_numpy(y_ref).to(tdtype)), ("forward",) + tag
+                        assert torch.equal(xd.grad.cpu(), torch.from_numpy(gi_ref).to(tdtype)), ("grad_input",) + tag
+                        tol = 1e-5 if tdtype is torch.float32 else 1e-2
+                        assert np.allclose(wd.grad.float().cpu().numpy(), gw64, rtol=tol, atol=tol * np.abs(gw64).max() + 1e-30), ("grad_weight",) + tag
+
+
 def test_strided_and_channels_last_inputs(dev, oracle_port, auto_path):
     rng = np.random.default_rng(9)
     x = rng.standard_normal((2, 6, 8, 12)).astype(np.float32)

@@ -56,5 +56,25 @@ for i, r in enumerate(rows[2:]):
         lines.append("\nhottest SASS lines (share of stall samples):\n")
         for s_, e_, t_ in sorted(data, reverse=True)[:10]:
             lines.append(f"* {100 * s_ / tot_s:.1f}% `{t_}` (executed {e_})")
+    # the same samples folded onto CUDA source lines (needs -lineinfo and --import-source on)
+    cs = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda", "--kernel-id", f":::{i + 1}"],
+                        capture_output=True, text=True).stdout
+    crows = list(csv.reader([l for l in cs.splitlines() if l.startswith('"')]))
+    if len(crows) > 2:
+        ch = next((r for r in crows[:3] if "Source" in r and "# Samples" in r), None)
+        if ch:
+            isrc, ismp, iex = ch.index("Source"), ch.index("# Samples"), ch.index("Instructions Executed")
+            cdata = []
+            for rr in crows:
+                if rr is ch or len(rr) <= iex:
+                    continue
+                try:
+                    cdata.append((int(rr[ismp] or 0), int(rr[iex] or 0), rr[0], rr[isrc].strip()[:110]))
+                except ValueError:
+                    pass
+            tot = sum(x[0] for x in cdata) or 1
+            lines.append("\nhottest CUDA source lines (share of stall samples, warp instructions executed):\n")
+            for s_, e_, ln, t_ in sorted(cdata, reverse=True)[:16]:
+                lines.append(f"* {100 * s_ / tot:.1f}% line {ln}: `{t_}` ({e_})")
 open(out, "w").write("\n".join(lines) + "\n")
 print("wrote", out)
