@@ -170,6 +170,8 @@ int ts_set_tuning(const char* spec) {
         else if (!strcmp(key, "halo_stages")) t.halo_stages = val;
         else if (!strcmp(key, "halo_warps")) t.halo_warps = val;
         else if (!strcmp(key, "halo_split")) t.halo_split = val != 0;
+        else if (!strcmp(key, "halo_compact")) t.halo_compact = val != 0;
+        else if (!strcmp(key, "halo_probe")) t.halo_probe = val;
         else if (!strcmp(key, "unit_order")) t.unit_order = val != 0;
         else if (!strcmp(key, "no_table")) t.no_table = val != 0;
         else if (!strcmp(key, "no_pdl")) t.no_pdl = val != 0;

@@ -39,6 +39,11 @@ namespace {
 
 using namespace ptx;
 
+#ifdef TS_HALO_SPIN
+#define TS_HALO_WAIT mbar_wait
+#else
+#define TS_HALO_WAIT mbar_wait_parked
+#endif
 constexpr int SMEM_LIMIT = 232448;
 constexpr int MAXT = 512;
 constexpr int TABLE_MAX_C = 512;    // channels whose shift parameters are tabulated in shared memory (36 bytes each)
@@ -72,6 +77,7 @@ struct alignas(64) HArgs {
     int split;                                // 3-D interpolating backward: x-window warps and grad-window warps (two pairs per thread)
     FastDivU d_GP, d_img, d_C, d_chunks;
     int table;                                // per-channel shift table in shared memory (C <= TABLE_MAX_C)
+    int probe;                                // tuning knob halo_probe (measurement only)
 };
 
 TS_D int level_axis(int level, int dim) { return level - (3 - dim); }
@@ -138,6 +144,37 @@ TS_D UnitGeom unit_geom(const HArgs& a, const UnitShift& us) {
     u.fits = ok;
     return u;
 }
+
+// ---- units ordered by window-misalignment class -------------------------------------------------
+// The misalignment of a unit's windows inside their 16-byte groups (0..3 words) is a property of the CHANNEL.  A body
+// with compile-time misalignment is free of select instructions (12 FSEL per 5-wide window otherwise, 72 per slab step
+// of the 3-D backward), but a switch over four inlined bodies per image group made ptxas spill.  So every CTA sorts the
+// channels by class once (class k < 4: every window's misalignment follows from the x window's = k; class 4: crops that
+// untie the windows, or a shift beyond the halo) and the persistent loop walks the units CLASS BY CLASS: one body per
+// class, each with its own unit loop, run one after the other -- nothing is live across them but the ring position.
+constexpr int NCLS = 5;
+TS_D int classify(const HArgs& a, const UnitShift& us) {
+    const UnitGeom ug = unit_geom(a, us);
+    if (!ug.fits) return 4;
+    const int wsx = ug.xc0 & 3;
+    if (a.mode == 2 && !((ug.vc0 & 3) == 0 && (ug.gc0 & 3) == (a.active ? wsx : ((4 - wsx) & 3)))) return 4;
+    return wsx;
+}
+struct UnitOrder {
+    const unsigned short* order;     // channels sorted by class (nullptr: identity, everything in class 4)
+    const int* cend;                 // cend[k] = units in classes 0..k
+    const int* coff;                 // coff[k] = channels in classes 0..k-1
+    int chunks, C;
+    // u is monotonic per caller: k only moves forward
+    TS_D void decode(int u, int& k, int& c, int& chunk, int unit_order) const {
+        while (u >= cend[k]) ++k;
+        const int base = k ? cend[k - 1] : 0, cnt = coff[k + 1] - coff[k], v = u - base;
+        int j;
+        if (unit_order) { chunk = v / cnt; j = v - chunk * cnt; }
+        else { j = v / chunks; chunk = v - j * chunks; }
+        c = order ? (int)order[coff[k] + j] : j;
+    }
+};
 
 // ---- window loads -----------------------------------------------------------------------------
 // 5 (or 4) consecutive fp32 starting `ws` words into the aligned 16-byte group at shared address `addr`.
@@ -215,15 +252,13 @@ TS_D void halo_walk(unsigned* list, float* tile, int pitch, int rows, int cols, 
 }
 
 TS_D void halo_apply(const unsigned* list, int n, float* tile, int lane) {
-    int e = lane;
-    for (; e + 96 < n; e += 128) {          // four independent cells in flight per lane
-        const unsigned e0 = list[e], e1 = list[e + 32], e2 = list[e + 64], e3 = list[e + 96];
+    // four independent cells in flight per lane in EVERY pass: indices past the end repeat the last cell (the same copy
+    // twice is harmless), so a tile costs ceil(n / 128) dependent list -> load -> store round trips, not one per 32 cells
+    for (int e = lane; e < n; e += 128) {
+        const int last = n - 1;
+        const unsigned e0 = list[e], e1 = list[min(e + 32, last)], e2 = list[min(e + 64, last)], e3 = list[min(e + 96, last)];
         const float v0 = tile[e0 >> 16], v1 = tile[e1 >> 16], v2 = tile[e2 >> 16], v3 = tile[e3 >> 16];
         tile[e0 & 0xffffu] = v0; tile[e1 & 0xffffu] = v1; tile[e2 & 0xffffu] = v2; tile[e3 & 0xffffu] = v3;
-    }
-    for (; e < n; e += 32) {
-        const unsigned e0 = list[e];
-        tile[e0 & 0xffffu] = tile[e0 >> 16];
     }
 }
 
@@ -406,19 +441,24 @@ TS_D void slow_backward(const HArgs& a, int c, int n0, int n1, const UnitShift& 
 
 // ---- producer ---------------------------------------------------------------------------------
 TS_D int slab_coord(int idx, int len, int pad) {
-    const int t = axis_index_literal(idx, len, pad);
+    // ONE thread evaluates this two or three times per stage: the literal remap (integer divisions, ~120 dependent
+    // instructions for reflect) made the producer the slowest stage of the 3-D pipeline under periodic / reflect /
+    // symmetric padding (measured: 0.66 ms against 0.56 ms with border padding).  Indices within one period of the axis --
+    // everything a slab inside the crop can ask for after reduce_shift -- take the division-free form.
+    const int P = remap_period(len, pad);
+    const int t = (P == 0 || (idx > -P && idx < len + P)) ? axis_index(idx, len, pad) : axis_index_literal(idx, len, pad);
     return t < 0 ? -1 : t;                 // outside under zeros padding: the copy engine delivers a zero tile
 }
 
-TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, const UnitShift* tbl) {
-    int s = 0, kk = 0;
-    const int C = (int)a.g.C, N = (int)a.g.N;
+TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, const UnitShift* tbl, const UnitOrder& uo) {
+    int s = 0, kk = 0, cls = 0;
+    const int N = (int)a.g.N;
     const bool bwd = a.mode == 2;
     const int steps = a.dim == 3 ? a.IA + 1 : 1;
     const UnitRange ur = unit_range(a.units, a.unit_order);
     for (int u = ur.u; u < ur.end; u += ur.step) {
         int chunk, c;
-        decode_unit(a, u, c, chunk);
+        uo.decode(u, cls, c, chunk, a.unit_order);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         const UnitShift us = unit_shift(a, tbl, c);
@@ -430,6 +470,13 @@ TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t
                 unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
                 const bool has_g = bwd && (a.dim == 2 || a.active || k >= 1);
                 const bool has_v = bwd && a.dim == 3 && k >= 1;
+#ifdef TS_HALO_PROBE
+                if (a.probe == 2) {          // no copies, the consumers compute on whatever the stage holds
+                    mbar_arrive(&full[s]);
+                    if (++s == a.stages) { s = 0; ++kk; }
+                    continue;
+                }
+#endif
                 mbar_expect_tx(&full[s], (unsigned)npl * (unsigned)(a.box_x + (has_g ? a.box_g : 0) + (has_v ? a.box_v : 0)));
                 int xs = 0, gs = 0, vs = 0;
                 if (a.dim == 3) {
@@ -455,10 +502,11 @@ TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t
 // One warp fills the halo cells of every stage (paddings other than zeros) between the copy engine and the consumers:
 // it waits for full[s], patches the tiles and arrives on ready[s]; the consumers wait for ready[s] instead of full[s].
 // It runs ahead of the consumers by the ring depth, so the arithmetic warps never meet at a barrier.
-TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* ready, int lane, const UnitShift* tbl, unsigned* lists) {
-    int s = 0;
+TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* ready, int lane, const UnitShift* tbl, unsigned* lists,
+                const UnitOrder& uo) {
+    int s = 0, cls = 0;
     unsigned phase = 0;
-    const int C = (int)a.g.C, N = (int)a.g.N;
+    const int N = (int)a.g.N;
     const bool bwd = a.mode == 2;
     const int steps = a.dim == 3 ? a.IA + 1 : 1;
     unsigned* list_x = lists;
@@ -467,7 +515,7 @@ TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* r
     const UnitRange ur = unit_range(a.units, a.unit_order);
     for (int u = ur.u; u < ur.end; u += ur.step) {
         int chunk, c;
-        decode_unit(a, u, c, chunk);
+        uo.decode(u, cls, c, chunk, a.unit_order);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
         const UnitShift us = unit_shift(a, tbl, c);
@@ -696,7 +744,7 @@ struct Body {
     TS_D void run_images2(unsigned char* smem, Ring& ring, unsigned char* dst, int npl, const PairCtx& pc0, float* ts) const {
         unsigned char* st = smem + (size_t)ring.s * a.stage_stride + GUARD;
         const unsigned sb = shared_addr(st);
-        mbar_wait(&wait_bar[ring.s], ring.phase);
+        TS_HALO_WAIT(&wait_bar[ring.s], ring.phase);
         const int total = npl * a.img_pairs;
         if (tid < total && pc0.rows) pair2<WSX, WSG, WSV>(sb, dst, pc0, ts);      // the thread's first pair: context cached per unit
         for (int p = tid + nt; p < total; p += nt) {
@@ -723,6 +771,15 @@ struct Body {
         constexpr bool DOX = MODE != 2 || ROLE != 2;
         constexpr bool DOG = MODE == 2 && ROLE != 1;
         if (pc.rows == 0) return;
+#ifdef TS_HALO_PROBE                   // measurement builds only (nvcc -DTS_HALO_PROBE; tuning knob halo_probe): results are WRONG when set
+        if (a.probe == 1) {            // the stage hand-off, the copies and the stores without loads / arithmetic
+            if (k >= 1) {
+                unsigned char* o = dst_img + pc.out_off + (long long)(k - 1) * a.IB * (a.IG * 16);
+                for (int j = 0; j < pc.rows; ++j) __stcs((float4*)(o + j * a.IG * 16), make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+            return;
+        }
+#endif
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
         const int it = k - 1, orow = a.IG * 16;
         unsigned char* o = dst_img + pc.out_off + (long long)it * a.IB * orow;
@@ -731,6 +788,7 @@ struct Body {
         const unsigned xa = sb + pc.xo, ga = sb + pc.go, va = sb + pc.vo;
         const int pxb = a.px * 4, pgb = a.pg * 4;
         const bool gwin = DOG && ACTIVE && pc.cmask != 0u;
+        float SL[2][5];
         if (DOX) { load5<WSX>(xa, wsx, nx.X[0]); load5<WSX>(xa + pxb, wsx, nx.X[1]); }
         if (gwin) { load5<WSG>(ga, wsg, nx.G[0]); load5<WSG>(ga + pgb, wsg, nx.G[1]); }
 #pragma unroll
@@ -743,8 +801,16 @@ struct Body {
             if (k < 1) continue;
             if (MODE != 2) {
                 float P[5], y[4];
+                // the slab lerp of row j + 1 is shared by both rows of the pair (same operations, same order: bit-exact)
+                if (j == 0) {
 #pragma unroll
-                for (int t = 0; t < 5; ++t) P[t] = col3(cy.X[j][t], nx.X[j][t], cy.X[j + 1][t], nx.X[j + 1][t], d[0], d[1]);
+                    for (int t = 0; t < 5; ++t) { SL[0][t] = lerp<float>(cy.X[0][t], nx.X[0][t], d[0]); SL[1][t] = lerp<float>(cy.X[1][t], nx.X[1][t], d[0]); }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) { SL[0][t] = SL[1][t]; SL[1][t] = lerp<float>(cy.X[2][t], nx.X[2][t], d[0]); }
+                }
+#pragma unroll
+                for (int t = 0; t < 5; ++t) P[t] = lerp<float>(SL[0][t], SL[1][t], d[1]);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
                 __stcs((float4*)(o + j * orow), make_float4(y[0], y[1], y[2], y[3]));
@@ -801,7 +867,7 @@ struct Body {
             // new windows are copied into the carried set instead (15 moves per step)
             for (int k = 0; k <= a.IA; ++k) {
                 const unsigned sb = shared_addr(smem + (size_t)ring.s * a.stage_stride + GUARD);
-                mbar_wait(&wait_bar[ring.s], ring.phase);
+                TS_HALO_WAIT(&wait_bar[ring.s], ring.phase);
                 step3<WSX, WSG, WSV, ROLE>(sb, dst_img, k, pc[0], ca[0], cb[0], ts);
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
@@ -814,14 +880,14 @@ struct Body {
         for (int k = 0; k <= a.IA; k += 2) {
             {
                 const unsigned sb = shared_addr(smem + (size_t)ring.s * a.stage_stride + GUARD);
-                mbar_wait(&wait_bar[ring.s], ring.phase);
+                TS_HALO_WAIT(&wait_bar[ring.s], ring.phase);
 #pragma unroll
                 for (int i = 0; i < NPT; ++i) step3<WSX, WSG, WSV, ROLE>(sb, dst_img, k, pc[i], cb[i], ca[i], ts);
                 release(ring);
             }
             if (k + 1 <= a.IA) {
                 const unsigned sb = shared_addr(smem + (size_t)ring.s * a.stage_stride + GUARD);
-                mbar_wait(&wait_bar[ring.s], ring.phase);
+                TS_HALO_WAIT(&wait_bar[ring.s], ring.phase);
 #pragma unroll
                 for (int i = 0; i < NPT; ++i) step3<WSX, WSG, WSV, ROLE>(sb, dst_img, k + 1, pc[i], ca[i], cb[i], ts);
                 release(ring);
@@ -845,15 +911,17 @@ if constexpr (SPLIT) {         // chosen at LAUNCH: both role layouts in one ker
         }
     }
 
+    // CLS 0..3: every window misalignment is a compile-time constant (x window: CLS words; grad_input window: the same
+    // for the interpolating backward, 4 - CLS for the sparse gather; unshifted grad window aligned); CLS 4: run-time
+    // misalignment (crops) or the element-wise routine (shift beyond the halo)
+    template <int CLS>
     TS_D void run_unit(unsigned char* smem, Ring& ring, int c, int n0, int n1) {
-        if (!ug.fits) {
+        if (CLS == 4 && !ug.fits) {
             if (MODE != 2) slow_forward<DIM, MODE == 1, POOL>(a, c, n0, n1, us, tid, nt);
             else slow_backward<DIM, ACTIVE>(a, c, n0, n1, us, tid, nt, acc);
             return;
         }
         const long long plane_bytes = a.out_plane_bytes;
-        // fast instantiations: every window misalignment known at compile time from the x window's
-        const bool derived = MODE != 2 || (wsv == 0 && wsg == (ACTIVE ? wsx : ((4 - wsx) & 3)));
         PairCtx pc0;
         pc0.rows = 0;
         if (DIM == 2) {
@@ -866,29 +934,26 @@ if constexpr (SPLIT) {         // chosen at LAUNCH: both role layouts in one ker
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
             unsigned char* dst = (unsigned char*)a.out + ((long long)nb * a.g.C + c) * plane_bytes;
             float ts[3] = {0.f, 0.f, 0.f};
-#if defined(TS_EXP_ONEWS)
-            run_images<1, ACTIVE ? 1 : 3, 0>(smem, ring, dst, npl, pc0, ts);
-#else
-            // One body per compile-time misalignment is free of select instructions, but ptxas allocates the four (or
-            // twelve, with the roles) inlined bodies of the heavy kernels together and spills ~75 registers in each
-            // (measured: 16 GB of local-memory traffic through L2 for cfg4's backward).  The interpolating and the 3-D
-            // backward therefore use the ONE body with run-time misalignment (a 12-select network per 5-wide window).
-            constexpr bool RTWS = MODE == 2 && (ACTIVE || DIM == 3);
-            if constexpr (RTWS) {
-                run_images<-1, -1, -1>(smem, ring, dst, npl, pc0, ts);
-            } else if (derived) {
-                switch (wsx) {
-                case 0: run_images<0, 0, 0>(smem, ring, dst, npl, pc0, ts); break;
-                case 1: run_images<1, ACTIVE ? 1 : 3, 0>(smem, ring, dst, npl, pc0, ts); break;
-                case 2: run_images<2, 2, 0>(smem, ring, dst, npl, pc0, ts); break;
-                default: run_images<3, ACTIVE ? 3 : 1, 0>(smem, ring, dst, npl, pc0, ts); break;
-                }
-            } else {
-                run_images<-1, -1, -1>(smem, ring, dst, npl, pc0, ts);
-            }
-#endif
+            if constexpr (CLS < 4) run_images<CLS, ACTIVE ? CLS : ((4 - CLS) & 3), 0>(smem, ring, dst, npl, pc0, ts);
+            else run_images<-1, -1, -1>(smem, ring, dst, npl, pc0, ts);
 #pragma unroll
             for (int k = 0; k < DIM; ++k) acc[k] += (double)ts[k];     // fp32 inside an image group, fp64 across
+        }
+    }
+
+    template <int CLS>
+    TS_D void run_class(unsigned char* smem, Ring& ring, const UnitOrder& uo, int& u, const UnitRange& ur) {
+        const int N = (int)a.g.N;
+        int k = CLS;
+        while (u < ur.end && u < uo.cend[CLS]) {
+            int chunk, c;
+            uo.decode(u, k, c, chunk, a.unit_order);
+            const int n0 = chunk * a.n_per_unit;
+            const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
+            begin_unit(c);
+            run_unit<CLS>(smem, ring, c, n0, n1);
+            end_unit(c, chunk);
+            u += ur.step;
         }
     }
 };
@@ -903,29 +968,57 @@ __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs 
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)a.nw); mbar_init(&ready[s], 1); }
         fence_barrier_init();
     }
-    UnitShift* tbl = (UnitShift*)(ready + a.stages);
-    if (a.table)
-        for (int c = threadIdx.x; c < (int)a.g.C; c += blockDim.x) tbl[c] = compute_unit_shift(a, c);
-    __syncthreads();
+    const int C = (int)a.g.C;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty, tbl); return; }
+    UnitShift* tbl = (UnitShift*)(ready + a.stages);
+    unsigned* lists = (unsigned*)(tbl + (a.table ? C : 0));
+    int* cend = (int*)(lists + (a.need_fix ? 2 * FIXCAP : 0));       // [NCLS] units in classes 0..k
+    int* coff = cend + NCLS;                                          // [NCLS + 1] channels in classes 0..k-1
+    unsigned short* order = (unsigned short*)(coff + NCLS + 1);       // [C] channels sorted by class
+    unsigned char* clsb = (unsigned char*)(order + (a.table ? C : 0)); // [C] class of a channel
+    if (a.table)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const UnitShift us = compute_unit_shift(a, c);
+            tbl[c] = us;
+            clsb[c] = (unsigned char)classify(a, us);
+        }
+    __syncthreads();
+    if (wid == 0) {
+        if (a.table) {                       // counting sort by class: ballot compaction, channel order kept inside a class
+            int base = 0;
+            for (int k = 0; k < NCLS; ++k) {
+                if (lane == 0) coff[k] = base;
+                for (int c0 = 0; c0 < C; c0 += 32) {
+                    const int c = c0 + lane;
+                    const bool mine = c < C && clsb[c] == k;
+                    const unsigned m = __ballot_sync(0xffffffffu, mine);
+                    if (mine) order[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)c;
+                    base += __popc(m);
+                }
+                if (lane == 0) cend[k] = base * a.chunks;
+            }
+            if (lane == 0) coff[NCLS] = base;
+        } else if (lane == 0) {              // no table (C > TABLE_MAX_C): one class, run-time misalignment
+            for (int k = 0; k < NCLS; ++k) { coff[k] = 0; cend[k] = k == NCLS - 1 ? a.units : 0; }
+            coff[NCLS] = C;
+        }
+    }
+    __syncthreads();
+    const UnitOrder uo = {a.table ? order : nullptr, cend, coff, a.chunks, C};
+    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty, tbl, uo); return; }
     if (wid > a.nw) {                                                         // launched only when the padding needs it
-        fixer(a, smem, full, ready, lane, tbl, (unsigned*)(tbl + (a.table ? (int)a.g.C : 0)));
+        fixer(a, smem, full, ready, lane, tbl, lists, uo);
         return;
     }
     Body<DIM, MODE, ACTIVE, SPLIT, POOL> body(a, threadIdx.x, a.nt, wid, lane, a.need_fix ? ready : full, empty, tbl);
     Ring ring = {0, 0u};
-    const int C = (int)a.g.C, N = (int)a.g.N;
     const UnitRange ur = unit_range(a.units, a.unit_order);
-    for (int u = ur.u; u < ur.end; u += ur.step) {
-        int chunk, c;
-        decode_unit(a, u, c, chunk);
-        const int n0 = chunk * a.n_per_unit;
-        const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
-        body.begin_unit(c);
-        body.run_unit(smem, ring, c, n0, n1);
-        body.end_unit(c, chunk);
-    }
+    int u = ur.u;
+    body.template run_class<0>(smem, ring, uo, u, ur);
+    body.template run_class<1>(smem, ring, uo, u, ur);
+    body.template run_class<2>(smem, ring, uo, u, ur);
+    body.template run_class<3>(smem, ring, uo, u, ur);
+    body.template run_class<4>(smem, ring, uo, u, ur);
 }
 
 long long round_up(long long v, long long q) { return (v + q - 1) / q * q; }
@@ -970,6 +1063,7 @@ bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, int pool, 
     a.d_C = make_fastdivu((unsigned)g.C);
     a.d_chunks = make_fastdivu((unsigned)a.chunks);
     a.table = g.C <= TABLE_MAX_C ? 1 : 0;
+    a.probe = tuning().halo_probe;
     a.pool = pool;
     a.out_plane_bytes = pool ? (long long)((a.OB + 1) / 2) * (a.OL / 2) * 4 : (mode == 2 ? g.in_plane : g.out_plane) * 4;
     a.need_fix = g.pad != TS_PAD_ZEROS;
@@ -1022,9 +1116,11 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     const int IB = mode == 2 ? B : OB, IG = (mode == 2 ? L : OL) / 4;
     int GP = IG;
     if (IG % 8 != 0 && (double)IG / (double)((IG + 7) / 8 * 8) >= 0.85) GP = (IG + 7) / 8 * 8;
+    if (d == 3 && t.halo_compact && ((IB + 1) / 2 * IG + 31) / 32 < ((IB + 1) / 2 * GP + 31) / 32) GP = IG;   // one warp fewer
     const int img_pairs = (IB + 1) / 2 * GP;
     const int max_nt = MAXT - 64;                          // producer warp + fixer warp
-    const long long table_bytes = (g.C <= TABLE_MAX_C ? g.C * 36 : 0) + (g.pad != TS_PAD_ZEROS ? 2 * FIXCAP * 4 : 0);   // + the fixer's cell lists
+    const long long table_bytes = (g.C <= TABLE_MAX_C ? g.C * 36 : 0) + (g.pad != TS_PAD_ZEROS ? 2 * FIXCAP * 4 : 0)      // + the fixer's cell lists
+                                  + (2 * NCLS + 1) * 4 + (g.C <= TABLE_MAX_C ? g.C * 3 : 0) + 16;                             // + the class order
     const long long budget = SMEM_LIMIT - 1024 - table_bytes;
     long long np;
     if (d == 3) {
@@ -1051,7 +1147,7 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     int warps;
     if (d == 3) {
         warps = (int)((pairs + 31) / 32);
-        if (mode == 2 && active && warps % 2 && warps < max_nt / 32) ++warps;      // x-window warps and grad-window warps
+        if (t.halo_split && mode == 2 && active && warps % 2 && warps < max_nt / 32) ++warps;      // x-window warps and grad-window warps
     } else {
         auto eff = [&](int w) {
             const long long nt = 32ll * w, passes = (pairs + nt - 1) / nt;

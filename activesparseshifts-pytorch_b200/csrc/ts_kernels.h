@@ -82,6 +82,8 @@ struct Tuning {
     int halo;          // halo rows / columns of the halo family (0 = 4)
     int halo_stages;   // ring depth of the halo family (0 = auto)
     int halo_warps;    // consumer warps of the 2-D halo kernels (0 = auto)
+    int halo_probe;    // measurement only (results are WRONG when set): 1 = 3-D consumers skip loads + arithmetic (pipeline rate), 2 = consumers do not wait for the data (compute rate)
+    int halo_compact;  // 3-D: 1 = pairs packed without padding the groups of a row to a multiple of 8 when that saves a consumer warp
     int halo_split;    // 3-D interpolating backward: 0 (default) = one pair per thread, 1 = x-window warps + grad-window warps (two pairs per thread)
     int unit_order;    // 1 (default): units dealt round-robin over (chunk, channel); 0: contiguous channel-major ranges per CTA
                        // (measured on B200: 4 % faster for 32-image shards, 5 % slower for cfg3 at N=256)

@@ -73,6 +73,7 @@ _CL_FORMATS = {4: torch.channels_last, 5: torch.channels_last_3d}
 
 _PLANAR = collections.OrderedDict()     # (data_ptr, shape, strides, version) -> planar copy made by the forward, for the backward
 _PLANAR_MAX = 2
+_LAST_PLANAR = [None]                   # (key, copy) of the forward that just ran, until autograd claims it (or the composite returns)
 
 
 def _dense(input, keep=False, take=False):
@@ -82,11 +83,14 @@ def _dense(input, keep=False, take=False):
     channels-last tensor goes through the library's own tiled transpose (``ts_nhwc_to_nchw``), anything
     else through ``.contiguous()``.
 
-    ``keep`` (forward of a tensor that requires grad): remember the planar copy; ``take`` (backward): reuse it instead of
-    converting the saved input a second time (0.26 ms per step for cfg3) -- at most ``_PLANAR_MAX`` copies are held."""
+    ``keep`` (forward): park the planar copy in ``_LAST_PLANAR``; when autograd records the call,
+    ``_setup_forward_context`` -- the one place that knows the call is differentiated: the CUDA kernel runs below the
+    Autograd key, with grad mode off -- moves it to ``_PLANAR``, otherwise the composite drops it when the operator
+    returns.  ``take`` (backward): reuse that copy instead of converting the saved input a second time (0.26 ms per step
+    for cfg3) -- at most ``_PLANAR_MAX`` copies are held."""
     if input.numel() < _COPY_THRESHOLD or input.is_contiguous():
         return input
-    key = (input.data_ptr(), tuple(input.shape), tuple(input.stride()), input._version, input.dtype)
+    key = _planar_key(input)
     if take:
         hit = _PLANAR.pop(key, None)
         if hit is not None:
@@ -102,10 +106,23 @@ def _dense(input, keep=False, take=False):
     else:
         out = input.contiguous()
     if keep:
-        _PLANAR[key] = out
+        _LAST_PLANAR[0] = (key, out)
+    return out
+
+
+def _planar_key(input):
+    return (input.data_ptr(), tuple(input.shape), tuple(input.stride()), input._version, input.dtype)
+
+
+def _claim_planar(input):
+    """Called while autograd records a forward: keep the planar copy that forward made for its backward."""
+    last, _LAST_PLANAR[0] = _LAST_PLANAR[0], None
+    if last is None or isinstance(input, torch._subclasses.FakeTensor):
+        return
+    if last[0] == _planar_key(input):
+        _PLANAR[last[0]] = last[1]
         while len(_PLANAR) > _PLANAR_MAX:
             _PLANAR.popitem(last=False)
-    return out
 
 
 def _stream(device):
@@ -159,7 +176,7 @@ def _forward_cuda(dim, input, weights, borders, new_size, padding_mode, active_f
     lb, rb = _borders_lists(borders, dim)
     out = torch.empty(list(new_size), dtype=input.dtype, device=input.device)
     w = weights.contiguous()
-    input = _dense(input, keep=torch.is_grad_enabled())      # (below the Autograd key requires_grad is not visible any more)
+    input = _dense(input, keep=True)
     geo, _ = _geometry(dim, input, lb, rb)
     if list(out.shape[2:]) != [rb[a] - lb[a] for a in range(dim)]:
         raise RuntimeError(f'{fn}: new_size {list(new_size)} does not match the borders')
@@ -343,6 +360,8 @@ def _setup_forward_context(ctx, inputs, output):
     input, weights, borders, new_size, padding_mode, active_flag = inputs
     ctx.save_for_backward(input, weights, borders)
     ctx.padding_mode, ctx.active_flag = padding_mode, active_flag
+    if _LAST_PLANAR[0] is not None:
+        _claim_planar(input)
 
 
 def _make_forward_backward(dim):
@@ -381,7 +400,10 @@ def check_borders(input, borders, dim):
 def _shift_composite(dim, input, weights, borders, padding_mode, active_flag):
     std_borders, new_size = check_borders(input, borders, dim)
     op = getattr(torch.ops.torchshifts, f'_shift{dim}d_forward')
-    return op(input, weights, std_borders, new_size, padding_mode, active_flag)
+    out = op(input, weights, std_borders, new_size, padding_mode, active_flag)
+    if not torch.compiler.is_compiling():
+        _LAST_PLANAR[0] = None      # a planar copy nobody claimed (no autograd): drop it now
+    return out
 
 
 def _bind(fn, dim):
