@@ -23,6 +23,7 @@
 // the whole CTA lifetime: the shifts, the remapped outer-axis offsets and the validity flags are
 // registers, and the inner loop over the pixels of a row is one remap + one byte load per channel.
 #include "ts_kernels.h"
+#include "ts_ptx.cuh"
 
 namespace ts {
 
@@ -638,6 +639,338 @@ int ring_run(const Geo& g, const RingPlan& pl, const void* x, void* y, uint8_t f
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Row-pipelined kernel (2-D, 1-byte elements, dense pixels, C = 128 / 256 / 512): the ring kernel's gather fed by a
+// producer warp instead of load / barrier / gather / barrier rounds.
+//
+// In NHWC a whole input row (S1 pixels x C channels) is CONTIGUOUS, so it is ONE bulk copy (cp.async.bulk, 14 KB for
+// cfg5) into a slot of a K-row ring, announced on that slot's `full` mbarrier.  A CTA owns a contiguous range of the
+// global list of output rows (N x OS0 rows dealt evenly: no wave tail, halo rows re-read only where a range starts); its W
+// consumer warps take output rows round-robin.  A warp that is about to gather output row o waits (in row order) until
+// the highest input row of o's window has landed, gathers, and releases every row below the window of its NEXT output
+// row by arriving on those slots' `empty` mbarriers (W arrivals free a slot for the producer).  Nothing ever waits for
+// a CTA-wide barrier: fetch, gather and store of different rows overlap inside one CTA (the ring kernel needed three
+// CTAs per SM to overlap its phases and still stalled on cp.async.wait_all + two __syncthreads per step).
+// The window of an output row is capped at WIN = K - W - 1 rows, so the rows in use never fill the ring; a tap whose
+// (remapped) row lies outside the window -- wrap-around paddings at the image edges, axis-0 shifts spread wider than WIN --
+// is read from global memory, exactly like in the ring kernel: the window only ever affects speed.
+struct RowsPlan {
+    int K, W, WIN;
+    unsigned grid, row_bytes, smem_bytes, off_bar, off_tab;
+};
+constexpr int ROWS_MAX_W = 12;
+
+struct RowsSeg { unsigned n; int o_a, o_b, lo, hi; };
+// the s-th piece of the CTA's range [r0, r1) of global output rows: one image's rows and the input rows it can reach
+TS_D bool rows_segment(const Geo& g, int WIN, unsigned& r, unsigned r1, int smin, int smax, RowsSeg& sg) {
+    if (r >= r1) return false;
+    const unsigned os0 = (unsigned)g.OS[0];
+    sg.n = r / os0;
+    sg.o_a = (int)(r - sg.n * os0);
+    const unsigned left = r1 - r;
+    sg.o_b = (unsigned)sg.o_a + left < os0 ? sg.o_a + (int)left : (int)os0;
+    r += (unsigned)(sg.o_b - sg.o_a);
+    const int top = sg.o_b - 1 + g.lb[0] - smax + WIN - 1, reach = sg.o_b - 1 + g.lb[0] - smin;
+    sg.lo = clampi(sg.o_a + g.lb[0] - smax, 0, g.S[0] - 1);
+    sg.hi = clampi(top < reach ? top : reach, 0, g.S[0] - 1);
+    if (sg.hi < sg.lo) sg.hi = sg.lo;
+    return true;
+}
+TS_D void rows_window(const Geo& g, int WIN, const RowsSeg& sg, int o, int smin, int smax, int& wlo, int& whi) {
+    const int a = o + g.lb[0] - smax, top = a + WIN - 1, reach = o + g.lb[0] - smin;
+    wlo = clampi(a, sg.lo, sg.hi);
+    whi = clampi(top < reach ? top : reach, sg.lo, sg.hi);
+    if (whi < wlo) whi = wlo;
+}
+
+template <int I, int CB> struct SpanRows {
+    static TS_D void load(const unsigned* a, unsigned (*val)[4]) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(val[I][v]) : "r"(a[v]), "n"(I * CB));
+        SpanRows<I + 1, CB>::load(a, val);
+    }
+};
+template <int CB> struct SpanRows<8, CB> {
+    static TS_D void load(const unsigned*, unsigned (*)[4]) {}
+};
+
+template <int PAD, int CB>
+__global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(Geo g, RowsPlan pl, const uint8_t* __restrict__ x,
+                                                                                  uint8_t* __restrict__ y, uint8_t fill,
+                                                                                  const void* __restrict__ w, int qkind, long long wzp) {
+    extern __shared__ __align__(128) unsigned char rsm[];
+    using namespace ptx;
+    uint64_t* full = (uint64_t*)(rsm + pl.off_bar);
+    uint64_t* empty = full + pl.K;
+    int* s0t = (int*)(rsm + pl.off_tab);        // axis-0 shift per channel
+    int* s1t = s0t + CB;                        // axis-1 shift per channel
+    int* red = s1t + CB;                        // [0] min, [1] max of the axis-0 shifts
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) rsm[pl.smem_bytes - 16u] = fill;       // the pad value, addressable like any ring byte
+    for (int c = tid; c < CB; c += (int)blockDim.x) {
+        int sx[2];
+        load_qshifts<2>(w, qkind, wzp, (long long)c, g, sx);
+        s0t[c] = sx[0];
+        s1t[c] = sx[1];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int mn = s0t[lane], mx = mn;
+        for (int c = lane + 32; c < CB; c += 32) { const int v = s0t[c]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+            mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+        }
+        if (lane == 0) { red[0] = mn; red[1] = mx; }
+    }
+    __syncthreads();
+    const int smin = red[0], smax = red[1];
+    // Shifts spread wider than the planned window: fewer consumer warps, wider windows (the rows in flight plus one free
+    // slot must fit the ring) as long as that covers the whole reach; beyond that the taps outside the window are read
+    // from global memory (slow: 2.3 ms for cfg5 with shifts in +-6 -- like the ring kernel, this kernel is built for the
+    // shifts layers learn).
+    int W = pl.W, WIN = pl.WIN;
+    if (smax - smin + 1 > WIN && pl.K - 2 - (smax - smin) >= 3) {      // (below 3 warps the global-memory fall-back is the lesser evil)
+        W = pl.K - 2 - (smax - smin);
+        WIN = pl.K - W - 1;
+    }
+    if (tid == 0) {
+        for (int k = 0; k < pl.K; ++k) { mbar_init(&full[k], 1); mbar_init(&empty[k], (unsigned)W); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const unsigned long long R = (unsigned long long)g.N * (unsigned long long)g.OS[0];
+    const unsigned r_begin = (unsigned)(R * blockIdx.x / gridDim.x), r_end = (unsigned)(R * (blockIdx.x + 1) / gridDim.x);
+    const int K = pl.K;
+    const unsigned row_bytes = pl.row_bytes;
+
+    if (warp == pl.W) {                        // ---- producer: one lane, one bulk copy per input row ----
+        if (lane != 0) return;
+        int slot = 0, round = 0;
+        unsigned r = r_begin;
+        RowsSeg sg;
+        while (rows_segment(g, WIN, r, r_end, smin, smax, sg)) {
+            const uint8_t* src = x + (long long)sg.n * g.xs[0] + (long long)sg.lo * g.xs[2];
+            for (int row = sg.lo; row <= sg.hi; ++row, src += g.xs[2]) {
+                if (round > 0) mbar_wait_relaxed(&empty[slot], (unsigned)((round - 1) & 1), 64);
+                mbar_expect_tx(&full[slot], row_bytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(rsm + (size_t)slot * row_bytes)),
+                             "l"(src), "r"(row_bytes), "r"(smem_u32(&full[slot]))
+                             : "memory");
+                if (++slot == K) { slot = 0; ++round; }
+            }
+        }
+        return;
+    }
+    if (warp >= W) return;
+
+    // ---- consumers ----
+    const unsigned base = shared_addr(rsm);
+    const unsigned fill_addr = base + pl.smem_bytes - 16u;
+    const int s1n = g.S[1], lb1 = g.lb[1], ow = g.OS[1];
+    const unsigned long long xs3 = (unsigned long long)g.xs[3];
+    int ready_slot = 0;                        // slot / phase of the next row this warp has not seen land yet
+    unsigned ready_phase = 0;
+    int ready_q = 0;                           // rows seen landed so far (q index of the next one)
+    int rel_slot = 0, rel_q = 0;               // next row to release
+    int qbase = 0;                             // q index of the current segment's first row
+    unsigned r = r_begin;
+    RowsSeg sg;
+    while (rows_segment(g, WIN, r, r_end, smin, smax, sg)) {
+        for (int o = sg.o_a + warp; o < sg.o_b; o += W) {
+            int wlo, whi;
+            rows_window(g, WIN, sg, o, smin, smax, wlo, whi);
+            const int q_lo = qbase + (wlo - sg.lo), q_hi = qbase + (whi - sg.lo);
+            // Rows below this window are never touched by this warp again: release them -- but only after having SEEN
+            // each of them land.  (Releasing a row it has not observed yet would let the producer refill the slot, and
+            // a refill that lands before the warp gets to that slot's barrier flips its parity twice: the wait for the
+            // older phase would then block for ever.  Observe-then-release keeps every warp at most one phase behind
+            // any barrier, and the warp never holds a row below the one it waits for, so the producer is never stuck.)
+            if (rel_q < q_lo) {
+                __syncwarp();
+                while (rel_q < q_lo) {
+                    if (ready_q <= rel_q) {
+                        mbar_wait_parked(&full[ready_slot], ready_phase);
+                        ++ready_q;
+                        if (++ready_slot == K) { ready_slot = 0; ready_phase ^= 1u; }
+                    }
+                    if (lane == 0) mbar_arrive(&empty[rel_slot]);
+                    ++rel_q;
+                    if (++rel_slot == K) rel_slot = 0;
+                }
+            }
+            while (ready_q <= q_hi) {
+                mbar_wait_parked(&full[ready_slot], ready_phase);
+                ++ready_q;
+                if (++ready_slot == K) { ready_slot = 0; ready_phase ^= 1u; }
+            }
+            int slot_lo = rel_slot;            // == q_lo mod K (rel_q == q_lo here)
+            uint8_t* yrow = y + (((long long)sg.n * g.OS[0] + o) * ow) * g.C;
+#pragma unroll 1
+            for (int ps = 0; ps < CB / 128; ++ps) {
+                const int cw = 128 * ps + 4 * lane;      // first of the thread's 4 channels in this pass
+                const int4 a0 = *reinterpret_cast<const int4*>(s0t + cw), a1 = *reinterpret_cast<const int4*>(s1t + cw);
+                const int s0v[4] = {a0.x, a0.y, a0.z, a0.w}, s1v[4] = {a1.x, a1.y, a1.z, a1.w};
+                unsigned row_addr[4], pitch[4];
+                int t0s[4];
+                bool from_global = false, all_ring = true;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int t0 = axis_index_c<PAD>(o + g.lb[0] - s0v[v], g.S[0]);
+                    t0s[v] = t0;
+                    const bool inw = t0 >= wlo && t0 <= whi;           // implies t0 >= 0
+                    int sl = slot_lo + (t0 - wlo);
+                    sl = sl >= K ? sl - K : sl;
+                    row_addr[v] = inw ? base + (unsigned)sl * row_bytes + (unsigned)(cw + v) : fill_addr;
+                    pitch[v] = inw ? (unsigned)CB : 0u;
+                    from_global = from_global || (t0 >= 0 && !inw);
+                    all_ring = all_ring && inw;
+                }
+                int s1_max = s1v[0], s1_min = s1v[0];
+#pragma unroll
+                for (int v = 1; v < 4; ++v) { s1_max = s1v[v] > s1_max ? s1v[v] : s1_max; s1_min = s1v[v] < s1_min ? s1v[v] : s1_min; }
+                const int p_lo = s1_max - lb1 > 0 ? s1_max - lb1 : 0;
+                const int p_hi = s1n - 1 - lb1 + s1_min < ow - 1 ? s1n - 1 - lb1 + s1_min : ow - 1;
+                uint8_t* yp = yrow + cw;
+                int p = 0;
+                if (!from_global) {
+                    for (; p < p_lo && p < ow; ++p, yp += CB) {            // leading pixels: some tap is left of the row
+                        unsigned val[4];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const int t1 = axis_index_c<PAD>(p + lb1 - s1v[v], s1n);
+                            val[v] = ring_byte(nullptr, t1 >= 0 ? row_addr[v] + (unsigned)t1 * pitch[v] : fill_addr);
+                        }
+                        store4(yp, val);
+                    }
+                    unsigned addr[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) addr[v] = row_addr[v] + (unsigned)(p + lb1 - s1v[v]) * pitch[v];
+                    if (all_ring) {
+                        for (; p + 7 <= p_hi; p += 8) {
+                            unsigned val[8][4];
+                            SpanRows<0, CB>::load(addr, val);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i, yp += CB) store4(yp, val[i]);
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) addr[v] += 8u * (unsigned)CB;
+                        }
+                    }
+                    for (; p <= p_hi; ++p, yp += CB) {
+                        unsigned val[4];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) { val[v] = ring_byte(nullptr, addr[v]); addr[v] += pitch[v]; }
+                        store4(yp, val);
+                    }
+                    for (; p < ow; ++p, yp += CB) {                        // trailing pixels
+                        unsigned val[4];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const int t1 = axis_index_c<PAD>(p + lb1 - s1v[v], s1n);
+                            val[v] = ring_byte(nullptr, t1 >= 0 ? row_addr[v] + (unsigned)t1 * pitch[v] : fill_addr);
+                        }
+                        store4(yp, val);
+                    }
+                } else {
+                    for (; p < ow; ++p, yp += CB) {
+                        unsigned val[4];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const int t1 = axis_index_c<PAD>(p + lb1 - s1v[v], s1n);
+                            if (t0s[v] >= 0 && pitch[v] == 0u) {     // valid row, not in this row's window
+                                const uint8_t* src = x + (long long)sg.n * g.xs[0] + (long long)t0s[v] * g.xs[2] + (cw + v);
+                                val[v] = t1 >= 0 ? (unsigned)load_ro(src + (unsigned long long)(unsigned)t1 * xs3) : (unsigned)fill;
+                            } else {
+                                val[v] = ring_byte(nullptr, t1 >= 0 ? row_addr[v] + (unsigned)t1 * pitch[v] : fill_addr);
+                            }
+                        }
+                        store4(yp, val);
+                    }
+                }
+            }
+        }
+        qbase += sg.hi - sg.lo + 1;
+    }
+    // rows this warp never needed (or no longer needs): see each of them land, then release it
+    __syncwarp();
+    while (rel_q < qbase) {
+        if (ready_q <= rel_q) {
+            mbar_wait_parked(&full[ready_slot], ready_phase);
+            ++ready_q;
+            if (++ready_slot == K) { ready_slot = 0; ready_phase ^= 1u; }
+        }
+        if (lane == 0) mbar_arrive(&empty[rel_slot]);
+        ++rel_q;
+        if (++rel_slot == K) rel_slot = 0;
+    }
+}
+
+bool plan_rows(const Geo& g, int esize, const void* x, const void* y, int sm_count, int max_grid_x, int ring_rows, RowsPlan* out) {
+    if (!tma_available()) return false;
+    if (g.dim != 2 || esize != 1 || g.xs[1] != 1) return false;
+    if (g.C != 128 && g.C != 256 && g.C != 512) return false;
+    if (g.xs[3] != g.C || g.xs[2] != g.C * (long long)g.S[1] || (g.xs[0] & 15) || g.xs[0] < 0) return false;   // dense rows
+    if (((uintptr_t)x & 15u) || ((uintptr_t)y & 3u)) return false;
+    const long long row_bytes = (long long)g.S[1] * g.C;
+    if (row_bytes % 16 || row_bytes >= (1 << 20)) return false;
+    if (g.N * (long long)g.OS[0] >= 0x7fffffffLL || g.N * (long long)g.S[0] >= 0x7fffffffLL) return false;
+    RowsPlan pl;
+    const long long tab = 2 * g.C * 4 + 16, avail = 227LL * 1024 - 1024 - tab - 16;
+    long long K = avail / (row_bytes + 16);
+    if (ring_rows > 0 && K > ring_rows) K = ring_rows;
+    if (K > 64) K = 64;
+    if (K < 7) return false;
+    // consumer warps: the windows of the rows in flight (W of them) plus one free slot must fit the ring, and a window
+    // should hold the reach of the shifts layers learn (|shift| <= 3: 7 rows) -- wider ones fall back to global loads
+    int W = K >= 20 ? 8 : (K >= 14 ? 6 : (int)K - 5);
+    if (W < 2) W = 2;
+    if (W > ROWS_MAX_W) W = ROWS_MAX_W;
+    pl.K = (int)K;
+    pl.W = W;
+    pl.WIN = (int)K - W - 1;
+    if (pl.WIN < 2) return false;
+    pl.row_bytes = (unsigned)row_bytes;
+    pl.off_bar = (unsigned)(K * row_bytes);
+    pl.off_tab = pl.off_bar + (unsigned)(2 * K * 8);
+    pl.smem_bytes = pl.off_tab + (unsigned)tab + 16u;
+    long long grid = sm_count;
+    const long long rows = g.N * (long long)g.OS[0];
+    if (grid > rows) grid = rows;
+    if (max_grid_x > 0 && grid > max_grid_x) grid = max_grid_x;
+    pl.grid = (unsigned)grid;
+    *out = pl;
+    return true;
+}
+
+template <int PAD, int CB>
+int rows_launch(const Geo& g, const RowsPlan& pl, const void* x, void* y, uint8_t fill, const void* w, int qkind, long long wzp,
+                cudaStream_t s) {
+    if (!ensure_dynamic_smem((const void*)k_gather_nhwc_rows<PAD, CB>, pl.smem_bytes)) return check_launch();
+    k_gather_nhwc_rows<PAD, CB><<<pl.grid, (pl.W + 1) * 32, pl.smem_bytes, s>>>(g, pl, (const uint8_t*)x, (uint8_t*)y, fill, w, qkind, wzp);
+    note_launch();
+    return check_launch();
+}
+template <int PAD>
+int rows_run_c(const Geo& g, const RowsPlan& pl, const void* x, void* y, uint8_t fill, const void* w, int qkind, long long wzp, cudaStream_t s) {
+    switch ((int)g.C) {
+    case 128: return rows_launch<PAD, 128>(g, pl, x, y, fill, w, qkind, wzp, s);
+    case 256: return rows_launch<PAD, 256>(g, pl, x, y, fill, w, qkind, wzp, s);
+    default: return rows_launch<PAD, 512>(g, pl, x, y, fill, w, qkind, wzp, s);
+    }
+}
+int rows_run(const Geo& g, const RowsPlan& pl, const void* x, void* y, uint8_t fill, const void* w, int qkind, long long wzp, cudaStream_t s) {
+    switch (g.pad) {
+    case TS_PAD_BORDER: return rows_run_c<TS_PAD_BORDER>(g, pl, x, y, fill, w, qkind, wzp, s);
+    case TS_PAD_PERIODIC: return rows_run_c<TS_PAD_PERIODIC>(g, pl, x, y, fill, w, qkind, wzp, s);
+    case TS_PAD_REFLECT: return rows_run_c<TS_PAD_REFLECT>(g, pl, x, y, fill, w, qkind, wzp, s);
+    case TS_PAD_SYMMETRIC: return rows_run_c<TS_PAD_SYMMETRIC>(g, pl, x, y, fill, w, qkind, wzp, s);
+    default: return rows_run_c<TS_PAD_ZEROS>(g, pl, x, y, fill, w, qkind, wzp, s);
+    }
+}
+
 template <typename E, int DIM, int VEC, int PAD>
 void run_dim(const Geo& g, const NhwcPlan& pl, const void* x, void* y, E fill, const void* w, int qkind, long long wzp, cudaStream_t s,
              bool emulate) {
@@ -747,10 +1080,17 @@ int nhwc_to_planar(const void* x, void* y, long long N, long long C, long long P
 
 // x: any strides (g.xs), meant for channel stride 1; y: dense [N, OS0(,OS1(,OS2)), C].
 // emulate: x / y / w are HOST pointers and the launch is walked on the host (tests only, no GPU work).
-// variant: 0 automatic (ring kernel when it applies, else direct), 1 direct only, 2 ring only; ring_rows > 0 caps the ring.
+// variant: 0 automatic (row-pipelined kernel, else ring kernel, else direct), 1 direct only, 2 ring only, 3 row-pipelined only;
+// ring_rows > 0 caps the ring.
 int nhwc_gather(const Geo& g, const void* x, void* y, unsigned long long fill, int esize, const void* w, int qkind,
                 long long wzp, int sm_count, int max_grid_x, int variant, int ring_rows, bool emulate, cudaStream_t s) {
     if (g.N * g.C == 0 || g.out_plane == 0) return TS_OK;
+    if (!emulate && (variant == 0 || variant == 3)) {      // row-pipelined kernel (no host emulation: GPU tests only)
+        RowsPlan wp;
+        if (plan_rows(g, esize, x, y, sm_count, max_grid_x, ring_rows, &wp))
+            return rows_run(g, wp, x, y, (uint8_t)fill, w, qkind, wzp, s);
+        if (variant == 3) return TS_ERR_UNSUPPORTED;
+    }
     if (variant != 1) {
         RingPlan rp;
         if (plan_ring(g, esize, x, y, sm_count, max_grid_x, ring_rows, &rp))

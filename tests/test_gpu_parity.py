@@ -831,7 +831,7 @@ def test_quantized_channels_last_native_kernel(dev, lib, oracle_port, auto_path)
     cases = [((2, 8, 6, 16), None), ((3, 3, 5, 7), None), ((2, 20, 9, 12), [[1, 0], [2, 1]]), ((1, 1028, 4, 6), None),
              ((2, 64, 56, 56), None), ((2, 6, 3, 4, 5), None), ((1, 16, 6, 10, 12), [[0, 1], [1, 0], [2, 1]]),
              ((4, 256, 1, 40), None), ((2, 128, 20, 24), [[2, 1], [0, 3]]), ((1, 96, 33, 17), None), ((3, 32, 8, 8), None),
-             ((300, 128, 9, 5), None)]
+             ((300, 128, 9, 5), None), ((3, 256, 30, 14), None), ((2, 512, 12, 8), [[1, 2], [0, 0]]), ((5, 128, 40, 12), [[3, 0], [1, 1]])]
     for shape, borders in cases:
         dim = len(shape) - 2
         fn = shift2d_quantized if dim == 2 else shift3d_quantized
@@ -855,6 +855,10 @@ def test_quantized_channels_last_native_kernel(dev, lib, oracle_port, auto_path)
             variants = [b"nhwc_variant=0,nhwc_ring_rows=0", b"nhwc_variant=1,nhwc_ring_rows=0"]
             if dim == 2 and npdt is not np.int32 and shape[1] % 32 == 0:
                 variants += [b"nhwc_variant=2,nhwc_ring_rows=0", b"nhwc_variant=2,nhwc_ring_rows=3"]
+            # the row-pipelined kernel (dense pixels, C = 128 / 256 / 512), also with a ring of 9 rows: windows of 2 rows,
+            # so most taps of the +-5 shifts are outside their window and come from global memory
+            if dim == 2 and npdt is not np.int32 and shape[1] in (128, 256, 512):
+                variants += [b"nhwc_variant=3,nhwc_ring_rows=0", b"nhwc_variant=3,nhwc_ring_rows=9"]
             for pad in range(5):
                 want = oracle_port.qforward(raw, wraw.astype(np.int64), 128, zp, pad, borders)
                 for variant in variants:
@@ -888,7 +892,7 @@ def test_full_size_cfg5_channels_last(dev, lib, oracle_port, auto_path):
         planar = shift2d_quantized(xq, qw, pad).int_repr()
         idx = [0, 131, 255]
         want = oracle_port.qforward(xq.int_repr()[idx].cpu().numpy(), raw, wzp, -128, pad)
-        for variant in (b"nhwc_variant=2", b"nhwc_variant=1", b"nhwc_variant=0"):       # ring, direct, automatic
+        for variant in (b"nhwc_variant=3", b"nhwc_variant=2", b"nhwc_variant=1", b"nhwc_variant=0"):       # row-pipelined, ring, direct, automatic
             assert lib.ts_set_tuning(variant) == 0
             y = shift2d_quantized(xcl, qw, pad)
             assert lib.ts_last_kernel_path() == NHWC and y.is_contiguous(memory_format=torch.channels_last)
