@@ -77,6 +77,7 @@ struct Tuning {
     int use_tma;       // 0: the automatic path choice never picks the TMA-tensor family
     int tma_stage_kb;  // target bytes per stage of the TMA-tensor kernels (0 = auto)
     int nhwc_variant;  // channels-last gather: 0 auto, 1 direct (L1) kernel only, 2 ring (shared-memory) kernel only
+    int nhwc_rows_warps; // consumer warps of the row-pipelined channels-last kernel (0 = auto)
     int nhwc_ring_rows;  // cap on the ring slots of the channels-last ring kernel (0 = as many as fit)
     int use_halo;      // 0: the automatic path choice never picks the halo family
     int halo;          // halo rows / columns of the halo family (0 = 4)

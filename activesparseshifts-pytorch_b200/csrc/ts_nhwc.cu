@@ -732,9 +732,13 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
     // from global memory (slow: 2.3 ms for cfg5 with shifts in +-6 -- like the ring kernel, this kernel is built for the
     // shifts layers learn).
     int W = pl.W, WIN = pl.WIN;
-    if (smax - smin + 1 > WIN && pl.K - 2 - (smax - smin) >= 3) {      // (below 3 warps the global-memory fall-back is the lesser evil)
-        W = pl.K - 2 - (smax - smin);
-        WIN = pl.K - W - 1;
+    {
+        constexpr int PP = CB / 128;
+        const int rows_fit = pl.K - 2 - (smax - smin);                   // rows in flight that leave the whole reach in the ring
+        if (smax - smin + 1 > WIN && rows_fit * PP >= 3) {               // (below 3 warps the global-memory fall-back is the lesser evil)
+            W = rows_fit * PP < W ? rows_fit * PP : W;
+            WIN = pl.K - (W + PP - 1) / PP - 1;
+        }
     }
     if (tid == 0) {
         for (int k = 0; k < pl.K; ++k) { mbar_init(&full[k], 1); mbar_init(&empty[k], (unsigned)W); }
@@ -768,6 +772,7 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
     if (warp >= W) return;
 
     // ---- consumers ----
+    constexpr int P = CB / 128;                // passes (tasks) per output row
     const unsigned base = shared_addr(rsm);
     const unsigned fill_addr = base + pl.smem_bytes - 16u;
     const int s1n = g.S[1], lb1 = g.lb[1], ow = g.OS[1];
@@ -780,7 +785,9 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
     unsigned r = r_begin;
     RowsSeg sg;
     while (rows_segment(g, WIN, r, r_end, smin, smax, sg)) {
-        for (int o = sg.o_a + warp; o < sg.o_b; o += W) {
+        // a task is (output row, pass of 128 channels): consecutive warps share a row, so W warps hold W / P rows
+        for (int t = warp; t < (sg.o_b - sg.o_a) * P; t += W) {
+            const int o = sg.o_a + t / P, ps = t % P;
             int wlo, whi;
             rows_window(g, WIN, sg, o, smin, smax, wlo, whi);
             const int q_lo = qbase + (wlo - sg.lo), q_hi = qbase + (whi - sg.lo);
@@ -809,8 +816,7 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
             }
             int slot_lo = rel_slot;            // == q_lo mod K (rel_q == q_lo here)
             uint8_t* yrow = y + (((long long)sg.n * g.OS[0] + o) * ow) * g.C;
-#pragma unroll 1
-            for (int ps = 0; ps < CB / 128; ++ps) {
+            {
                 const int cw = 128 * ps + 4 * lane;      // first of the thread's 4 channels in this pass
                 const int4 a0 = *reinterpret_cast<const int4*>(s0t + cw), a1 = *reinterpret_cast<const int4*>(s1t + cw);
                 const int s0v[4] = {a0.x, a0.y, a0.z, a0.w}, s1v[4] = {a1.x, a1.y, a1.z, a1.w};
@@ -923,14 +929,19 @@ bool plan_rows(const Geo& g, int esize, const void* x, const void* y, int sm_cou
     if (ring_rows > 0 && K > ring_rows) K = ring_rows;
     if (K > 64) K = 64;
     if (K < 7) return false;
-    // consumer warps: the windows of the rows in flight (W of them) plus one free slot must fit the ring, and a window
-    // should hold the reach of the shifts layers learn (|shift| <= 3: 7 rows) -- wider ones fall back to global loads
-    int W = K >= 20 ? 8 : (K >= 14 ? 6 : (int)K - 5);
-    if (W < 2) W = 2;
+    // consumer warps: a task is (output row, pass of 128 channels), so W warps hold W / P rows; the windows of the rows in
+    // flight plus the prefetched rows must fit the ring, and a window should hold the reach of the shifts layers learn
+    // (|shift| <= 3: 7 rows) -- wider ones fall back to global loads.  Measured on cfg5 (K = 15): more warps win until the
+    // ring has fewer than ~3 free slots for the producer.
+    const int P = (int)(g.C / 128);
+    int W = K >= 20 ? 8 * P : (K >= 14 ? 6 * P : ((int)K - 5) * P);
+    if (tuning().nhwc_rows_warps > 0) W = tuning().nhwc_rows_warps;
     if (W > ROWS_MAX_W) W = ROWS_MAX_W;
+    if ((W + P - 1) / P > (int)K - 3) W = ((int)K - 3) * P;
+    if (W < 2) W = 2;
     pl.K = (int)K;
     pl.W = W;
-    pl.WIN = (int)K - W - 1;
+    pl.WIN = (int)K - (W + P - 1) / P - 1;
     if (pl.WIN < 2) return false;
     pl.row_bytes = (unsigned)row_bytes;
     pl.off_bar = (unsigned)(K * row_bytes);

@@ -18,7 +18,7 @@ dev = torch.device("cuda:0")
 CASES = {"cfg1": ((8, 64, 32, 32), 0, False, torch.float32), "cfg3": ((256, 256, 56, 56), 0, False, torch.float32), "cfg3a": ((256, 256, 56, 56), 0, True, torch.float32),
          "cfg3r": ((256, 256, 56, 56), 3, False, torch.float32), "cfg3ra": ((256, 256, 56, 56), 3, True, torch.float32),
          "cfg4": ((32, 128, 16, 56, 56), 0, True, torch.float32), "cfg4r": ((32, 128, 16, 56, 56), 3, True, torch.float32),
-         "cfg4rs": ((32, 128, 16, 56, 56), 3, False, torch.float32), "cfg4b": ((32, 128, 16, 56, 56), 1, True, torch.float32), "cfg5": ((256, 256, 56, 56), 0, False, torch.qint8),
+         "cfg4rs": ((32, 128, 16, 56, 56), 3, False, torch.float32), "cfg4b": ((32, 128, 16, 56, 56), 1, True, torch.float32), "cfg5": ((256, 256, 56, 56), 0, False, torch.qint8), "cfg5cl": ((256, 256, 56, 56), 0, False, torch.qint8),
          "cfg2": ((64, 512, 4096), 2, True, torch.float32), "cfg2h": ((64, 512, 4096), 2, True, torch.bfloat16)}
 shape, pad, active, dtype = CASES[sys.argv[1]]
 specs = sys.argv[2:] or [""]
@@ -33,6 +33,8 @@ quant = dtype in (torch.qint8, torch.quint8)
 if quant:
     x = torch.quantize_per_tensor(torch.rand(shape, device=dev), 1 / 255., -128, dtype)
     wq = quantize_shift_weights(w * 3)
+    if sys.argv[1].endswith("cl"):
+        x = x.contiguous(memory_format=torch.channels_last)
 else:
     x = torch.randn(shape, device=dev).to(dtype); g = torch.randn(shape, device=dev).to(dtype); w = w.to(dtype)
 n = x.numel()
