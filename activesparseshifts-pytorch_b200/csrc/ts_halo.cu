@@ -466,12 +466,12 @@ TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t
         for (int nb = n0; nb < n1; nb += a.np) {
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
             for (int k = 0; k < steps; ++k) {
-                if (kk > 0) mbar_wait_relaxed(&empty[s], (unsigned)((kk - 1) & 1), 100);
+                if (kk > 0) mbar_wait_parked(&empty[s], (unsigned)((kk - 1) & 1));
                 unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
                 const bool has_g = bwd && (a.dim == 2 || a.active || k >= 1);
                 const bool has_v = bwd && a.dim == 3 && k >= 1;
 #ifdef TS_HALO_PROBE
-                if (a.probe == 2) {          // no copies, the consumers compute on whatever the stage holds
+                if ((a.probe & 3) == 2) {    // no copies, the consumers compute on whatever the stage holds
                     mbar_arrive(&full[s]);
                     if (++s == a.stages) { s = 0; ++kk; }
                     continue;
@@ -537,10 +537,13 @@ TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* r
             for (int k = 0; k < steps; ++k) {
                 unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
                 const bool has_g = bwd && (a.dim == 2 || a.active || k >= 1);
-                mbar_wait_relaxed(&full[s], phase, 40);
+                mbar_wait_parked(&full[s], phase);
                 for (int pl = 0; pl < npl; ++pl) {
                     float* tx = (float*)(st + (size_t)pl * a.tile_x);
                     float* tg = (float*)(st + a.off_g + (size_t)pl * a.tile_g);
+#ifdef TS_HALO_PROBE
+                    if (a.probe & 8) continue;
+#endif
                     if (use_list) {
                         halo_apply(list_x, nx, tx, lane);
                         if (has_g) halo_apply(list_g, ng, tg, lane);
@@ -549,6 +552,9 @@ TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* r
                         if (has_g) halo_walk(nullptr, tg, a.pg, a.OB, a.OL, a.hr, a.hc, a.g.pad, hg, lane);
                     }
                 }
+#ifdef TS_HALO_PROBE
+                if (!(a.probe & 4))
+#endif
                 fence_proxy_async();             // the next TMA load of this stage must not overtake these generic-proxy writes
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ready[s]);
@@ -579,7 +585,7 @@ struct PairCtx {
     unsigned cmask;            // bit t of nibble j: element t of row j takes part (inside the crop)
 };
 
-template <int MODE>
+template <int MODE, bool CROP>
 TS_D PairCtx pair_ctx(const HArgs& a, const UnitGeom& ug, const Pair& q, bool valid) {
     PairCtx p;
     p.rows = !valid ? 0 : (q.r + 1 < a.IB ? 2 : 1);
@@ -588,9 +594,10 @@ TS_D PairCtx pair_ctx(const HArgs& a, const UnitGeom& ug, const Pair& q, bool va
     p.go = p.vo = 0;
     p.cmask = 0xffu;
     if (MODE == 2) {
-        unsigned m = 0;
+        unsigned m = p.rows == 2 ? 0xffu : (p.rows == 1 ? 0x0fu : 0u);
+        if (CROP) m = 0;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; CROP && j < 2; ++j) {
             const int ob = q.r + j - a.lbB;
             if (ob < 0 || ob >= a.OB) continue;
 #pragma unroll
@@ -620,7 +627,9 @@ struct Ring {
 // ROLE (3-D interpolating backward only): 0 = a thread does everything for ONE pair; 1 = grad_weight terms (x windows) of
 // TWO pairs; 2 = grad_input (grad windows + stores) of TWO pairs.  Splitting the two halves of the arithmetic over
 // different warps halves the window state a thread carries from slab to slab (30 instead of 60 registers).
-template <int DIM, int MODE, bool ACTIVE, bool SPLIT, bool POOL>
+// CROP (backward only): the call has a border crop, so grad values outside the crop are masked element by element; without
+// one every mask is full and the mask code (48 of 510 instructions per slab step of the 3-D backward) is compiled out.
+template <int DIM, int MODE, bool ACTIVE, bool SPLIT, bool POOL, bool CROP>
 struct Body {
     const HArgs& a;
     const int tid, nt, wid, lane;
@@ -712,12 +721,12 @@ struct Body {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             if (j >= pc.rows) continue;
-            const unsigned m = (pc.cmask >> (4 * j)) & 15u;
+            const unsigned m = CROP ? (pc.cmask >> (4 * j)) & 15u : 15u;
             float y[4] = {0.f, 0.f, 0.f, 0.f};
             if (m) {
                 float gv[4];
                 load4<WSV>(va + j * a.pg * 4, wsv, gv);
-                if (m != 15u) {
+                if (CROP && m != 15u) {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) gv[t] = (m >> t) & 1u ? gv[t] : 0.f;
                 }
@@ -731,7 +740,7 @@ struct Body {
                 } else {
                     load4<WSG>(ga + j * a.pg * 4, wsg, y);
                 }
-                if (m != 15u) {
+                if (CROP && m != 15u) {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) y[t] = (m >> t) & 1u ? y[t] : 0.f;
                 }
@@ -750,7 +759,7 @@ struct Body {
         for (int p = tid + nt; p < total; p += nt) {
             Pair q;
             if (!decode_pair(a, p, q)) continue;
-            const PairCtx pc = pair_ctx<MODE>(a, ug, q, true);
+            const PairCtx pc = pair_ctx<MODE, CROP>(a, ug, q, true);
             pair2<WSX, WSG, WSV>(sb, dst, pc, ts);
         }
         release(ring);
@@ -772,7 +781,7 @@ struct Body {
         constexpr bool DOG = MODE == 2 && ROLE != 1;
         if (pc.rows == 0) return;
 #ifdef TS_HALO_PROBE                   // measurement builds only (nvcc -DTS_HALO_PROBE; tuning knob halo_probe): results are WRONG when set
-        if (a.probe == 1) {            // the stage hand-off, the copies and the stores without loads / arithmetic
+        if ((a.probe & 3) == 1) {      // the stage hand-off, the copies and the stores without loads / arithmetic
             if (k >= 1) {
                 unsigned char* o = dst_img + pc.out_off + (long long)(k - 1) * a.IB * (a.IG * 16);
                 for (int j = 0; j < pc.rows; ++j) __stcs((float4*)(o + j * a.IG * 16), make_float4(0.f, 0.f, 0.f, 0.f));
@@ -783,7 +792,7 @@ struct Body {
         const float d[3] = {us.d[0], us.d[1], us.d[2]};
         const int it = k - 1, orow = a.IG * 16;
         unsigned char* o = dst_img + pc.out_off + (long long)it * a.IB * orow;
-        const bool slab_pass = MODE != 2 || (it - a.lbA >= 0 && it - a.lbA < a.OA);
+        const bool slab_pass = MODE != 2 || !CROP || (it - a.lbA >= 0 && it - a.lbA < a.OA);
         const unsigned cm = (k >= 1 && slab_pass) ? pc.cmask : 0u;
         const unsigned xa = sb + pc.xo, ga = sb + pc.go, va = sb + pc.vo;
         const int pxb = a.px * 4, pgb = a.pg * 4;
@@ -815,13 +824,13 @@ struct Body {
                 for (int t = 0; t < 4; ++t) y[t] = lerp<float>(P[t], P[t + 1], d[2]);
                 __stcs((float4*)(o + j * orow), make_float4(y[0], y[1], y[2], y[3]));
             } else {
-                const unsigned m = (cm >> (4 * j)) & 15u;
+                const unsigned m = CROP ? (cm >> (4 * j)) & 15u : 15u;       // (no crop: k >= 1 and the row exists here)
                 float y[4] = {0.f, 0.f, 0.f, 0.f};
                 if (m) {
                     if (DOX) {
                         float gv[4];
                         load4<WSV>(va + j * a.OL * 4, wsv, gv);
-                        if (m != 15u) {
+                        if (CROP && m != 15u) {
 #pragma unroll
                             for (int t = 0; t < 4; ++t) gv[t] = (m >> t) & 1u ? gv[t] : 0.f;
                         }
@@ -837,7 +846,7 @@ struct Body {
                         } else {
                             load4<WSG>(ga + j * pgb, wsg, y);
                         }
-                        if (m != 15u) {
+                        if (CROP && m != 15u) {
 #pragma unroll
                             for (int t = 0; t < 4; ++t) y[t] = (m >> t) & 1u ? y[t] : 0.f;
                         }
@@ -860,7 +869,7 @@ struct Body {
             Pair q;
             const bool valid = p < npl * a.img_pairs && decode_pair(a, p, q);
             if (!valid) { q.pl = 0; q.r = 0; q.cg = 0; }
-            pc[i] = pair_ctx<MODE>(a, ug, q, valid);
+            pc[i] = pair_ctx<MODE, CROP>(a, ug, q, valid);
         }
         if constexpr (MODE != 2) {
             // forward: four compile-time misalignment bodies; unrolling the slab loop by two on top of that spills, so the
@@ -928,7 +937,7 @@ if constexpr (SPLIT) {         // chosen at LAUNCH: both role layouts in one ker
             Pair q;
             const bool valid = tid < a.pairs && decode_pair(a, tid, q);
             if (!valid) { q.pl = 0; q.r = 0; q.cg = 0; }
-            pc0 = pair_ctx<MODE>(a, ug, q, valid);
+            pc0 = pair_ctx<MODE, CROP>(a, ug, q, valid);
         }
         for (int nb = n0; nb < n1; nb += a.np) {
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
@@ -958,7 +967,7 @@ if constexpr (SPLIT) {         // chosen at LAUNCH: both role layouts in one ker
     }
 };
 
-template <int DIM, int MODE, bool ACTIVE, bool SPLIT, bool POOL>
+template <int DIM, int MODE, bool ACTIVE, bool SPLIT, bool POOL, bool CROP = false>
 __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
@@ -1010,7 +1019,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs 
         fixer(a, smem, full, ready, lane, tbl, lists, uo);
         return;
     }
-    Body<DIM, MODE, ACTIVE, SPLIT, POOL> body(a, threadIdx.x, a.nt, wid, lane, a.need_fix ? ready : full, empty, tbl);
+    Body<DIM, MODE, ACTIVE, SPLIT, POOL, CROP> body(a, threadIdx.x, a.nt, wid, lane, a.need_fix ? ready : full, empty, tbl);
     Ring ring = {0, 0u};
     const UnitRange ur = unit_range(a.units, a.unit_order);
     int u = ur.u;
@@ -1067,7 +1076,7 @@ bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, int pool, 
     a.pool = pool;
     a.out_plane_bytes = pool ? (long long)((a.OB + 1) / 2) * (a.OL / 2) * 4 : (mode == 2 ? g.in_plane : g.out_plane) * 4;
     a.need_fix = g.pad != TS_PAD_ZEROS;
-    a.split = (tuning().halo_split && d == 3 && mode == 2 && active && p.warps % 2 == 0 && a.pairs <= a.nt) ? 1 : 0;
+    a.split = 0;      // (the role-split 3-D backward -- x-window warps and grad-window warps -- measured 1.7x slower and is no longer built)
     a.d_GP = make_fastdivu((unsigned)a.GP);
     a.d_img = make_fastdivu((unsigned)a.img_pairs);
     if (!make_tensor_map5(&a.map_x, x, 4, g.N, g.C, a.A, a.B, a.L, a.px, a.bpx, 1, 1)) return false;
@@ -1137,7 +1146,7 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     while (np > 1 && budget / (stride_of(np) + 24) < min_stages + 1) --np;
     long long stages = budget / (stride_of(np) + 24);
     if (stages < min_stages) return p;
-    const int want = t.halo_stages > 0 ? t.halo_stages : (d == 3 ? 6 : 4);     // tools/knob_sweep.py cfg3ra / cfg4r
+    const int want = t.halo_stages > 0 ? t.halo_stages : (d == 3 ? 6 : (mode == 2 ? 5 : 4));     // tools/knob_sweep.py cfg3ra / cfg4r
     if (stages > want) stages = want;
     if (np * per_image >= (1 << 20)) return p;             // mbarrier tx-count range
     const long long pairs = np * img_pairs;
@@ -1199,11 +1208,17 @@ int halo_backward(const Geo& g, const HaloPlan& p, int active, const void* grad,
     HArgs a;
     if (!make_args(g, p, 2, active ? 1 : 0, 0, x, grad, gi, w, partials, &a)) return TS_ERR_UNSUPPORTED;
     int rc;
-    switch (g.dim * 2 + (active ? 1 : 0)) {
-    case 4: rc = launch(k_halo<2, 2, false, false, false>, a, p, s); break;
-    case 5: rc = launch(k_halo<2, 2, true, false, false>, a, p, s); break;
-    case 6: rc = launch(k_halo<3, 2, false, false, false>, a, p, s); break;
-    default: rc = a.split ? launch(k_halo<3, 2, true, true, false>, a, p, s) : launch(k_halo<3, 2, true, false, false>, a, p, s); break;
+    bool crop = false;
+    for (int ax = 0; ax < g.dim; ++ax) crop = crop || g.lb[ax] != 0 || g.OS[ax] != g.S[ax];
+    switch (g.dim * 2 + (active ? 1 : 0) + (crop ? 8 : 0)) {
+    case 4: rc = launch(k_halo<2, 2, false, false, false, false>, a, p, s); break;
+    case 5: rc = launch(k_halo<2, 2, true, false, false, false>, a, p, s); break;
+    case 6: rc = launch(k_halo<3, 2, false, false, false, false>, a, p, s); break;
+    case 7: rc = launch(k_halo<3, 2, true, false, false, false>, a, p, s); break;
+    case 12: rc = launch(k_halo<2, 2, false, false, false, true>, a, p, s); break;
+    case 13: rc = launch(k_halo<2, 2, true, false, false, true>, a, p, s); break;
+    case 14: rc = launch(k_halo<3, 2, false, false, false, true>, a, p, s); break;
+    default: rc = launch(k_halo<3, 2, true, false, false, true>, a, p, s); break;
     }
     if (rc != TS_OK) return rc;
     return launch_reduce_partials<float>(partials, p.slots, (int)(g.C * g.dim), gw, peers, s);
