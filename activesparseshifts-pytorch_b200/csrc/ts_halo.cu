@@ -450,7 +450,11 @@ TS_D int slab_coord(int idx, int len, int pad) {
     return t < 0 ? -1 : t;                 // outside under zeros padding: the copy engine delivers a zero tile
 }
 
-TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, const UnitShift* tbl, const UnitOrder& uo) {
+// The whole producer WARP runs this.  The slab coordinates of a unit's steps depend on the channel only: lane k works them
+// out for step k once per unit (one elected thread evaluating the remaps every stage was near the critical path of the 3-D
+// pipeline: reflect / symmetric padding ran 8 % behind border padding for ~20 extra dependent instructions per stage), and the
+// (up to three) tensor copies of an image are issued by three different lanes.
+TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, const UnitShift* tbl, const UnitOrder& uo, int lane) {
     int s = 0, kk = 0, cls = 0;
     const int N = (int)a.g.N;
     const bool bwd = a.mode == 2;
@@ -465,32 +469,39 @@ TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t
         if (!unit_geom(a, us).fits) continue;              // consumers take the element-wise routine for this unit
         for (int nb = n0; nb < n1; nb += a.np) {
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
+            int xs_l = 0, gs_l = 0, vs_l = 0;              // coordinates of step (k & ~31) + lane
             for (int k = 0; k < steps; ++k) {
-                if (kk > 0) mbar_wait_parked(&empty[s], (unsigned)((kk - 1) & 1));
+                if (a.dim == 3 && (k & 31) == 0) {
+                    const int kl = k + lane;
+                    xs_l = slab_coord((bwd ? kl : kl + a.lbA) - us.sx[0], a.A, a.g.pad);
+                    if (bwd) {
+                        gs_l = a.active ? slab_coord(kl - a.lbA - us.sg[0], a.OA, a.g.pad) : slab_coord(kl - 1 - a.lbA + us.sg[0], a.OA, a.g.pad);
+                        const int oa = kl - 1 - a.lbA;
+                        vs_l = (oa >= 0 && oa < a.OA) ? oa : -1;
+                    }
+                }
+                const int xs = __shfl_sync(0xffffffffu, xs_l, k & 31), gs = __shfl_sync(0xffffffffu, gs_l, k & 31),
+                          vs = __shfl_sync(0xffffffffu, vs_l, k & 31);
                 unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
                 const bool has_g = bwd && (a.dim == 2 || a.active || k >= 1);
                 const bool has_v = bwd && a.dim == 3 && k >= 1;
+                if (lane == 0) {
+                    if (kk > 0) mbar_wait_parked(&empty[s], (unsigned)((kk - 1) & 1));
 #ifdef TS_HALO_PROBE
-                if ((a.probe & 3) == 2) {    // no copies, the consumers compute on whatever the stage holds
-                    mbar_arrive(&full[s]);
-                    if (++s == a.stages) { s = 0; ++kk; }
-                    continue;
-                }
+                    if ((a.probe & 3) == 2) mbar_arrive(&full[s]);     // no copies, the consumers compute on whatever the stage holds
+                    else
 #endif
-                mbar_expect_tx(&full[s], (unsigned)npl * (unsigned)(a.box_x + (has_g ? a.box_g : 0) + (has_v ? a.box_v : 0)));
-                int xs = 0, gs = 0, vs = 0;
-                if (a.dim == 3) {
-                    xs = slab_coord((bwd ? k : k + a.lbA) - us.sx[0], a.A, a.g.pad);
-                    if (bwd) {
-                        gs = a.active ? slab_coord(k - a.lbA - us.sg[0], a.OA, a.g.pad) : slab_coord(k - 1 - a.lbA + us.sg[0], a.OA, a.g.pad);
-                        const int oa = k - 1 - a.lbA;
-                        vs = (oa >= 0 && oa < a.OA) ? oa : -1;
-                    }
+                    mbar_expect_tx(&full[s], (unsigned)npl * (unsigned)(a.box_x + (has_g ? a.box_g : 0) + (has_v ? a.box_v : 0)));
                 }
-                for (int pl = 0; pl < npl; ++pl) {
-                    tma_load_5d(st + (size_t)pl * a.tile_x, &a.map_x, -a.hc, -a.hr, xs, c, nb + pl, &full[s]);
-                    if (has_g) tma_load_5d(st + a.off_g + (size_t)pl * a.tile_g, &a.map_g, -a.hc, -a.hr, gs, c, nb + pl, &full[s]);
-                    if (has_v) tma_load_5d(st + a.off_v + (size_t)pl * a.tile_v, &a.map_v, 0, 0, vs, c, nb + pl, &full[s]);
+                __syncwarp();                              // the slot is free and its byte count posted before any lane copies into it
+#ifdef TS_HALO_PROBE
+                if ((a.probe & 3) != 2)
+#endif
+                for (int job = lane; job < 3 * npl; job += 32) {
+                    const int pl = job / 3, what = job - 3 * pl;
+                    if (what == 0) tma_load_5d(st + (size_t)pl * a.tile_x, &a.map_x, -a.hc, -a.hr, xs, c, nb + pl, &full[s]);
+                    else if (what == 1) { if (has_g) tma_load_5d(st + a.off_g + (size_t)pl * a.tile_g, &a.map_g, -a.hc, -a.hr, gs, c, nb + pl, &full[s]); }
+                    else if (has_v) tma_load_5d(st + a.off_v + (size_t)pl * a.tile_v, &a.map_v, 0, 0, vs, c, nb + pl, &full[s]);
                 }
                 if (++s == a.stages) { s = 0; ++kk; }
             }
@@ -1014,7 +1025,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs 
     }
     __syncthreads();
     const UnitOrder uo = {a.table ? order : nullptr, cend, coff, a.chunks, C};
-    if (wid == a.nw) { if (lane == 0) producer(a, smem, full, empty, tbl, uo); return; }
+    if (wid == a.nw) { producer(a, smem, full, empty, tbl, uo, lane); return; }
     if (wid > a.nw) {                                                         // launched only when the padding needs it
         fixer(a, smem, full, ready, lane, tbl, lists, uo);
         return;
