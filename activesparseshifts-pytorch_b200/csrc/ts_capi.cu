@@ -2,6 +2,7 @@
 // logic, path selection (staged vs generic) and launch bookkeeping.  No torch types, no
 // allocation, no synchronisation; every entry point only enqueues kernels on the caller's stream.
 #include <atomic>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,18 +28,23 @@ int check_launch() {
 }
 
 bool ensure_dynamic_smem(const void* func, size_t bytes) {
+    // The attribute belongs to the (function, device) pair of the PROCESS: the memo is shared by all threads (autograd runs
+    // backward kernels on its own threads -- a per-thread memo let one thread lower the limit another thread relied on)
+    // and the limit only ever grows.
     struct Slot { const void* func; int dev; size_t bytes; };
-    static thread_local Slot seen[64];
-    static thread_local int used = 0;
+    static std::mutex mu;
+    static Slot seen[256];
+    static int used = 0;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lock(mu);
     int i = 0;
     for (; i < used; ++i)
         if (seen[i].func == func && seen[i].dev == dev) break;
     if (i < used && seen[i].bytes >= bytes) return true;
     if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
     if (i == used) {
-        if (used == 64) return true;          // table full: keep setting the attribute per launch for the rest
+        if (used == 256) return true;         // table full: keep setting the attribute per launch for the rest
         ++used;
     }
     seen[i] = Slot{func, dev, bytes};
@@ -334,12 +340,13 @@ size_t ts_shift_backward_workspace_bytes(const ts_geometry* gin, int dtype) {
             if (tp.ok && (size_t)tp.slots > slots) slots = (size_t)tp.slots;
         }
         for (int pad = 0; pad < 2; ++pad)
-            for (int active = 0; active < 2; ++active) {
-                Geo gh = g;
-                gh.pad = pad;
-                const HaloPlan hp = plan_halo(gh, 2, active, dtype, true, nullptr, nullptr, nullptr, sms, true);
-                if (hp.ok && (size_t)hp.slots > slots) slots = (size_t)hp.slots;
-            }
+            for (int active = 0; active < 2; ++active)
+                for (int pool = 0; pool < 2; ++pool) {      // (pool: ts_shift2d_avgpool2_backward shares this query)
+                    Geo gh = g;
+                    gh.pad = pad;
+                    const HaloPlan hp = plan_halo(gh, 2, active, dtype, true, nullptr, nullptr, nullptr, sms, true, pool != 0);
+                    if (hp.ok && (size_t)hp.slots > slots) slots = (size_t)hp.slots;
+                }
         bytes = slots * (size_t)(g.C * g.dim) * sizeof(double) + 16;
     }
     last_geo = *gin; last_dtype = dtype; last_epoch = epoch; last_bytes = bytes;
@@ -410,6 +417,26 @@ static int backward_impl(const ts_geometry* gin, int dtype, int padding, int act
     }
     t_last_path = TS_PATH_GENERIC;
     return generic_backward(g, dtype, active, grad, x, weights, grad_input, grad_weight, (double*)workspace, peers, s);
+}
+
+int ts_shift2d_avgpool2_backward(const ts_geometry* gin, int dtype, int padding, int active, const void* grad_pooled, const void* x,
+                                 const void* weights, void* grad_input, void* grad_weight, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    Geo g;
+    int rc = make_geo(gin, padding, &g);
+    if (rc != TS_OK) return rc;
+    if (g.dim != 2 || dtype != TS_F32) return TS_ERR_UNSUPPORTED;
+    if (g.N * g.C == 0 || g.in_plane == 0 || g.out_plane == 0) return TS_ERR_UNSUPPORTED;     // (empty tensors: the two-step path)
+    if (!grad_pooled || !x || !weights || !grad_input || !grad_weight) return TS_ERR_INVALID_ARGUMENT;
+    if (!workspace || ((uintptr_t)workspace & 15) || workspace_bytes < ts_shift_backward_workspace_bytes(gin, dtype))
+        return TS_ERR_WORKSPACE;
+    int sms = 0;
+    if ((rc = sm_count(&sms)) != TS_OK) return rc;
+    const HaloPlan hp = plan_halo(g, 2, active, dtype, x_is_dense(g), x, grad_input, grad_pooled, sms, true, true);
+    if (!hp.ok) return TS_ERR_UNSUPPORTED;
+    t_last_path = TS_PATH_HALO;
+    return halo_backward(g, hp, active, grad_pooled, x, weights, grad_input, grad_weight, (double*)workspace, nullptr,
+                         (cudaStream_t)stream, true);
 }
 
 int ts_shift_backward(const ts_geometry* gin, int dtype, int padding, int active, const void* grad, const void* x,

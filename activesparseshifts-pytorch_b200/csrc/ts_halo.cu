@@ -53,6 +53,7 @@ struct alignas(64) HArgs {
     CUtensorMap map_x;       // x,    box {px, bpx, 1, 1, 1}
     CUtensorMap map_g;       // grad, box {pg, bpg, 1, 1, 1}
     CUtensorMap map_v;       // grad, box {OL, OB, 1, 1, 1}   (dense slab: unshifted grad of the 3-D backward)
+                             // fused avg-pool backward: the POOLED grad, box {PW, PH, 1, 1, 1}
     Geo g;
     const float* x;
     const float* grad;
@@ -75,9 +76,11 @@ struct alignas(64) HArgs {
     int pool;                                 // forward only: 2x2 / stride 2 / ceil_mode average pooling fused into the store
     int need_fix;                             // padding != zeros: a fixer warp patches the halo of every stage
     int split;                                // 3-D interpolating backward: x-window warps and grad-window warps (two pairs per thread)
-    FastDivU d_GP, d_img, d_C, d_chunks;
+    FastDivU d_GP, d_img, d_C, d_chunks, d_PW;
     int table;                                // per-channel shift table in shared memory (C <= TABLE_MAX_C)
     int probe;                                // tuning knob halo_probe (measurement only)
+    int nfix;                                 // fixer warps (1; 4 when they also expand the pooled gradient)
+    int pool_bwd, PH, PW;                     // backward fused with the adjoint of avg_pool2d(2, 2, ceil_mode): pooled rows / columns
 };
 
 TS_D int level_axis(int level, int dim) { return level - (3 - dim); }
@@ -251,6 +254,37 @@ TS_D void halo_walk(unsigned* list, float* tile, int pitch, int rows, int cols, 
     }
 }
 
+
+// pooled-gradient kernels: the same walk, with a mode that CLEARS the cells (zeros padding of a tile that was written by
+// pool_expand, not by the copy engine)
+TS_D void halo_walk_z(unsigned* list, float* tile, int pitch, int rows, int cols, int hr, int hc, int pad, const HaloRange& h, int lane,
+                    bool zero = false) {
+    const int nrt = h.rn_lo < 0 ? -h.rn_lo : 0, nrb = h.rn_hi > rows - 1 ? h.rn_hi - (rows - 1) : 0;
+    const int nct = h.cn_lo < 0 ? -h.cn_lo : 0, ncb = h.cn_hi > cols - 1 ? h.cn_hi - (cols - 1) : 0;
+    const int wc = h.cn_hi - h.cn_lo + 1;
+    // the division-free remap is valid for indices within one period of the axis: halo <= hr (hc) < len
+    const bool rb = rows > hr + 1, cb = cols > hc + 1;
+    for (int ri = 0; ri < nrt + nrb; ++ri) {
+        const int r = ri < nrt ? h.rn_lo + ri : rows + (ri - nrt);
+        const int sr = remap_any(r, rows, pad, rb);
+        for (int c = h.cn_lo + lane; c <= h.cn_hi; c += 32) {
+            const unsigned dst = (unsigned)((r + hr) * pitch + c + hc);
+            const unsigned src = zero ? dst : (unsigned)((sr + hr) * pitch + remap_any(c, cols, pad, cb) + hc);
+            if (list) list[ri * wc + (c - h.cn_lo)] = dst | (src << 16); else tile[dst] = zero ? 0.f : tile[src];
+        }
+    }
+    const int nA = (nrt + nrb) * wc;
+    for (int k = 0; k < nct + ncb; ++k) {
+        const int c = k < nct ? h.cn_lo + k : cols + (k - nct);
+        const int sc = remap_any(c, cols, pad, cb);
+        for (int r = lane; r < rows; r += 32) {
+            const unsigned dst = (unsigned)((r + hr) * pitch + c + hc), src = zero ? dst : (unsigned)((r + hr) * pitch + sc + hc);
+            if (list) list[nA + k * rows + r] = dst | (src << 16); else tile[dst] = zero ? 0.f : tile[src];
+        }
+    }
+}
+
+// ZERO: the listed cells are cleared (zeros padding of a tile the copy engine did not fill)
 TS_D void halo_apply(const unsigned* list, int n, float* tile, int lane) {
     // four independent cells in flight per lane in EVERY pass: indices past the end repeat the last cell (the same copy
     // twice is harmless), so a tile costs ceil(n / 128) dependent list -> load -> store round trips, not one per 32 cells
@@ -259,6 +293,56 @@ TS_D void halo_apply(const unsigned* list, int n, float* tile, int lane) {
         const unsigned e0 = list[e], e1 = list[min(e + 32, last)], e2 = list[min(e + 64, last)], e3 = list[min(e + 96, last)];
         const float v0 = tile[e0 >> 16], v1 = tile[e1 >> 16], v2 = tile[e2 >> 16], v3 = tile[e3 >> 16];
         tile[e0 & 0xffffu] = v0; tile[e1 & 0xffffu] = v1; tile[e2 & 0xffffu] = v2; tile[e3 & 0xffffu] = v3;
+    }
+}
+
+
+// pooled-gradient kernels: the cells of a list dealt to `stride` threads (several fixer warps); ZERO clears them
+template <bool ZERO>
+TS_D void halo_apply_m(const unsigned* list, int n, float* tile, int lane, const int stride = 32) {
+    // four independent cells in flight per lane in EVERY pass: indices past the end repeat the last cell (the same copy
+    // twice is harmless), so a tile costs ceil(n / 128) dependent list -> load -> store round trips, not one per 32 cells
+    // (lane: index among the `stride` threads that share the list)
+    for (int e = lane; e < n; e += 4 * stride) {
+        const int last = n - 1;
+        const unsigned e0 = list[e], e1 = list[min(e + stride, last)], e2 = list[min(e + 2 * stride, last)], e3 = list[min(e + 3 * stride, last)];
+        const float v0 = ZERO ? 0.f : tile[e0 >> 16], v1 = ZERO ? 0.f : tile[e1 >> 16], v2 = ZERO ? 0.f : tile[e2 >> 16],
+                    v3 = ZERO ? 0.f : tile[e3 >> 16];
+        tile[e0 & 0xffffu] = v0; tile[e1 & 0xffffu] = v1; tile[e2 & 0xffffu] = v2; tile[e3 & 0xffffu] = v3;
+    }
+}
+
+// Adjoint of avg_pool2d(kernel 2, stride 2, ceil_mode=True) while staging: every element of a pooling window receives the
+// pooled gradient divided by the window's element count (ATen's avg_pool2d_backward: 4, or 2 for the last row of an odd
+// height; /4 and /2 are exact as multiplications).  pooled: dense [PH][PW]; tile: the grad tile, data at (hr, hc).
+TS_D void sts64(unsigned addr, float a, float b) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory"); }
+TS_D void pool_expand(const float* pooled, float* tile, int PH, int PW, int OB, int pitch, int hr, int hc, int lane, int stride,
+                      const FastDivU& dPW) {
+    // A few warps expand a plane between the copy engine and the arithmetic warps, so they must not crawl: shared-window
+    // addresses (no generic stores), a flat index over the pooled cells, four independent cells in flight per thread
+    // (lane: index among the `stride` expanding threads)
+    const unsigned src = shared_addr(pooled), dst = shared_addr(tile) + (unsigned)((hr * pitch + hc) * 4);
+    const int n = PH * PW, pb = pitch * 4;
+    for (int p0 = lane; p0 < n; p0 += 4 * stride) {
+        float v[4];
+        unsigned o[4];
+        bool two[4], on[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int p = p0 + stride * i;
+            on[i] = p < n;
+            const int q = on[i] ? p : 0;
+            const int pr = (int)fdivu((unsigned)q, dPW), pc = q - pr * PW;
+            two[i] = 2 * pr + 1 < OB;
+            o[i] = dst + (unsigned)(2 * pr * pb + 8 * pc);
+            v[i] = __uint_as_float(lds32(src + 4u * (unsigned)q)) * (two[i] ? 0.25f : 0.5f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!on[i]) continue;
+            sts64(o[i], v[i], v[i]);
+            if (two[i]) sts64(o[i] + (unsigned)pb, v[i], v[i]);
+        }
     }
 }
 
@@ -300,8 +384,8 @@ TS_D void wp2(const float* x0, const float* x1, const float* gv, const float* d,
 
 // ---- element-wise routine for channels whose shift does not fit the halo ------------------------
 // (global loads, literal remap; mirrors ts_generic.cu.  All consumer threads of the CTA share the unit.)
-template <int DIM>
-TS_D void fetch8(const float* __restrict__ vol, const int* idx, const int* sizes, int pad, float* v) {
+template <int DIM, class Load>
+TS_D void fetch8f(Load ld, const int* idx, const int* sizes, int pad, float* v) {
     int t[DIM][2];
 #pragma unroll
     for (int ax = 0; ax < DIM; ++ax) {
@@ -318,8 +402,12 @@ TS_D void fetch8(const float* __restrict__ vol, const int* idx, const int* sizes
             ok = ok && i >= 0;
             off = off * sizes[ax] + i;
         }
-        v[q] = ok ? vol[off] : 0.f;
+        v[q] = ok ? ld(off) : 0.f;
     }
+}
+template <int DIM>
+TS_D void fetch8(const float* __restrict__ vol, const int* idx, const int* sizes, int pad, float* v) {
+    fetch8f<DIM>([vol](long long off) { return vol[off]; }, idx, sizes, pad, v);
 }
 
 template <int DIM, bool ACTIVE>
@@ -382,7 +470,7 @@ TS_D void slow_forward(const HArgs& a, int c, int n0, int n1, const UnitShift& u
     }
 }
 
-template <int DIM, bool ACTIVE>
+template <int DIM, bool ACTIVE, bool PBWD>
 TS_D void slow_backward(const HArgs& a, int c, int n0, int n1, const UnitShift& us, int tid, int nt, double* acc) {
     const Geo& g = a.g;
     const int plane = (int)g.in_plane;
@@ -390,10 +478,18 @@ TS_D void slow_backward(const HArgs& a, int c, int n0, int n1, const UnitShift& 
     float d[3] = {us.d[0], us.d[1], us.d[2]};
 #pragma unroll
     for (int ax = 0; ax < DIM; ++ax) { sx[ax] = us.sx[ax + 3 - DIM]; sg[ax] = us.sg[ax + 3 - DIM]; }
+    constexpr bool pool = PBWD;                 // 2-D only: a.grad is the POOLED gradient, expanded on the fly
+    const int PW = a.PW, OL = a.OL, OB = a.OB;
     for (int n = n0; n < n1; ++n) {
         const float* xp = a.x + ((long long)n * g.C + c) * g.in_plane;
-        const float* gp = a.grad + ((long long)n * g.C + c) * g.out_plane;
+        const float* gp = a.grad + ((long long)n * g.C + c) * (pool ? (long long)a.PH * a.PW : g.out_plane);
         float* gip = a.out + ((long long)n * g.C + c) * g.in_plane;
+        // gradient of the shift's output at linear offset `off` of the (cropped) output plane
+        auto gld = [gp, PW, OL, OB](long long off) {
+            if (!pool) return gp[off];
+            const int r = (int)(off / OL), cc = (int)(off - (long long)r * OL), pr = r >> 1;
+            return gp[pr * PW + (cc >> 1)] * (2 * pr + 1 < OB ? 0.25f : 0.5f);
+        };
         for (int e = tid; e < plane; e += nt) {
             int pos[DIM], rem = e, o[DIM];
 #pragma unroll
@@ -408,7 +504,7 @@ TS_D void slow_backward(const HArgs& a, int c, int n0, int n1, const UnitShift& 
             }
             float r = 0.f;
             if (pass) {
-                const float gv = gp[goff];
+                const float gv = gld(goff);
                 int idx[DIM];
 #pragma unroll
                 for (int ax = 0; ax < DIM; ++ax) idx[ax] = pos[ax] - sx[ax];
@@ -420,7 +516,7 @@ TS_D void slow_backward(const HArgs& a, int c, int n0, int n1, const UnitShift& 
                 if (ACTIVE) {
 #pragma unroll
                     for (int ax = 0; ax < DIM; ++ax) idx[ax] = o[ax] - sg[ax];
-                    fetch8<DIM>(gp, idx, g.OS, g.pad, v);
+                    fetch8f<DIM>(gld, idx, g.OS, g.pad, v);
                     r = interpolate<float, DIM>(v, d);
                 } else {
                     bool in = true;
@@ -431,7 +527,7 @@ TS_D void slow_backward(const HArgs& a, int c, int n0, int n1, const UnitShift& 
                         in = in && t >= 0;
                         off = off * g.OS[ax] + t;
                     }
-                    r = in ? gp[off] : 0.f;
+                    r = in ? gld(off) : 0.f;
                 }
             }
             gip[e] = r;
@@ -491,7 +587,7 @@ TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t
                     if ((a.probe & 3) == 2) mbar_arrive(&full[s]);     // no copies, the consumers compute on whatever the stage holds
                     else
 #endif
-                    mbar_expect_tx(&full[s], (unsigned)npl * (unsigned)(a.box_x + (has_g ? a.box_g : 0) + (has_v ? a.box_v : 0)));
+                    mbar_expect_tx(&full[s], (unsigned)npl * (unsigned)(a.box_x + (has_g ? (a.pool_bwd ? a.box_v : a.box_g) : 0) + (has_v ? a.box_v : 0)));
                 }
                 __syncwarp();                              // the slot is free and its byte count posted before any lane copies into it
 #ifdef TS_HALO_PROBE
@@ -500,7 +596,10 @@ TS_D void producer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t
                 for (int job = lane; job < 3 * npl; job += 32) {
                     const int pl = job / 3, what = job - 3 * pl;
                     if (what == 0) tma_load_5d(st + (size_t)pl * a.tile_x, &a.map_x, -a.hc, -a.hr, xs, c, nb + pl, &full[s]);
-                    else if (what == 1) { if (has_g) tma_load_5d(st + a.off_g + (size_t)pl * a.tile_g, &a.map_g, -a.hc, -a.hr, gs, c, nb + pl, &full[s]); }
+                    else if (what == 1) {
+                        if (has_g && a.pool_bwd) tma_load_5d(st + a.off_v + (size_t)pl * a.tile_v, &a.map_v, 0, 0, 0, c, nb + pl, &full[s]);   // pooled grad, dense
+                        else if (has_g) tma_load_5d(st + a.off_g + (size_t)pl * a.tile_g, &a.map_g, -a.hc, -a.hr, gs, c, nb + pl, &full[s]);
+                    }
                     else if (has_v) tma_load_5d(st + a.off_v + (size_t)pl * a.tile_v, &a.map_v, 0, 0, vs, c, nb + pl, &full[s]);
                 }
                 if (++s == a.stages) { s = 0; ++kk; }
@@ -564,6 +663,93 @@ TS_D void fixer(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* r
                     }
                 }
 #ifdef TS_HALO_PROBE
+                if (!(a.probe & 4))
+#endif
+                fence_proxy_async();             // the next TMA load of this stage must not overtake these generic-proxy writes
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready[s]);
+                if (++s == a.stages) { s = 0; phase ^= 1u; }
+            }
+        }
+    }
+}
+
+
+// MULTI: several fixer warps (the pooled-gradient expansion); the single-warp instantiation keeps compile-time strides
+// (with run-time ones the forward of cfg4 lost 20 %: that kernel runs at the pace of its fixer warp).
+template <bool MULTI>
+TS_D void fixer_pool(const HArgs& a, unsigned char* smem, uint64_t* full, uint64_t* ready, int lane, int fw, const UnitShift* tbl, unsigned* lists,
+                const UnitOrder& uo) {
+    // fw: index of this warp among the a.nfix fixer warps (1, or 4 when the pooled gradient is expanded here: they split
+    // the cells of every tile and meet at a named barrier between the expansion and the halo copies that read it)
+    int s = 0, cls = 0;
+    unsigned phase = 0;
+    const int N = (int)a.g.N;
+    const bool bwd = a.mode == 2;
+    const int steps = a.dim == 3 ? a.IA + 1 : 1;
+    const int nf = MULTI ? a.nfix : 1, fl = MULTI ? fw * 32 + lane : lane, fstride = MULTI ? 32 * nf : 32;
+    auto fsync = [nf]() { if (MULTI) named_barrier(1, 32 * nf); else __syncwarp(); };
+    unsigned* list_x = lists;
+    unsigned* list_g = lists + FIXCAP;
+    const bool listable = a.px * a.bpx < 65536 && a.pg * a.bpg < 65536;
+    const UnitRange ur = unit_range(a.units, a.unit_order);
+    for (int u = ur.u; u < ur.end; u += ur.step) {
+        int chunk, c;
+        uo.decode(u, cls, c, chunk, a.unit_order);
+        const int n0 = chunk * a.n_per_unit;
+        const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
+        const UnitShift us = unit_shift(a, tbl, c);
+        if (!unit_geom(a, us).fits) continue;
+        const int xr_lo = (bwd ? 0 : a.lbB) - us.sx[1], xc_lo = (bwd ? 0 : a.lbL) - us.sx[2];
+        const int sgr = a.active ? -us.sg[1] : us.sg[1], sgc = a.active ? -us.sg[2] : us.sg[2], ex = a.active ? 1 : 0;
+        const HaloRange hx = {xr_lo, xr_lo + a.IB, xc_lo, xc_lo + 4 * a.IG};
+        const HaloRange hg = {sgr, a.OB - 1 + sgr + ex, sgc, a.OL - 1 + sgc + ex};
+        const int nx = halo_cells(hx, a.B, a.L), ng = bwd ? halo_cells(hg, a.OB, a.OL) : 0;
+        const bool use_list = listable && nx <= FIXCAP && ng <= FIXCAP;
+        // x tile: the copy engine's zero fill IS the zeros padding.  grad tile of the fused avg-pool backward: written by
+        // pool_expand below, so its reachable halo is cleared (zeros padding) or patched like any other tile.
+        const bool fix_x = a.g.pad != TS_PAD_ZEROS, fix_g = bwd && (fix_x || a.pool_bwd), zero_g = a.pool_bwd && !fix_x;
+        if (use_list) {
+            fsync();                            // every fixer thread is done with the previous unit's lists
+            if (fw == 0) {
+                if (fix_x) halo_walk_z(list_x, nullptr, a.px, a.B, a.L, a.hr, a.hc, a.g.pad, hx, lane);
+                if (fix_g) halo_walk_z(list_g, nullptr, a.pg, a.OB, a.OL, a.hr, a.hc, a.g.pad, hg, lane, zero_g);
+            }
+            fsync();
+        }
+        for (int nb = n0; nb < n1; nb += a.np) {
+            const int npl = n1 - nb < a.np ? n1 - nb : a.np;
+            for (int k = 0; k < steps; ++k) {
+                unsigned char* st = smem + (size_t)s * a.stage_stride + GUARD;
+                const bool has_g = bwd && (a.dim == 2 || a.active || k >= 1);
+                mbar_wait_parked(&full[s], phase);
+#ifdef TS_HALO_PROBE
+                if (!(a.probe & 8)) {
+#endif
+                if (MULTI && a.pool_bwd) {
+                    for (int pl = 0; pl < npl; ++pl)
+                        pool_expand((const float*)(st + a.off_v + (size_t)pl * a.tile_v), (float*)(st + a.off_g + (size_t)pl * a.tile_g), a.PH, a.PW,
+                                    a.OB, a.pg, a.hr, a.hc, fl, fstride, a.d_PW);
+                    fsync();                     // the halo cells below copy from cells other fixer threads have just written
+                }
+                for (int pl = 0; pl < npl; ++pl) {
+                    float* tx = (float*)(st + (size_t)pl * a.tile_x);
+                    float* tg = (float*)(st + a.off_g + (size_t)pl * a.tile_g);
+                    if (use_list) {
+                        if (MULTI) {
+                            if (fix_x) halo_apply_m<false>(list_x, nx, tx, fl, fstride);
+                            if (has_g && fix_g) { if (zero_g) halo_apply_m<true>(list_g, ng, tg, fl, fstride); else halo_apply_m<false>(list_g, ng, tg, fl, fstride); }
+                        } else {
+                            if (fix_x) halo_apply_m<false>(list_x, nx, tx, lane);
+                            if (has_g && fix_g) halo_apply_m<false>(list_g, ng, tg, lane);
+                        }
+                    } else if (fw == 0) {
+                        if (fix_x) halo_walk_z(nullptr, tx, a.px, a.B, a.L, a.hr, a.hc, a.g.pad, hx, lane);
+                        if (has_g && fix_g) halo_walk_z(nullptr, tg, a.pg, a.OB, a.OL, a.hr, a.hc, a.g.pad, hg, lane, zero_g);
+                    }
+                }
+#ifdef TS_HALO_PROBE
+                }
                 if (!(a.probe & 4))
 #endif
                 fence_proxy_async();             // the next TMA load of this stage must not overtake these generic-proxy writes
@@ -938,7 +1124,7 @@ if constexpr (SPLIT) {         // chosen at LAUNCH: both role layouts in one ker
     TS_D void run_unit(unsigned char* smem, Ring& ring, int c, int n0, int n1) {
         if (CLS == 4 && !ug.fits) {
             if (MODE != 2) slow_forward<DIM, MODE == 1, POOL>(a, c, n0, n1, us, tid, nt);
-            else slow_backward<DIM, ACTIVE>(a, c, n0, n1, us, tid, nt, acc);
+            else slow_backward<DIM, ACTIVE, POOL && MODE == 2>(a, c, n0, n1, us, tid, nt, acc);
             return;
         }
         const long long plane_bytes = a.out_plane_bytes;
@@ -985,7 +1171,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs 
     uint64_t* empty = full + a.stages;
     uint64_t* ready = empty + a.stages;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)a.nw); mbar_init(&ready[s], 1); }
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)a.nw); mbar_init(&ready[s], (POOL && MODE == 2) ? (unsigned)a.nfix : 1u); }
         fence_barrier_init();
     }
     const int C = (int)a.g.C;
@@ -1027,7 +1213,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_halo(const __grid_constant__ HArgs 
     const UnitOrder uo = {a.table ? order : nullptr, cend, coff, a.chunks, C};
     if (wid == a.nw) { producer(a, smem, full, empty, tbl, uo, lane); return; }
     if (wid > a.nw) {                                                         // launched only when the padding needs it
-        fixer(a, smem, full, ready, lane, tbl, lists, uo);
+        // (the pooled-gradient expansion and its multi-warp fixer exist only in the POOL && MODE == 2 instantiations: the same
+        // code merely PRESENT in the other kernels changed ptxas' schedule of their hot loops -- cfg4 forward 0.31 -> 0.37 ms)
+        if constexpr (POOL && MODE == 2) fixer_pool<true>(a, smem, full, ready, lane, wid - a.nw - 1, tbl, lists, uo);
+        else fixer(a, smem, full, ready, lane, tbl, lists, uo);
         return;
     }
     Body<DIM, MODE, ACTIVE, SPLIT, POOL, CROP> body(a, threadIdx.x, a.nt, wid, lane, a.need_fix ? ready : full, empty, tbl);
@@ -1046,13 +1235,13 @@ long long round_up(long long v, long long q) { return (v + q - 1) / q * q; }
 template <class K>
 int launch(K kernel, const HArgs& a, const HaloPlan& p, cudaStream_t s) {
     if (!ensure_dynamic_smem((const void*)kernel, p.smem_bytes)) return check_launch();
-    kernel<<<p.grid, (p.warps + 1 + (a.need_fix ? 1 : 0)) * 32, p.smem_bytes, s>>>(a);
+    kernel<<<p.grid, (p.warps + 1 + (a.need_fix ? a.nfix : 0)) * 32, p.smem_bytes, s>>>(a);
     note_launch();
     return check_launch();
 }
 
 bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, int pool, const void* x, const void* grad, void* out, const void* w,
-               double* partials, HArgs* o) {
+               double* partials, HArgs* o, bool pool_bwd = false) {
     HArgs& a = *o;
     memset(&a, 0, sizeof(a));
     const int d = g.dim;
@@ -1086,12 +1275,19 @@ bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, int pool, 
     a.probe = tuning().halo_probe;
     a.pool = pool;
     a.out_plane_bytes = pool ? (long long)((a.OB + 1) / 2) * (a.OL / 2) * 4 : (mode == 2 ? g.in_plane : g.out_plane) * 4;
-    a.need_fix = g.pad != TS_PAD_ZEROS;
+    a.pool_bwd = pool_bwd ? 1 : 0;
+    a.PH = (a.OB + 1) / 2; a.PW = a.OL / 2;
+    a.need_fix = g.pad != TS_PAD_ZEROS || pool_bwd;
+    a.nfix = pool_bwd ? 4 : 1;
+    if (pool_bwd) a.box_v = a.PW * a.PH * 4;
+    a.d_PW = make_fastdivu((unsigned)(a.PW > 0 ? a.PW : 1));
     a.split = 0;      // (the role-split 3-D backward -- x-window warps and grad-window warps -- measured 1.7x slower and is no longer built)
     a.d_GP = make_fastdivu((unsigned)a.GP);
     a.d_img = make_fastdivu((unsigned)a.img_pairs);
     if (!make_tensor_map5(&a.map_x, x, 4, g.N, g.C, a.A, a.B, a.L, a.px, a.bpx, 1, 1)) return false;
-    if (mode == 2) {
+    if (mode == 2 && pool_bwd) {
+        if (!make_tensor_map5(&a.map_v, grad, 4, g.N, g.C, 1, a.PH, a.PW, a.PW, a.PH, 1, 1)) return false;
+    } else if (mode == 2) {
         if (!make_tensor_map5(&a.map_g, grad, 4, g.N, g.C, a.OA, a.OB, a.OL, a.pg, a.bpg, 1, 1)) return false;
         if (d == 3 && !make_tensor_map5(&a.map_v, grad, 4, g.N, g.C, a.OA, a.OB, a.OL, a.OL, a.OB, 1, 1)) return false;
     }
@@ -1102,7 +1298,7 @@ bool make_args(const Geo& g, const HaloPlan& p, int mode, int active, int pool, 
 
 // ---- planning -----------------------------------------------------------------------------------
 HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, const void* x, const void* out, const void* grad,
-                   int sm_count, bool forced) {
+                   int sm_count, bool forced, bool pool_bwd) {
     HaloPlan p;
     memset(&p, 0, sizeof(p));
     p.ok = false;
@@ -1116,6 +1312,7 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     const int B = g.S[d - 2], L = g.S[d - 1];
     const int OB = g.OS[d - 2], OL = g.OS[d - 1];
     if (L % 4 || OL % 4) return p;
+    if (pool_bwd && (mode != 2 || d != 2 || OL % 8)) return p;      // pooled rows of a multiple of 16 bytes (TMA)
     if (((uintptr_t)x & 15) || ((uintptr_t)out & 15) || ((uintptr_t)grad & 15)) return p;
     if (g.N >= (1ll << 31) || g.C >= (1ll << 31)) return p;
     if (g.in_plane * 4 >= (1ll << 40) / (g.C > 0 ? g.C : 1)) return p;
@@ -1132,14 +1329,16 @@ HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, 
     p.tile_x = (int)round_up((long long)p.px * p.bpx * 4, 128);
     p.tile_g = mode == 2 ? (int)round_up((long long)p.pg * p.bpg * 4, 128) : 0;
     p.tile_v = (mode == 2 && d == 3) ? (int)round_up((long long)OL * OB * 4, 128) : 0;
+    p.tile_p = pool_bwd ? (int)round_up((long long)((OB + 1) / 2) * (OL / 2) * 4, 128) : 0;
+    if (pool_bwd) p.tile_v = p.tile_p;
     const long long per_image = (long long)p.tile_x + p.tile_g + p.tile_v;
     const int IB = mode == 2 ? B : OB, IG = (mode == 2 ? L : OL) / 4;
     int GP = IG;
     if (IG % 8 != 0 && (double)IG / (double)((IG + 7) / 8 * 8) >= 0.85) GP = (IG + 7) / 8 * 8;
     if (d == 3 && t.halo_compact && ((IB + 1) / 2 * IG + 31) / 32 < ((IB + 1) / 2 * GP + 31) / 32) GP = IG;   // one warp fewer
     const int img_pairs = (IB + 1) / 2 * GP;
-    const int max_nt = MAXT - 64;                          // producer warp + fixer warp
-    const long long table_bytes = (g.C <= TABLE_MAX_C ? g.C * 36 : 0) + (g.pad != TS_PAD_ZEROS ? 2 * FIXCAP * 4 : 0)      // + the fixer's cell lists
+    const int max_nt = MAXT - 64 - (pool_bwd ? 96 : 0);    // producer warp + fixer warp(s)
+    const long long table_bytes = (g.C <= TABLE_MAX_C ? g.C * 36 : 0) + ((g.pad != TS_PAD_ZEROS || pool_bwd) ? 2 * FIXCAP * 4 : 0)      // + the fixer's cell lists
                                   + (2 * NCLS + 1) * 4 + (g.C <= TABLE_MAX_C ? g.C * 3 : 0) + 16;                             // + the class order
     const long long budget = SMEM_LIMIT - 1024 - table_bytes;
     long long np;
@@ -1215,12 +1414,19 @@ int halo_forward2d(const Geo& g, const HaloPlan& p, int active, int pool, const 
 }
 
 int halo_backward(const Geo& g, const HaloPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
-                  double* partials, const ts_peer_group* peers, cudaStream_t s) {
+                  double* partials, const ts_peer_group* peers, cudaStream_t s, bool pool_bwd) {
     HArgs a;
-    if (!make_args(g, p, 2, active ? 1 : 0, 0, x, grad, gi, w, partials, &a)) return TS_ERR_UNSUPPORTED;
+    if (!make_args(g, p, 2, active ? 1 : 0, 0, x, grad, gi, w, partials, &a, pool_bwd)) return TS_ERR_UNSUPPORTED;
     int rc;
     bool crop = false;
     for (int ax = 0; ax < g.dim; ++ax) crop = crop || g.lb[ax] != 0 || g.OS[ax] != g.S[ax];
+    if (pool_bwd) {
+        if (g.dim != 2) return TS_ERR_UNSUPPORTED;
+        if (active) rc = crop ? launch(k_halo<2, 2, true, false, true, true>, a, p, s) : launch(k_halo<2, 2, true, false, true, false>, a, p, s);
+        else rc = crop ? launch(k_halo<2, 2, false, false, true, true>, a, p, s) : launch(k_halo<2, 2, false, false, true, false>, a, p, s);
+        if (rc != TS_OK) return rc;
+        return launch_reduce_partials<float>(partials, p.slots, (int)(g.C * g.dim), gw, peers, s);
+    }
     switch (g.dim * 2 + (active ? 1 : 0) + (crop ? 8 : 0)) {
     case 4: rc = launch(k_halo<2, 2, false, false, false, false>, a, p, s); break;
     case 5: rc = launch(k_halo<2, 2, true, false, false, false>, a, p, s); break;

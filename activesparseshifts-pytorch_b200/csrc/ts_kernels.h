@@ -156,17 +156,20 @@ struct HaloPlan {
     int hr, hc;                 // halo rows / columns on each side of a staged slab
     int px, bpx, pg, bpg;       // row pitch (elements) and rows of the x / grad tiles in shared memory
     int tile_x, tile_g, tile_v; // bytes per tile (128-byte multiples); tile_v: dense grad slab (3-D backward)
+    int tile_p;                 // pooled-gradient tile of the fused avg-pool backward (0 otherwise)
     int np, GP, positions, ncol;
     int stages, stage_stride, warps, n_per_unit, units, grid, slots;
     size_t smem_bytes;
 };
 // mode: 0 sparse forward (2-D only), 1 active forward, 2 backward (active = interpolating backward).  fp32, dims 2 and 3,
 // every padding, border crops.
+// pool_bwd (mode 2, 2-D): `grad` is the gradient of the 2x2 / stride-2 / ceil_mode average pooling of the shift's output;
+// the kernel expands it while staging (ts_shift2d_avgpool2_backward).
 HaloPlan plan_halo(const Geo& g, int mode, int active, int dtype, bool dense_x, const void* x, const void* out, const void* grad,
-                   int sm_count, bool forced);
+                   int sm_count, bool forced, bool pool_bwd = false);
 int halo_active_forward(const Geo& g, const HaloPlan& p, const void* x, const void* w, void* y, cudaStream_t s);
 int halo_forward2d(const Geo& g, const HaloPlan& p, int active, int pool, const void* x, const void* w, void* y, cudaStream_t s);
 int halo_backward(const Geo& g, const HaloPlan& p, int active, const void* grad, const void* x, const void* w, void* gi, void* gw,
-                  double* partials, const ts_peer_group* peers, cudaStream_t s);
+                  double* partials, const ts_peer_group* peers, cudaStream_t s, bool pool_bwd = false);
 
 }  // namespace ts

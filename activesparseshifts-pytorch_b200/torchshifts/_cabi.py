@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     'ts_set_kernel_path', 'ts_launch_count', 'ts_set_tuning', 'ts_check_borders', 'ts_debug_remap',
     'ts_debug_remap_reduced', 'ts_debug_split_f32', 'ts_debug_split_f64', 'ts_shift_forward',
     'ts_shift_backward_workspace_bytes', 'ts_shift_backward', 'ts_qshift_forward', 'ts_shift_backward_allreduce',
-    'ts_qshift_forward_nhwc', 'ts_debug_nhwc_emulate', 'ts_nhwc_to_nchw', 'ts_shift2d_avgpool2_forward',
+    'ts_qshift_forward_nhwc', 'ts_debug_nhwc_emulate', 'ts_nhwc_to_nchw', 'ts_shift2d_avgpool2_forward', 'ts_shift2d_avgpool2_backward',
 )
 
 
@@ -77,6 +77,7 @@ class NativeLibrary:
             'ts_shift2d_avgpool2_forward': (i, [gp, i, i, i, vp, vp, vp, vp]),
             'ts_shift_backward_workspace_bytes': (sz, [gp, i]),
             'ts_shift_backward': (i, [gp, i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]),
+            'ts_shift2d_avgpool2_backward': (i, [gp, i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]),
             'ts_qshift_forward': (i, [gp, i, i, i64, vp, vp, i, i64, vp, vp]),
             'ts_qshift_forward_nhwc': (i, [gp, i, i, i64, vp, vp, i, i64, vp, vp]),
             'ts_debug_nhwc_emulate': (i, [gp, i, i, i64, vp, vp, i, i64, vp, i, i, i, i]),

@@ -223,12 +223,52 @@ def _pool_setup_context(ctx, inputs, output):
 
 
 def _pool_backward(ctx, grad_pooled):
-    # adjoint of the pooling (every window element receives grad / count), then the shift backward
     input, weights, borders = ctx.saved_tensors
-    like = torch.empty(ctx.new_size, dtype=grad_pooled.dtype, device=grad_pooled.device)
-    grad_y = torch.ops.aten.avg_pool2d_backward(grad_pooled.contiguous(), like, [2, 2], [2, 2], [0, 0], True, True, None)
-    grad_input, grad_weight = torch.ops.torchshifts._shift2d_backward(grad_y, weights, input, borders, ctx.padding_mode, ctx.active_flag)
+    op = torch.ops.torchshifts._shift2d_avgpool2_backward
+    grad_input, grad_weight = op(grad_pooled, weights, input, borders, ctx.new_size, ctx.padding_mode, ctx.active_flag)
     return grad_input, grad_weight, None, None, None, None
+
+
+def _pool_backward_cuda(grad_pooled, weights, input, borders, new_size, padding_mode, active_flag):
+    """Backward of the fused shift + avg_pool2d(2, 2, ceil_mode): ONE kernel (ts_shift2d_avgpool2_backward) that expands the
+    pooled gradient while staging it -- the full-size gradient of the shift's output never exists in HBM.  Shapes the fused
+    kernel does not serve take ATen's avg_pool2d_backward followed by the shift backward (same values)."""
+    fn = 'shift2d_avgpool2_backward'
+    _check_mode(padding_mode)
+    _same_device_and_type(fn, input, weights, grad_pooled)
+    lb, rb = _borders_lists(borders, 2)
+    oh, ow = rb[0] - lb[0], rb[1] - lb[1]
+    if list(grad_pooled.shape) != [input.shape[0], input.shape[1], (oh + 1) // 2, (ow + 1) // 2]:
+        raise RuntimeError(f'{fn}: grad has shape {list(grad_pooled.shape)}, the pooled output is '
+                           f'{[input.shape[0], input.shape[1], (oh + 1) // 2, (ow + 1) // 2]}')
+    if input.dtype == torch.float32 and input.is_contiguous() and ow % 8 == 0 and input.dim() == 4 and input.numel() > 0:
+        grad = grad_pooled.contiguous()
+        w = weights.contiguous()
+        out_grad = torch.empty(input.shape, dtype=input.dtype, device=input.device)
+        weights_grad = torch.empty(w.shape, dtype=w.dtype, device=w.device)
+        geo, key = _geometry(2, input, lb, rb)
+        dev = input.device
+        with _guard(dev):
+            for attempt in (0, 1):
+                nbytes = _workspace_bytes(geo, key, 0, dev)
+                workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+                st = _NATIVE.lib.ts_shift2d_avgpool2_backward(ct.byref(geo), 0, int(padding_mode), int(bool(active_flag)), grad.data_ptr(),
+                                                              input.data_ptr(), w.data_ptr(), out_grad.data_ptr(), weights_grad.data_ptr(),
+                                                              workspace.data_ptr(), nbytes, _stream(dev))
+                if st != 3:
+                    break
+                _WS_CACHE.clear()
+        if st == 0:
+            return out_grad, weights_grad
+        if st != 2:        # TS_ERR_UNSUPPORTED: fall through to the two-step path
+            _NATIVE.check(st, 'ts_shift2d_avgpool2_backward')
+    like = torch.empty(list(new_size), dtype=grad_pooled.dtype, device=grad_pooled.device)
+    grad_y = torch.ops.aten.avg_pool2d_backward(grad_pooled.contiguous(), like, [2, 2], [2, 2], [0, 0], True, True, None)
+    return _backward_cuda(2, grad_y, weights, input, borders, padding_mode, active_flag)
+
+
+def _pool_backward_meta(grad_pooled, weights, input, borders, new_size, padding_mode, active_flag):
+    return input.new_empty(input.shape), weights.new_empty(weights.shape)
 
 
 def _backward_cuda(dim, grad, weights, input, borders, padding_mode, active_flag):
@@ -450,4 +490,11 @@ def register(native):
     lib.impl(pool, _no_cpu, 'CPU')
     torch.library.register_fake(f'torchshifts::{pool}', _pool_forward_meta, lib=lib)
     torch.library.register_autograd(f'torchshifts::{pool}', _pool_backward, setup_context=_pool_setup_context, lib=lib)
+    poolb = '_shift2d_avgpool2_backward'
+    lib.define(f'{poolb}(Tensor grad, Tensor weights, Tensor input, Tensor borders, int[] new_size, int padding_mode, '
+               f'bool active_flag) -> (Tensor, Tensor)')
+    lib.impl(poolb, _pool_backward_cuda, 'CUDA')
+    lib.impl(poolb, _no_cpu, 'CPU')
+    torch.library.register_fake(f'torchshifts::{poolb}', _pool_backward_meta, lib=lib)
+    torch.library.register_autograd(f'torchshifts::{poolb}', _double_backward, setup_context=_setup_backward_context, lib=lib)
     _LIB = lib

@@ -127,6 +127,19 @@ int ts_shift2d_avgpool2_forward(const ts_geometry* g, int dtype, int padding, in
 
 size_t ts_shift_backward_workspace_bytes(const ts_geometry* g, int dtype);
 
+/* Backward of ts_shift2d_avgpool2_forward in ONE pass: grad_pooled is the gradient of the pooled output, dense
+ * [N, C, ceil(O0/2), O1/2]; the adjoint of the pooling (ATen's avg_pool2d_backward: every element of a window receives
+ * grad / count) is applied while the gradient is staged in shared memory, so the full-size gradient of the shift's output
+ * is never written to or read from HBM (2.25 instead of 4.25 tensor passes for the layer's backward).  g describes the
+ * SHIFT (x sizes, crop), exactly as for the forward; grad_input / grad_weight / workspace as for ts_shift_backward (the same
+ * ts_shift_backward_workspace_bytes).  fp32, dim 2, dense x, O1 a multiple of 8, planes that fit a stage: otherwise
+ * TS_ERR_UNSUPPORTED (callers then expand with avg_pool2d_backward and call ts_shift_backward).  Replaces the pair
+ * at::avg_pool2d_backward + shiftnd_backward of modules/shifts.py:85-89 on that path. */
+int ts_shift2d_avgpool2_backward(const ts_geometry* g, int dtype, int padding, int active,
+                                 const void* grad_pooled, const void* x, const void* weights,
+                                 void* grad_input, void* grad_weight,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* grad: dense [N,C,rb-lb]; grad_input: dense like x's logical shape; grad_weight: dense [C,dim]
  * in `dtype`, fully overwritten (deterministic two-pass reduction, no atomics).
  * workspace: >= ts_shift_backward_workspace_bytes(), 16-byte aligned. */

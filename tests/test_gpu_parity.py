@@ -644,7 +644,9 @@ def test_fused_avgpool_epilogue(dev, lib, oracle_port, auto_path):
     for shape, pad_name, active, ks, conv_pad, fused in [((2, 8, 16, 16), 'zeros', False, 3, 1, True), ((2, 8, 15, 20), 'reflect', True, 3, 1, True),
                                                          ((3, 4, 18, 28), 'periodic', False, 5, 0, True), ((2, 4, 17, 16), 'symmetric', True, 5, 0, True),
                                                          ((2, 6, 16, 24), 'border', True, 3, 1, True), ((2, 4, 9, 22), 'zeros', True, 3, 1, False),
-                                                         ((2, 4, 18, 26), 'reflect', False, 3, 0, False)]:
+                                                         ((2, 4, 18, 26), 'reflect', False, 3, 0, False), ((2, 4, 17, 24), 'symmetric', True, 3, 1, True),
+                                                         ((2, 4, 19, 44), 'zeros', True, 5, 0, True), ((3, 5, 21, 40), 'periodic', False, 3, 1, True),
+                                                         ((2, 3, 56, 56), 'zeros', False, 3, 1, True), ((2, 3, 31, 36), 'reflect', True, 5, 0, True)]:
         torch.manual_seed(3)
         m = torchshifts.Shift2d(shape[1], padding=pad_name, active_flag=active, sparsity_term=0,
                                 emulate_dw={'kernel_size': ks, 'stride': 2, 'padding': conv_pad}).to(dev)
@@ -676,10 +678,32 @@ def test_fused_avgpool_epilogue(dev, lib, oracle_port, auto_path):
         two = torch.nn.functional.avg_pool2d(shift2d_func(x2, w2, pad, active, m.cut_borders), 2, 2, ceil_mode=True)
         assert torch.equal(two, out)
         g = torch.from_numpy(rng.standard_normal(want.shape).astype(np.float32)).to(dev)
+        before = lib.ts_launch_count()
         out.backward(g)
+        # the fused backward (pooling adjoint applied while the gradient is staged: needs pooled rows of a multiple of 16 bytes)
+        # is ONE shift kernel + the pass-2 reduction; otherwise ATen's avg_pool2d_backward runs first
+        if fused and ow % 8 == 0:
+            assert lib.ts_launch_count() - before == 2, (shape, lib.ts_launch_count() - before)
+            # (the kernel path is recorded per thread and autograd ran the backward on its own: ask the operator directly)
+            std = torch.tensor([0, shape[2], 0, shape[3], 0, 1], dtype=torch.int32)
+            if borders is not None:
+                std = torch.tensor([borders[0][0], shape[2] - borders[0][1], borders[1][0], shape[3] - borders[1][1], 0, 1], dtype=torch.int32)
+            lib.ts_set_kernel_path(1); lib.ts_set_kernel_path(0)
+            gi_d, gw_d = torch.ops.torchshifts._shift2d_avgpool2_backward(g, m.weight.detach(), xd.detach(), std, list(y.shape), pad, active)
+            assert lib.ts_last_kernel_path() == HALO, (shape, lib.ts_last_kernel_path())
+            assert torch.equal(gi_d, xd.grad) and torch.equal(gw_d, m.weight.grad)
         two.backward(g)
-        assert torch.equal(xd.grad, x2.grad)
+        assert torch.equal(xd.grad, x2.grad), (shape, pad_name, active)
         assert torch.allclose(m.weight.grad, w2.grad, rtol=1e-5, atol=1e-6)
+        # and against the oracle: pooling adjoint in numpy (grad / count to every element of the window), then the shift backward
+        gy = np.zeros(y.shape, np.float32)
+        gp = g.cpu().numpy()
+        for i in range(oh):
+            cnt = np.float32((2 if 2 * (i // 2) + 1 < oh else 1) * 2)
+            gy[:, :, i, :] = np.repeat(gp[:, :, i // 2, :], 2, axis=-1)[..., :ow] / cnt
+        if ow % 2 == 0:
+            gi_ref, _ = oracle_port.backward(gy, x, w, pad, active, borders)
+            assert np.array_equal(xd.grad.cpu().numpy(), gi_ref), (shape, pad_name, active)
 
 
 def test_cuda_graph_capture_and_replay(dev, lib, oracle_port, auto_path):
