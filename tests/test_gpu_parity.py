@@ -452,6 +452,17 @@ def test_full_size_cfg2_shift1d_active_periodic(dev, lib, oracle_port, auto_path
     shift1d_func(x[:2], wq, 2, True).backward(g[:2])
     _, gw64 = oracle_port.backward(g[:2].double().cpu().numpy(), x[:2].double().cpu().numpy(), w.detach().double().cpu().numpy(), 2, True)
     assert _gw_close(wq.grad.cpu().numpy(), gw64)
+    # bf16 at FULL size (the named configuration): fp32 arithmetic on the bf16 values, one rounding at the store -- so
+    # forward and grad_input equal the fp32 oracle rounded once, bit for bit, on the sampled images
+    xf, wf, gf = x.bfloat16(), w.detach().bfloat16(), g.bfloat16()
+    xfr, wfr = xf.clone().requires_grad_(True), wf.clone().requires_grad_(True)
+    yf = shift1d_func(xfr, wfr, 2, True)
+    yf.backward(gf)
+    for n in (0, 37, 63):
+        xs, gs, ws = xf[n:n + 1].float().cpu().numpy(), gf[n:n + 1].float().cpu().numpy(), wf.float().cpu().numpy()
+        assert torch.equal(yf[n:n + 1].detach().cpu(), torch.from_numpy(oracle_port.forward(xs, ws, 2, True)).bfloat16()), n
+        assert torch.equal(xfr.grad[n:n + 1].cpu(), torch.from_numpy(oracle_port.backward(gs, xs, ws, 2, True)[0]).bfloat16()), n
+    del xf, gf, xfr, yf
     # bf16 variant against the fp32 oracle on rounded inputs
     xb, wb, gb = x[:4].bfloat16(), w.detach().bfloat16(), g[:4].bfloat16()
     xbr, wbr = xb.clone().requires_grad_(True), wb.clone().requires_grad_(True)
@@ -896,6 +907,31 @@ def test_quantized_channels_last_native_kernel(dev, lib, oracle_port, auto_path)
                 lib.ts_set_tuning(b"nhwc_variant=0,nhwc_ring_rows=0")
                 # the planar path on the same tensor gives the same integers
                 assert np.array_equal(fn(xq, qw, pad, cut).int_repr().cpu().numpy(), want)
+
+
+def test_quantized_degenerate_zero_scale_weights(dev, oracle_port, auto_path):
+    """all-equal float weights give quantize_shift_weights a scale of 0.  torch then stores an integer
+    representation of all 0 when the weights are quantized on the CPU (where the reference's quantized modules live: every
+    channel shifts by 0 - 128 = -128) and all 255 when they are quantized on a CUDA device (+127); the kernels consume
+    whatever integers the tensor holds, exactly like the reference's `weights.int_repr().long() - zero_point`."""
+    from torchshifts.quantized.functional import shift2d_quantized
+    from torchshifts.quantized.modules.shifts import quantize_shift_weights
+    from oracle.oracle import quantize_shift_weights_np
+    rng = np.random.default_rng(77)
+    w = torch.full((6, 2), 1.25)
+    raw_cpu, wzp = quantize_shift_weights_np(w.numpy())
+    assert wzp == 128 and not raw_cpu.any()
+    xr = rng.integers(0, 255, size=(2, 6, 12, 20), endpoint=True).astype(np.uint8)
+    xq = torch._make_per_tensor_quantized_tensor(torch.from_numpy(xr).to(dev), 0.05, 7)
+    for qw in (quantize_shift_weights(w).to(dev), quantize_shift_weights(w.to(dev))):
+        assert qw.q_scale() == 0 and qw.q_zero_point() == 128
+        raw = qw.int_repr().cpu().numpy().astype(np.int64)
+        assert len(np.unique(raw)) == 1 and int(raw.flat[0]) in (0, 255)
+        for pad in range(5):
+            want = oracle_port.qforward(xr, raw, 128, 7, pad)
+            for t in (xq, xq.contiguous(memory_format=torch.channels_last)):
+                assert np.array_equal(shift2d_quantized(t, qw, pad).int_repr().cpu().numpy(), want), (pad, int(raw.flat[0]))
+    assert not quantize_shift_weights(w).int_repr().any()          # the CPU behaviour SURVEY a15 records
 
 
 def test_full_size_cfg5_channels_last(dev, lib, oracle_port, auto_path):
