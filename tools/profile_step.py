@@ -18,7 +18,7 @@ shape, dim, pad, active = {"cfg3": ((256, 256, 56, 56), 2, 0, False), "cfg2": ((
                            "cfg4": ((32, 128, 16, 56, 56), 3, 0, True), "cfg1": ((8, 64, 32, 32), 2, 0, False),
                            "cfg4r": ((32, 128, 16, 56, 56), 3, 3, True), "cfg3r": ((256, 256, 56, 56), 2, 3, False),
                            "cfg2z": ((64, 512, 4096), 1, 0, True), "cfg3n32": ((32, 256, 56, 56), 2, 0, False),
-                           "cfg3ra": ((256, 256, 56, 56), 2, 3, True), "cfg5": ((256, 256, 56, 56), 2, 0, False), "cfg2h": ((64, 512, 4096), 1, 2, True), "cfg4b": ((32, 128, 16, 56, 56), 3, 1, True)}[cfg]
+                           "cfg3ra": ((256, 256, 56, 56), 2, 3, True), "cfg5": ((256, 256, 56, 56), 2, 0, False), "cfg5cl": ((256, 256, 56, 56), 2, 0, False), "cfg4": ((32, 128, 16, 56, 56), 3, 0, True), "cfg2h": ((64, 512, 4096), 1, 2, True), "cfg4b": ((32, 128, 16, 56, 56), 3, 1, True)}[cfg]
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 x = torch.randn(shape, device=dev)
@@ -29,10 +29,12 @@ borders = torch.tensor([0, sp[0], 0, sp[1], 0, sp[2]], dtype=torch.int32)
 fwd = getattr(torch.ops.torchshifts, f"_shift{dim}d_forward")
 bwd = getattr(torch.ops.torchshifts, f"_shift{dim}d_backward")
 with torch.no_grad():
-    if cfg == "cfg5":
+    if cfg in ("cfg5", "cfg5cl"):
         from torchshifts.quantized.modules.shifts import quantize_shift_weights
         xq = torch.quantize_per_tensor(torch.rand(shape, device=dev), 1 / 255., -128, torch.qint8)
         qw = quantize_shift_weights(w * 3)
+        if cfg == "cfg5cl":
+            xq = xq.contiguous(memory_format=torch.channels_last)
         for _ in range(steps):
             y = fwd(xq, qw, borders, list(shape), pad, False)
     else:
