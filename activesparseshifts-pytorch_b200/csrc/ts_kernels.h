@@ -100,6 +100,7 @@ struct StagedPlan {
     bool ok;           // staged path applicable
     int vec_bytes;     // bytes per thread item (16 / 8 / 4)
     int planes_per_step, stages, stage_stride, warps, grid, units, n_per_unit, slots;  // slots = partial slots (backward)
+    bool table;        // per-channel shift parameters tabulated in shared memory
     int ta, tiles;     // slabs per tile (3-D volumes are tiled over their first axis), tiles per image
     int xs, gvs, gis;  // slab slots per image: x, grad at the output position, grad for grad_input (0: shares gvs)
     int gp;            // padded items per row of the item index space

@@ -117,6 +117,7 @@ struct SArgs {
     int slab_x, slab_g;                       // bytes of one slab of x / of grad
     int np, stages, stage_stride, nw, n_per_unit, units, chunks, unit_order;
     int off_gv, off_gi;                       // byte offsets of the grad regions inside a stage (after GUARD)
+    int table;                                // per-channel shift parameters tabulated in shared memory (arithmetic kernels, C <= 512)
     int img_items;                            // TA * IB * GP
     long long img_stride;                     // output bytes between consecutive images of one channel
     FastDiv d_img, d_GP, d_IB;
@@ -169,6 +170,11 @@ TS_D UnitShift unit_shift(const SArgs& a, long long c) {
     return u;
 }
 
+// Tabulated once per CTA (like the TMA and halo families): the split + reduction of a weight is a few hundred dependent
+// instructions (64-bit conversions and a 64-bit modulo), paid per UNIT by every consumer warp and -- on the critical path of
+// the pipeline -- by the producer, whose next copies waited for it at every unit boundary.
+TS_D UnitShift unit_shift_t(const SArgs& a, const UnitShift* tbl, long long c) { return tbl ? tbl[c] : unit_shift(a, c); }
+
 // ---- producer ---------------------------------------------------------------------------------
 // slab held by slot k of the three regions for tile origin a0 (negative: nothing to copy -> zeros padding)
 TS_D int x_slot_slab(const SArgs& a, const UnitShift& us, int a0, int k) {
@@ -191,7 +197,7 @@ TS_D int gi_slot_slab(const SArgs& a, const UnitShift& us, int a0, int k) {
 // The whole producer WARP runs this: lane 0 waits for the slot and posts the byte count, then the copies of a stage are
 // dealt to the lanes (one elected thread spent ~40 instructions per copy on addresses at single-thread issue rates:
 // with many small slabs per stage -- 16-bit rows, 12 copies of 8 KB -- the consumers waited for the producer, not for HBM).
-TS_D void producer(const SArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int lane) {
+TS_D void producer(const SArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int lane, const UnitShift* tbl) {
     int s = 0, k = 0;
     const int C = (int)a.g.C, N = (int)a.g.N;
     const int per_img = a.xs + (a.mode == 2 ? a.gvs + a.gis : 0);
@@ -201,7 +207,7 @@ TS_D void producer(const SArgs& a, unsigned char* smem, uint64_t* full, uint64_t
         unit_decode(u, C, a.chunks, a.unit_order, c, chunk);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
-        const UnitShift us = unit_shift(a, c);
+        const UnitShift us = unit_shift_t(a, tbl, c);
         for (int nb = n0; nb < n1; nb += a.np) {
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
             for (int t = 0; t < a.tiles; ++t) {
@@ -848,10 +854,11 @@ struct ActiveFwdBody {
     int R, nchunk;        // rows per strip / strips per column of the interior box (per unit)
     UDiv d_nchunk;
     LineWalk lw;          // DIM == 1 only
+    const UnitShift* tbl = nullptr;
 
     TS_D ActiveFwdBody(const SArgs& a_, int tid_, int nt_) : a(a_), tid(tid_), nt(nt_), any_interior(false), R(1), nchunk(1) {}
     TS_D void begin_unit(int c) {
-        us = unit_shift(a, c);
+        us = unit_shift_t(a, tbl, c);
         // rows: 0 <= ob + lbB - s1, ob + lbB - s1 + 1 <= B-1 ; groups: 0 <= cs, cs + V + 1 <= L
         in.b_lo = us.sx[1] - a.lbB;
         in.b_hi = a.B - 1 - a.lbB + us.sx[1];
@@ -1068,13 +1075,14 @@ struct BackwardBody {
     int R, nchunk;        // rows per strip / strips per column of the interior box (per unit)
     UDiv d_nchunk;
     LineWalk lw;          // DIM == 1 only
+    const UnitShift* tbl = nullptr;
     double acc[DIM];
 
     TS_D BackwardBody(const SArgs& a_, int tid_, int nt_, int wid_, int lane_)
         : a(a_), tid(tid_), nt(nt_), wid(wid_), lane(lane_), any_interior(false) {}
 
     TS_D void begin_unit(int c) {
-        us = unit_shift(a, c);
+        us = unit_shift_t(a, tbl, c);
 #pragma unroll
         for (int k = 0; k < DIM; ++k) acc[k] = 0.0;
         // rows (input row ib, output row ob = ib - lbB):
@@ -1553,23 +1561,29 @@ struct BackwardBody {
 };
 
 // ---- kernels -----------------------------------------------------------------------------------
-TS_D void setup_barriers(const SArgs& a, unsigned char* smem, uint64_t*& full, uint64_t*& empty) {
+TS_D const UnitShift* setup_barriers(const SArgs& a, unsigned char* smem, uint64_t*& full, uint64_t*& empty) {
     full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
     empty = full + a.stages;
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)a.nw); }
         fence_barrier_init();
     }
+    UnitShift* tbl = nullptr;
+    if (a.table) {
+        tbl = (UnitShift*)(empty + a.stages);
+        for (int c = threadIdx.x; c < (int)a.g.C; c += blockDim.x) tbl[c] = unit_shift(a, c);
+    }
     __syncthreads();
+    return tbl;
 }
 
 template <int G, int ES>
 __global__ void __launch_bounds__(MAXT_GATHER, 1) k_staged_gather(const __grid_constant__ SArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    setup_barriers(a, smem, full, empty);
+    const UnitShift* tbl = setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { producer(a, smem, full, empty, lane); return; }
+    if (wid == a.nw) { producer(a, smem, full, empty, lane, tbl); return; }
     GatherBody<G, ES> body(a, threadIdx.x, a.nw * 32);
     consumer_loop(a, smem, full, empty, lane, body);
 }
@@ -1578,10 +1592,11 @@ template <typename ST, int DIM>
 __global__ void __launch_bounds__(MAXT_ARITH, 1) k_staged_active_forward(const __grid_constant__ SArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    setup_barriers(a, smem, full, empty);
+    const UnitShift* tbl = setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { producer(a, smem, full, empty, lane); return; }
+    if (wid == a.nw) { producer(a, smem, full, empty, lane, tbl); return; }
     ActiveFwdBody<ST, DIM> body(a, threadIdx.x, a.nw * 32);
+    body.tbl = tbl;
     consumer_loop(a, smem, full, empty, lane, body);
 }
 
@@ -1589,10 +1604,11 @@ template <typename ST, int DIM, bool ACTIVE>
 __global__ void __launch_bounds__(MAXT_ARITH, 1) k_staged_backward(const __grid_constant__ SArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    setup_barriers(a, smem, full, empty);
+    const UnitShift* tbl = setup_barriers(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { producer(a, smem, full, empty, lane); return; }
+    if (wid == a.nw) { producer(a, smem, full, empty, lane, tbl); return; }
     BackwardBody<ST, DIM, ACTIVE> body(a, threadIdx.x, a.nw * 32, wid, lane);
+    body.tbl = tbl;
     consumer_loop(a, smem, full, empty, lane, body);
 }
 
@@ -1638,6 +1654,7 @@ SArgs make_args(const Geo& g, const StagedPlan& p, int mode, int active, int es)
     a.unit_order = tuning().unit_order;
     a.off_gv = p.off_gv;
     a.off_gi = p.off_gi;
+    a.table = p.table ? 1 : 0;
     a.img_items = a.TA * a.IB * a.GP;
     a.img_stride = g.C * (mode == 2 ? g.in_plane : g.out_plane) * es;
     a.d_img = make_fastdiv((unsigned)a.img_items);
@@ -1680,7 +1697,8 @@ StagedPlan plan_staged(const Geo& g, int mode, int active, int esize, int dtype,
     const long long IB = mode == 2 ? B : OB;
     const int ex = mode != 0 ? 1 : 0;                       // +1 neighbour slab for the arithmetic kernels
     const int ctas = (mode == 0 && t.ctas_per_sm > 1) ? t.ctas_per_sm : 1;     // byte mover only: several small pipelines per SM
-    const long long budget = SMEM_LIMIT / ctas - 1024;
+    const long long table_bytes = (mode != 0 && g.C <= 512 && !t.no_table) ? (g.C * 36 + 15) / 16 * 16 : 0;     // per-channel shift table
+    const long long budget = SMEM_LIMIT / ctas - 1024 - table_bytes;
     // bytes of one image's slots for a tile of `ta` slabs
     auto slots = [&](long long ta, int* xs, int* gvs, int* gis) {
         const int x_ = (int)(d == 3 ? ta + ex : 1);
@@ -1774,7 +1792,8 @@ StagedPlan plan_staged(const Geo& g, int mode, int active, int esize, int dtype,
     p.gp = GP;
     p.off_gv = (int)(np * xs * slab_x);
     p.off_gi = (int)(np * xs * slab_x + np * gvs * slab_g);
-    p.smem_bytes = (size_t)(stages * stride_of(np) + 16 * stages + 64);
+    p.smem_bytes = (size_t)(stages * stride_of(np) + 16 * stages + 64 + table_bytes);
+    p.table = table_bytes != 0;
     return p;
 }
 
