@@ -641,7 +641,7 @@ int ring_run(const Geo& g, const RingPlan& pl, const void* x, void* y, uint8_t f
 
 
 // ------------------------------------------------------------------------------------------
-// Row-pipelined kernel (2-D, 1-byte elements, dense pixels, C = 128 / 256 / 512): the ring kernel's gather fed by a
+// Row-pipelined kernel (2-D, 1-byte elements, dense pixels, C a multiple of 128; compile-time pixel pitch for 128 / 256 / 512): the ring kernel's gather fed by a
 // producer warp instead of load / barrier / gather / barrier rounds.
 //
 // In NHWC a whole input row (S1 pixels x C channels) is CONTIGUOUS, so it is ONE bulk copy (cp.async.bulk, 14 KB for
@@ -704,11 +704,12 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
     uint64_t* full = (uint64_t*)(rsm + pl.off_bar);
     uint64_t* empty = full + pl.K;
     int* s0t = (int*)(rsm + pl.off_tab);        // axis-0 shift per channel
-    int* s1t = s0t + CB;                        // axis-1 shift per channel
-    int* red = s1t + CB;                        // [0] min, [1] max of the axis-0 shifts
+    const int cb = CB > 0 ? CB : (int)g.C;      // bytes of a pixel = channels (CB == 0: any multiple of 128, run-time pitch)
+    int* s1t = s0t + cb;                        // axis-1 shift per channel
+    int* red = s1t + cb;                        // [0] min, [1] max of the axis-0 shifts
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) rsm[pl.smem_bytes - 16u] = fill;       // the pad value, addressable like any ring byte
-    for (int c = tid; c < CB; c += (int)blockDim.x) {
+    for (int c = tid; c < cb; c += (int)blockDim.x) {
         int sx[2];
         load_qshifts<2>(w, qkind, wzp, (long long)c, g, sx);
         s0t[c] = sx[0];
@@ -717,7 +718,7 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
     __syncthreads();
     if (warp == 0) {
         int mn = s0t[lane], mx = mn;
-        for (int c = lane + 32; c < CB; c += 32) { const int v = s0t[c]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+        for (int c = lane + 32; c < cb; c += 32) { const int v = s0t[c]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const int a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
@@ -733,7 +734,7 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
     // shifts layers learn).
     int W = pl.W, WIN = pl.WIN;
     {
-        constexpr int PP = CB / 128;
+        const int PP = cb / 128;
         const int rows_fit = pl.K - 2 - (smax - smin);                   // rows in flight that leave the whole reach in the ring
         if (smax - smin + 1 > WIN && rows_fit * PP >= 3) {               // (below 3 warps the global-memory fall-back is the lesser evil)
             W = rows_fit * PP < W ? rows_fit * PP : W;
@@ -772,7 +773,7 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
     if (warp >= W) return;
 
     // ---- consumers ----
-    constexpr int P = CB / 128;                // passes (tasks) per output row
+    const int P = cb / 128;                    // passes (tasks) per output row
     const unsigned base = shared_addr(rsm);
     const unsigned fill_addr = base + pl.smem_bytes - 16u;
     const int s1n = g.S[1], lb1 = g.lb[1], ow = g.OS[1];
@@ -831,7 +832,7 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
                     int sl = slot_lo + (t0 - wlo);
                     sl = sl >= K ? sl - K : sl;
                     row_addr[v] = inw ? base + (unsigned)sl * row_bytes + (unsigned)(cw + v) : fill_addr;
-                    pitch[v] = inw ? (unsigned)CB : 0u;
+                    pitch[v] = inw ? (unsigned)cb : 0u;
                     from_global = from_global || (t0 >= 0 && !inw);
                     all_ring = all_ring && inw;
                 }
@@ -843,7 +844,7 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
                 uint8_t* yp = yrow + cw;
                 int p = 0;
                 if (!from_global) {
-                    for (; p < p_lo && p < ow; ++p, yp += CB) {            // leading pixels: some tap is left of the row
+                    for (; p < p_lo && p < ow; ++p, yp += cb) {            // leading pixels: some tap is left of the row
                         unsigned val[4];
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
@@ -858,20 +859,27 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
                     if (all_ring) {
                         for (; p + 7 <= p_hi; p += 8) {
                             unsigned val[8][4];
-                            SpanRows<0, CB>::load(addr, val);
+                            if constexpr (CB > 0) {
+                                SpanRows<0, CB>::load(addr, val);
+                            } else {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i, yp += CB) store4(yp, val[i]);
+                                for (int i = 0; i < 8; ++i)
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) addr[v] += 8u * (unsigned)CB;
+                                    for (int v = 0; v < 4; ++v) val[i][v] = ring_byte(nullptr, addr[v] + (unsigned)(i * cb));
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i, yp += cb) store4(yp, val[i]);
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) addr[v] += 8u * (unsigned)cb;
                         }
                     }
-                    for (; p <= p_hi; ++p, yp += CB) {
+                    for (; p <= p_hi; ++p, yp += cb) {
                         unsigned val[4];
 #pragma unroll
                         for (int v = 0; v < 4; ++v) { val[v] = ring_byte(nullptr, addr[v]); addr[v] += pitch[v]; }
                         store4(yp, val);
                     }
-                    for (; p < ow; ++p, yp += CB) {                        // trailing pixels
+                    for (; p < ow; ++p, yp += cb) {                        // trailing pixels
                         unsigned val[4];
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
@@ -881,7 +889,7 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
                         store4(yp, val);
                     }
                 } else {
-                    for (; p < ow; ++p, yp += CB) {
+                    for (; p < ow; ++p, yp += cb) {
                         unsigned val[4];
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
@@ -917,7 +925,7 @@ __global__ void __launch_bounds__((ROWS_MAX_W + 1) * 32, 1) k_gather_nhwc_rows(G
 bool plan_rows(const Geo& g, int esize, const void* x, const void* y, int sm_count, int max_grid_x, int ring_rows, RowsPlan* out) {
     if (!tma_available()) return false;
     if (g.dim != 2 || esize != 1 || g.xs[1] != 1) return false;
-    if (g.C != 128 && g.C != 256 && g.C != 512) return false;
+    if (g.C % 128 != 0 || g.C > 2048) return false;
     if (g.xs[3] != g.C || g.xs[2] != g.C * (long long)g.S[1] || (g.xs[0] & 15) || g.xs[0] < 0) return false;   // dense rows
     if (((uintptr_t)x & 15u) || ((uintptr_t)y & 3u)) return false;
     const long long row_bytes = (long long)g.S[1] * g.C;
@@ -969,7 +977,8 @@ int rows_run_c(const Geo& g, const RowsPlan& pl, const void* x, void* y, uint8_t
     switch ((int)g.C) {
     case 128: return rows_launch<PAD, 128>(g, pl, x, y, fill, w, qkind, wzp, s);
     case 256: return rows_launch<PAD, 256>(g, pl, x, y, fill, w, qkind, wzp, s);
-    default: return rows_launch<PAD, 512>(g, pl, x, y, fill, w, qkind, wzp, s);
+    case 512: return rows_launch<PAD, 512>(g, pl, x, y, fill, w, qkind, wzp, s);
+    default: return rows_launch<PAD, 0>(g, pl, x, y, fill, w, qkind, wzp, s);        // any other multiple of 128: run-time pixel pitch
     }
 }
 int rows_run(const Geo& g, const RowsPlan& pl, const void* x, void* y, uint8_t fill, const void* w, int qkind, long long wzp, cudaStream_t s) {
