@@ -248,6 +248,35 @@ def test_rows_every_window_phase(dev, oracle_port, auto_path):
                         assert np.allclose(wd.grad.float().cpu().numpy(), gw64, rtol=tol, atol=tol * np.abs(gw64).max() + 1e-30), ("grad_weight",) + tag
 
 
+def test_more_channels_than_the_shift_table_holds(dev, lib, oracle_port, auto_path):
+    """The bandwidth families tabulate the per-channel shift parameters in shared memory for C <= 512 and (halo family) sort
+    the channels by window-misalignment class there; above that they fall back to per-unit evaluation / a single run-time
+    class.  C = 520 through every family that accepts the shape (forced), all paddings, against the oracle."""
+    rng = np.random.default_rng(23)
+    for shape, dim in (((2, 520, 8, 16), 2), ((1, 520, 3, 6, 8), 3), ((2, 520, 64), 1)):
+        x = rng.standard_normal(shape).astype(np.float32)
+        w = ((rng.random((shape[1], dim)) * 2 - 1) * 2.5).astype(np.float32)
+        for pad in range(5):
+            for active in (False, True):
+                y_ref = oracle_port.forward(x, w, pad, active)
+                g = rng.standard_normal(y_ref.shape).astype(np.float32)
+                gi_ref, _ = oracle_port.backward(g, x, w, pad, active)
+                _, gw64 = oracle_port.backward(g.astype(np.float64), x.astype(np.float64), w.astype(np.float64), pad, active)
+                for path in (0, 2, 3, 5):
+                    lib.ts_set_kernel_path(path)
+                    try:
+                        y, gi, gw = _run_cuda(dev, dim, x, w, g, pad, active, None)
+                    except RuntimeError as e:
+                        assert path != 0 and "UNSUPPORTED" in str(e), (shape, pad, active, path, str(e)[:120])
+                        continue
+                    finally:
+                        lib.ts_set_kernel_path(0)
+                    tag = (shape, pad, active, path)
+                    assert np.array_equal(y, y_ref), ("forward",) + tag
+                    assert np.array_equal(gi, gi_ref), ("grad_input",) + tag
+                    assert _gw_close(gw, gw64), ("grad_weight",) + tag
+
+
 def test_strided_and_channels_last_inputs(dev, oracle_port, auto_path):
     rng = np.random.default_rng(9)
     x = rng.standard_normal((2, 6, 8, 12)).astype(np.float32)

@@ -21,6 +21,8 @@ CASES = {"cfg1": ((8, 64, 32, 32), 0, False, torch.float32), "cfg3": ((256, 256,
          "cfg4rs": ((32, 128, 16, 56, 56), 3, False, torch.float32), "cfg4b": ((32, 128, 16, 56, 56), 1, True, torch.float32), "cfg5": ((256, 256, 56, 56), 0, False, torch.qint8), "cfg5cl": ((256, 256, 56, 56), 0, False, torch.qint8),
          "cfg2": ((64, 512, 4096), 2, True, torch.float32), "cfg2h": ((64, 512, 4096), 2, True, torch.bfloat16),
          "cfg2h8k": ((32, 512, 8192), 2, True, torch.bfloat16), "cfg2h2k": ((128, 512, 2048), 2, True, torch.bfloat16),
+         "cfg3d": ((128, 256, 56, 56), 0, False, torch.float64), "cfg3da": ((128, 256, 56, 56), 3, True, torch.float64),
+         "cfg4d": ((16, 128, 16, 56, 56), 3, True, torch.float64),
          "cfg2f2k": ((128, 512, 2048), 2, True, torch.float32), "cfg2f8k": ((32, 512, 8192), 2, True, torch.float32)}
 shape, pad, active, dtype = CASES[sys.argv[1]]
 specs = sys.argv[2:] or [""]
