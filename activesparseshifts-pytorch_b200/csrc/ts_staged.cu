@@ -197,6 +197,9 @@ TS_D int gi_slot_slab(const SArgs& a, const UnitShift& us, int a0, int k) {
 // The whole producer WARP runs this: lane 0 waits for the slot and posts the byte count, then the copies of a stage are
 // dealt to the lanes (one elected thread spent ~40 instructions per copy on addresses at single-thread issue rates:
 // with many small slabs per stage -- 16-bit rows, 12 copies of 8 KB -- the consumers waited for the producer, not for HBM).
+// TBL: the shift table exists (arithmetic kernels).  A template, not a run-time test: the byte mover's instantiation must stay
+// the code it was -- the same source with a dead `tbl ? ... : ...` in it made ptxas schedule k_staged_gather 10 % slower.
+template <bool TBL>
 TS_D void producer(const SArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int lane, const UnitShift* tbl) {
     int s = 0, k = 0;
     const int C = (int)a.g.C, N = (int)a.g.N;
@@ -207,7 +210,8 @@ TS_D void producer(const SArgs& a, unsigned char* smem, uint64_t* full, uint64_t
         unit_decode(u, C, a.chunks, a.unit_order, c, chunk);
         const int n0 = chunk * a.n_per_unit;
         const int n1 = n0 + a.n_per_unit < N ? n0 + a.n_per_unit : N;
-        const UnitShift us = unit_shift_t(a, tbl, c);
+        UnitShift us;
+        if constexpr (TBL) us = unit_shift_t(a, tbl, c); else us = unit_shift(a, c);
         for (int nb = n0; nb < n1; nb += a.np) {
             const int npl = n1 - nb < a.np ? n1 - nb : a.np;
             for (int t = 0; t < a.tiles; ++t) {
@@ -1561,6 +1565,7 @@ struct BackwardBody {
 };
 
 // ---- kernels -----------------------------------------------------------------------------------
+template <bool TBL>
 TS_D const UnitShift* setup_barriers(const SArgs& a, unsigned char* smem, uint64_t*& full, uint64_t*& empty) {
     full = (uint64_t*)(smem + (size_t)a.stages * a.stage_stride);
     empty = full + a.stages;
@@ -1569,9 +1574,11 @@ TS_D const UnitShift* setup_barriers(const SArgs& a, unsigned char* smem, uint64
         fence_barrier_init();
     }
     UnitShift* tbl = nullptr;
-    if (a.table) {
-        tbl = (UnitShift*)(empty + a.stages);
-        for (int c = threadIdx.x; c < (int)a.g.C; c += blockDim.x) tbl[c] = unit_shift(a, c);
+    if constexpr (TBL) {
+        if (a.table) {
+            tbl = (UnitShift*)(empty + a.stages);
+            for (int c = threadIdx.x; c < (int)a.g.C; c += blockDim.x) tbl[c] = unit_shift(a, c);
+        }
     }
     __syncthreads();
     return tbl;
@@ -1581,9 +1588,9 @@ template <int G, int ES>
 __global__ void __launch_bounds__(MAXT_GATHER, 1) k_staged_gather(const __grid_constant__ SArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    const UnitShift* tbl = setup_barriers(a, smem, full, empty);
+    setup_barriers<false>(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { producer(a, smem, full, empty, lane, tbl); return; }
+    if (wid == a.nw) { producer<false>(a, smem, full, empty, lane, nullptr); return; }
     GatherBody<G, ES> body(a, threadIdx.x, a.nw * 32);
     consumer_loop(a, smem, full, empty, lane, body);
 }
@@ -1592,9 +1599,9 @@ template <typename ST, int DIM>
 __global__ void __launch_bounds__(MAXT_ARITH, 1) k_staged_active_forward(const __grid_constant__ SArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    const UnitShift* tbl = setup_barriers(a, smem, full, empty);
+    const UnitShift* tbl = setup_barriers<true>(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { producer(a, smem, full, empty, lane, tbl); return; }
+    if (wid == a.nw) { producer<true>(a, smem, full, empty, lane, tbl); return; }
     ActiveFwdBody<ST, DIM> body(a, threadIdx.x, a.nw * 32);
     body.tbl = tbl;
     consumer_loop(a, smem, full, empty, lane, body);
@@ -1604,9 +1611,9 @@ template <typename ST, int DIM, bool ACTIVE>
 __global__ void __launch_bounds__(MAXT_ARITH, 1) k_staged_backward(const __grid_constant__ SArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full, *empty;
-    const UnitShift* tbl = setup_barriers(a, smem, full, empty);
+    const UnitShift* tbl = setup_barriers<true>(a, smem, full, empty);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid == a.nw) { producer(a, smem, full, empty, lane, tbl); return; }
+    if (wid == a.nw) { producer<true>(a, smem, full, empty, lane, tbl); return; }
     BackwardBody<ST, DIM, ACTIVE> body(a, threadIdx.x, a.nw * 32, wid, lane);
     body.tbl = tbl;
     consumer_loop(a, smem, full, empty, lane, body);
