@@ -41,9 +41,11 @@ class HostShiftPipeline:
         cshape = (self.chunk, self.C) + self.spatial
         self._xd = [torch.empty(cshape, dtype=dtype, device=self.device) for _ in range(slots)]
         self._gd = [torch.empty(cshape, dtype=dtype, device=self.device) for _ in range(slots)]
-        self._s_in = torch.cuda.Stream(self.device)
-        self._s_comp = torch.cuda.Stream(self.device)
-        self._s_out = torch.cuda.Stream(self.device)
+        # distinct priorities: streams of different priority never share a hardware queue, so the two copy directions and the
+        # kernels cannot serialise behind each other through a false queue dependency (see bench.py)
+        self._s_in = torch.cuda.Stream(self.device, priority=0)
+        self._s_comp = torch.cuda.Stream(self.device, priority=-1)
+        self._s_out = torch.cuda.Stream(self.device, priority=-2)
         self._borders = torch.tensor([0, self.spatial[0], 0, self.spatial[1] if self.dim > 1 else 1,
                                       0, self.spatial[2] if self.dim > 2 else 1], dtype=torch.int32)
         esz = torch.empty((), dtype=dtype).element_size()
@@ -71,6 +73,12 @@ class HostShiftPipeline:
         self.gw_device = gw_total
         self._s_comp.wait_stream(cur)
         free = [None] * self.slots           # event: slot's device inputs may be overwritten
+        # Outputs of a chunk (allocated by the operators on the compute stream) are kept alive per slot until the copy-out of
+        # that slot has finished AND the compute stream has been ordered behind it; only then are the references dropped, so
+        # the caching allocator hands the same few blocks back to the compute stream.  (tensor.record_stream() instead made
+        # the allocator decide by event queries at allocation time: whenever a copy-out was still in flight it called
+        # cudaMalloc -- a device-wide synchronisation -- and one pipeline instance in four ran at half speed or worse.)
+        held = [None] * self.slots           # (y, grad_input, copy-out-done event) of the slot's previous chunk
         nchunks = (self.N + self.chunk - 1) // self.chunk
         for i in range(nchunks):
             lo, hi = i * self.chunk, min(self.N, (i + 1) * self.chunk)
@@ -86,6 +94,9 @@ class HostShiftPipeline:
                 ready.record(self._s_in)
             with torch.cuda.stream(self._s_comp):
                 self._s_comp.wait_event(ready)
+                if held[k] is not None:
+                    self._s_comp.wait_event(held[k][2])      # the slot's previous outputs have left the device ...
+                    held[k] = None                           # ... so their blocks may serve this chunk's outputs
                 new_size = [n, self.C] + list(self.spatial)
                 y = fwd(xd, weight, self._borders, new_size, padding_mode, active_flag)
                 gi, gw = bwd(gd, weight, xd, self._borders, padding_mode, active_flag)
@@ -97,8 +108,13 @@ class HostShiftPipeline:
                 self._s_out.wait_event(done)
                 self.y_host[lo:hi].copy_(y, non_blocking=True)
                 self.gi_host[lo:hi].copy_(gi, non_blocking=True)
-                y.record_stream(self._s_out)
-                gi.record_stream(self._s_out)
+                out_done = torch.cuda.Event()
+                out_done.record(self._s_out)
+                held[k] = (y, gi, out_done)
+        for k in range(self.slots):                          # order the compute stream behind the last copies before the references go
+            if held[k] is not None:
+                self._s_comp.wait_event(held[k][2])
+        held = None
         cur.wait_stream(self._s_comp)
         cur.wait_stream(self._s_out)
         cur.wait_stream(self._s_in)

@@ -384,6 +384,11 @@ def measure_device_resident(args, N, dev, world, rank, fused, lib, sampler=None,
 
 
 def run_ours(args):
+    # The host pipeline runs copy-in, compute and copy-out on three streams; with the default 8 hardware connections two of them
+    # can land on the same queue (which one depends on how many streams the process created before) and then the two copy
+    # directions serialise: 68 instead of 36 ms per step, measured run to run on the same box.  More connections, set before
+    # the CUDA context exists, make that aliasing unlikely; the pipeline's streams also get distinct priorities.
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import torch
     import torch.distributed as dist
     import torchshifts  # noqa: F401
@@ -440,14 +445,30 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         k = max(3, min(args.steps, 10))
+        trace = []
         t0 = time.perf_counter()
         for _ in range(k):
             gw = pipe.forward_backward(wh, 0, False)
             if world > 1:
                 dist.all_reduce(gw)                 # the host pipeline reduces its per-chunk grad_weight once per step
             pipe.read_back_grad_weight(gw)          # the C x 2 result goes back to the host as well
+            if os.environ.get("TS_BENCH_E2E_TRACE"):
+                torch.cuda.synchronize(); trace.append(time.perf_counter())
         torch.cuda.synchronize()
         e_ms = (time.perf_counter() - t0) / k * 1e3
+        if trace:
+            print("[e2e trace] ms per step:", " ".join(f"{(b - a) * 1e3:.1f}" for a, b in zip([t0] + trace[:-1], trace)), file=sys.stderr)
+        if os.environ.get("TS_BENCH_E2E_REPEAT"):           # diagnostic: does a NEW pipeline instance (new pinned buffers, new streams) change the rate?
+            for rep in range(int(os.environ["TS_BENCH_E2E_REPEAT"])):
+                p2 = HostShift2dPipeline(N, C, H, W, device=dev)
+                p2.x_host.copy_(pipe.x_host); p2.g_host.copy_(pipe.g_host)
+                p2.forward_backward(wh, 0, False); torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                for _ in range(4):
+                    p2.read_back_grad_weight(p2.forward_backward(wh, 0, False))
+                torch.cuda.synchronize()
+                print(f"[e2e repeat {rep}] {(time.perf_counter() - t1) / 4 * 1e3:.1f} ms per step", file=sys.stderr)
+                del p2
         if world > 1:
             t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

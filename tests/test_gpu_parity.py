@@ -277,6 +277,32 @@ def test_more_channels_than_the_shift_table_holds(dev, lib, oracle_port, auto_pa
                     assert _gw_close(gw, gw64), ("grad_weight",) + tag
 
 
+def test_host_pipeline_matches_the_operators(dev, oracle_port, auto_path):
+    """torchshifts.host.HostShiftPipeline (bench.py's e2e leg: pinned host buffers, three streams, chunks through a ring of
+    device slots, operator outputs handed back to the allocator only behind the copy-out) gives what one call of the
+    operators on the whole tensor gives, step after step, also with a ragged last chunk and more chunks than slots."""
+    from torchshifts.host import HostShift2dPipeline
+    from torchshifts.functional import shift2d_func
+    torch.manual_seed(11)
+    N, C, H, W = 23, 8, 12, 16
+    pipe = HostShift2dPipeline(N, C, H, W, device=dev, chunk=4, slots=3)
+    w = (torch.rand(C, 2, device=dev) * 2 - 1) * 2
+    for step, (pad, active) in enumerate(((0, False), (3, True), (0, False))):
+        pipe.x_host.normal_(); pipe.g_host.normal_()
+        gw = pipe.forward_backward(w, pad, active)
+        pipe.read_back_grad_weight(gw)
+        torch.cuda.synchronize()
+        xd = pipe.x_host.to(dev).requires_grad_(True)
+        wd = w.clone().requires_grad_(True)
+        y = shift2d_func(xd, wd, pad, active)
+        y.backward(pipe.g_host.to(dev))
+        assert torch.equal(pipe.y_host, y.detach().cpu()), step
+        assert torch.equal(pipe.gi_host, xd.grad.cpu()), step
+        assert torch.allclose(pipe.gw_host, wd.grad.cpu(), rtol=1e-5, atol=1e-5 * float(wd.grad.abs().max())), step
+        y_ref = oracle_port.forward(pipe.x_host.numpy(), w.cpu().numpy(), pad, active)
+        assert np.array_equal(pipe.y_host.numpy(), y_ref), step
+
+
 def test_strided_and_channels_last_inputs(dev, oracle_port, auto_path):
     rng = np.random.default_rng(9)
     x = rng.standard_normal((2, 6, 8, 12)).astype(np.float32)
